@@ -1,0 +1,198 @@
+"""ctypes binding of libpdn_b200.so (C ABI declared in include/pdn_b200.h).
+
+The reference has no native interface; its GPU seam is ``Device.xp -> cupy``
+(reference pydynet/cuda.py:90-91).  This module is the replacement seam: every device-side array
+operation of the package goes through the functions bound here.  There is NO CPU fallback: if the shared
+library (or a CUDA device) is missing, using a cuda device raises ``RuntimeError`` — exactly the error the
+reference raises when CuPy is absent (reference pydynet/cuda.py:67-69).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_PKG = os.path.dirname(_HERE)
+LIB_PATH = os.path.join(_PKG, "libpdn_b200.so")
+CSRC = os.path.join(_PKG, "csrc")
+
+# enums (must match include/pdn_b200.h)
+F32, F64, F16, I64, I32, BOOL, BF16, U8 = range(8)
+ADD, SUB, MUL, DIV, POW, MAXIMUM, MINIMUM = range(7)
+EQ, NE, LT, LE, GT, GE = range(16, 22)
+NEG, EXP, LOG, ABS, SIGN, SIGMOID, TANH, SQRT, SQUARE, RECIP, SILU, RELU = range(12)
+T_EQ_MUL, T_DIV_GRAD_Y, T_POW_GRAD_X, T_SIGMOID_GRAD, T_TANH_GRAD, T_FMA, T_SILU_GRAD, T_WHERE = range(8)
+R_SUM, R_MEAN, R_MAX, R_MIN, R_ARGMAX, R_ARGMIN = range(6)
+
+_lib = None
+_load_error = None
+MISSING = []  # declared in include/pdn_b200.h but absent from the built library
+
+vp, i64, i32, f32, f64, u32, u64 = C.c_void_p, C.c_int64, C.c_int, C.c_float, C.c_double, C.c_uint32, C.c_uint64
+pi64 = C.POINTER(C.c_int64)
+
+_PROTOS = {
+    "pdn_device_count": [C.POINTER(i32)],
+    "pdn_init": [i32],
+    "pdn_set_device": [i32],
+    "pdn_get_device": [C.POINTER(i32)],
+    "pdn_device_name": [C.c_char_p, i32],
+    "pdn_sm_count": [C.POINTER(i32)],
+    "pdn_malloc": [C.POINTER(vp), C.c_size_t],
+    "pdn_free": [vp],
+    "pdn_malloc_host": [C.POINTER(vp), C.c_size_t],
+    "pdn_free_host": [vp],
+    "pdn_mem_stats": [C.POINTER(u64), C.POINTER(u64), C.POINTER(u64)],
+    "pdn_empty_cache": [],
+    "pdn_memcpy_h2d": [vp, vp, C.c_size_t],
+    "pdn_memcpy_d2h": [vp, vp, C.c_size_t],
+    "pdn_memcpy_d2d": [vp, vp, C.c_size_t],
+    "pdn_memcpy_h2d_async": [vp, vp, C.c_size_t],
+    "pdn_memcpy_d2h_async": [vp, vp, C.c_size_t],
+    "pdn_memset": [vp, i32, C.c_size_t],
+    "pdn_sync": [],
+    "pdn_event_create": [C.POINTER(vp)],
+    "pdn_event_destroy": [vp],
+    "pdn_event_record": [vp],
+    "pdn_event_elapsed_ms": [vp, vp, C.POINTER(f32)],
+    "pdn_graph_begin": [],
+    "pdn_graph_end": [C.POINTER(vp)],
+    "pdn_graph_launch": [vp],
+    "pdn_graph_destroy": [vp],
+    "pdn_fill": [vp, i32, i32, pi64, pi64, f64],
+    "pdn_copy": [vp, i32, vp, i32, i32, pi64, pi64, pi64],
+    "pdn_ew_binary": [i32, i32, vp, vp, vp, i32, pi64, pi64, pi64, pi64],
+    "pdn_ew_binary_scalar": [i32, i32, vp, f64, i32, vp, i32, pi64, pi64, pi64],
+    "pdn_ew_unary": [i32, i32, vp, vp, i32, pi64, pi64, pi64],
+    "pdn_ew_ternary": [i32, i32, vp, vp, vp, vp, i32, pi64, pi64, pi64, pi64, pi64],
+    "pdn_reduce": [i32, i32, vp, vp, i32, pi64, pi64, u32],
+    "pdn_index_gather": [vp, i32, vp, i32, C.POINTER(vp), pi64, pi64, i64, i32, pi64, pi64, i32, pi64, pi64],
+    "pdn_index_scatter": [vp, i32, vp, i32, C.POINTER(vp), pi64, pi64, i64, i32, pi64, pi64, i32, pi64, pi64, i32],
+    "pdn_gemm": [i32, vp, vp, vp, i64, i64, i64, i64, i64, i64, i64, i64, pi64, pi64, pi64, pi64, vp, i32, i32],
+    "pdn_gemm_last_path": [],
+    "pdn_softmax_fwd": [i32, vp, vp, i64, i64, i32],
+    "pdn_softmax_bwd": [i32, vp, vp, vp, i64, i64, i32],
+    "pdn_rmsnorm_fwd": [vp, vp, vp, vp, i64, i64, f32],
+    "pdn_rmsnorm_bwd": [vp, vp, vp, vp, vp, vp, i64, i64, C.POINTER(i32)],
+    "pdn_bnorm_stats": [vp, vp, vp, i64, i64, i64],
+    "pdn_bnorm_apply": [vp, vp, vp, vp, vp, vp, i64, i64, i64, f32],
+    "pdn_bnorm_bwd": [vp, vp, vp, vp, vp, vp, vp, vp, i64, i64, i64, f32],
+    "pdn_conv2d_fwd": [vp, vp, vp, vp, i64, i64, i64, i64, i64, i32, i32, i32],
+    "pdn_conv2d_bwd_data": [vp, vp, vp, i64, i64, i64, i64, i64, i32, i32, i32],
+    "pdn_conv2d_bwd_weight": [vp, vp, vp, vp, i64, i64, i64, i64, i64, i32, i32, i32],
+    "pdn_pool2d_fwd": [vp, vp, i64, i64, i64, i64, i32, i32, i32, i32],
+    "pdn_pool2d_bwd": [vp, vp, vp, vp, i64, i64, i64, i64, i32, i32, i32, i32],
+    "pdn_attention_fwd": [vp, vp, vp, vp, vp, vp, i64, i64, i64, i64, i64, pi64, pi64, pi64, f32],
+    "pdn_attention_bwd": [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i64, i64, i64, i64, i64, pi64, pi64, pi64, f32],
+    "pdn_gru_seq_fwd": [vp, vp, vp, vp, vp, vp, vp, vp, i64, i64, i64],
+    "pdn_gru_seq_bwd": [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i64, i64, i64],
+    "pdn_lstm_seq_fwd": [vp, vp, vp, vp, vp, vp, vp, i64, i64, i64],
+    "pdn_lstm_seq_bwd": [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i64, i64, i64],
+    "pdn_ce_loss_fwd": [vp, vp, vp, vp, i64, i64, i32],
+    "pdn_ce_loss_bwd": [vp, vp, vp, vp, vp, i64, i64, i32],
+    "pdn_adam_step": [vp, vp, vp, vp, i64, f32, f32, f32, f32, f32, i32, f32],
+    "pdn_adam_multi": [i32, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), pi64, f32, f32, f32, f32, f32, i32, f32],
+    "pdn_rope_kv_append": [vp, vp, vp, vp, vp, vp, vp, i64, i64, i64, i64, i64, i64],
+    "pdn_swiglu": [vp, vp, vp, i64],
+    "pdn_nccl_unique_id": [C.c_char_p],
+    "pdn_nccl_init": [i32, i32, C.c_char_p],
+    "pdn_allreduce_sum_f32": [vp, i64],
+    "pdn_allreduce_wait": [],
+    "pdn_nccl_destroy": [],
+}
+_NO_STATUS = {"pdn_gemm_last_path"}
+
+
+class PdnError(RuntimeError):
+    pass
+
+
+def build(verbose: bool = False) -> str:
+    """Compile csrc/*.cu for sm_100a into libpdn_b200.so (in-tree). Cross-compiles without a GPU."""
+    out = subprocess.run(["bash", os.path.join(CSRC, "build.sh")], capture_output=True, text=True)
+    if verbose or out.returncode != 0:
+        print(out.stdout)
+        print(out.stderr)
+    if out.returncode != 0:
+        raise PdnError("building libpdn_b200.so failed:\n" + out.stderr[-4000:])
+    return LIB_PATH
+
+
+def load():
+    """Load the shared library (once). Raises PdnError if it is missing — never falls back to NumPy."""
+    global _lib, _load_error
+    if _lib is not None:
+        return _lib
+    if _load_error is not None:
+        raise _load_error
+    if not os.path.exists(LIB_PATH):
+        _load_error = PdnError(
+            f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(pydynet_b200 has no CPU fallback for cuda devices)")
+        raise _load_error
+    try:
+        lib = C.CDLL(LIB_PATH, mode=C.RTLD_GLOBAL)
+    except OSError as e:  # pragma: no cover
+        _load_error = PdnError(f"cannot load {LIB_PATH}: {e}")
+        raise _load_error
+    lib.pdn_last_error.restype = C.c_char_p
+    lib.pdn_last_error.argtypes = []
+    lib.pdn_kernel_launch_count.restype = u64
+    lib.pdn_kernel_launch_count.argtypes = []
+    lib.pdn_reset_launch_count.restype = None
+    lib.pdn_reset_launch_count.argtypes = []
+    for name, args in _PROTOS.items():
+        try:
+            fn = getattr(lib, name)
+        except AttributeError:  # header declares it, library does not export it: surfaced by tests/test_abi.py
+            MISSING.append(name)
+            continue
+        fn.argtypes = args
+        fn.restype = i32
+    _lib = lib
+    return lib
+
+
+def declared_symbols():
+    return sorted(list(_PROTOS) + ["pdn_last_error", "pdn_kernel_launch_count", "pdn_reset_launch_count"])
+
+
+def check(status: int):
+    if status != 0:
+        msg = _lib.pdn_last_error().decode(errors="replace") if _lib is not None else "?"
+        if status == 3:
+            raise MemoryError(f"pdn_b200: out of device memory: {msg}")
+        raise PdnError(f"pdn_b200 error {status}: {msg}")
+
+
+def call(name: str, *args):
+    """Call a status-returning entry point and raise on error."""
+    st = getattr(load(), name)(*args)
+    if st != 0:
+        check(st)
+
+
+_device_count = None
+
+
+def device_count() -> int:
+    global _device_count
+    if _device_count is None:
+        try:
+            lib = load()
+        except PdnError:
+            _device_count = 0
+            return 0
+        n = i32(0)
+        lib.pdn_device_count(C.byref(n))
+        _device_count = int(n.value)
+    return _device_count
+
+
+def launch_count() -> int:
+    return int(load().pdn_kernel_launch_count())
+
+
+def reset_launch_count():
+    load().pdn_reset_launch_count()

@@ -1,0 +1,19 @@
+#!/bin/bash
+# Builds libpdn_b200.so in-tree for sm_100a (cross-compiles without a GPU).
+set -e
+cd "$(dirname "$0")"
+NVCC=${NVCC:-/usr/local/cuda/bin/nvcc}
+FLAGS="-gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC -Xcompiler -Wall -Xcompiler -Wno-unused-function --expt-relaxed-constexpr"
+mkdir -p build
+pids=()
+for f in *.cu; do
+  o=build/${f%.cu}.o
+  if [ ! -f "$o" ] || [ "$f" -nt "$o" ] || [ common.cuh -nt "$o" ] || [ ../../include/pdn_b200.h -nt "$o" ] || [ gemm_args.h -nt "$o" ]; then
+    $NVCC $FLAGS $EXTRA -c "$f" -o "$o" &
+    pids+=($!)
+  fi
+done
+for p in "${pids[@]}"; do wait $p; done
+NCCL_INC=$(python -c "import nvidia.nccl,os;print(os.path.join(list(nvidia.nccl.__path__)[0],'include'))" 2>/dev/null || true)
+$NVCC -shared -o ../libpdn_b200.so build/*.o -lcudart $NCCL_LINK
+echo "built $(pwd)/../libpdn_b200.so"

@@ -1,0 +1,423 @@
+// gemm_tc.cu — fp32-parity GEMM on the Blackwell tensor cores (tcgen05.mma, accumulators in TMEM,
+// operands staged by TMA into 128B-swizzled shared memory, mbarrier producer/consumer pipeline).
+//
+// fp32 parity (<=1e-4 normwise vs the reference NumPy sgemm) comes from a 2-term BF16 split
+// of each operand: x = hi + lo, C = Ahi·Bhi + Ahi·Blo + Alo·Bhi accumulated in fp32 TMEM (3 BF16 MMAs per
+// product, ~16 effective mantissa bits, 4.5e-6 measured normwise error in emulation).
+//
+// Two kernels:
+//   k_pack_split   fp32 operand with arbitrary (row, col, batch) element strides -> K-major bf16 planes
+//                  [batch][hi|lo][rows][Kp]; this absorbs every transposed / strided / broadcast view the
+//                  reference feeds to `@` (tensor.py:657-676) so the MMA kernel sees one canonical layout.
+//   k_gemm_tc      one CTA per 128xBN output tile; warp 0 = TMA producer, warp 1 = MMA issuer (one elected
+//                  lane), warp 2 = TMEM allocator, warps 4-7 = epilogue (tcgen05.ld -> +bias/+C -> st.global).
+#include "common.cuh"
+#include "gemm_args.h"
+#include <cuda.h>
+#include <cudaTypedefs.h>
+#include <stdlib.h>
+
+namespace pdn {
+
+
+// ------------------------------------------------------------------ PTX wrappers --------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_LOOP:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra WAIT_DONE;\n"
+      "bra WAIT_LOOP;\n"
+      "WAIT_DONE:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_load_4d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(
+          smem_u32(dst)),
+      "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t cols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(cols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t addr, uint32_t cols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(cols) : "memory");
+}
+// D[tmem] (+)= A[smem desc] * B[smem desc], kind::f16 (bf16 inputs, fp32 accumulate)
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrive on an mbarrier once all previously issued tcgen05.mma of this thread have completed
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// 32 lanes x 32 consecutive fp32 columns -> 32 registers per thread
+__device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, float* v) {
+  uint32_t* r = reinterpret_cast<uint32_t*>(v);
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+        "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+        "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// K-major, 128B-swizzled shared-memory operand descriptor (rows of 64 bf16 = 128 B; 8-row groups 1024 B apart)
+__device__ __forceinline__ uint64_t make_smem_desc_sw128(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFF);  // start address, 16 B units
+  d |= (uint64_t)1 << 16;                  // leading byte offset (unused for swizzled K-major), 16 B units
+  d |= (uint64_t)(1024 >> 4) << 32;        // stride byte offset between 8-row core groups
+  d |= (uint64_t)1 << 46;                  // descriptor version (Blackwell)
+  d |= (uint64_t)2 << 61;                  // layout type: SWIZZLE_128B
+  return d;
+}
+// instruction descriptor: c=f32, a=b=bf16, both K-major, M x N
+__host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+// ------------------------------------------------------------------ operand packing -----------
+struct PackArgs {
+  const float* src;
+  __nv_bfloat16* dst;      // [pbatch][2][R][Kp]
+  int64_t R, K, Kp;
+  int64_t r_stride, k_stride;  // element strides of the source along rows / k
+  int64_t nb[3], bs[3];        // source batch shape / strides (only dims with stride != 0 are walked)
+};
+
+__global__ void __launch_bounds__(256) k_pack_split(PackArgs p) {
+  __shared__ float tile[32][33];
+  // blockIdx.z enumerates the operand's own distinct batches
+  int64_t z = blockIdx.z, off = 0;
+  {
+    int64_t rem = z;
+    for (int d = 2; d >= 0; --d) {
+      int64_t n = (p.bs[d] != 0 && p.nb[d] > 1) ? p.nb[d] : 1;
+      off += (rem % n) * p.bs[d];
+      rem /= n;
+    }
+  }
+  const float* src = p.src + off;
+  __nv_bfloat16* hi = p.dst + (size_t)z * 2 * p.R * p.Kp;
+  __nv_bfloat16* lo = hi + (size_t)p.R * p.Kp;
+  const int64_t r0 = (int64_t)blockIdx.y * 32, k0 = (int64_t)blockIdx.x * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
+  const bool k_fast = (p.k_stride == 1) || (p.r_stride != 1);
+  if (k_fast) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      int64_t r = r0 + ty + i * 8, k = k0 + tx;
+      tile[ty + i * 8][tx] = (r < p.R && k < p.K) ? src[r * p.r_stride + k * p.k_stride] : 0.f;
+    }
+  } else {  // rows are the unit-stride axis of the source: read along rows, transpose through smem
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      int64_t r = r0 + tx, k = k0 + ty + i * 8;
+      tile[tx][ty + i * 8] = (r < p.R && k < p.K) ? src[r * p.r_stride + k * p.k_stride] : 0.f;
+    }
+  }
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    int64_t r = r0 + ty + i * 8, k = k0 + tx;
+    if (r < p.R && k < p.Kp) {
+      float         x = tile[ty + i * 8][tx];
+      __nv_bfloat16 h = __float2bfloat16_rn(x);
+      hi[r * p.Kp + k] = h;
+      lo[r * p.Kp + k] = __float2bfloat16_rn(x - __bfloat162float(h));
+    }
+  }
+}
+
+// ------------------------------------------------------------------ the MMA kernel -------------
+constexpr int TC_BM = 128;
+constexpr int TC_BK = 64;  // 64 bf16 = 128 B = one swizzle span
+
+template <int BN>
+struct TcCfg {
+  static constexpr int kStageBytes = 2 * (TC_BM * TC_BK * 2) + 2 * (BN * TC_BK * 2);  // Ahi, Alo, Bhi, Blo
+  static constexpr int kStages = (BN == 128) ? 3 : 2;
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int kTmemCols = BN;  // fp32 accumulator columns (power of two >= 32)
+};
+
+struct TcArgs {
+  float* C; const float* bias;
+  int64_t M, N, K, ldc;
+  int64_t nb[3], c_bs[3];
+  int64_t a_pbs[3], b_pbs[3];  // packed-batch index strides per batch dim
+  int accumulate;
+};
+
+template <int BN>
+__global__ void __launch_bounds__(256, 1) k_gemm_tc(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
+                                                   TcArgs g) {
+  using Cfg = TcCfg<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t*  smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint64_t* full_bar = (uint64_t*)(smem + Cfg::kStages * Cfg::kStageBytes);
+  uint64_t* empty_bar = full_bar + Cfg::kStages;
+  uint64_t* accum_bar = empty_bar + Cfg::kStages;
+  uint32_t* tmem_slot = (uint32_t*)(accum_bar + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n_blk = blockIdx.x, m_blk = blockIdx.y;
+  int64_t   z = blockIdx.z;
+  const int64_t i2 = z % g.nb[2]; z /= g.nb[2];
+  const int64_t i1 = z % g.nb[1]; z /= g.nb[1];
+  const int64_t i0 = z;
+  const int     a_batch = (int)(i0 * g.a_pbs[0] + i1 * g.a_pbs[1] + i2 * g.a_pbs[2]);
+  const int     b_batch = (int)(i0 * g.b_pbs[0] + i1 * g.b_pbs[1] + i2 * g.b_pbs[2]);
+  const int     num_kb = (int)((g.K + TC_BK - 1) / TC_BK);
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&mapA);
+    tma_prefetch_desc(&mapB);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < Cfg::kStages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(accum_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc(tmem_slot, Cfg::kTmemCols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===== TMA producer =====
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        uint8_t* st = smem + stage * Cfg::kStageBytes;
+        mbar_expect_tx(&full_bar[stage], Cfg::kStageBytes);
+        const int k = kb * TC_BK;
+        tma_load_4d(&mapA, &full_bar[stage], st, k, m_blk * TC_BM, 0, a_batch);
+        tma_load_4d(&mapA, &full_bar[stage], st + TC_BM * TC_BK * 2, k, m_blk * TC_BM, 1, a_batch);
+        tma_load_4d(&mapB, &full_bar[stage], st + 2 * TC_BM * TC_BK * 2, k, n_blk * BN, 0, b_batch);
+        tma_load_4d(&mapB, &full_bar[stage], st + 2 * TC_BM * TC_BK * 2 + BN * TC_BK * 2, k, n_blk * BN, 1, b_batch);
+        if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer (single elected lane) =====
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(TC_BM, BN);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(&full_bar[stage], phase);
+        tc_fence_after();
+        const uint32_t sa = smem_u32(smem + stage * Cfg::kStageBytes);
+        const uint64_t d_ahi = make_smem_desc_sw128(sa);
+        const uint64_t d_alo = make_smem_desc_sw128(sa + TC_BM * TC_BK * 2);
+        const uint64_t d_bhi = make_smem_desc_sw128(sa + 2 * TC_BM * TC_BK * 2);
+        const uint64_t d_blo = make_smem_desc_sw128(sa + 2 * TC_BM * TC_BK * 2 + BN * TC_BK * 2);
+#pragma unroll
+        for (int k = 0; k < TC_BK / 16; ++k) {
+          const uint64_t adv = (uint64_t)((k * 16 * 2) >> 4);  // 32 B per UMMA_K step inside the swizzle span
+          // small cross terms first, then the leading term
+          umma_bf16(tmem_base, d_alo + adv, d_bhi + adv, idesc, (kb | k) ? 1u : 0u);
+          umma_bf16(tmem_base, d_ahi + adv, d_blo + adv, idesc, 1u);
+          umma_bf16(tmem_base, d_ahi + adv, d_bhi + adv, idesc, 1u);
+        }
+        umma_commit(&empty_bar[stage]);  // frees this smem stage once the MMAs above have read it
+        if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
+      }
+      umma_commit(accum_bar);  // accumulator complete
+    }
+  } else if (warp >= 4) {
+    // ===== epilogue: TMEM -> registers -> (+bias, +C) -> global =====
+    const int q = warp & 3;  // TMEM lane quarter this warp may access
+    mbar_wait(accum_bar, 0);
+    tc_fence_after();
+    const int64_t row = (int64_t)m_blk * TC_BM + q * 32 + lane;
+    float* crow = g.C + i0 * g.c_bs[0] + i1 * g.c_bs[1] + i2 * g.c_bs[2] + row * g.ldc;
+    const bool vec_ok = ((g.ldc & 3) == 0) && ((((uintptr_t)g.C) & 15) == 0) && (((g.c_bs[0] | g.c_bs[1] | g.c_bs[2]) & 3) == 0);
+#pragma unroll 1
+    for (int c0 = 0; c0 < BN; c0 += 32) {
+      float v[32];
+      tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
+      tmem_ld_wait();
+      const int64_t col0 = (int64_t)n_blk * BN + c0;
+      if (row < g.M && col0 < g.N) {
+        if (g.bias) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (col0 + j < g.N) v[j] += __ldg(g.bias + col0 + j);
+        }
+        if (vec_ok && col0 + 32 <= g.N) {
+          float4* c4 = reinterpret_cast<float4*>(crow + col0);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            float4 o = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+            if (g.accumulate) {
+              float4 p = c4[j];
+              o.x += p.x; o.y += p.y; o.z += p.z; o.w += p.w;
+            }
+            c4[j] = o;
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (col0 + j < g.N) crow[col0 + j] = g.accumulate ? crow[col0 + j] + v[j] : v[j];
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc(tmem_base, Cfg::kTmemCols);
+}
+
+// ------------------------------------------------------------------ host side ------------------
+static PFN_cuTensorMapEncodeTiled_v12000 g_encode = nullptr;
+
+static int get_encode_fn() {
+  if (g_encode) return 0;
+  void*                           fn = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
+  if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || !fn) {
+    set_error("cuTensorMapEncodeTiled not available from the driver (err %d, q %d)", (int)e, (int)qres);
+    return PDN_ERR_CUDA;
+  }
+  g_encode = (PFN_cuTensorMapEncodeTiled_v12000)fn;
+  return 0;
+}
+
+// 4-D map over packed planes [batch][2][R][Kp] (bf16), box = 64 (k) x box_rows x 1 x 1, 128B swizzle
+static int make_map(CUtensorMap* map, const void* base, int64_t R, int64_t K, int64_t Kp, int64_t nbatch, int box_rows) {
+  cuuint64_t dims[4] = {(cuuint64_t)K, (cuuint64_t)R, 2, (cuuint64_t)nbatch};
+  cuuint64_t strides[3] = {(cuuint64_t)Kp * 2, (cuuint64_t)R * Kp * 2, (cuuint64_t)R * Kp * 4};
+  cuuint32_t box[4] = {(cuuint32_t)TC_BK, (cuuint32_t)box_rows, 1, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult   r = g_encode(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed with CUresult %d (R=%lld K=%lld Kp=%lld batch=%lld)", (int)r, (long long)R, (long long)K,
+              (long long)Kp, (long long)nbatch);
+    return PDN_ERR_CUDA;
+  }
+  return 0;
+}
+
+bool gemm_tc_eligible(const GemmArgs& g) {
+  if (g.M < 64 || g.N < 32 || g.K < 32) return false;
+  double work = (double)g.M * (double)g.N * (double)g.K;
+  if (work < (double)(1 << 21)) return false;  // tiny products: launch-bound, FFMA tile kernel is fine
+  int64_t nbatch = g.nb[0] * g.nb[1] * g.nb[2];
+  if (nbatch > 65535) return false;
+  if ((g.M + TC_BM - 1) / TC_BM > 65535) return false;
+  if (g.M > 0x7fffffff || g.N > 0x7fffffff || g.K > 0x7fffffff) return false;
+  return true;
+}
+
+static int pack_operand(const float* src, int64_t R, int64_t K, int64_t r_stride, int64_t k_stride, const int64_t* nb,
+                        const int64_t* bs, Scratch* buf, int64_t* Kp_out, int64_t* pbatch_out, int64_t* pbs_out) {
+  int64_t Kp = (K + 7) & ~(int64_t)7;
+  int64_t pb = 1;
+  PackArgs p;
+  for (int d = 2; d >= 0; --d) {
+    bool walk = (bs[d] != 0 && nb[d] > 1);
+    pbs_out[d] = walk ? pb : 0;
+    if (walk) pb *= nb[d];
+    p.nb[d] = nb[d];
+    p.bs[d] = bs[d];
+  }
+  PDN_CHECK(pb <= 65535, "gemm_tc: too many operand batches");
+  PDN_TRY(buf->alloc((size_t)pb * 2 * R * Kp * sizeof(__nv_bfloat16)));
+  p.src = src;
+  p.dst = (__nv_bfloat16*)buf->p;
+  p.R = R; p.K = K; p.Kp = Kp;
+  p.r_stride = r_stride; p.k_stride = k_stride;
+  dim3 grd((unsigned)((Kp + 31) / 32), (unsigned)((R + 31) / 32), (unsigned)pb);
+  PDN_CHECK(grd.y <= 65535, "gemm_tc: operand has too many rows for the pack grid");
+  k_pack_split<<<grd, 256, 0, stream()>>>(p);
+  PDN_LAUNCHED("pack_split");
+  *Kp_out = Kp;
+  *pbatch_out = pb;
+  return 0;
+}
+
+template <int BN>
+static int launch_tc(const GemmArgs& g, const CUtensorMap& mA, const CUtensorMap& mB, const TcArgs& t) {
+  using Cfg = TcCfg<BN>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    PDN_CUDA(cudaFuncSetAttribute(k_gemm_tc<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    attr_set = true;
+  }
+  int64_t nbatch = g.nb[0] * g.nb[1] * g.nb[2];
+  dim3    grd((unsigned)((g.N + BN - 1) / BN), (unsigned)((g.M + TC_BM - 1) / TC_BM), (unsigned)nbatch);
+  k_gemm_tc<BN><<<grd, 256, Cfg::kSmemBytes, stream()>>>(mA, mB, t);
+  PDN_LAUNCHED("gemm_tc");
+  return 0;
+}
+
+int gemm_tc_launch(const GemmArgs& g) {
+  PDN_TRY(get_encode_fn());
+  Scratch bufA, bufB;
+  int64_t KpA, KpB, pbA, pbB;
+  TcArgs  t;
+  // A: rows = M, k along a_cs.  B: rows = N (we need Bᵀ K-major), k along b_rs.
+  PDN_TRY(pack_operand((const float*)g.A, g.M, g.K, g.a_rs, g.a_cs, g.nb, g.a_bs, &bufA, &KpA, &pbA, t.a_pbs));
+  PDN_TRY(pack_operand((const float*)g.B, g.N, g.K, g.b_cs, g.b_rs, g.nb, g.b_bs, &bufB, &KpB, &pbB, t.b_pbs));
+  const int   BN = (g.N > 128 && getenv("PDN_TC_BN128") == nullptr) ? 256 : 128;
+  CUtensorMap mA, mB;
+  PDN_TRY(make_map(&mA, bufA.p, g.M, g.K, KpA, pbA, TC_BM));
+  PDN_TRY(make_map(&mB, bufB.p, g.N, g.K, KpB, pbB, BN));
+  t.C = (float*)g.C;
+  t.bias = (const float*)g.bias;
+  t.M = g.M; t.N = g.N; t.K = g.K; t.ldc = g.ldc;
+  for (int i = 0; i < 3; ++i) { t.nb[i] = g.nb[i]; t.c_bs[i] = g.c_bs[i]; }
+  t.accumulate = g.accumulate;
+  if (BN == 256) return launch_tc<256>(g, mA, mB, t);
+  return launch_tc<128>(g, mA, mB, t);
+}
+
+}  // namespace pdn

@@ -1,0 +1,378 @@
+// runtime.cu — device/stream/allocator/event/graph plumbing of libpdn_b200.so.
+// Replaces what the reference gets from CuPy's runtime + memory pool (reference pydynet/cuda.py:16-32,
+// tensor.py:80,90): nothing here is ported, the reference has no native runtime.
+#include "common.cuh"
+
+#include <stdarg.h>
+#include <map>
+#include <mutex>
+#include <unordered_map>
+#include <vector>
+
+namespace pdn {
+
+static thread_local char g_err[1024] = "";
+static uint64_t          g_launches = 0;
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+int cuda_fail(cudaError_t e, const char* what, const char* file, int line) {
+  set_error("CUDA error %d (%s) at %s:%d in `%s`", (int)e, cudaGetErrorString(e), file, line, what);
+  return e == cudaErrorMemoryAllocation ? PDN_ERR_OOM : PDN_ERR_CUDA;
+}
+
+int after_launch(const char* name) {
+  ++g_launches;
+  cudaError_t e = cudaPeekAtLastError();
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    set_error("kernel launch `%s` failed: %s", name, cudaGetErrorString(e));
+    return PDN_ERR_CUDA;
+  }
+  return 0;
+}
+
+// ---- per-device state -----------------------------------------------------------------------
+struct DevState {
+  bool         inited = false;
+  cudaStream_t compute = nullptr;
+  cudaStream_t comm = nullptr;
+  int          sms = 0;
+  // caching allocator: free blocks by size; live blocks by pointer
+  std::multimap<size_t, void*>      free_blocks;
+  std::unordered_map<void*, size_t> live;
+  uint64_t in_use = 0, cached = 0, n_malloc = 0;
+};
+static DevState   g_dev[16];
+static std::mutex g_mu;
+static bool       g_capturing = false;
+
+static DevState* cur() {
+  int d = 0;
+  if (cudaGetDevice(&d) != cudaSuccess || d < 0 || d >= 16) return nullptr;
+  return &g_dev[d];
+}
+
+int ensure_init() {
+  DevState* s = cur();
+  if (!s) {
+    set_error("no CUDA device available (cudaGetDevice failed) — libpdn_b200 has no CPU fallback");
+    return PDN_ERR_CUDA;
+  }
+  if (s->inited) return 0;
+  int d = 0;
+  PDN_CUDA(cudaGetDevice(&d));
+  cudaDeviceProp prop;
+  PDN_CUDA(cudaGetDeviceProperties(&prop, d));
+  s->sms = prop.multiProcessorCount;
+  PDN_CUDA(cudaStreamCreateWithFlags(&s->compute, cudaStreamNonBlocking));
+  PDN_CUDA(cudaStreamCreateWithFlags(&s->comm, cudaStreamNonBlocking));
+  s->inited = true;
+  return 0;
+}
+
+cudaStream_t stream() {
+  DevState* s = cur();
+  return s && s->inited ? s->compute : nullptr;
+}
+cudaStream_t comm_stream() {
+  DevState* s = cur();
+  return s && s->inited ? s->comm : nullptr;
+}
+int sm_count() {
+  DevState* s = cur();
+  return s && s->sms > 0 ? s->sms : 148;
+}
+
+static size_t round_size(size_t b) {
+  if (b == 0) b = 1;
+  if (b <= (1u << 20)) return (b + 511) & ~(size_t)511;            // 512 B granules up to 1 MiB
+  return (b + ((size_t)2 << 20) - 1) & ~(((size_t)2 << 20) - 1);  // 2 MiB granules above (one TLB page)
+}
+
+static void release_cached(DevState* s) {
+  for (auto& kv : s->free_blocks) cudaFree(kv.second);
+  s->free_blocks.clear();
+  s->cached = 0;
+}
+
+int dev_alloc(void** p, size_t bytes) {
+  PDN_TRY(ensure_init());
+  DevState* s = cur();
+  size_t    want = round_size(bytes);
+  std::lock_guard<std::mutex> lk(g_mu);
+  auto it = s->free_blocks.lower_bound(want);
+  // accept a cached block only if it wastes < 25 % (or is an exact granule match)
+  if (it != s->free_blocks.end() && (it->first == want || it->first <= want + want / 4)) {
+    *p = it->second;
+    size_t got = it->first;
+    s->free_blocks.erase(it);
+    s->cached -= got;
+    s->live[*p] = got;
+    s->in_use += got;
+    return 0;
+  }
+  if (g_capturing) {
+    set_error("allocation of %zu bytes missed the cache during CUDA-graph capture (warm the step up first)", want);
+    return PDN_ERR_INVALID;
+  }
+  cudaError_t e = cudaMalloc(p, want);
+  if (e == cudaErrorMemoryAllocation) {
+    cudaGetLastError();
+    cudaStreamSynchronize(s->compute);
+    release_cached(s);
+    e = cudaMalloc(p, want);
+  }
+  if (e != cudaSuccess) {
+    *p = nullptr;
+    return cuda_fail(e, "cudaMalloc", __FILE__, __LINE__);
+  }
+  s->n_malloc++;
+  s->live[*p] = want;
+  s->in_use += want;
+  return 0;
+}
+
+void dev_free(void* p) {
+  if (!p) return;
+  DevState* s = cur();
+  if (!s) return;
+  std::lock_guard<std::mutex> lk(g_mu);
+  auto it = s->live.find(p);
+  if (it == s->live.end()) {  // allocated on another device: search
+    for (auto& d : g_dev) {
+      auto jt = d.live.find(p);
+      if (jt != d.live.end()) {
+        d.free_blocks.emplace(jt->second, p);
+        d.cached += jt->second;
+        d.in_use -= jt->second;
+        d.live.erase(jt);
+        return;
+      }
+    }
+    return;
+  }
+  // single compute stream => a freed block can be handed out again immediately (stream order)
+  s->free_blocks.emplace(it->second, p);
+  s->cached += it->second;
+  s->in_use -= it->second;
+  s->live.erase(it);
+}
+
+}  // namespace pdn
+
+using namespace pdn;
+
+extern "C" {
+
+const char* pdn_last_error(void) { return g_err; }
+
+int pdn_device_count(int* n) {
+  cudaError_t e = cudaGetDeviceCount(n);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    *n = 0;
+  }
+  return 0;
+}
+
+int pdn_init(int device) {
+  PDN_CUDA(cudaSetDevice(device));
+  return ensure_init();
+}
+int pdn_set_device(int device) {
+  PDN_CUDA(cudaSetDevice(device));
+  return ensure_init();
+}
+int pdn_get_device(int* device) {
+  PDN_CUDA(cudaGetDevice(device));
+  return 0;
+}
+int pdn_device_name(char* buf, int buflen) {
+  int d = 0;
+  PDN_CUDA(cudaGetDevice(&d));
+  cudaDeviceProp prop;
+  PDN_CUDA(cudaGetDeviceProperties(&prop, d));
+  snprintf(buf, buflen, "%s (sm_%d%d, %d SMs)", prop.name, prop.major, prop.minor, prop.multiProcessorCount);
+  return 0;
+}
+int pdn_sm_count(int* n) {
+  PDN_TRY(ensure_init());
+  *n = sm_count();
+  return 0;
+}
+
+int pdn_malloc(void** p, size_t bytes) { return dev_alloc(p, bytes); }
+int pdn_free(void* p) {
+  dev_free(p);
+  return 0;
+}
+int pdn_malloc_host(void** p, size_t bytes) {
+  PDN_CUDA(cudaMallocHost(p, bytes ? bytes : 1));
+  return 0;
+}
+int pdn_free_host(void* p) {
+  PDN_CUDA(cudaFreeHost(p));
+  return 0;
+}
+int pdn_mem_stats(uint64_t* bytes_in_use, uint64_t* bytes_cached, uint64_t* n_cuda_malloc) {
+  PDN_TRY(ensure_init());
+  DevState* s = cur();
+  *bytes_in_use = s->in_use;
+  *bytes_cached = s->cached;
+  *n_cuda_malloc = s->n_malloc;
+  return 0;
+}
+int pdn_empty_cache(void) {
+  PDN_TRY(ensure_init());
+  DevState* s = cur();
+  PDN_CUDA(cudaStreamSynchronize(s->compute));
+  std::lock_guard<std::mutex> lk(g_mu);
+  release_cached(s);
+  return 0;
+}
+
+int pdn_memcpy_h2d(void* dst, const void* src, size_t bytes) {
+  PDN_TRY(ensure_init());
+  if (!bytes) return 0;
+  // pageable source: cudaMemcpyAsync stages and returns once the source is consumed
+  PDN_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, stream()));
+  PDN_CUDA(cudaStreamSynchronize(stream()));
+  return 0;
+}
+int pdn_memcpy_d2h(void* dst, const void* src, size_t bytes) {
+  PDN_TRY(ensure_init());
+  if (bytes) PDN_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, stream()));
+  PDN_CUDA(cudaStreamSynchronize(stream()));
+  return 0;
+}
+int pdn_memcpy_d2d(void* dst, const void* src, size_t bytes) {
+  PDN_TRY(ensure_init());
+  if (bytes) PDN_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, stream()));
+  return 0;
+}
+int pdn_memcpy_h2d_async(void* dst, const void* src, size_t bytes) {
+  PDN_TRY(ensure_init());
+  if (bytes) PDN_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, stream()));
+  return 0;
+}
+int pdn_memcpy_d2h_async(void* dst, const void* src, size_t bytes) {
+  PDN_TRY(ensure_init());
+  if (bytes) PDN_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, stream()));
+  return 0;
+}
+int pdn_memset(void* dst, int byte, size_t bytes) {
+  PDN_TRY(ensure_init());
+  if (bytes) PDN_CUDA(cudaMemsetAsync(dst, byte, bytes, stream()));
+  return 0;
+}
+int pdn_sync(void) {
+  PDN_TRY(ensure_init());
+  PDN_CUDA(cudaStreamSynchronize(stream()));
+  PDN_CUDA(cudaStreamSynchronize(comm_stream()));
+  return 0;
+}
+
+uint64_t pdn_kernel_launch_count(void) { return g_launches; }
+void     pdn_reset_launch_count(void) { g_launches = 0; }
+
+int pdn_event_create(void** ev) {
+  PDN_TRY(ensure_init());
+  cudaEvent_t e;
+  PDN_CUDA(cudaEventCreate(&e));
+  *ev = (void*)e;
+  return 0;
+}
+int pdn_event_destroy(void* ev) {
+  PDN_CUDA(cudaEventDestroy((cudaEvent_t)ev));
+  return 0;
+}
+int pdn_event_record(void* ev) {
+  PDN_TRY(ensure_init());
+  PDN_CUDA(cudaEventRecord((cudaEvent_t)ev, stream()));
+  return 0;
+}
+int pdn_event_elapsed_ms(void* start, void* stop, float* ms) {
+  PDN_CUDA(cudaEventSynchronize((cudaEvent_t)stop));
+  PDN_CUDA(cudaEventElapsedTime(ms, (cudaEvent_t)start, (cudaEvent_t)stop));
+  return 0;
+}
+
+int pdn_graph_begin(void) {
+  PDN_TRY(ensure_init());
+  PDN_CHECK(!g_capturing, "graph capture already active");
+  PDN_CUDA(cudaStreamBeginCapture(stream(), cudaStreamCaptureModeThreadLocal));
+  g_capturing = true;
+  return 0;
+}
+int pdn_graph_end(void** graph_exec) {
+  PDN_CHECK(g_capturing, "no graph capture active");
+  g_capturing = false;
+  cudaGraph_t g;
+  PDN_CUDA(cudaStreamEndCapture(stream(), &g));
+  cudaGraphExec_t ge;
+  cudaError_t     e = cudaGraphInstantiate(&ge, g, 0);
+  cudaGraphDestroy(g);
+  if (e != cudaSuccess) return cuda_fail(e, "cudaGraphInstantiate", __FILE__, __LINE__);
+  *graph_exec = (void*)ge;
+  return 0;
+}
+int pdn_graph_launch(void* graph_exec) {
+  PDN_CUDA(cudaGraphLaunch((cudaGraphExec_t)graph_exec, stream()));
+  ++g_launches;
+  return 0;
+}
+int pdn_graph_destroy(void* graph_exec) {
+  PDN_CUDA(cudaGraphExecDestroy((cudaGraphExec_t)graph_exec));
+  return 0;
+}
+
+}  // extern "C"
+
+// ---- shared host helper: dimension collapsing -------------------------------------------------
+namespace pdn {
+int make_desc(int ndim, const int64_t* shape, int nops, const int64_t* const* strides, StridedDesc* out) {
+  PDN_CHECK(ndim >= 0 && ndim <= PDN_MAXD, "ndim %d out of range (max %d)", ndim, PDN_MAXD);
+  PDN_CHECK(nops >= 1 && nops <= 4, "bad operand count");
+  int64_t sh[PDN_MAXD], st[4][PDN_MAXD];
+  int     nd = 0;
+  int64_t n = 1;
+  for (int i = 0; i < ndim; ++i) {
+    PDN_CHECK(shape[i] >= 0, "negative dimension");
+    n *= shape[i];
+    if (shape[i] == 1) continue;  // size-1 dims carry no information
+    sh[nd] = shape[i];
+    for (int o = 0; o < nops; ++o) st[o][nd] = strides[o][i];
+    ++nd;
+  }
+  // merge dim k+1 into k when for every operand stride[k] == shape[k+1]*stride[k+1]
+  int w = 0;
+  for (int k = 0; k < nd; ++k) {
+    if (w > 0) {
+      bool merge = true;
+      for (int o = 0; o < nops; ++o)
+        if (st[o][w - 1] != sh[k] * st[o][k]) merge = false;
+      if (merge) {
+        sh[w - 1] *= sh[k];
+        for (int o = 0; o < nops; ++o) st[o][w - 1] = st[o][k];
+        continue;
+      }
+    }
+    sh[w] = sh[k];
+    for (int o = 0; o < nops; ++o) st[o][w] = st[o][k];
+    ++w;
+  }
+  out->ndim = w;
+  out->n = n;
+  for (int k = 0; k < PDN_MAXD; ++k) {
+    out->shape[k] = k < w ? sh[k] : 1;
+    for (int o = 0; o < 4; ++o) out->s[o][k] = (k < w && o < nops) ? st[o][k] : 0;
+  }
+  return 0;
+}
+}  // namespace pdn

@@ -1,0 +1,128 @@
+"""Device selection — the reference's only plugin seam (reference pydynet/cuda.py:16-99).
+
+``Device.xp`` returns NumPy for ``cpu`` and :mod:`pydynet_b200.backend` (hand-written sm_100a kernels behind a
+ctypes C ABI) for ``cuda`` — the slot CuPy occupies in the reference.  A cuda device that cannot be served
+(no libpdn_b200.so, no GPU) raises ``RuntimeError`` like the reference does without CuPy (cuda.py:67-69);
+nothing silently falls back to the CPU.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from .backend import lib as _L
+
+
+def is_available() -> bool:
+    return _L.device_count() > 0
+
+
+def device_count() -> int:
+    return _L.device_count()
+
+
+def current_device() -> int:
+    d = C.c_int(0)
+    _L.call("pdn_get_device", C.byref(d))
+    return int(d.value)
+
+
+def set_device(device: int) -> None:
+    _L.call("pdn_set_device", int(device))
+
+
+def synchronize() -> None:
+    _L.call("pdn_sync")
+
+
+class Device:
+    __slots__ = ("device", "device_id", "_prev")
+
+    def __init__(self, device=None) -> None:
+        self._prev = None
+        if isinstance(device, Device):
+            self.device = device.device
+            self.device_id = device.device_id
+            return
+        self.device_id = None
+        if device is None:
+            self.device = "cpu"
+        elif isinstance(device, str):
+            if device == "cpu":
+                self.device = "cpu"
+            elif device.startswith("cuda"):
+                rest = device[4:]
+                if rest == "":
+                    rest = ":0"
+                cuda_id = rest.split(":")[-1]
+                if not rest.startswith(":") or not cuda_id.isdigit():
+                    raise ValueError(f'Wrong cuda id "{cuda_id}"!')
+                self.device = "cuda"
+                self.device_id = int(cuda_id)
+            else:
+                raise ValueError(f'Unknown device "{device}"!')
+        elif isinstance(device, (int, np.integer)):
+            self.device = "cuda"
+            self.device_id = int(device)
+        else:
+            raise ValueError(f"Unknown device {device!r}!")
+        if self.device == "cuda":
+            if not is_available():
+                raise RuntimeError("Cuda device is not supported on this system.")
+            if self.device_id >= device_count():
+                raise RuntimeError(f"cuda:{self.device_id} requested but only {device_count()} device(s) present.")
+            _ensure_init(self.device_id)
+
+    def __repr__(self) -> str:
+        if self.device == "cpu":
+            return "Device(type='cpu')"
+        return "Device(type='cuda', index={})".format(self.device_id)
+
+    def __eq__(self, other) -> bool:
+        if not isinstance(other, Device):
+            other = Device(other)
+        return self.device == other.device and self.device_id == other.device_id
+
+    def __hash__(self):
+        return hash((self.device, self.device_id))
+
+    @property
+    def is_cuda(self) -> bool:
+        return self.device == "cuda"
+
+    @property
+    def xp(self):
+        if self.device == "cpu":
+            return np
+        from . import backend
+        return backend
+
+    def __enter__(self):
+        if self.device == "cuda":
+            cur = current_device()
+            if cur != self.device_id:
+                self._prev = cur
+                set_device(self.device_id)
+        return self
+
+    def __exit__(self, *exc):
+        if self._prev is not None:
+            set_device(self._prev)
+            self._prev = None
+
+
+_inited = set()
+
+
+def _ensure_init(dev_id: int):
+    if dev_id not in _inited:
+        cur = None
+        try:
+            cur = current_device()
+        except Exception:
+            pass
+        _L.call("pdn_init", dev_id)
+        if cur is not None and cur != dev_id and cur in _inited:
+            _L.call("pdn_set_device", cur)
+        _inited.add(dev_id)
