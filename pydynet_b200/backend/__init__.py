@@ -233,3 +233,5 @@ class _Random:
 
 
 random = _Random()
+
+from . import ext  # noqa: E402,F401

@@ -1,0 +1,411 @@
+"""Parity against golden vectors produced by the UNMODIFIED reference (tests/golden/make_golden.py ran
+/root/reference's NumPy path; the .npz files are committed).  Each case runs on the cpu device (host engine logic,
+no GPU needed) and on cuda:0 (hand-written kernels, marked gpu).
+
+Tolerance (BASELINE north_star): 1e-4 relative for fp32 — applied normwise, ``|got - ref|_2 <= 1e-4 * |ref|_2`` plus an
+absolute floor of 1e-4 * max|ref| per element for gradients (SURVEY.md §8c explains why elementwise relative error is
+meaningless under cancellation); exact for indices / argmax / shapes / dtypes.
+"""
+import os
+
+import numpy as np
+import pytest
+
+import pydynet_b200 as pdn
+import pydynet_b200.nn as nn
+import pydynet_b200.nn.functional as F
+from pydynet_b200.optim import Adam, SGD, Adagrad, Adadelta
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+DEVICES = [pytest.param("cpu", id="cpu"), pytest.param("cuda:0", id="cuda", marks=pytest.mark.gpu)]
+f32 = np.float32
+RTOL = 1e-4
+
+
+def gold(name):
+    return np.load(os.path.join(GOLD, name + ".npz"))
+
+
+def close(got, ref, rtol=RTOL, what=""):
+    if isinstance(got, pdn.Tensor):
+        got = got.numpy()
+    elif hasattr(got, "get"):
+        got = got.get()
+    got, ref = np.asarray(got, dtype=np.float64), np.asarray(ref, dtype=np.float64)
+    assert got.shape == ref.shape, f"{what}: shape {got.shape} vs {ref.shape}"
+    scale = np.linalg.norm(ref)
+    err = np.linalg.norm(got - ref)
+    assert err <= rtol * max(scale, 1e-30) + 1e-12, f"{what}: normwise rel err {err / max(scale, 1e-30):.3e}"
+    floor = rtol * max(np.abs(ref).max(), 1e-30)
+    bad = np.abs(got - ref) > 10 * floor + 10 * rtol * np.abs(ref)
+    assert not bad.any(), f"{what}: {bad.sum()} elements off, max abs err {np.abs(got - ref).max():.3e}"
+
+
+def T(a, dev, rg=False):
+    a = np.asarray(a)
+    return pdn.Tensor(a, dtype=a.dtype, device=dev, requires_grad=rg)
+
+
+def load_params(module, g, prefix):
+    for name, p in module._parameters.items():
+        key = prefix + name
+        if key in g.files:
+            with p.device:
+                p.data[...] = g[key]
+
+
+def check_params(module, g, prefix, thin=False, rtol=RTOL):
+    for name, p in module._parameters.items():
+        key = prefix + name
+        if key in g.files:
+            got = p.numpy()
+            if thin and got.size > 100_000:
+                got = got[::16]
+            close(got, g[key], rtol, key)
+
+
+def check_grads(module, g, prefix, thin=False, rtol=RTOL):
+    n = 0
+    for name, p in module._parameters.items():
+        key = prefix + name
+        if key in g.files:
+            got = np.asarray(p.grad.get() if hasattr(p.grad, "get") else p.grad)
+            if thin and got.size > 100_000:
+                got = got[::16]
+            close(got, g[key], rtol, key)
+            n += 1
+    assert n > 0
+
+
+# ---------------------------------------------------------------------------------- functional
+@pytest.mark.parametrize("device", DEVICES)
+def test_softmax_family(device):
+    g = gold("functional")
+    for name, fn in (("softmax", lambda t: F.softmax(t, axis=-1)), ("log_softmax", lambda t: F.log_softmax(t, axis=-1, keepdims=True))):
+        t = T(g[f"{name}.x"], device, True)
+        out = fn(t)
+        (out * T(g[f"{name}.w"], device)).sum().backward()
+        close(out, g[f"{name}.out"], what=name)
+        close(t.grad, g[f"{name}.gx"], what=name + ".gx")
+    t = T(g["softmax.x"], device, True)
+    out = F.softmax(t, axis=1)
+    (out * T(g["softmax.w"], device)).sum().backward()
+    close(out, g["softmax_ax1.out"])
+    close(t.grad, g["softmax_ax1.gx"])
+
+
+@pytest.mark.parametrize("device", DEVICES)
+def test_losses(device):
+    g = gold("functional")
+    for red in ("mean", "sum"):
+        for kind, tgt in (("int", g["ce.target"]), ("onehot", g["ce.onehot"])):
+            t = T(g["ce.logits"], device, True)
+            loss = F.cross_entropy_loss(t, T(tgt, device), red)
+            loss.backward()
+            close(loss, g[f"ce.{kind}.{red}.loss"], what=f"ce.{kind}.{red}")
+            close(t.grad, g[f"ce.{kind}.{red}.g"], what=f"ce.{kind}.{red}.g")
+    t = T(g["mse.a"], device, True)
+    loss = F.mse_loss(t, T(g["mse.b"], device))
+    loss.backward()
+    close(loss, g["mse.loss"])
+    close(t.grad, g["mse.g"])
+    t = T(g["mse.a"], device, True)
+    loss = F.nll_loss(t, T(g["mse.b"], device), "sum")
+    loss.backward()
+    close(loss, g["nll.loss"])
+    close(t.grad, g["nll.g"])
+    with pytest.raises(ValueError):
+        F.mse_loss(t, t, "median")
+
+
+@pytest.mark.parametrize("device", DEVICES)
+def test_activations(device):
+    g = gold("functional")
+    fns = {"relu": F.relu, "leaky": lambda t: F.leaky_relu(t, 0.1), "silu": F.silu, "sigmoid": F.sigmoid, "tanh": F.tanh}
+    for name, fn in fns.items():
+        t = T(g["act.x"], device, True)
+        out = fn(t)
+        (out * out).sum().backward()
+        close(out, g[f"act.{name}.out"], what=name)
+        close(t.grad, g[f"act.{name}.g"], what=name + ".g")
+
+
+@pytest.mark.parametrize("device", DEVICES)
+@pytest.mark.parametrize("i", range(4))
+def test_conv2d(device, i):
+    g = gold("functional")
+    N, C, H, W, O, k, s, p = g[f"conv{i}.cfg"]
+    tx, tk, tb = T(g[f"conv{i}.x"], device, True), T(g[f"conv{i}.k"], device, True), T(g[f"conv{i}.b"], device, True)
+    out = F.conv2d(tx, tk, int(p), int(s)) + tb
+    (out * T(g[f"conv{i}.w"], device)).sum().backward()
+    close(out, g[f"conv{i}.out"], what="conv out")
+    close(tx.grad, g[f"conv{i}.gx"], what="conv gx")
+    close(tk.grad, g[f"conv{i}.gk"], what="conv gk")
+    close(tb.grad, g[f"conv{i}.gb"], what="conv gb")
+    # module form (bias fused on cuda)
+    conv = nn.Conv2d(int(C), int(O), int(k), int(s), int(p), dtype=f32).to(device)
+    with conv.device:
+        conv.weight.data[...] = g[f"conv{i}.k"]
+        conv.bias.data[...] = g[f"conv{i}.b"]
+    tx = T(g[f"conv{i}.x"], device, True)
+    out = conv(tx)
+    (out * T(g[f"conv{i}.w"], device)).sum().backward()
+    close(out, g[f"conv{i}.out"], what="Conv2d out")
+    close(tx.grad, g[f"conv{i}.gx"], what="Conv2d gx")
+    close(conv.weight.grad, g[f"conv{i}.gk"], what="Conv2d gk")
+    close(conv.bias.grad, g[f"conv{i}.gb"], what="Conv2d gb")
+
+
+@pytest.mark.parametrize("device", DEVICES)
+@pytest.mark.parametrize("i", range(3))
+def test_pool2d(device, i):
+    g = gold("functional")
+    N, C, H, W, k, s, p = (int(v) for v in g[f"pool{i}.cfg"])
+    for mode, fn in (("max", F.max_pool2d), ("avg", F.avg_pool2d)):
+        tx = T(g[f"pool{i}.x"], device, True)
+        out = fn(tx, k, s, p)
+        (out * T(g[f"pool{i}.{mode}.w"], device)).sum().backward()
+        close(out, g[f"pool{i}.{mode}.out"], what=f"pool {mode}")
+        close(tx.grad, g[f"pool{i}.{mode}.gx"], what=f"pool {mode} gx")  # includes a tied window: all maxima get grad
+
+
+@pytest.mark.parametrize("device", DEVICES)
+def test_pool1d_and_embedding(device):
+    g = gold("functional")
+    x1 = T(g["pool1d.x"], device)
+    close(F.max_pool1d(x1, 2, 2, 0), g["pool1d.max"])
+    close(F.avg_pool1d(x1, 3, 1, 1), g["pool1d.avg"])
+    emb = nn.Embedding(12, 6, padding_idx=0, dtype=f32).to(device)
+    with emb.device:
+        emb.weight.data[...] = g["emb.weight"]
+    out = emb(T(g["emb.ids"], device))
+    (out * T(g["emb.w"], device)).sum().backward()
+    close(out, g["emb.out"])
+    close(emb.weight.grad, g["emb.g"], what="embedding grad (last write wins)")
+
+
+# ---------------------------------------------------------------------------------- modules
+def test_seeded_constructors_match_reference_rng_order():
+    g = gold("modules")
+    np.random.seed(3)
+    mods = {"lin": nn.Linear(5, 4, dtype=f32), "conv": nn.Conv2d(2, 3, 3, dtype=f32), "gru": nn.GRUCell(4, 3, dtype=f32),
+            "lstm": nn.LSTMCell(4, 3, dtype=f32), "rnn": nn.RNNCell(4, 3, dtype=f32)}
+    for nm, m in mods.items():
+        for name, p in m._parameters.items():
+            np.testing.assert_array_equal(p.data, g[f"init_{nm}.{name}"], err_msg=f"{nm}.{name}")
+    assert str(nn.Linear(2, 2).weight.dtype) == str(g["init_default_dtype"])
+
+
+@pytest.mark.parametrize("device", DEVICES)
+@pytest.mark.parametrize("nm", ["bn1", "ln"])
+def test_feature_stat_norms(device, nm):
+    g = gold("modules")
+    mod = (nn.BatchNorm1d(6, dtype=f32) if nm == "bn1" else nn.LayerNorm(6, dtype=f32)).to(device)
+    load_params(mod, g, f"{nm}.p0.")
+    mod.train()
+    try:
+        for step in range(2):
+            tx = T(g[f"{nm}.s{step}.x"], device, True)
+            for p in mod.parameters():
+                p.zero_grad()
+            out = mod(tx)
+            (out * T(g[f"{nm}.s{step}.w"], device)).sum().backward()
+            close(out, g[f"{nm}.s{step}.out"], what="out")
+            close(tx.grad, g[f"{nm}.s{step}.gx"], what="gx")
+            close(mod.scale.grad, g[f"{nm}.s{step}.gscale"], what="gscale")
+            close(mod.shift.grad, g[f"{nm}.s{step}.gshift"], what="gshift")
+            close(mod.running_mean, g[f"{nm}.s{step}.rm"], what="running_mean")
+            close(mod.running_var, g[f"{nm}.s{step}.rv"], what="running_var")
+        mod.eval()
+        assert not pdn.autograd.is_grad_enable()  # reference quirk: eval() switches autograd off globally
+        close(mod(T(g[f"{nm}.s1.x"], device)), g[f"{nm}.eval.out"], what="eval")
+    finally:
+        pdn.autograd.set_grad_enabled(True)
+
+
+@pytest.mark.parametrize("device", DEVICES)
+def test_rmsnorm_dropout(device):
+    g = gold("modules")
+    rms = nn.RMSNorm(6, dtype=f32).to(device)
+    with rms.device:
+        rms.weight.data[...] = g["rms.weight"]
+    tx = T(g["rms.x"], device, True)
+    out = rms(tx)
+    (out * T(g["rms.w"], device)).sum().backward()
+    close(out, g["rms.out"])
+    close(tx.grad, g["rms.gx"])
+    close(rms.weight.grad, g["rms.gw"])
+    np.random.seed(9)
+    close(nn.Dropout(0.3)(T(g["drop.x"], device)), g["drop.out"])
+
+
+REC = {"gru": (nn.GRU, dict(num_layers=1)), "gru2b": (nn.GRU, dict(num_layers=2, bidirectional=True, batch_first=True)),
+       "lstm": (nn.LSTM, dict(num_layers=1)), "lstm2b": (nn.LSTM, dict(num_layers=2, bidirectional=True)),
+       "rnn2": (nn.RNN, dict(num_layers=2, nonlinearity="relu"))}
+
+
+@pytest.mark.parametrize("device", DEVICES)
+@pytest.mark.parametrize("nm", list(REC))
+def test_recurrent(device, nm):
+    g = gold("modules")
+    cls, kw = REC[nm]
+    mod = cls(5, 7, dtype=f32, **kw).to(device)
+    load_params(mod, g, f"{nm}.p.")
+    tx = T(g[f"{nm}.x"], device, True)
+    out, hn = mod(tx)
+    extra = 0
+    if isinstance(hn, tuple):
+        hn, cn = hn
+        close(cn, g[f"{nm}.cn"], what="cn")
+        extra = (cn * cn).sum()
+    ((out * T(g[f"{nm}.w"], device)).sum() + (hn * hn).sum() + extra).backward()
+    close(out, g[f"{nm}.out"], what="out")
+    close(hn, g[f"{nm}.hn"], what="hn")
+    close(tx.grad, g[f"{nm}.gx"], what="gx")
+    check_grads(mod, g, f"{nm}.g.")
+
+
+@pytest.mark.parametrize("device", DEVICES)
+@pytest.mark.parametrize("nm", ["adam", "sgd", "adagrad", "adadelta"])
+def test_optimizers(device, nm):
+    g = gold("modules")
+    mk = {"adam": lambda ps: Adam(ps, lr=1e-2, weight_decay=0.01), "sgd": lambda ps: SGD(ps, lr=1e-2, momentum=0.9),
+          "adagrad": lambda ps: Adagrad(ps, lr=1e-1), "adadelta": lambda ps: Adadelta(ps, lr=1.0)}[nm]
+    w, b = T(g["opt.w0"].copy(), device, True), T(g["opt.b0"].copy(), device, True)
+    opt = mk([w, b])
+    for s in range(3):
+        opt.zero_grad()
+        ((T(g["opt.xs"][s], device) @ w + b)**2).mean().backward()
+        opt.step()
+        close(w, g[f"opt.{nm}.w{s}"], what=f"{nm} w step {s}")
+        close(b, g[f"opt.{nm}.b{s}"], what=f"{nm} b step {s}")
+
+
+# ---------------------------------------------------------------------------------- models
+@pytest.mark.parametrize("device", DEVICES)
+def test_lenet_two_adam_steps(device):
+    """BASELINE config 2 at batch 8. Conv grads are compared at 2e-3: one fp32 max-pool tie flips 1.3e-3 of the conv
+    gradient even between the reference's own fp32 and fp64 runs (SURVEY.md §8c noise floor)."""
+    from workloads.lenet import ConvNet, train_step
+    g = gold("lenet")
+    net = ConvNet().to(device)
+    load_params(net, g, "p0.")
+    opt = Adam(net.parameters(), lr=1e-3)
+    net.train()
+    X, y = T(g["X"], device), T(g["y"], device)
+    out = net(X)
+    close(out, g["logits0"], what="logits")
+    assert (out.numpy().argmax(1) == g["logits0"].argmax(1)).all()
+    loss = F.cross_entropy_loss(out, y)
+    opt.zero_grad()
+    loss.backward()
+    close(loss, g["loss0"], what="loss0")
+    check_grads(net, g, "g0.", thin=True, rtol=2e-3)
+    opt.step()
+    loss = train_step(net, opt, X, y)
+    close(loss, g["loss1"], rtol=1e-3, what="loss1")
+    check_params(net, g, "p2.", thin=True, rtol=1e-3)
+
+
+@pytest.mark.parametrize("device", DEVICES)
+def test_transformer_encoder_two_adam_steps(device):
+    """BASELINE config 4 at (d32, h4, S12, B6). Mathematically-zero gradients (the bias in front of the batch-statistic
+    "LayerNorm") are rounding noise that Adam amplifies: grads use an absolute floor, parameters after two
+    steps are compared at 2e-3 normwise."""
+    from workloads.encoder import Transformer, construct_mask, logistic_loss
+    g = gold("transformer")
+    net = Transformer(32, 1, 4, 3, 0.05, 40, 12).to(device)
+    load_params(net, g, "p0.")
+    opt = Adam(net.parameters(), lr=5e-4)
+    net.train()
+    try:
+        X, y = T(g["X"], device), T(g["y"], device)
+        gmax = max(np.abs(g[k]).max() for k in g.files if k.startswith("g0."))
+        for s in range(2):
+            out = net(X, construct_mask(X))
+            loss = logistic_loss(out, y)
+            opt.zero_grad()
+            loss.backward()
+            if s == 0:
+                close(out, g["out0"], what="out0")
+                for name, p in net._parameters.items():
+                    if "g0." + name in g.files:
+                        got = p.grad.get() if hasattr(p.grad, "get") else p.grad
+                        assert np.abs(np.asarray(got) - g["g0." + name]).max() <= 2e-4 * gmax, name
+            close(loss, g[f"loss{s}"], what=f"loss{s}")
+            opt.step()
+        for name, p in net._parameters.items():
+            if "p2." + name in g.files and "feed_forward.2.bias" not in name and "shift" not in name:
+                close(p, g["p2." + name], rtol=2e-3, what=name)
+        net.eval()
+        close(net(X, construct_mask(X)), g["eval_out"], rtol=2e-3, what="eval")
+    finally:
+        pdn.autograd.set_grad_enabled(True)
+
+
+@pytest.mark.parametrize("device", DEVICES)
+def test_gru_regressor_two_adam_steps(device):
+    from workloads.gru import GRURegressor
+    g = gold("gru")
+    net = GRURegressor(6, 10).to(device)
+    load_params(net, g, "p0.")
+    opt = Adam(net.parameters(), lr=0.01)
+    X, Y = T(g["X"], device), T(g["Y"], device)
+    for s in range(2):
+        pred = net(X, None)
+        loss = F.mse_loss(pred, Y)
+        opt.zero_grad()
+        loss.backward()
+        if s == 0:
+            close(pred, g["pred0"], what="pred0")
+            check_grads(net, g, "g0.")
+        close(loss, g[f"loss{s}"], what=f"loss{s}")
+        opt.step()
+    check_params(net, g, "p2.", rtol=1e-3)
+
+
+@pytest.mark.parametrize("device", DEVICES)
+def test_llama_finetune_forward_backward(device):
+    from workloads.llama import Llama
+    g = gold("llama")
+    V, D, H, FF, S, B, L = (int(v) for v in g["cfg"])
+    net = Llama(V, D, H, FF, S, B, L, f32).to(device)
+    load_params(net, g, "p.")
+    try:
+        net.train(True)
+        logits = net.forward_logits(T(g["ft.ids"], device))
+        close(logits, g["ft.logits"], what="logits")
+        loss = nn.CrossEntropyLoss()(logits.reshape(-1, V), T(g["ft.tgt"].reshape(-1), device))
+        loss.backward()
+        close(loss, g["ft.loss"], what="loss")
+        for k in g.files:
+            if k.startswith("ft.g."):
+                p = net._parameters[k[5:]]
+                close(p.grad, g[k], what=k)
+    finally:
+        pdn.autograd.set_grad_enabled(True)
+
+
+@pytest.mark.parametrize("device", DEVICES)
+def test_llama_greedy_generation_tokens_exact(device):
+    """Greedy decode with the KV cache: token ids must equal the reference's exactly (argmax is bit-exact work)."""
+    from workloads.llama import Llama
+    g = gold("llama")
+    V, D, H, FF, S, B, L = (int(v) for v in g["cfg"])
+    net = Llama(V, D, H, FF, S, B, L, f32).to(device)
+    load_params(net, g, "p.")
+    try:
+        net.eval()
+        with pdn.no_grad():
+            prompt = T(g["gen.prompt"], device)
+            close(net(prompt, 0), g["gen.prefill_logits"], what="prefill logits")
+            for layer in net.layers:
+                with layer.attention.cache_k.device:
+                    layer.attention.cache_k.data[...] = 0
+                    layer.attention.cache_v.data[...] = 0
+            toks = [t.numpy() for t in net.generate(prompt, 40)]
+        toks = np.concatenate(toks, axis=1)
+        np.testing.assert_array_equal(toks, g["gen.tokens"])
+        close(net.layers[0].attention.cache_k, g["gen.cache_k0"], what="kv cache")
+    finally:
+        pdn.autograd.set_grad_enabled(True)
