@@ -163,8 +163,9 @@ int pdn_softmax_bwd(int dtype, const void* y, const void* g, void* dx, int64_t r
 
 /* RMSNorm over the last axis (norm.py:245-248): y = x / sqrt(mean(x^2) + eps) * w ; rstd[rows] saved */
 int pdn_rmsnorm_fwd(const float* x, const float* w, float* y, float* rstd, int64_t rows, int64_t n, float eps);
-int pdn_rmsnorm_bwd(const float* x, const float* w, const float* rstd, const float* g, float* dx, float* dw_partial,
-                    int64_t rows, int64_t n, int* n_partial_rows);
+/* dx (nullable) and dw[n] (nullable; zeroed here, accumulated with atomics) of the composite */
+int pdn_rmsnorm_bwd(const float* x, const float* w, const float* rstd, const float* g, float* dx, float* dw, int64_t rows,
+                    int64_t n);
 
 /* Batch-statistic normalisation shared by BatchNorm1d/2d and the reference's "LayerNorm" (norm.py:58-73,
  * 132-147,203-218): x viewed as [outer, C, inner], statistics per channel c over outer*inner elements
@@ -199,15 +200,18 @@ int pdn_pool2d_bwd(const float* x, const float* y, const float* g, float* dx, in
 /* softmax(q kᵀ * scale + mask) v, per (batch, head) — llm/llama/model.py:112-121,
  * examples/pydynet/transformer.py:93-104. q [B,H,Lq,D], k/v [B,H,Lk,D] given by element strides
  * (batch, head, row; the D axis is unit-stride) so head-split views of [B,L,H*D] projections and KV-cache
- * views are consumed in place. mask nullable additive [Lq,Lk] (−inf allowed). out [B,Lq,H,D] contiguous
- * (= the transpose(0,2,1,3).reshape(B,L,-1) the models apply next). lse [B,H,Lq] saved for backward. */
+ * views are consumed in place. mask: nullable additive term (−inf allowed), unit stride along keys, element strides
+ * mask_str = {batch, query-row} (0 = broadcast) — covers the causal [Lq,Lk] mask of Llama and the [B,1,1,Lk] padding
+ * mask of the encoder. out [B,Lq,H,D] contiguous (= the transpose(0,2,1,3).reshape(B,L,-1) the models apply next).
+ * lse [B,H,Lq] saved for backward. D <= 128. */
 int pdn_attention_fwd(const float* q, const float* k, const float* v, const float* mask, float* out, float* lse,
                       int64_t B, int64_t H, int64_t Lq, int64_t Lk, int64_t D, const int64_t* q_str,
-                      const int64_t* k_str, const int64_t* v_str, float scale);
+                      const int64_t* k_str, const int64_t* v_str, const int64_t* mask_str, float scale);
+/* dq [B,Lq,H,D], dk/dv [B,Lk,H,D] contiguous (each nullable; dk/dv are zeroed here and accumulated atomically) */
 int pdn_attention_bwd(const float* q, const float* k, const float* v, const float* mask, const float* out,
                       const float* lse, const float* g_out, float* dq, float* dk, float* dv, int64_t B, int64_t H,
                       int64_t Lq, int64_t Lk, int64_t D, const int64_t* q_str, const int64_t* k_str,
-                      const int64_t* v_str, float scale);
+                      const int64_t* v_str, const int64_t* mask_str, float scale);
 
 /* ---------------------------------------------------------------- recurrent ----------------- */
 /* GRU sequence (rnn.py:529-544 cell, :702-708 loop). xp1 [T,B,2H] = x@Wx1+b1 and xp2 [T,B,H] = x@Wx2+b2 are
@@ -250,6 +254,7 @@ int pdn_rope_kv_append(float* q, float* k, const float* v, const float* cosT, co
                        float* cache_v, int64_t B, int64_t L, int64_t H, int64_t D, int64_t S, int64_t pos0);
 /* out = silu(gate) * up  (FeedForward.forward model.py:56-58), gate/up are the two halves [rows, F] */
 int pdn_swiglu(const float* gate, const float* up, float* out, int64_t n);
+int pdn_swiglu_bwd(const float* gate, const float* up, const float* g, float* dgate, float* dup, int64_t n);
 
 /* ---------------------------------------------------------------- data-parallel comm -------- */
 /* Not in the reference (single process); defined by BASELINE north_star: NCCL all-reduce of the flat

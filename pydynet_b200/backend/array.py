@@ -106,7 +106,7 @@ class ndarray:
                 a = a.astype(np.float64)
             else:
                 raise TypeError(f"cannot move dtype {a.dtype} to the device")
-        a = np.ascontiguousarray(a)
+        a = np.require(a, requirements='C')  # (np.ascontiguousarray would promote 0-d to 1-d)
         out = ndarray.empty(a.shape, a.dtype)
         if a.size:
             L.call("pdn_memcpy_h2d", out.ptr, a.ctypes.data, a.nbytes)
@@ -368,6 +368,11 @@ def _apply_basic(a: ndarray, key):
     (first_axis, [index arrays]) for adjacent integer-array indices."""
     if not isinstance(key, tuple):
         key = (key, )
+    if len(key) == 1 and isinstance(key[0], (bool, np.bool_)):
+        # NumPy: a[True] is a[None], a[False] is an empty selection (the reference hits this through `t == 1`, which is
+        # Python identity because Tensor defines no __eq__ — examples/pydynet/transformer.py:242-243)
+        view = a._view((1, ) + a.shape, (0, ) + a.estrides)
+        return (view, None) if key[0] else (view._view((0, ) + a.shape, (0, ) + a.estrides), None)
     # whole-array boolean mask
     if len(key) == 1 and ((isinstance(key[0], ndarray) and key[0].dtype == np.bool_) or
                           (isinstance(key[0], np.ndarray) and key[0].dtype == np.bool_)):
@@ -449,7 +454,7 @@ def _index_args(view: ndarray, adv):
             x = x if x.dtype == np.int64 else x.astype(np.int64)
             x = x.broadcast_to(bshape).ascontiguous() if x.shape != tuple(bshape) else x.ascontiguous()
         else:
-            x = ndarray.from_host(np.ascontiguousarray(np.broadcast_to(np.asarray(x, dtype=np.int64), bshape)))
+            x = ndarray.from_host(np.array(np.broadcast_to(np.asarray(x, dtype=np.int64), bshape), order='C'))
         dev_idx.append(x)
     ptrs = (C.c_void_p * 4)(*[x.ptr for x in dev_idx])
     outer_shape, outer_st = view.shape[:first], view.estrides[:first]

@@ -74,7 +74,7 @@ _PROTOS = {
     "pdn_softmax_fwd": [i32, vp, vp, i64, i64, i32],
     "pdn_softmax_bwd": [i32, vp, vp, vp, i64, i64, i32],
     "pdn_rmsnorm_fwd": [vp, vp, vp, vp, i64, i64, f32],
-    "pdn_rmsnorm_bwd": [vp, vp, vp, vp, vp, vp, i64, i64, C.POINTER(i32)],
+    "pdn_rmsnorm_bwd": [vp, vp, vp, vp, vp, vp, i64, i64],
     "pdn_bnorm_stats": [vp, vp, vp, i64, i64, i64],
     "pdn_bnorm_apply": [vp, vp, vp, vp, vp, vp, i64, i64, i64, f32],
     "pdn_bnorm_bwd": [vp, vp, vp, vp, vp, vp, vp, vp, i64, i64, i64, f32],
@@ -83,8 +83,8 @@ _PROTOS = {
     "pdn_conv2d_bwd_weight": [vp, vp, vp, vp, i64, i64, i64, i64, i64, i32, i32, i32],
     "pdn_pool2d_fwd": [vp, vp, i64, i64, i64, i64, i32, i32, i32, i32],
     "pdn_pool2d_bwd": [vp, vp, vp, vp, i64, i64, i64, i64, i32, i32, i32, i32],
-    "pdn_attention_fwd": [vp, vp, vp, vp, vp, vp, i64, i64, i64, i64, i64, pi64, pi64, pi64, f32],
-    "pdn_attention_bwd": [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i64, i64, i64, i64, i64, pi64, pi64, pi64, f32],
+    "pdn_attention_fwd": [vp, vp, vp, vp, vp, vp, i64, i64, i64, i64, i64, pi64, pi64, pi64, pi64, f32],
+    "pdn_attention_bwd": [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i64, i64, i64, i64, i64, pi64, pi64, pi64, pi64, f32],
     "pdn_gru_seq_fwd": [vp, vp, vp, vp, vp, vp, vp, vp, i64, i64, i64],
     "pdn_gru_seq_bwd": [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i64, i64, i64],
     "pdn_lstm_seq_fwd": [vp, vp, vp, vp, vp, vp, vp, i64, i64, i64],
@@ -95,6 +95,7 @@ _PROTOS = {
     "pdn_adam_multi": [i32, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), pi64, f32, f32, f32, f32, f32, i32, f32],
     "pdn_rope_kv_append": [vp, vp, vp, vp, vp, vp, vp, i64, i64, i64, i64, i64, i64],
     "pdn_swiglu": [vp, vp, vp, i64],
+    "pdn_swiglu_bwd": [vp, vp, vp, vp, vp, i64],
     "pdn_nccl_unique_id": [C.c_char_p],
     "pdn_nccl_init": [i32, i32, C.c_char_p],
     "pdn_allreduce_sum_f32": [vp, i64],

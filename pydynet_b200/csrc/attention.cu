@@ -1,0 +1,261 @@
+// attention.cu — fused softmax(q kᵀ·scale + mask)·v and the Llama RoPE + KV-cache append.
+//
+// Replaces the 5-node score/softmax/PV chain the reference's models build by hand (llm/llama/model.py:112-121,
+// examples/pydynet/transformer.py:93-104: the S×S score tensor plus ≥5 temporaries) with one kernel that never
+// materialises scores: one warp per (batch, head, query row), keys in chunks of 32 (one key per lane for q·k, then
+// the lanes switch to owning head-dim columns for p·v), online softmax with warp-shuffle max/sum reductions.
+// fp32 FFMA throughout (1e-4 parity with the NumPy path); q/k/v are consumed through element strides so head-split
+// views of [B,L,H*D] projections and [B,S,H,D] KV-cache slices are read in place. This kernel serves decode / prefill /
+// small training shapes; large training shapes go through the tcgen05 GEMM path (nn/_fused.py picks).
+#include "common.cuh"
+#include <math.h>
+
+namespace pdn {
+
+constexpr int ATT_MAXD = 128;           // head dim limit (4 columns per lane)
+constexpr int ATT_DPL = ATT_MAXD / 32;  // output columns owned per lane
+
+struct AttArgs {
+  const float *q, *k, *v, *mask;
+  float *out, *lse;
+  int64_t B, H, Lq, Lk, D;
+  int64_t qs[3], ks[3], vs[3];  // element strides: batch, head, row (D axis is unit stride)
+  int64_t mask_bs, mask_qs;     // mask element strides for batch and query row (0 = broadcast); key axis unit stride
+  float scale;
+};
+
+__global__ void __launch_bounds__(128) k_attention_fwd(AttArgs a) {
+  extern __shared__ float sm[];  // per warp: q row [D]
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const int64_t w = (int64_t)blockIdx.x * 4 + wib;
+  const int64_t total = a.B * a.H * a.Lq;
+  if (w >= total) return;
+  const int64_t iq = w % a.Lq, h = (w / a.Lq) % a.H, b = w / (a.Lq * a.H);
+  const int D = (int)a.D;
+  float* qsm = sm + wib * ATT_MAXD;
+  const float* qrow = a.q + b * a.qs[0] + h * a.qs[1] + iq * a.qs[2];
+  for (int d = lane; d < D; d += 32) qsm[d] = qrow[d] * a.scale;
+  __syncwarp();
+  const float* kb = a.k + b * a.ks[0] + h * a.ks[1];
+  const float* vb = a.v + b * a.vs[0] + h * a.vs[1];
+  const float* mrow = a.mask ? a.mask + b * a.mask_bs + iq * a.mask_qs : nullptr;
+  float m = -INFINITY, l = 0.f;
+  float acc[ATT_DPL];
+#pragma unroll
+  for (int i = 0; i < ATT_DPL; ++i) acc[i] = 0.f;
+  const bool vec = (D % 4 == 0) && ((a.ks[2] & 3) == 0) && ((((uintptr_t)kb) & 15) == 0);
+  for (int64_t j0 = 0; j0 < a.Lk; j0 += 32) {
+    const int64_t j = j0 + lane;
+    float s = -INFINITY;
+    if (j < a.Lk) {
+      const float* kr = kb + j * a.ks[2];
+      float dot = 0.f;
+      if (vec) {
+        for (int d = 0; d < D; d += 4) {
+          float4 kk = *reinterpret_cast<const float4*>(kr + d);
+          dot += qsm[d] * kk.x + qsm[d + 1] * kk.y + qsm[d + 2] * kk.z + qsm[d + 3] * kk.w;
+        }
+      } else {
+        for (int d = 0; d < D; ++d) dot += qsm[d] * kr[d];
+      }
+      s = dot;
+      if (mrow) s += mrow[j];
+    }
+    const float cm = warp_max(s);
+    const float mn = fmaxf(m, cm);
+    // mn == -inf only while every key so far is masked out: keep the state empty
+    const float corr = (mn == -INFINITY) ? 1.f : __expf(m - mn);
+    const float p = (s == -INFINITY) ? 0.f : __expf(s - mn);
+    l = l * corr + warp_sum(p);
+    m = mn;
+#pragma unroll
+    for (int i = 0; i < ATT_DPL; ++i) acc[i] *= corr;
+    const int cnt = (int)((a.Lk - j0) < 32 ? (a.Lk - j0) : 32);
+    for (int t = 0; t < cnt; ++t) {
+      const float pt = __shfl_sync(0xffffffffu, p, t);
+      const float* vr = vb + (j0 + t) * a.vs[2];
+#pragma unroll
+      for (int i = 0; i < ATT_DPL; ++i) {
+        int d = lane + i * 32;
+        if (d < D) acc[i] += pt * vr[d];
+      }
+    }
+  }
+  const float inv = 1.f / l;
+  float* orow = a.out + ((b * a.Lq + iq) * a.H + h) * a.D;
+#pragma unroll
+  for (int i = 0; i < ATT_DPL; ++i) {
+    int d = lane + i * 32;
+    if (d < D) orow[d] = acc[i] * inv;
+  }
+  if (lane == 0 && a.lse) a.lse[(b * a.H + h) * a.Lq + iq] = m + logf(l);
+}
+
+struct AttBwdArgs {
+  AttArgs f;
+  const float* g;  // grad of out, [B, Lq, H, D] contiguous
+  float *dq, *dk, *dv;  // dq [B,Lq,H,D]; dk/dv [B,Lk,H,D] contiguous, pre-zeroed (atomic accumulation)
+};
+
+// one warp per (b, h, query row): Δ = Σ_d g·o ; for each key: p = exp(s - lse), dv_j += p g, ds = p (g·v_j − Δ),
+// dq += ds k_j scale, dk_j += ds q scale
+__global__ void __launch_bounds__(128) k_attention_bwd(AttBwdArgs a) {
+  extern __shared__ float sm[];  // per warp: q*scale [D], g [D]
+  const AttArgs& f = a.f;
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const int64_t w = (int64_t)blockIdx.x * 4 + wib;
+  const int64_t total = f.B * f.H * f.Lq;
+  if (w >= total) return;
+  const int64_t iq = w % f.Lq, h = (w / f.Lq) % f.H, b = w / (f.Lq * f.H);
+  const int D = (int)f.D;
+  float* qsm = sm + wib * 2 * ATT_MAXD;
+  float* gsm = qsm + ATT_MAXD;
+  const float* qrow = f.q + b * f.qs[0] + h * f.qs[1] + iq * f.qs[2];
+  const int64_t orow = ((b * f.Lq + iq) * f.H + h) * f.D;
+  float delta = 0.f;
+  for (int d = lane; d < D; d += 32) {
+    qsm[d] = qrow[d] * f.scale;
+    float gg = a.g[orow + d];
+    gsm[d] = gg;
+    delta += gg * f.out[orow + d];
+  }
+  delta = warp_sum(delta);
+  __syncwarp();
+  const float lse = f.lse[(b * f.H + h) * f.Lq + iq];
+  const float* kb = f.k + b * f.ks[0] + h * f.ks[1];
+  const float* vb = f.v + b * f.vs[0] + h * f.vs[1];
+  const float* mrow = f.mask ? f.mask + b * f.mask_bs + iq * f.mask_qs : nullptr;
+  float dq[ATT_DPL];
+#pragma unroll
+  for (int i = 0; i < ATT_DPL; ++i) dq[i] = 0.f;
+  for (int64_t j0 = 0; j0 < f.Lk; j0 += 32) {
+    const int64_t j = j0 + lane;
+    float p = 0.f, ds = 0.f;
+    if (j < f.Lk) {
+      const float *kr = kb + j * f.ks[2], *vr = vb + j * f.vs[2];
+      float dot = 0.f, gv = 0.f;
+      for (int d = 0; d < D; ++d) {
+        dot += qsm[d] * kr[d];
+        gv += gsm[d] * vr[d];
+      }
+      float s = dot + (mrow ? mrow[j] : 0.f);
+      p = (s == -INFINITY) ? 0.f : __expf(s - lse);
+      ds = p * (gv - delta);
+    }
+    const int cnt = (int)((f.Lk - j0) < 32 ? (f.Lk - j0) : 32);
+    for (int t = 0; t < cnt; ++t) {
+      const float pt = __shfl_sync(0xffffffffu, p, t);
+      const float dst = __shfl_sync(0xffffffffu, ds, t);
+      if (pt == 0.f && dst == 0.f) continue;
+      const float* kr = kb + (j0 + t) * f.ks[2];
+      const int64_t kvrow = ((b * f.Lk + j0 + t) * f.H + h) * f.D;
+#pragma unroll
+      for (int i = 0; i < ATT_DPL; ++i) {
+        int d = lane + i * 32;
+        if (d < D) {
+          dq[i] += dst * kr[d];
+          if (a.dv) atomicAdd(a.dv + kvrow + d, pt * gsm[d]);
+          if (a.dk) atomicAdd(a.dk + kvrow + d, dst * qsm[d]);  // qsm already carries the scale
+        }
+      }
+    }
+  }
+  if (a.dq) {
+#pragma unroll
+    for (int i = 0; i < ATT_DPL; ++i) {
+      int d = lane + i * 32;
+      if (d < D) a.dq[orow + d] = dq[i] * f.scale;
+    }
+  }
+}
+
+// ---------------------------------------------------------------- RoPE + KV append -------------------------------
+// q,k: [B*L, H, D] contiguous rows (row r = b*L + l, position pos0 + l); pairs (2i, 2i+1) rotated by angle[pos][i].
+// k (rotated) and v rows are also written into the caches [Bmax, S, H, D] at [b, pos0 + l].
+__global__ void __launch_bounds__(256) k_rope_kv_append(float* __restrict__ q, float* __restrict__ k, const float* __restrict__ v,
+                                                        const float* __restrict__ cosT, const float* __restrict__ sinT, float* __restrict__ ck,
+                                                        float* __restrict__ cv, int64_t B, int64_t L, int64_t H, int64_t D, int64_t S, int64_t pos0) {
+  const int64_t half = D / 2, total = B * L * H * half;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t pi = i % half, hh = (i / half) % H, r = i / (half * H);
+    const int64_t b = r / L, l = r % L, pos = pos0 + l;
+    const float c = cosT[pos * half + pi], s = sinT[pos * half + pi];
+    const int64_t e = (r * H + hh) * D + 2 * pi;
+    float2 qq = *reinterpret_cast<float2*>(q + e);
+    *reinterpret_cast<float2*>(q + e) = make_float2(qq.x * c - qq.y * s, qq.x * s + qq.y * c);
+    float2 kk = *reinterpret_cast<float2*>(k + e);
+    float2 kr = make_float2(kk.x * c - kk.y * s, kk.x * s + kk.y * c);
+    *reinterpret_cast<float2*>(k + e) = kr;
+    if (ck) {
+      const int64_t ce = ((b * S + pos) * H + hh) * D + 2 * pi;
+      *reinterpret_cast<float2*>(ck + ce) = kr;
+      *reinterpret_cast<float2*>(cv + ce) = *reinterpret_cast<const float2*>(v + e);
+    }
+  }
+}
+
+}  // namespace pdn
+
+using namespace pdn;
+
+static int fill_att(AttArgs& a, const float* q, const float* k, const float* v, const float* mask, float* out, float* lse, int64_t B, int64_t H,
+                    int64_t Lq, int64_t Lk, int64_t D, const int64_t* q_str, const int64_t* k_str, const int64_t* v_str, const int64_t* mask_str,
+                    float scale) {
+  PDN_CHECK(D >= 1 && D <= ATT_MAXD, "attention: head dim %lld not in [1, %d]", (long long)D, ATT_MAXD);
+  a.q = q; a.k = k; a.v = v; a.mask = mask; a.out = out; a.lse = lse;
+  a.B = B; a.H = H; a.Lq = Lq; a.Lk = Lk; a.D = D;
+  for (int i = 0; i < 3; ++i) { a.qs[i] = q_str[i]; a.ks[i] = k_str[i]; a.vs[i] = v_str[i]; }
+  a.mask_bs = mask && mask_str ? mask_str[0] : 0;
+  a.mask_qs = mask && mask_str ? mask_str[1] : 0;
+  a.scale = scale;
+  return 0;
+}
+
+extern "C" {
+
+int pdn_attention_fwd(const float* q, const float* k, const float* v, const float* mask, float* out, float* lse, int64_t B, int64_t H, int64_t Lq,
+                      int64_t Lk, int64_t D, const int64_t* q_str, const int64_t* k_str, const int64_t* v_str, const int64_t* mask_str,
+                      float scale) {
+  PDN_TRY(ensure_init());
+  AttArgs a;
+  PDN_TRY(fill_att(a, q, k, v, mask, out, lse, B, H, Lq, Lk, D, q_str, k_str, v_str, mask_str, scale));
+  const int64_t total = B * H * Lq;
+  if (total == 0) return 0;
+  PDN_CHECK(Lk > 0, "attention: no keys");
+  PDN_CHECK((total + 3) / 4 <= 0x7fffffff, "attention: too many query rows");
+  k_attention_fwd<<<(unsigned)((total + 3) / 4), 128, 4 * ATT_MAXD * sizeof(float), stream()>>>(a);
+  PDN_LAUNCHED("attention_fwd");
+  return 0;
+}
+
+int pdn_attention_bwd(const float* q, const float* k, const float* v, const float* mask, const float* out, const float* lse, const float* g_out,
+                      float* dq, float* dk, float* dv, int64_t B, int64_t H, int64_t Lq, int64_t Lk, int64_t D, const int64_t* q_str,
+                      const int64_t* k_str, const int64_t* v_str, const int64_t* mask_str, float scale) {
+  PDN_TRY(ensure_init());
+  AttBwdArgs a;
+  PDN_TRY(fill_att(a.f, q, k, v, mask, const_cast<float*>(out), const_cast<float*>(lse), B, H, Lq, Lk, D, q_str, k_str, v_str, mask_str, scale));
+  a.g = g_out; a.dq = dq; a.dk = dk; a.dv = dv;
+  const size_t kv_bytes = (size_t)(B * Lk * H * D) * sizeof(float);
+  if (dk) PDN_CUDA(cudaMemsetAsync(dk, 0, kv_bytes, stream()));
+  if (dv) PDN_CUDA(cudaMemsetAsync(dv, 0, kv_bytes, stream()));
+  const int64_t total = B * H * Lq;
+  if (total == 0) return 0;
+  k_attention_bwd<<<(unsigned)((total + 3) / 4), 128, 8 * ATT_MAXD * sizeof(float), stream()>>>(a);
+  PDN_LAUNCHED("attention_bwd");
+  return 0;
+}
+
+int pdn_rope_kv_append(float* q, float* k, const float* v, const float* cosT, const float* sinT, float* cache_k, float* cache_v, int64_t B,
+                       int64_t L, int64_t H, int64_t D, int64_t S, int64_t pos0) {
+  PDN_TRY(ensure_init());
+  PDN_CHECK(D % 2 == 0, "rope: head dim must be even");
+  PDN_CHECK(!cache_k || pos0 + L <= S, "rope_kv_append: positions [%lld, %lld) exceed the cache length %lld", (long long)pos0, (long long)(pos0 + L),
+            (long long)S);
+  const int64_t total = B * L * H * (D / 2);
+  if (total == 0) return 0;
+  k_rope_kv_append<<<grid_for(total, 256), 256, 0, stream()>>>(q, k, v, cosT, sinT, cache_k, cache_v, B, L, H, D, S, pos0);
+  PDN_LAUNCHED("rope_kv_append");
+  return 0;
+}
+
+}  // extern "C"

@@ -8,12 +8,12 @@ mkdir -p build
 pids=()
 for f in *.cu; do
   o=build/${f%.cu}.o
-  if [ ! -f "$o" ] || [ "$f" -nt "$o" ] || [ common.cuh -nt "$o" ] || [ ../../include/pdn_b200.h -nt "$o" ] || [ gemm_args.h -nt "$o" ]; then
+  if [ ! -f "$o" ] || [ "$f" -nt "$o" ] || [ common.cuh -nt "$o" ] || [ ../../include/pdn_b200.h -nt "$o" ] || [ gemm_args.h -nt "$o" ] || [ gemm_tc.h -nt "$o" ]; then
     $NVCC $FLAGS $EXTRA -c "$f" -o "$o" &
     pids+=($!)
   fi
 done
-for p in "${pids[@]}"; do wait $p; done
+for p in "${pids[@]}"; do wait $p || { echo "BUILD FAILED"; exit 1; }; done
 NCCL_INC=$(python -c "import nvidia.nccl,os;print(os.path.join(list(nvidia.nccl.__path__)[0],'include'))" 2>/dev/null || true)
 $NVCC -shared -o ../libpdn_b200.so build/*.o -lcudart $NCCL_LINK
 echo "built $(pwd)/../libpdn_b200.so"

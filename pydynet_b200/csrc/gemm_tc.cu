@@ -13,6 +13,7 @@
 //                  lane), warp 2 = TMEM allocator, warps 4-7 = epilogue (tcgen05.ld -> +bias/+C -> st.global).
 #include "common.cuh"
 #include "gemm_args.h"
+#include "gemm_tc.h"
 #include <cuda.h>
 #include <cudaTypedefs.h>
 #include <stdlib.h>
@@ -119,6 +120,7 @@ struct PackArgs {
   __nv_bfloat16* dst;      // [pbatch][2][R][Kp]
   int64_t R, K, Kp;
   int64_t r_stride, k_stride;  // element strides of the source along rows / k
+  int64_t k_inner, k_outer_stride;  // k = ko * k_inner + ki -> offset ko * k_outer_stride + ki * k_stride (k_inner = K: flat)
   int64_t nb[3], bs[3];        // source batch shape / strides (only dims with stride != 0 are walked)
 };
 
@@ -140,17 +142,18 @@ __global__ void __launch_bounds__(256) k_pack_split(PackArgs p) {
   const int64_t r0 = (int64_t)blockIdx.y * 32, k0 = (int64_t)blockIdx.x * 32;
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
   const bool k_fast = (p.k_stride == 1) || (p.r_stride != 1);
+  auto koff = [&](int64_t k) { return (k / p.k_inner) * p.k_outer_stride + (k % p.k_inner) * p.k_stride; };
   if (k_fast) {
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       int64_t r = r0 + ty + i * 8, k = k0 + tx;
-      tile[ty + i * 8][tx] = (r < p.R && k < p.K) ? src[r * p.r_stride + k * p.k_stride] : 0.f;
+      tile[ty + i * 8][tx] = (r < p.R && k < p.K) ? src[r * p.r_stride + koff(k)] : 0.f;
     }
   } else {  // rows are the unit-stride axis of the source: read along rows, transpose through smem
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       int64_t r = r0 + tx, k = k0 + ty + i * 8;
-      tile[tx][ty + i * 8] = (r < p.R && k < p.K) ? src[r * p.r_stride + k * p.k_stride] : 0.f;
+      tile[tx][ty + i * 8] = (r < p.R && k < p.K) ? src[r * p.r_stride + koff(k)] : 0.f;
     }
   }
   __syncthreads();
@@ -178,13 +181,6 @@ struct TcCfg {
   static constexpr int kTmemCols = BN;  // fp32 accumulator columns (power of two >= 32)
 };
 
-struct TcArgs {
-  float* C; const float* bias;
-  int64_t M, N, K, ldc;
-  int64_t nb[3], c_bs[3];
-  int64_t a_pbs[3], b_pbs[3];  // packed-batch index strides per batch dim
-  int accumulate;
-};
 
 template <int BN>
 __global__ void __launch_bounds__(256, 1) k_gemm_tc(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
@@ -200,12 +196,16 @@ __global__ void __launch_bounds__(256, 1) k_gemm_tc(const __grid_constant__ CUte
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_blk = blockIdx.x, m_blk = blockIdx.y;
   int64_t   z = blockIdx.z;
+  const int split = (int)(z % g.splits); z /= g.splits;
   const int64_t i2 = z % g.nb[2]; z /= g.nb[2];
   const int64_t i1 = z % g.nb[1]; z /= g.nb[1];
   const int64_t i0 = z;
   const int     a_batch = (int)(i0 * g.a_pbs[0] + i1 * g.a_pbs[1] + i2 * g.a_pbs[2]);
   const int     b_batch = (int)(i0 * g.b_pbs[0] + i1 * g.b_pbs[1] + i2 * g.b_pbs[2]);
-  const int     num_kb = (int)((g.K + TC_BK - 1) / TC_BK);
+  const int     all_kb = (int)((g.K + TC_BK - 1) / TC_BK);
+  const int     kb_per = (all_kb + g.splits - 1) / g.splits;
+  const int     kb_begin = split * kb_per;
+  const int     num_kb = max(0, min(all_kb, kb_begin + kb_per) - kb_begin);  // may be 0 for trailing splits
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&mapA);
@@ -234,7 +234,7 @@ __global__ void __launch_bounds__(256, 1) k_gemm_tc(const __grid_constant__ CUte
         mbar_wait(&empty_bar[stage], phase ^ 1);
         uint8_t* st = smem + stage * Cfg::kStageBytes;
         mbar_expect_tx(&full_bar[stage], Cfg::kStageBytes);
-        const int k = kb * TC_BK;
+        const int k = (kb_begin + kb) * TC_BK;
         tma_load_4d(&mapA, &full_bar[stage], st, k, m_blk * TC_BM, 0, a_batch);
         tma_load_4d(&mapA, &full_bar[stage], st + TC_BM * TC_BK * 2, k, m_blk * TC_BM, 1, a_batch);
         tma_load_4d(&mapB, &full_bar[stage], st + 2 * TC_BM * TC_BK * 2, k, n_blk * BN, 0, b_batch);
@@ -267,29 +267,52 @@ __global__ void __launch_bounds__(256, 1) k_gemm_tc(const __grid_constant__ CUte
         umma_commit(&empty_bar[stage]);  // frees this smem stage once the MMAs above have read it
         if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
       }
-      umma_commit(accum_bar);  // accumulator complete
+      if (num_kb > 0) umma_commit(accum_bar);  // accumulator complete
     }
   } else if (warp >= 4) {
     // ===== epilogue: TMEM -> registers -> (+bias, +C) -> global =====
     const int q = warp & 3;  // TMEM lane quarter this warp may access
-    mbar_wait(accum_bar, 0);
-    tc_fence_after();
+    if (num_kb > 0) {
+      mbar_wait(accum_bar, 0);
+      tc_fence_after();
+    }
     const int64_t row = (int64_t)m_blk * TC_BM + q * 32 + lane;
-    float* crow = g.C + i0 * g.c_bs[0] + i1 * g.c_bs[1] + i2 * g.c_bs[2] + row * g.ldc;
-    const bool vec_ok = ((g.ldc & 3) == 0) && ((((uintptr_t)g.C) & 15) == 0) && (((g.c_bs[0] | g.c_bs[1] | g.c_bs[2]) & 3) == 0);
+    float*        cbase = g.C + i0 * g.c_bs[0] + i1 * g.c_bs[1] + i2 * g.c_bs[2];
+    float*        crow = cbase + row * g.ldc;
+    int64_t       img = 0, pix = 0;
+    if (g.nchw_hw > 0) { img = row / g.nchw_hw; pix = row - img * g.nchw_hw; }
+    const bool atomic = g.splits > 1;
+    const bool add_bias = g.bias != nullptr && split == 0;
+    const bool vec_ok = !atomic && g.nchw_hw == 0 && ((g.ldc & 3) == 0) && ((((uintptr_t)g.C) & 15) == 0) &&
+                        (((g.c_bs[0] | g.c_bs[1] | g.c_bs[2]) & 3) == 0);
+    if (num_kb > 0 || (!atomic && !g.accumulate)) {
 #pragma unroll 1
     for (int c0 = 0; c0 < BN; c0 += 32) {
       float v[32];
-      tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
-      tmem_ld_wait();
+      if (num_kb > 0) {
+        tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
+        tmem_ld_wait();
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = 0.f;
+      }
       const int64_t col0 = (int64_t)n_blk * BN + c0;
       if (row < g.M && col0 < g.N) {
-        if (g.bias) {
+        if (add_bias) {
 #pragma unroll
           for (int j = 0; j < 32; ++j)
             if (col0 + j < g.N) v[j] += __ldg(g.bias + col0 + j);
         }
-        if (vec_ok && col0 + 32 <= g.N) {
+        if (g.nchw_hw > 0) {
+          float* p0 = cbase + img * g.N * g.nchw_hw + pix;
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (col0 + j < g.N) {
+              float* p = p0 + (col0 + j) * g.nchw_hw;
+              if (atomic) atomicAdd(p, v[j]);
+              else *p = g.accumulate ? *p + v[j] : v[j];
+            }
+        } else if (vec_ok && col0 + 32 <= g.N) {
           float4* c4 = reinterpret_cast<float4*>(crow + col0);
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
@@ -303,9 +326,13 @@ __global__ void __launch_bounds__(256, 1) k_gemm_tc(const __grid_constant__ CUte
         } else {
 #pragma unroll
           for (int j = 0; j < 32; ++j)
-            if (col0 + j < g.N) crow[col0 + j] = g.accumulate ? crow[col0 + j] + v[j] : v[j];
+            if (col0 + j < g.N) {
+              if (atomic) atomicAdd(crow + col0 + j, v[j]);
+              else crow[col0 + j] = g.accumulate ? crow[col0 + j] + v[j] : v[j];
+            }
         }
       }
+    }
     }
   }
   tc_fence_before();
@@ -357,14 +384,14 @@ bool gemm_tc_eligible(const GemmArgs& g) {
   return true;
 }
 
-static int pack_operand(const float* src, int64_t R, int64_t K, int64_t r_stride, int64_t k_stride, const int64_t* nb,
-                        const int64_t* bs, Scratch* buf, int64_t* Kp_out, int64_t* pbatch_out, int64_t* pbs_out) {
+int pack_operand_ex(const float* src, int64_t R, int64_t K, int64_t r_stride, int64_t k_stride, int64_t k_inner, int64_t k_outer_stride,
+                    const int64_t* nb, const int64_t* bs, Scratch* buf, PackedOperand* out) {
   int64_t Kp = (K + 7) & ~(int64_t)7;
   int64_t pb = 1;
   PackArgs p;
   for (int d = 2; d >= 0; --d) {
     bool walk = (bs[d] != 0 && nb[d] > 1);
-    pbs_out[d] = walk ? pb : 0;
+    out->pbs[d] = walk ? pb : 0;
     if (walk) pb *= nb[d];
     p.nb[d] = nb[d];
     p.bs[d] = bs[d];
@@ -375,49 +402,87 @@ static int pack_operand(const float* src, int64_t R, int64_t K, int64_t r_stride
   p.dst = (__nv_bfloat16*)buf->p;
   p.R = R; p.K = K; p.Kp = Kp;
   p.r_stride = r_stride; p.k_stride = k_stride;
+  p.k_inner = k_inner > 0 ? k_inner : (K > 0 ? K : 1);
+  p.k_outer_stride = k_outer_stride;
   dim3 grd((unsigned)((Kp + 31) / 32), (unsigned)((R + 31) / 32), (unsigned)pb);
   PDN_CHECK(grd.y <= 65535, "gemm_tc: operand has too many rows for the pack grid");
   k_pack_split<<<grd, 256, 0, stream()>>>(p);
   PDN_LAUNCHED("pack_split");
-  *Kp_out = Kp;
-  *pbatch_out = pb;
+  out->planes = buf->p; out->R = R; out->K = K; out->Kp = Kp; out->nbatch = pb;
   return 0;
 }
 
 template <int BN>
-static int launch_tc(const GemmArgs& g, const CUtensorMap& mA, const CUtensorMap& mB, const TcArgs& t) {
+static int launch_tc(const CUtensorMap& mA, const CUtensorMap& mB, const TcArgs& t) {
   using Cfg = TcCfg<BN>;
   static bool attr_set = false;
   if (!attr_set) {
     PDN_CUDA(cudaFuncSetAttribute(k_gemm_tc<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
     attr_set = true;
   }
-  int64_t nbatch = g.nb[0] * g.nb[1] * g.nb[2];
-  dim3    grd((unsigned)((g.N + BN - 1) / BN), (unsigned)((g.M + TC_BM - 1) / TC_BM), (unsigned)nbatch);
+  int64_t nbatch = t.nb[0] * t.nb[1] * t.nb[2] * t.splits;
+  PDN_CHECK(nbatch <= 65535, "gemm_tc: batch x split count %lld exceeds the grid", (long long)nbatch);
+  dim3    grd((unsigned)((t.N + BN - 1) / BN), (unsigned)((t.M + TC_BM - 1) / TC_BM), (unsigned)nbatch);
   k_gemm_tc<BN><<<grd, 256, Cfg::kSmemBytes, stream()>>>(mA, mB, t);
   PDN_LAUNCHED("gemm_tc");
   return 0;
 }
 
-int gemm_tc_launch(const GemmArgs& g) {
+// C (+)= A·Bᵀ on pre-packed bf16 hi/lo planes. `t` carries C, bias, M/N/K, ldc, batches, accumulate, nchw_hw;
+// splits <= 0 picks a split-K factor that fills the SMs when the tile grid is small and K is long.
+int gemm_tc_packed(const PackedOperand& A, const PackedOperand& B, TcArgs t, int splits) {
   PDN_TRY(get_encode_fn());
-  Scratch bufA, bufB;
-  int64_t KpA, KpB, pbA, pbB;
-  TcArgs  t;
-  // A: rows = M, k along a_cs.  B: rows = N (we need Bᵀ K-major), k along b_rs.
-  PDN_TRY(pack_operand((const float*)g.A, g.M, g.K, g.a_rs, g.a_cs, g.nb, g.a_bs, &bufA, &KpA, &pbA, t.a_pbs));
-  PDN_TRY(pack_operand((const float*)g.B, g.N, g.K, g.b_cs, g.b_rs, g.nb, g.b_bs, &bufB, &KpB, &pbB, t.b_pbs));
-  const int   BN = (g.N > 128 && getenv("PDN_TC_BN128") == nullptr) ? 256 : 128;
+  const int BN = (t.N > 128 && getenv("PDN_TC_BN128") == nullptr) ? 256 : 128;
+  for (int i = 0; i < 3; ++i) { t.a_pbs[i] = A.pbs[i]; t.b_pbs[i] = B.pbs[i]; }
+  const int64_t nbatch = t.nb[0] * t.nb[1] * t.nb[2];
+  const int64_t tiles = ((t.M + TC_BM - 1) / TC_BM) * ((t.N + BN - 1) / BN) * nbatch;
+  const int     num_kb = (int)((t.K + TC_BK - 1) / TC_BK);
+  if (splits <= 0) {
+    splits = 1;
+    if (tiles < sm_count() / 2 && num_kb >= 8) {
+      int64_t want = (sm_count() + tiles - 1) / tiles;
+      int64_t cap = num_kb / 4;
+      splits = (int)(want < cap ? want : cap);
+      if (splits < 1) splits = 1;
+      if (nbatch * splits > 65535) splits = 1;
+    }
+  }
+  t.splits = splits;
+  if (splits > 1 && !t.accumulate) {
+    // atomics accumulate into C: clear the destination region first
+    if (t.nchw_hw > 0 || nbatch > 1) {
+      PDN_CHECK(t.c_clear_bytes > 0, "gemm_tc: split-K needs the destination extent");
+      PDN_CUDA(cudaMemsetAsync(t.C, 0, t.c_clear_bytes, stream()));
+    } else if (t.ldc == t.N) {
+      PDN_CUDA(cudaMemsetAsync(t.C, 0, (size_t)t.M * t.N * sizeof(float), stream()));
+    } else {
+      PDN_CUDA(cudaMemset2DAsync(t.C, (size_t)t.ldc * sizeof(float), 0, (size_t)t.N * sizeof(float), (size_t)t.M, stream()));
+    }
+  }
   CUtensorMap mA, mB;
-  PDN_TRY(make_map(&mA, bufA.p, g.M, g.K, KpA, pbA, TC_BM));
-  PDN_TRY(make_map(&mB, bufB.p, g.N, g.K, KpB, pbB, BN));
+  PDN_TRY(make_map(&mA, A.planes, A.R, A.K, A.Kp, A.nbatch, TC_BM));
+  PDN_TRY(make_map(&mB, B.planes, B.R, B.K, B.Kp, B.nbatch, BN));
+  if (BN == 256) return launch_tc<256>(mA, mB, t);
+  return launch_tc<128>(mA, mB, t);
+}
+
+int gemm_tc_launch(const GemmArgs& g) {
+  Scratch       bufA, bufB;
+  PackedOperand A, B;
+  // A: rows = M, k along a_cs.  B: rows = N (we need Bᵀ K-major), k along b_rs.
+  PDN_TRY(pack_operand_ex((const float*)g.A, g.M, g.K, g.a_rs, g.a_cs, 0, 0, g.nb, g.a_bs, &bufA, &A));
+  PDN_TRY(pack_operand_ex((const float*)g.B, g.N, g.K, g.b_cs, g.b_rs, 0, 0, g.nb, g.b_bs, &bufB, &B));
+  TcArgs t;
   t.C = (float*)g.C;
   t.bias = (const float*)g.bias;
   t.M = g.M; t.N = g.N; t.K = g.K; t.ldc = g.ldc;
-  for (int i = 0; i < 3; ++i) { t.nb[i] = g.nb[i]; t.c_bs[i] = g.c_bs[i]; }
+  int64_t nbatch = 1;
+  for (int i = 0; i < 3; ++i) { t.nb[i] = g.nb[i]; t.c_bs[i] = g.c_bs[i]; nbatch *= g.nb[i]; }
   t.accumulate = g.accumulate;
-  if (BN == 256) return launch_tc<256>(g, mA, mB, t);
-  return launch_tc<128>(g, mA, mB, t);
+  t.nchw_hw = 0;
+  t.c_clear_bytes = 0;
+  // split-K only for single-batch products (batched ones already fill the grid or have strided C)
+  return gemm_tc_packed(A, B, t, nbatch > 1 ? 1 : 0);
 }
 
 }  // namespace pdn

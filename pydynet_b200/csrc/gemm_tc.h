@@ -1,0 +1,29 @@
+// gemm_tc.h — internal interface of the tcgen05 GEMM (gemm_tc.cu) for kernels that produce pre-packed operands
+// (conv.cu's im2col gather writes the bf16 hi/lo planes directly instead of materialising an fp32 column matrix).
+#pragma once
+#include "common.cuh"
+namespace pdn {
+
+// K-major bf16 planes [nbatch][2 (hi, lo)][R][Kp]; pbs = packed-batch index stride per GEMM batch dim (0 = broadcast)
+struct PackedOperand {
+  void*   planes;
+  int64_t R, K, Kp, nbatch;
+  int64_t pbs[3];
+};
+
+struct TcArgs {
+  float* C; const float* bias;
+  int64_t M, N, K, ldc;
+  int64_t nb[3], c_bs[3];
+  int64_t a_pbs[3], b_pbs[3];  // filled by gemm_tc_packed
+  int accumulate;
+  int splits;       // split-K factor; > 1 => epilogue accumulates with atomics
+  int64_t nchw_hw;  // 0: C row-major [M, N] (ldc). > 0: row m = (img, pix) of an NCHW tensor: C[img][col][pix], hw = nchw_hw
+  size_t c_clear_bytes;  // extent of C to clear before a split-K launch when C is not a plain [M, N] matrix
+};
+
+int pack_operand_ex(const float* src, int64_t R, int64_t K, int64_t r_stride, int64_t k_stride, int64_t k_inner, int64_t k_outer_stride,
+                    const int64_t* nb, const int64_t* bs, Scratch* buf, PackedOperand* out);
+int gemm_tc_packed(const PackedOperand& A, const PackedOperand& B, TcArgs t, int splits);
+
+}  // namespace pdn

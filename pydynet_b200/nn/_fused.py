@@ -49,3 +49,220 @@ def _call(name, *args):
 def sequence(cell, x, state):
     """Fused whole-sequence recurrence for one layer/direction; None = not applicable, caller runs the per-step loop."""
     return None
+
+
+def _c(a):
+    """C-contiguous fp32 device array."""
+    return a if a.is_contiguous else a.copy()
+
+
+def _empty(shape):
+    from ..backend.array import ndarray
+    return ndarray.empty(shape, F32)
+
+
+def _needs(*ts):
+    return is_grad_enable() and any(t is not None and t.requires_grad for t in ts)
+
+
+# ---------------------------------------------------------------------------------- linear -------------------
+@fused_op
+def linear(x, weight, bias):
+    """x @ W + b as one GEMM with the bias added in the epilogue (F.linear, reference functional.py:7-11); backward
+    contracts dW over all leading dims at once and reduces db with one column-sum."""
+    bk = _bk()
+    with x.device:
+        xd = x.data
+        lead = xd.shape[:-1]
+        x2 = bk.ext._flat2d(xd) if xd.ndim != 2 else xd
+        out = bk.gemm_into(None, x2, weight.data, bias=_c(bias.data) if bias is not None else None)
+        data = out.reshape(lead + (weight.shape[1], )) if xd.ndim != 2 else out
+
+    def backward(g):
+        g2 = bk.ext._flat2d(g) if g.ndim != 2 else g
+        gx = gw = gb = None
+        if x.requires_grad:
+            gx = bk.gemm_into(None, g2, weight.data.swapaxes(0, 1))
+            gx = gx.reshape(x.shape) if xd.ndim != 2 else gx
+        if weight.requires_grad:
+            gw = bk.gemm_into(None, x2.swapaxes(0, 1), g2)
+        if bias is not None and bias.requires_grad:
+            gb = g2.sum(axis=0)
+        return gx, gw, gb
+
+    ins = (x, weight) + ((bias, ) if bias is not None else ())
+    return _result(data, x.device, ins, (lambda g: backward(g)[:len(ins)]), "linear")
+
+
+# ---------------------------------------------------------------------------------- rows ---------------------
+@fused_op
+def softmax(x, log=False):
+    """softmax / log_softmax over the last axis: one kernel forward, one backward (reference functional.py:43-58)."""
+    with x.device:
+        xd = _c(x.data)
+        n = xd.shape[-1]
+        rows = xd.size // n if n else 0
+        y = _empty(xd.shape)
+        _call("pdn_softmax_fwd", 0, xd.ptr, y.ptr, rows, n, int(log))
+
+    def backward(g):
+        g = _c(g)
+        dx = _empty(xd.shape)
+        _call("pdn_softmax_bwd", 0, y.ptr, g.ptr, dx.ptr, rows, n, int(log))
+        return (dx, )
+
+    return _result(y, x.device, (x, ), backward, "log_softmax" if log else "softmax")
+
+
+@fused_op
+def rmsnorm(x, weight, eps):
+    with x.device:
+        xd, w = _c(x.data), _c(weight.data)
+        n = xd.shape[-1]
+        rows = xd.size // n
+        y, rstd = _empty(xd.shape), _empty((rows, ))
+        _call("pdn_rmsnorm_fwd", xd.ptr, w.ptr, y.ptr, rstd.ptr, rows, n, eps)
+
+    def backward(g):
+        g = _c(g)
+        dx = _empty(xd.shape) if x.requires_grad else None
+        dw = _empty((n, )) if weight.requires_grad else None
+        _call("pdn_rmsnorm_bwd", xd.ptr, w.ptr, rstd.ptr, g.ptr, dx.ptr if dx is not None else None, dw.ptr if dw is not None else None,
+              rows, n)
+        return dx, dw
+
+    return _result(y, x.device, (x, weight), backward, "rmsnorm")
+
+
+@fused_op
+def swiglu(gate, up):
+    """silu(gate) * up (reference llm/llama/model.py:56-58) in one pass."""
+    with gate.device:
+        a, b = _c(gate.data), _c(up.data)
+        out = _empty(a.shape)
+        _call("pdn_swiglu", a.ptr, b.ptr, out.ptr, a.size)
+
+    def backward(g):
+        g = _c(g)
+        da, db = _empty(a.shape), _empty(a.shape)
+        _call("pdn_swiglu_bwd", a.ptr, b.ptr, g.ptr, da.ptr, db.ptr, a.size)
+        return da, db
+
+    return _result(out, gate.device, (gate, up), backward, "swiglu")
+
+
+@fused_op
+def silu(x):
+    from ..backend import lib as L
+    from ..backend.array import _unary, ternary
+    with x.device:
+        out = _unary(L.SILU, x.data)
+    return _result(out, x.device, (x, ), lambda g: (ternary(L.T_SILU_GRAD, x.data, g, g), ), "silu")
+
+
+@fused_op
+def cross_entropy(logits, target, reduction):
+    """log-sum-exp + target pick + mean/sum in one kernel (reference functional.py:364-381, integer targets)."""
+    bk = _bk()
+    with logits.device:
+        x = _c(logits.data)
+        N, Cn = x.shape
+        t = target.data if target.data.dtype == np.int64 else target.data.astype(np.int64)
+        t = _c(t)
+        loss, lse = _empty(()), _empty((N, ))
+        mean = int(reduction == "mean")
+        _call("pdn_ce_loss_fwd", x.ptr, t.ptr, loss.ptr, lse.ptr, N, Cn, mean)
+
+    def backward(g):
+        g = _c(g if g.dtype == F32 else g.astype(F32))
+        dx = _empty(x.shape)
+        _call("pdn_ce_loss_bwd", x.ptr, t.ptr, lse.ptr, g.ptr, dx.ptr, N, Cn, mean)
+        return (dx, )
+
+    return _result(loss, logits.device, (logits, ), backward, "cross_entropy")
+
+
+# ---------------------------------------------------------------------------------- attention ----------------
+_ATT_FFMA_LIMIT = 1 << 29  # B*H*Lq*Lk*D multiply-adds served by the one-warp-per-query kernel; larger -> GEMM path
+
+
+def attention_fits(xq, xk) -> bool:
+    B, Lq, H, D = xq.shape
+    return D <= 128 and B * H * Lq * xk.shape[1] * D <= _ATT_FFMA_LIMIT
+
+
+def _i64(vals):
+    return (C.c_int64 * len(vals))(*[int(v) for v in vals])
+
+
+def _bhl_strides(a):
+    """(batch, head, row) element strides of a [B, L, H, D] array whose D axis is unit-stride."""
+    return _i64((a.estrides[0], a.estrides[2], a.estrides[1]))
+
+
+def _mask_args(mask, B, H, Lq, Lk):
+    if mask is None:
+        return None, None, None
+    m = mask.data if isinstance(mask, Tensor) else mask
+    if m.dtype != F32:
+        m = m.astype(F32)
+    mv = m.broadcast_to((B, H, Lq, Lk))
+    if mv.estrides[1] != 0 and H > 1 or (Lk > 1 and mv.estrides[3] != 1):
+        m = mv.copy()[:, 0]  # per-head masks are not supported by the kernel; none of the reference models use them
+        mv = m.broadcast_to((B, H, Lq, Lk))
+    return mv, mv.ptr, _i64((mv.estrides[0] if B > 1 else 0, mv.estrides[2] if Lq > 1 else 0))
+
+
+def _unit_last(a):
+    return a if (a.shape[-1] == 1 or a.estrides[-1] == 1) else a.copy()
+
+
+@fused_op
+def attention(xq, xk, xv, mask, scale):
+    """softmax(q kᵀ·scale + mask) v for [B, L, H, D] head-split views; returns [B, Lq, H*D]
+    (llm/llama/model.py:112-121, examples/pydynet/transformer.py:93-104). One kernel forward, one backward."""
+    with xq.device:
+        q, k, v = _unit_last(xq.data), _unit_last(xk.data), _unit_last(xv.data)
+        B, Lq, H, D = q.shape
+        Lk = k.shape[1]
+        out, lse = _empty((B, Lq, H, D)), _empty((B, H, Lq))
+        keep, mptr, mstr = _mask_args(mask, B, H, Lq, Lk)
+        _call("pdn_attention_fwd", q.ptr, k.ptr, v.ptr, mptr, out.ptr, lse.ptr, B, H, Lq, Lk, D, _bhl_strides(q), _bhl_strides(k),
+              _bhl_strides(v), mstr, scale)
+
+    def backward(g):
+        g = _c(g.reshape(B, Lq, H, D))
+        dq = _empty((B, Lq, H, D)) if xq.requires_grad else None
+        dk = _empty((B, Lk, H, D)) if xk.requires_grad else None
+        dv = _empty((B, Lk, H, D)) if xv.requires_grad else None
+        _call("pdn_attention_bwd", q.ptr, k.ptr, v.ptr, mptr, out.ptr, lse.ptr, g.ptr, dq.ptr if dq is not None else None,
+              dk.ptr if dk is not None else None, dv.ptr if dv is not None else None, B, H, Lq, Lk, D, _bhl_strides(q), _bhl_strides(k),
+              _bhl_strides(v), mstr, scale)
+        _ = keep
+        return dq, dk, dv
+
+    return _result(out.reshape(B, Lq, H * D), xq.device, (xq, xk, xv), backward, "attention")
+
+
+@fused_op
+def llama_cached_attention(att, xq, xk, xv, start_pos, mask, scale):
+    """Inference step of the Llama attention block (reference llm/llama/model.py:101-121): interleaved-pair RoPE on q and k,
+    append k/v to the per-layer KV cache at [start_pos, start_pos+L), attention of the new queries over cache[:start_pos+L].
+    Two kernels (rope_kv_append, attention_fwd) instead of ~40 eager nodes. Inference only (no tape)."""
+    assert not _needs(xq, xk, xv), "llama_cached_attention is the eval-mode path"
+    model_cos, model_sin = att._rope_tables
+    with xq.device:
+        q, k, v = _c(xq.data), _c(xk.data), _c(xv.data)
+        if q is xq.data and getattr(q, "buf", None) is not None:
+            pass  # projection outputs are fresh buffers; rotating them in place is safe
+        B, L, H, D = q.shape
+        ck, cv = att.cache_k.data, att.cache_v.data
+        S = ck.shape[1]
+        _call("pdn_rope_kv_append", q.ptr, k.ptr, v.ptr, model_cos.ptr, model_sin.ptr, ck.ptr, cv.ptr, B, L, H, D, S, int(start_pos))
+        Lk = int(start_pos) + L
+        out = _empty((B, L, H, D))
+        keep, mptr, mstr = _mask_args(mask, B, H, L, Lk)
+        cstr = _i64((ck.estrides[0], ck.estrides[2], ck.estrides[1]))
+        _call("pdn_attention_fwd", q.ptr, ck.ptr, cv.ptr, mptr, out.ptr, None, B, H, L, Lk, D, _bhl_strides(q), cstr, cstr, mstr, scale)
+        _ = keep
+    return _result(out.reshape(B, L, H * D), xq.device, (), None, "llama_cached_attention")

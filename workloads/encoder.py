@@ -27,7 +27,7 @@ class SelfAttention(nn.Module):
         xq, xk, xv = (proj(values).reshape(N, L, H, D) for proj in (self.Q, self.K, self.V))
         if mask is not None:
             mask[mask.eq(1)] = np.float32('-inf')
-        if _fused.usable(xq, xk, xv, op="attention"):
+        if _fused.usable(xq, xk, xv, op="attention") and _fused.attention_fits(xq, xk):
             out = _fused.attention(xq, xk, xv, mask, 1.0 / D**.5)  # (N, L, H*D)
         else:
             scores = xq.transpose(0, 2, 1, 3) @ xk.transpose(0, 2, 3, 1) / D**.5

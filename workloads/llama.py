@@ -70,7 +70,8 @@ class Attention(nn.Module):
         H, D = self.n_heads, self.head_dim
         xq, xk, xv = (proj(x).reshape(B, L, H, D) for proj in (self.Q, self.K, self.V))
         scale = 1.0 / math.sqrt(D)
-        if not self._train and _fused.usable(xq, xk, xv, op="llama_cached_attention"):
+        if not self._train and not pdn.autograd.is_grad_enable() and _fused.usable(xq, xk, xv, op="llama_cached_attention"):
+            self._rope_tables = self._rope_src()
             out = _fused.llama_cached_attention(self, xq, xk, xv, start_pos, mask, scale)
             return self.O(out)
         xq, xk = apply_rotary_emb(xq, xk, freqs_cos, freqs_sin)
@@ -79,7 +80,7 @@ class Attention(nn.Module):
             self.cache_v[:B, start_pos:start_pos + L] = xv
             xk = self.cache_k[:B, :start_pos + L]
             xv = self.cache_v[:B, :start_pos + L]
-        if _fused.usable(xq, xk, xv, op="attention"):
+        if _fused.usable(xq, xk, xv, op="attention") and _fused.attention_fits(xq, xk):
             out = _fused.attention(xq, xk, xv, mask, scale)
         else:
             scores = xq.transpose(0, 2, 1, 3) @ xk.transpose(0, 2, 3, 1) / math.sqrt(D)
@@ -117,6 +118,8 @@ class Llama(nn.Module):
         self.freqs_sin = nn.Parameter(sin, False)
         self.layers = nn.ModuleList(
             [TransformerBlock(embed_dim, n_heads, ffn_dim, max_seq_len, max_batch_size, dtype) for _ in range(n_layers)])
+        for layer in self.layers:  # the fused inference path reads the full RoPE tables by position
+            layer.attention._rope_src = lambda: (self.freqs_cos.data, self.freqs_sin.data)
         self.norm = nn.RMSNorm(embed_dim, dtype=dtype)
         self.lm_head = nn.Linear(embed_dim, vocab_size, dtype=dtype)
 
