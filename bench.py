@@ -1,0 +1,313 @@
+"""bench.py — BASELINE metric: Llama3-6L (vocab 32000, dim 288, 6 heads, ffn 768) greedy-generation tokens/s.
+
+A "step" is one pass of the hot path over one batch: B prompts (4 tokens each) are prefetched and decoded greedily with
+the KV cache until the total length is 256 — the reference's own benchmark loop (llm/llama/infer.py:51-64, metric =
+total length / elapsed, prompt tokens included), batched through the model's ``max_batch_size``.  Synthetic N(0, 0.05)
+weights of the named architecture (no checkpoints are reachable offline).
+
+  python bench.py [--gpus N --steps K --warmup W]         our arm: pydynet_b200 on cuda (one process per GPU under torchrun)
+  python bench.py --impl reference ...                    CPU arm: the reference algorithm (oracle port, NumPy) on host cores
+
+Prints ONE JSON line (rank 0). See DESIGN.md §Measurement for every field.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+CFG = dict(V=32000, D=288, H=6, FF=768, S=1024, L=6)
+PROMPT_LEN, TOTAL_LEN = 4, int(os.environ.get("PDN_BENCH_TOTAL_LEN", 256))  # the env override exists for short ncu captures only
+
+
+def _peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            p = json.load(f)
+        return p["hbm_gbs"], p.get("bf16_tflops_sustained", p["bf16_tflops"]), "measured"
+    except Exception:
+        return 6650.0, 1400.0, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows, self.proc, self.index = [], None, index
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.index)],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def __exit__(self, *exc):
+        if self.proc is not None:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+
+    def summary(self):
+        sm = [float(r[0]) for r in self.rows if len(r) >= 6 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 6 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({n for r in self.rows if len(r) >= 6 for n, v in zip(names, r[2:6]) if v.lower().startswith("active")})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons, "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------- our arm
+def build_model(B, device):
+    import pydynet_b200 as pdn
+    from oracle.pdn_oracle import synthetic_llama_params  # weight generator only (shared with the CPU arm)
+    from workloads.llama import Llama
+    params = synthetic_llama_params(CFG["V"], CFG["D"], CFG["H"], CFG["FF"], CFG["L"], seed=0, std=0.05)
+    net = Llama(CFG["V"], CFG["D"], CFG["H"], CFG["FF"], CFG["S"], B, CFG["L"], np.float32).to(device)
+    for name, p in net._parameters.items():
+        if name in params:
+            with p.device:
+                p.data[...] = params[name]
+    net.eval()
+    return net, params
+
+
+def generate_resident(net, prompt_dev):
+    """Device-resident pass: prompt already in HBM, token ids stay on the device (one D2H at the end, outside)."""
+    return [t for t in net.generate(prompt_dev, TOTAL_LEN)]
+
+
+def generate_e2e(net, prompt_host, device, pinned):
+    """End-to-end pass through the public API the way reference llm/llama/infer.py:44-58 drives it: host prompt -> device,
+    every generated id read back to the host as it is produced."""
+    import pydynet_b200 as pdn
+    ids = pdn.Tensor(prompt_host, device=device)
+    out = []
+    for t in net.generate(ids, TOTAL_LEN):
+        out.append(t.numpy())
+    return np.concatenate(out, axis=1)
+
+
+class KernelTimer:
+    """CUDA-event bracket around every launch of one entry point inside the timed region (events are recorded on the
+    library's compute stream, the stream the kernel is launched on)."""
+
+    def __init__(self, lib, entry, predicate):
+        self.lib, self.entry, self.pred, self.pairs, self.on = lib, entry, predicate, [], False
+        self.pool = []
+
+    def install(self):
+        import ctypes as C
+        L = self.lib
+        orig = L.call
+        timer = self
+
+        def call(name, *args):
+            if timer.on and name == timer.entry and timer.pred(args):
+                if timer.pool:
+                    e0, e1 = timer.pool.pop()
+                else:
+                    e0, e1 = C.c_void_p(), C.c_void_p()
+                    orig("pdn_event_create", C.byref(e0))
+                    orig("pdn_event_create", C.byref(e1))
+                orig("pdn_event_record", e0)
+                orig(name, *args)
+                orig("pdn_event_record", e1)
+                timer.pairs.append((e0, e1))
+            else:
+                orig(name, *args)
+
+        L.call = call  # every binding site resolves lib.call at call time
+
+    def collect(self):
+        import ctypes as C
+        ms = C.c_float()
+        tot, n = 0.0, 0
+        for e0, e1 in self.pairs:
+            self.lib.load().pdn_event_elapsed_ms(e0, e1, C.byref(ms))
+            tot += ms.value
+            n += 1
+        self.pool.extend(self.pairs)
+        self.pairs = []
+        return tot, n
+
+
+def run_ours(args):
+    rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("gloo", rank=rank, world_size=world)  # control plane only: barrier + max of timings
+    import ctypes as C
+    import pydynet_b200 as pdn
+    from pydynet_b200.backend import lib
+    device = f"cuda:{local}"
+    B = args.batch
+    net, params = build_model(B, device)
+    rng = np.random.default_rng(100 + rank)
+    prompt_host = rng.integers(1, CFG["V"], (B, PROMPT_LEN))
+    prompt_dev = pdn.Tensor(prompt_host, device=device)
+
+    def barrier():
+        pdn.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+
+    # the dominant kernel of a decode step (profiles/r1_launches.md): the lm_head GEMM [B,288] x [288,32000]
+    timer = KernelTimer(lib, "pdn_gemm", lambda a: int(a[5]) == CFG["V"])
+    timer.install()
+    with pdn.no_grad():
+        for _ in range(max(args.warmup, 3)):
+            generate_resident(net, prompt_dev)
+        barrier()
+        ev0, ev1 = C.c_void_p(), C.c_void_p()
+        lib.call("pdn_event_create", C.byref(ev0))
+        lib.call("pdn_event_create", C.byref(ev1))
+        lib.reset_launch_count()
+        timer.on = True
+        with ClockSampler(local) as clk:
+            t0 = time.perf_counter()
+            lib.call("pdn_event_record", ev0)
+            for _ in range(args.steps):
+                toks = generate_resident(net, prompt_dev)
+            lib.call("pdn_event_record", ev1)
+            barrier()
+            wall = time.perf_counter() - t0
+        timer.on = False
+        ms = C.c_float()
+        lib.load().pdn_event_elapsed_ms(ev0, ev1, C.byref(ms))
+        launches = lib.launch_count()
+        k_ms, k_n = timer.collect()
+        dev_s = max(ms.value / 1e3, 1e-9)
+        # end-to-end arm: host prompt in, every id read back to the host (reference infer.py loop)
+        for _ in range(2):
+            generate_e2e(net, prompt_host, device, None)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            out = generate_e2e(net, prompt_host, device, None)
+        barrier()
+        e2e_s = time.perf_counter() - t0
+    pdn.autograd.set_grad_enabled(True)
+    if dist is not None:
+        import torch
+        t = torch.tensor([dev_s, e2e_s, wall], dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dev_s, e2e_s, wall = (float(v) for v in t)
+        lt = torch.tensor([launches], dtype=torch.int64)
+        dist.all_reduce(lt)
+        launches = int(lt[0])
+    tokens = world * B * TOTAL_LEN * args.steps
+    hbm, tf, which = _peaks()
+    # lm_head GEMM: algorithmic bytes per launch = A [B,288] + W [288,32000] + bias + C [B,32000], fp32
+    alg_bytes = 4.0 * (B * CFG["D"] + CFG["D"] * CFG["V"] + CFG["V"] + B * CFG["V"])
+    alg_flops = 2.0 * B * CFG["D"] * CFG["V"]
+    k_avg_s = (k_ms / max(k_n, 1)) / 1e3
+    res = {
+        "metric": "llama3_6L_greedy_generation_tokens_per_s", "value": tokens / dev_s, "unit": "tokens/s", "n_gpus": world,
+        "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": dev_s / args.steps * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "configs[2]: llm/llama 6-layer Llama3 inference, total length 256 (4 prompt + 252 greedy decode steps), "
+                               f"batch {B} sequences per GPU, vocab 32000 dim 288 heads 6 ffn 768, KV cache",
+                   "batch_per_gpu": B, "seq_len": TOTAL_LEN, "parallelism": f"replicas x{world} (no data-path collective)",
+                   "l2_policy": "inputs larger than L2: per step the KV cache (B*14.2 MB) + weights (97.7 MB) exceed the 126 MB L2"},
+        "e2e": {"value": tokens / e2e_s, "unit": "tokens/s", "h2d_bytes_per_step": int(prompt_host.nbytes),
+                "d2h_bytes_per_step": int(B * (TOTAL_LEN - PROMPT_LEN) * 8)},
+        "gpu_launches": int(launches),
+        "wall_ms_per_step": wall / args.steps * 1e3,
+        "roofline": {"kernel": "lm_head GEMM (pack_split + gemm_tc, tcgen05 BF16x3)", "bound": "hbm", "achieved": alg_bytes / max(k_avg_s, 1e-12) / 1e9,
+                     "peak": hbm, "unit": "GB/s", "frac": alg_bytes / max(k_avg_s, 1e-12) / 1e9 / hbm, "traffic": None, "peak_source": which,
+                     "launch_us": k_avg_s * 1e6, "launches_timed": k_n, "tensor_tflops_alg": alg_flops / max(k_avg_s, 1e-12) / 1e12},
+        "clocks": clk.summary(),
+    }
+    if rank == 0:
+        if args.cpu_baseline and world == 1:
+            res["cpu_baseline"] = cpu_baseline(params, args.cpu_batch, args.cpu_total_len)
+        print(json.dumps(res))
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+# ------------------------------------------------------------------------------------------------- CPU arm
+def cpu_baseline(params, B, total_len, steps=1):
+    """The reference algorithm (oracle port: NumPy restatement of llm/llama/model.py, parity-pinned by
+    tests/test_oracle.py) on the host cores, on a bounded sample of the same workload."""
+    from oracle.pdn_oracle import LlamaOracle
+    try:
+        from threadpoolctl import threadpool_info
+        threads = max([i.get("num_threads", 1) for i in threadpool_info()] or [1])
+    except Exception:
+        threads = os.cpu_count()
+    rng = np.random.default_rng(100)
+    prompt = rng.integers(1, CFG["V"], (B, PROMPT_LEN))
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        m = LlamaOracle(params, CFG["H"], CFG["S"], B, CFG["L"])
+        m.generate(prompt, total_len)
+    dt = time.perf_counter() - t0
+    return {"value": B * total_len * steps / dt, "unit": "tokens/s", "cores": int(threads), "kind": "port",
+            "sample": f"batch {B}, total length {total_len} (4 prompt + {total_len - PROMPT_LEN} decode steps) x {steps} pass(es), "
+                      f"{dt:.1f} s of NumPy/OpenBLAS work, os.cpu_count()={os.cpu_count()}"}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", 0))
+    if rank != 0:
+        return
+    from oracle.pdn_oracle import synthetic_llama_params
+    params = synthetic_llama_params(CFG["V"], CFG["D"], CFG["H"], CFG["FF"], CFG["L"], seed=0, std=0.05)
+    B, total = args.cpu_batch, args.cpu_total_len
+    for _ in range(min(args.warmup, 1)):
+        cpu_baseline(params, B, min(total, 8))
+    t0 = time.perf_counter()
+    base = cpu_baseline(params, B, total, steps=args.steps)
+    dt = time.perf_counter() - t0
+    res = {"impl": "reference", "metric": "llama3_6L_greedy_generation_tokens_per_s", "value": base["value"], "unit": "tokens/s",
+           "n_gpus": int(os.environ.get("WORLD_SIZE", 1)), "steps": args.steps, "warmup": min(args.warmup, 1), "ms_per_step": dt / args.steps * 1e3,
+           "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+           "config": {"workload": "configs[2]: llm/llama 6-layer Llama3 inference on host cores (oracle port of the reference NumPy path), "
+                                  f"bounded sample: batch {B}, total length {total}"},
+           "cpu_baseline": base, "e2e": {"value": base["value"], "unit": "tokens/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+           "gpu_launches": 0}
+    print(json.dumps(res))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=int(os.environ.get("PDN_BENCH_BATCH", 128)))
+    ap.add_argument("--cpu-batch", type=int, default=128)
+    ap.add_argument("--cpu-total-len", type=int, default=24)
+    ap.add_argument("--no-cpu-baseline", dest="cpu_baseline", action="store_false")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

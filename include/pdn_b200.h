@@ -177,6 +177,16 @@ int pdn_bnorm_apply(const float* x, const float* mean, const float* var, const f
 int pdn_bnorm_bwd(const float* x, const float* mean, const float* var, const float* scale, const float* g,
                   float* dx, float* dscale, float* dshift, int64_t outer, int64_t C, int64_t inner, float eps);
 
+/* Data-parallel variants (equal shards): local partial sums pre-scaled by 1/m_global, to be summed across ranks with
+ * pdn_allreduce_sum_f32_inline so that every rank normalises with the GLOBAL batch statistics — what the single-process
+ * reference computes on the whole batch. which = 0: mean partial; 1: centred-square partial. */
+int pdn_bnorm_partial(const float* x, const float* mean, float* out, int64_t outer, int64_t C, int64_t inner, int which,
+                      float inv_m_global);
+int pdn_bnorm_bwd_reduce(const float* x, const float* mean, const float* var, const float* g, float* mg, float* mgx,
+                         int64_t outer, int64_t C, int64_t inner, float eps, float inv_m_global);
+int pdn_bnorm_bwd_dx(const float* x, const float* mean, const float* var, const float* scale, const float* g,
+                     const float* mg, const float* mgx, float* dx, int64_t outer, int64_t C, int64_t inner, float eps);
+
 /* ---------------------------------------------------------------- conv / pool --------------- */
 /* F.conv2d (functional.py:254-281): pad → im2col → GEMM → NCHW, fused; x [N,C,H,W], w [O,C,k,k],
  * bias nullable [O] (Conv2d.forward conv.py:99-103), y [N,O,oh,ow] all C-contiguous fp32. */
@@ -220,7 +230,7 @@ int pdn_attention_bwd(const float* q, const float* k, const float* v, const floa
 int pdn_gru_seq_fwd(const float* xp1, const float* xp2, const float* h0, const float* Wh1, const float* Wh2,
                     float* hs, float* zr, float* nn, int64_t T, int64_t B, int64_t H);
 /* backward through time: g_hs [T,B,H] (grad of every output step; may be all-zero but not NULL), returns
- * dxp1 [T,B,2H], dxp2 [T,B,H], dh0 [B,H], dWh1, dWh2 (accumulated, caller zeroes). */
+ * dxp1 [T,B,2H], dxp2 [T,B,H], dh0 [B,H], dWh1 [H,2H], dWh2 [H,H] (overwritten; nullable). */
 int pdn_gru_seq_bwd(const float* g_hs, const float* h0, const float* hs, const float* zr, const float* nn,
                     const float* Wh1, const float* Wh2, float* dxp1, float* dxp2, float* dh0, float* dWh1,
                     float* dWh2, int64_t T, int64_t B, int64_t H);
@@ -261,8 +271,10 @@ int pdn_swiglu_bwd(const float* gate, const float* up, const float* g, float* dg
  * parameter-gradient bucket over NVLink. */
 int pdn_nccl_unique_id(char* id128);
 int pdn_nccl_init(int rank, int world, const char* id128);
+int pdn_nccl_world(int* rank, int* world);
 int pdn_allreduce_sum_f32(float* buf, int64_t n);      /* on the comm stream, ordered after compute stream */
 int pdn_allreduce_wait(void);                          /* compute stream waits for the comm stream */
+int pdn_allreduce_sum_f32_inline(float* buf, int64_t n); /* small reductions on the compute stream itself */
 int pdn_nccl_destroy(void);
 
 #ifdef __cplusplus

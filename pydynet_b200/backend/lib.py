@@ -98,7 +98,12 @@ _PROTOS = {
     "pdn_swiglu_bwd": [vp, vp, vp, vp, vp, i64],
     "pdn_nccl_unique_id": [C.c_char_p],
     "pdn_nccl_init": [i32, i32, C.c_char_p],
+    "pdn_nccl_world": [C.POINTER(i32), C.POINTER(i32)],
     "pdn_allreduce_sum_f32": [vp, i64],
+    "pdn_allreduce_sum_f32_inline": [vp, i64],
+    "pdn_bnorm_partial": [vp, vp, vp, i64, i64, i64, i32, f32],
+    "pdn_bnorm_bwd_reduce": [vp, vp, vp, vp, vp, vp, i64, i64, i64, f32, f32],
+    "pdn_bnorm_bwd_dx": [vp, vp, vp, vp, vp, vp, vp, vp, i64, i64, i64, f32],
     "pdn_allreduce_wait": [],
     "pdn_nccl_destroy": [],
 }

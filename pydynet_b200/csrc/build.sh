@@ -14,6 +14,5 @@ for f in *.cu; do
   fi
 done
 for p in "${pids[@]}"; do wait $p || { echo "BUILD FAILED"; exit 1; }; done
-NCCL_INC=$(python -c "import nvidia.nccl,os;print(os.path.join(list(nvidia.nccl.__path__)[0],'include'))" 2>/dev/null || true)
-$NVCC -shared -o ../libpdn_b200.so build/*.o -lcudart $NCCL_LINK
+$NVCC -shared -o ../libpdn_b200.so build/*.o -lcudart -ldl
 echo "built $(pwd)/../libpdn_b200.so"

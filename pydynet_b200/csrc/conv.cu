@@ -1,0 +1,263 @@
+// conv.cu — Conv2d forward / backward-data / backward-weight as tcgen05 GEMMs over gathered operands, and Pool2d.
+//
+// The reference convolves by materialising an fp32 im2col matrix (zero-pad -> 6-D strided view -> .copy() -> reshape ->
+// sgemm -> NCHW transpose view; backward = np.add.at scatter — functional.py:194-281). Here the im2col gather writes the
+// GEMM's operand format directly (K-major bf16 hi/lo planes of the BF16x3 split, gemm_tc.cu), so there is no fp32 column
+// matrix, no pad copy and no scatter-add:
+//   forward        y[n,o,pix]   = Σ_ckk  col(x)[(n,pix), ckk] · W[o, ckk]          epilogue writes NCHW (+ bias[o])
+//   backward-data  dx[n,c,pix'] = Σ_okk  gat(g)[(n,pix'), okk] · W[o, c, kk]        (transposed-conv gather: no col2im atomics)
+//   backward-weight dW[o, ckk]  = Σ_m    gᵀ[o, m] · colᵀ(x)[ckk, m]                 split-K over m = (n, pix)
+// Pooling is a direct window kernel (the reference runs it through the same im2col + max/mean + add.at).
+#include "common.cuh"
+#include "gemm_tc.h"
+
+namespace pdn {
+
+struct ConvGeom {
+  int64_t N, C, H, W, O, oh, ow;
+  int     k, stride, pad;
+};
+
+// MODE 0: im2col of x — row m = (n, oy, ox), column kk = (c, ky, kx)
+// MODE 1: transposed-conv gather of g — row m = (n, y, x) of the INPUT grid, column kk = (o, ky, kx)
+template <int MODE>
+__device__ __forceinline__ float conv_fetch(const float* __restrict__ src, const ConvGeom& g, int64_t m, int64_t kk, int64_t Mtot, int64_t Ktot) {
+  if (m >= Mtot || kk >= Ktot) return 0.f;
+  const int kx = (int)(kk % g.k), ky = (int)((kk / g.k) % g.k);
+  const int64_t ch = kk / ((int64_t)g.k * g.k);
+  if (MODE == 0) {
+    const int64_t ox = m % g.ow, oy = (m / g.ow) % g.oh, n = m / (g.ow * g.oh);
+    const int64_t iy = oy * g.stride + ky - g.pad, ix = ox * g.stride + kx - g.pad;
+    if (iy < 0 || iy >= g.H || ix < 0 || ix >= g.W) return 0.f;
+    return __ldg(src + ((n * g.C + ch) * g.H + iy) * g.W + ix);
+  } else {
+    const int64_t x = m % g.W, y = (m / g.W) % g.H, n = m / (g.W * g.H);
+    const int64_t ty = y + g.pad - ky, tx = x + g.pad - kx;
+    if (ty < 0 || tx < 0 || ty % g.stride || tx % g.stride) return 0.f;
+    const int64_t oy = ty / g.stride, ox = tx / g.stride;
+    if (oy >= g.oh || ox >= g.ow) return 0.f;
+    return __ldg(src + ((n * g.O + ch) * g.oh + oy) * g.ow + ox);
+  }
+}
+
+// Writes planes [2][R][Kp]: ROWS_M ? (R = Mtot, k index = kk) : (R = Ktot, k index = m). 32x32 tile through smem so that
+// both the gather (along m = consecutive pixels) and the plane stores (along the plane's k axis) are coalesced.
+template <int MODE, bool ROWS_M>
+__global__ void __launch_bounds__(256) k_conv_pack(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, ConvGeom g, int64_t Mtot,
+                                                   int64_t Ktot, int64_t Kp) {
+  __shared__ float tile[32][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int64_t m0 = (int64_t)blockIdx.x * 32, kk0 = (int64_t)blockIdx.y * 32;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) tile[ty + i * 8][tx] = conv_fetch<MODE>(src, g, m0 + tx, kk0 + ty + i * 8, Mtot, Ktot);
+  __syncthreads();
+  const int64_t R = ROWS_M ? Mtot : Ktot;
+  __nv_bfloat16* hi = dst;
+  __nv_bfloat16* lo = dst + (size_t)R * Kp;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    int64_t row, col;
+    float   v;
+    if (ROWS_M) { row = m0 + ty + i * 8; col = kk0 + tx; v = tile[tx][ty + i * 8]; }
+    else        { row = kk0 + ty + i * 8; col = m0 + tx; v = tile[ty + i * 8][tx]; }
+    if (row < R && col < Kp) {
+      __nv_bfloat16 h = __float2bfloat16_rn(v);
+      hi[row * Kp + col] = h;
+      lo[row * Kp + col] = __float2bfloat16_rn(v - __bfloat162float(h));
+    }
+  }
+}
+
+template <int MODE, bool ROWS_M>
+static int conv_pack(const float* src, const ConvGeom& g, int64_t Mtot, int64_t Ktot, Scratch* buf, PackedOperand* out) {
+  const int64_t R = ROWS_M ? Mtot : Ktot, K = ROWS_M ? Ktot : Mtot;
+  const int64_t Kp = (K + 7) & ~(int64_t)7;
+  PDN_TRY(buf->alloc((size_t)2 * R * Kp * sizeof(__nv_bfloat16)));
+  // the grid walks (m tiles, kk tiles); pad columns [K, Kp) are covered because conv_fetch returns 0 out of range
+  const int64_t m_ext = ROWS_M ? Mtot : Kp, kk_ext = ROWS_M ? Kp : Ktot;
+  dim3 grd((unsigned)((m_ext + 31) / 32), (unsigned)((kk_ext + 31) / 32));
+  PDN_CHECK(grd.y <= 65535, "conv: C*k*k too large for the pack grid");
+  k_conv_pack<MODE, ROWS_M><<<grd, 256, 0, stream()>>>(src, (__nv_bfloat16*)buf->p, g, Mtot, Ktot, Kp);
+  PDN_LAUNCHED("conv_pack");
+  out->planes = buf->p; out->R = R; out->K = K; out->Kp = Kp; out->nbatch = 1;
+  out->pbs[0] = out->pbs[1] = out->pbs[2] = 0;
+  return 0;
+}
+
+static int make_geom(ConvGeom& g, int64_t N, int64_t C, int64_t H, int64_t W, int64_t O, int k, int stride, int pad) {
+  PDN_CHECK(k >= 1 && stride >= 1 && pad >= 0, "conv: bad kernel/stride/pad");
+  PDN_CHECK(H + 2 * pad >= k && W + 2 * pad >= k, "conv: kernel larger than the padded input");
+  g.N = N; g.C = C; g.H = H; g.W = W; g.O = O; g.k = k; g.stride = stride; g.pad = pad;
+  g.oh = (H + 2 * pad - k) / stride + 1;
+  g.ow = (W + 2 * pad - k) / stride + 1;
+  return 0;
+}
+
+static void tc_defaults(TcArgs& t) {
+  for (int i = 0; i < 3; ++i) { t.nb[i] = 1; t.c_bs[i] = 0; t.a_pbs[i] = 0; t.b_pbs[i] = 0; }
+  t.bias = nullptr; t.accumulate = 0; t.splits = 1; t.nchw_hw = 0; t.c_clear_bytes = 0;
+}
+
+// per-output-channel sum of an NCHW tensor: dbias[o] = Σ_{n,pix} g[n,o,pix]
+__global__ void __launch_bounds__(256) k_channel_sum(const float* __restrict__ g, float* __restrict__ out, int64_t N, int64_t O, int64_t hw) {
+  __shared__ float red[32];
+  const int64_t o = blockIdx.x;
+  float s = 0.f;
+  for (int64_t i = threadIdx.x; i < N * hw; i += blockDim.x) {
+    int64_t n = i / hw, p = i - n * hw;
+    s += g[(n * O + o) * hw + p];
+  }
+  s = block_sum<float>(s, red);
+  if (threadIdx.x == 0) out[o] = s;
+}
+
+// ---------------------------------------------------------------- pooling ----------------------------------------
+struct PoolGeom {
+  int64_t N, C, H, W, oh, ow;
+  int     k, stride, pad, mode;
+};
+
+__global__ void __launch_bounds__(256) k_pool_fwd(const float* __restrict__ x, float* __restrict__ y, PoolGeom g) {
+  const int64_t total = g.N * g.C * g.oh * g.ow;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t ox = i % g.ow, oy = (i / g.ow) % g.oh, nc = i / (g.ow * g.oh);
+    const float* xp = x + nc * g.H * g.W;
+    float acc = g.mode == 0 ? -INFINITY : 0.f;
+    for (int ky = 0; ky < g.k; ++ky)
+      for (int kx = 0; kx < g.k; ++kx) {
+        const int64_t iy = oy * g.stride + ky - g.pad, ix = ox * g.stride + kx - g.pad;
+        // zero padding takes part in the max / mean exactly like the reference's xp.pad (functional.py:235-251)
+        const float v = (iy < 0 || iy >= g.H || ix < 0 || ix >= g.W) ? 0.f : xp[iy * g.W + ix];
+        acc = g.mode == 0 ? fmaxf(acc, v) : acc + v;
+      }
+    y[i] = g.mode == 0 ? acc : acc / (float)(g.k * g.k);
+  }
+}
+
+// one thread per INPUT element gathers from every window that contains it (no atomics): max mode gives the window's full
+// gradient to every element equal to the window max (tensor.py:741-747)
+__global__ void __launch_bounds__(256) k_pool_bwd(const float* __restrict__ x, const float* __restrict__ y, const float* __restrict__ gy,
+                                                  float* __restrict__ dx, PoolGeom g) {
+  const int64_t total = g.N * g.C * g.H * g.W;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t ix = i % g.W, iy = (i / g.W) % g.H, nc = i / (g.W * g.H);
+    const float xv = x[i];
+    const float *yp = y + nc * g.oh * g.ow, *gp = gy + nc * g.oh * g.ow;
+    float acc = 0.f;
+    for (int ky = 0; ky < g.k; ++ky) {
+      const int64_t ty = iy + g.pad - ky;
+      if (ty < 0 || ty % g.stride) continue;
+      const int64_t oy = ty / g.stride;
+      if (oy >= g.oh) continue;
+      for (int kx = 0; kx < g.k; ++kx) {
+        const int64_t tx = ix + g.pad - kx;
+        if (tx < 0 || tx % g.stride) continue;
+        const int64_t ox = tx / g.stride;
+        if (ox >= g.ow) continue;
+        const float gg = gp[oy * g.ow + ox];
+        if (g.mode == 0) acc += (yp[oy * g.ow + ox] == xv) ? gg : 0.f;
+        else acc += gg / (float)(g.k * g.k);
+      }
+    }
+    dx[i] = acc;
+  }
+}
+
+}  // namespace pdn
+
+using namespace pdn;
+
+extern "C" {
+
+int pdn_conv2d_fwd(const float* x, const float* w, const float* bias, float* y, int64_t N, int64_t C, int64_t H, int64_t W, int64_t O, int k,
+                   int stride, int pad) {
+  PDN_TRY(ensure_init());
+  ConvGeom g;
+  PDN_TRY(make_geom(g, N, C, H, W, O, k, stride, pad));
+  const int64_t M = N * g.oh * g.ow, K = C * k * k;
+  if (M == 0 || O == 0) return 0;
+  Scratch       bufA, bufB;
+  PackedOperand A, B;
+  PDN_TRY((conv_pack<0, true>(x, g, M, K, &bufA, &A)));
+  const int64_t one[3] = {1, 1, 1}, zero[3] = {0, 0, 0};
+  PDN_TRY(pack_operand_ex(w, O, K, K, 1, 0, 0, one, zero, &bufB, &B));
+  TcArgs t;
+  tc_defaults(t);
+  t.C = y; t.bias = bias; t.M = M; t.N = O; t.K = K; t.ldc = O;
+  t.nchw_hw = g.oh * g.ow;
+  t.c_clear_bytes = (size_t)M * O * sizeof(float);
+  return gemm_tc_packed(A, B, t, 1);
+}
+
+int pdn_conv2d_bwd_data(const float* gy, const float* w, float* dx, int64_t N, int64_t C, int64_t H, int64_t W, int64_t O, int k, int stride,
+                        int pad) {
+  PDN_TRY(ensure_init());
+  ConvGeom g;
+  PDN_TRY(make_geom(g, N, C, H, W, O, k, stride, pad));
+  const int64_t M = N * H * W, K = O * k * k;
+  if (M == 0 || C == 0) return 0;
+  Scratch       bufA, bufB;
+  PackedOperand A, B;
+  PDN_TRY((conv_pack<1, true>(gy, g, M, K, &bufA, &A)));
+  // B rows = input channel c; k index (o, ky, kx) -> W[o, c, ky, kx]
+  const int64_t one[3] = {1, 1, 1}, zero[3] = {0, 0, 0};
+  PDN_TRY(pack_operand_ex(w, C, K, (int64_t)k * k, 1, (int64_t)k * k, C * (int64_t)k * k, one, zero, &bufB, &B));
+  TcArgs t;
+  tc_defaults(t);
+  t.C = dx; t.M = M; t.N = C; t.K = K; t.ldc = C;
+  t.nchw_hw = H * W;
+  t.c_clear_bytes = (size_t)M * C * sizeof(float);
+  return gemm_tc_packed(A, B, t, 1);
+}
+
+int pdn_conv2d_bwd_weight(const float* x, const float* gy, float* dw, float* dbias, int64_t N, int64_t C, int64_t H, int64_t W, int64_t O, int k,
+                          int stride, int pad) {
+  PDN_TRY(ensure_init());
+  ConvGeom g;
+  PDN_TRY(make_geom(g, N, C, H, W, O, k, stride, pad));
+  const int64_t hw = g.oh * g.ow, M = N * hw, K = C * k * k;
+  if (dbias && O > 0) {
+    k_channel_sum<<<(unsigned)O, 256, 0, stream()>>>(gy, dbias, N, O, hw);
+    PDN_LAUNCHED("channel_sum");
+  }
+  if (!dw || O == 0 || K == 0) return 0;
+  if (M == 0) {
+    PDN_CUDA(cudaMemsetAsync(dw, 0, (size_t)O * K * sizeof(float), stream()));
+    return 0;
+  }
+  Scratch       bufA, bufB;
+  PackedOperand A, B;
+  // A rows = o, contraction index m = (n, pix): g[n, o, pix]
+  const int64_t one[3] = {1, 1, 1}, zero[3] = {0, 0, 0};
+  PDN_TRY(pack_operand_ex(gy, O, M, hw, 1, hw, O * hw, one, zero, &bufA, &A));
+  PDN_TRY((conv_pack<0, false>(x, g, M, K, &bufB, &B)));
+  TcArgs t;
+  tc_defaults(t);
+  t.C = dw; t.M = O; t.N = K; t.K = M; t.ldc = K;
+  return gemm_tc_packed(A, B, t, 0);
+}
+
+int pdn_pool2d_fwd(const float* x, float* y, int64_t N, int64_t C, int64_t H, int64_t W, int k, int stride, int pad, int mode) {
+  PDN_TRY(ensure_init());
+  PDN_CHECK(k >= 1 && stride >= 1 && pad >= 0 && (mode == 0 || mode == 1), "pool: bad arguments");
+  PoolGeom g{N, C, H, W, (H + 2 * pad - k) / stride + 1, (W + 2 * pad - k) / stride + 1, k, stride, pad, mode};
+  const int64_t total = N * C * g.oh * g.ow;
+  if (total == 0) return 0;
+  k_pool_fwd<<<grid_for(total, 256), 256, 0, stream()>>>(x, y, g);
+  PDN_LAUNCHED("pool_fwd");
+  return 0;
+}
+
+int pdn_pool2d_bwd(const float* x, const float* y, const float* gy, float* dx, int64_t N, int64_t C, int64_t H, int64_t W, int k, int stride,
+                   int pad, int mode) {
+  PDN_TRY(ensure_init());
+  PDN_CHECK(k >= 1 && stride >= 1 && pad >= 0 && (mode == 0 || mode == 1), "pool: bad arguments");
+  PoolGeom g{N, C, H, W, (H + 2 * pad - k) / stride + 1, (W + 2 * pad - k) / stride + 1, k, stride, pad, mode};
+  const int64_t total = N * C * H * W;
+  if (total == 0) return 0;
+  k_pool_bwd<<<grid_for(total, 256), 256, 0, stream()>>>(x, y, gy, dx, g);
+  PDN_LAUNCHED("pool_bwd");
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,191 @@
+// norm.cu — per-feature batch-statistic normalisation shared by BatchNorm1d/2d and the reference's "LayerNorm"
+// (norm.py:58-73, 132-147, 203-218: mean / biased variance per feature over every other axis). x is viewed as
+// [outer, C, inner]; the reference runs ~12 eager array expressions (each a full HBM pass); here: two reduction passes
+// for the statistics (mean, then centred squares — same two-pass definition as the reference, not E[x^2]-E[x]^2), one
+// pass to apply, and for backward one dual-reduction pass + one elementwise pass.
+#include "common.cuh"
+
+namespace pdn {
+
+// MODE 0: s1 += x            MODE 1: s1 += (x - mean)^2        MODE 2: s1 += g, s2 += g * (x - mean) * rstd
+// inner == 1 : block = 32 channels x 8 row-lanes, rows strided by gridDim.y chunks (coalesced along C)
+template <int MODE>
+__global__ void __launch_bounds__(256) k_feat_reduce_rows(const float* __restrict__ x, const float* __restrict__ g, const float* __restrict__ mean,
+                                                          const float* __restrict__ var, float eps, float* __restrict__ s1, float* __restrict__ s2,
+                                                          int64_t rows, int64_t C, float inv_m) {
+  __shared__ float r1[8][33], r2[8][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int64_t c = (int64_t)blockIdx.x * 32 + tx;
+  float a1 = 0.f, a2 = 0.f;
+  if (c < C) {
+    const float mu = MODE >= 1 ? mean[c] : 0.f;
+    const float rs = MODE == 2 ? rsqrtf(var[c] + eps) : 0.f;
+    for (int64_t r = (int64_t)blockIdx.y * 8 + ty; r < rows; r += (int64_t)gridDim.y * 8) {
+      const float xv = x[r * C + c];
+      if (MODE == 0) a1 += xv;
+      else if (MODE == 1) { float d = xv - mu; a1 += d * d; }
+      else { float gv = g[r * C + c]; a1 += gv; a2 += gv * (xv - mu) * rs; }
+    }
+  }
+  r1[ty][tx] = a1; r2[ty][tx] = a2;
+  __syncthreads();
+  if (ty == 0 && c < C) {
+#pragma unroll
+    for (int i = 1; i < 8; ++i) { a1 += r1[i][tx]; a2 += r2[i][tx]; }
+    atomicAdd(s1 + c, a1 * inv_m);
+    if (MODE == 2) atomicAdd(s2 + c, a2 * inv_m);
+  }
+}
+
+// inner > 1 : block = (channel, chunk); threads walk j = (o, i) with i fastest (coalesced along inner)
+template <int MODE>
+__global__ void __launch_bounds__(256) k_feat_reduce_chan(const float* __restrict__ x, const float* __restrict__ g, const float* __restrict__ mean,
+                                                          const float* __restrict__ var, float eps, float* __restrict__ s1, float* __restrict__ s2,
+                                                          int64_t outer, int64_t C, int64_t inner, float inv_m) {
+  __shared__ float red[32];
+  const int64_t c = blockIdx.x, m = outer * inner;
+  const float mu = MODE >= 1 ? mean[c] : 0.f;
+  const float rs = MODE == 2 ? rsqrtf(var[c] + eps) : 0.f;
+  float a1 = 0.f, a2 = 0.f;
+  for (int64_t j = (int64_t)blockIdx.y * blockDim.x + threadIdx.x; j < m; j += (int64_t)gridDim.y * blockDim.x) {
+    const int64_t o = j / inner, i = j - o * inner;
+    const int64_t e = (o * C + c) * inner + i;
+    const float xv = x[e];
+    if (MODE == 0) a1 += xv;
+    else if (MODE == 1) { float d = xv - mu; a1 += d * d; }
+    else { float gv = g[e]; a1 += gv; a2 += gv * (xv - mu) * rs; }
+  }
+  a1 = block_sum<float>(a1, red);
+  if (MODE == 2) a2 = block_sum<float>(a2, red);
+  if (threadIdx.x == 0) {
+    atomicAdd(s1 + c, a1 * inv_m);
+    if (MODE == 2) atomicAdd(s2 + c, a2 * inv_m);
+  }
+}
+
+__global__ void __launch_bounds__(256) k_feat_apply(const float* __restrict__ x, const float* __restrict__ mean, const float* __restrict__ var,
+                                                    const float* __restrict__ scale, const float* __restrict__ shift, float* __restrict__ y,
+                                                    int64_t total, int64_t C, int64_t inner, float eps) {
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t c = (e / inner) % C;
+    y[e] = (x[e] - mean[c]) * rsqrtf(var[c] + eps) * scale[c] + shift[c];
+  }
+}
+
+// dx = scale * rstd * (g - mean(g) - xhat * mean(g * xhat)); mg / mgx arrive already divided by m
+__global__ void __launch_bounds__(256) k_feat_bwd_dx(const float* __restrict__ x, const float* __restrict__ g, const float* __restrict__ mean,
+                                                     const float* __restrict__ var, const float* __restrict__ scale, const float* __restrict__ mg,
+                                                     const float* __restrict__ mgx, float* __restrict__ dx, int64_t total, int64_t C, int64_t inner,
+                                                     float eps) {
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t c = (e / inner) % C;
+    const float rs = rsqrtf(var[c] + eps);
+    const float xhat = (x[e] - mean[c]) * rs;
+    dx[e] = scale[c] * rs * (g[e] - mg[c] - xhat * mgx[c]);
+  }
+}
+
+__global__ void k_scale_vec(float* a, float* b, float s, int64_t n) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) { a[i] *= s; if (b) b[i] *= s; }
+}
+
+template <int MODE>
+static int feat_reduce(const float* x, const float* g, const float* mean, const float* var, float eps, float* s1, float* s2, int64_t outer,
+                       int64_t C, int64_t inner, float inv_m) {
+  PDN_CUDA(cudaMemsetAsync(s1, 0, (size_t)C * sizeof(float), stream()));
+  if (s2) PDN_CUDA(cudaMemsetAsync(s2, 0, (size_t)C * sizeof(float), stream()));
+  const int sms = sm_count();
+  if (inner == 1) {
+    int64_t gx = (C + 31) / 32;
+    int64_t gy = (sms * 4 + gx - 1) / gx;
+    if (gy > (outer + 7) / 8) gy = (outer + 7) / 8;
+    if (gy < 1) gy = 1;
+    if (gy > 65535) gy = 65535;
+    k_feat_reduce_rows<MODE><<<dim3((unsigned)gx, (unsigned)gy), 256, 0, stream()>>>(x, g, mean, var, eps, s1, s2, outer, C, inv_m);
+  } else {
+    int64_t m = outer * inner;
+    int64_t gy = (sms * 4 + C - 1) / C;
+    if (gy > (m + 255) / 256) gy = (m + 255) / 256;
+    if (gy < 1) gy = 1;
+    if (gy > 65535) gy = 65535;
+    PDN_CHECK(C <= 0x7fffffff, "feature norm: too many channels");
+    k_feat_reduce_chan<MODE><<<dim3((unsigned)C, (unsigned)gy), 256, 0, stream()>>>(x, g, mean, var, eps, s1, s2, outer, C, inner, inv_m);
+  }
+  PDN_LAUNCHED("feat_reduce");
+  return 0;
+}
+
+}  // namespace pdn
+
+using namespace pdn;
+
+extern "C" {
+
+int pdn_bnorm_stats(const float* x, float* mean, float* var, int64_t outer, int64_t C, int64_t inner) {
+  PDN_TRY(ensure_init());
+  if (C == 0) return 0;
+  PDN_CHECK(outer * inner > 0, "feature norm: empty reduction");
+  const float inv_m = 1.f / (float)(outer * inner);
+  PDN_TRY((feat_reduce<0>(x, nullptr, nullptr, nullptr, 0.f, mean, nullptr, outer, C, inner, inv_m)));
+  PDN_TRY((feat_reduce<1>(x, nullptr, mean, nullptr, 0.f, var, nullptr, outer, C, inner, inv_m)));
+  return 0;
+}
+
+/* data-parallel building blocks: local partial statistics scaled by 1/m_global so that a cross-rank SUM gives the global
+ * mean / variance / gradient means (equal shards). which = 0: mean partial, 1: centred-square partial (needs the global mean) */
+int pdn_bnorm_partial(const float* x, const float* mean, float* out, int64_t outer, int64_t C, int64_t inner, int which, float inv_m_global) {
+  PDN_TRY(ensure_init());
+  if (C == 0) return 0;
+  if (which == 0) return feat_reduce<0>(x, nullptr, nullptr, nullptr, 0.f, out, nullptr, outer, C, inner, inv_m_global);
+  return feat_reduce<1>(x, nullptr, mean, nullptr, 0.f, out, nullptr, outer, C, inner, inv_m_global);
+}
+
+/* backward phase 1: mg[c] = Σ_local g / m_global, mgx[c] = Σ_local g·xhat / m_global (all-reduce these, then phase 2) */
+int pdn_bnorm_bwd_reduce(const float* x, const float* mean, const float* var, const float* g, float* mg, float* mgx, int64_t outer, int64_t C,
+                         int64_t inner, float eps, float inv_m_global) {
+  PDN_TRY(ensure_init());
+  if (C == 0) return 0;
+  return feat_reduce<2>(x, g, mean, var, eps, mg, mgx, outer, C, inner, inv_m_global);
+}
+
+/* backward phase 2: dx from the (global) means; then mg, mgx are rescaled by m_local_scale to become this rank's share of
+ * dshift / dscale (their cross-rank sum — done by the gradient all-reduce — is the global gradient) */
+int pdn_bnorm_bwd_dx(const float* x, const float* mean, const float* var, const float* scale, const float* g, const float* mg, const float* mgx,
+                     float* dx, int64_t outer, int64_t C, int64_t inner, float eps) {
+  PDN_TRY(ensure_init());
+  const int64_t total = outer * C * inner;
+  if (total == 0 || !dx) return 0;
+  k_feat_bwd_dx<<<grid_for(total, 256), 256, 0, stream()>>>(x, g, mean, var, scale, mg, mgx, dx, total, C, inner, eps);
+  PDN_LAUNCHED("feat_bwd_dx");
+  return 0;
+}
+
+int pdn_bnorm_apply(const float* x, const float* mean, const float* var, const float* scale, const float* shift, float* y, int64_t outer,
+                    int64_t C, int64_t inner, float eps) {
+  PDN_TRY(ensure_init());
+  const int64_t total = outer * C * inner;
+  if (total == 0) return 0;
+  k_feat_apply<<<grid_for(total, 256), 256, 0, stream()>>>(x, mean, var, scale, shift, y, total, C, inner, eps);
+  PDN_LAUNCHED("feat_apply");
+  return 0;
+}
+
+int pdn_bnorm_bwd(const float* x, const float* mean, const float* var, const float* scale, const float* g, float* dx, float* dscale,
+                  float* dshift, int64_t outer, int64_t C, int64_t inner, float eps) {
+  PDN_TRY(ensure_init());
+  const int64_t total = outer * C * inner;
+  if (total == 0) return 0;
+  const float m = (float)(outer * inner);
+  // dshift <- mean(g), dscale <- mean(g * xhat) (scaled by 1/m inside the reduction), used by dx, then rescaled to sums
+  PDN_TRY((feat_reduce<2>(x, g, mean, var, eps, dshift, dscale, outer, C, inner, 1.f / m)));
+  if (dx) {
+    k_feat_bwd_dx<<<grid_for(total, 256), 256, 0, stream()>>>(x, g, mean, var, scale, dshift, dscale, dx, total, C, inner, eps);
+    PDN_LAUNCHED("feat_bwd_dx");
+  }
+  k_scale_vec<<<(unsigned)((C + 255) / 256), 256, 0, stream()>>>(dshift, dscale, m, C);
+  PDN_LAUNCHED("scale_vec");
+  return 0;
+}
+
+}  // extern "C"

@@ -46,11 +46,6 @@ def _call(name, *args):
     lib.call(name, *args)
 
 
-def sequence(cell, x, state):
-    """Fused whole-sequence recurrence for one layer/direction; None = not applicable, caller runs the per-step loop."""
-    return None
-
-
 def _c(a):
     """C-contiguous fp32 device array."""
     return a if a.is_contiguous else a.copy()
@@ -266,3 +261,188 @@ def llama_cached_attention(att, xq, xk, xv, start_pos, mask, scale):
         _call("pdn_attention_fwd", q.ptr, ck.ptr, cv.ptr, mptr, out.ptr, None, B, H, L, Lk, D, _bhl_strides(q), cstr, cstr, mstr, scale)
         _ = keep
     return _result(out.reshape(B, L, H * D), xq.device, (), None, "llama_cached_attention")
+
+
+# ---------------------------------------------------------------------------------- conv / pool --------------
+@fused_op
+def conv2d(x, kernel, padding, stride, bias=None):
+    """F.conv2d (+ Conv2d's (1,O,1,1) bias) as gathered tcgen05 GEMMs (csrc/conv.cu); NCHW contiguous result
+    (reference functional.py:254-281, conv.py:99-103)."""
+    with x.device:
+        xd, wd = _c(x.data), _c(kernel.data)
+        N, Cin, H, W = xd.shape
+        O, _, k, _ = wd.shape
+        oh, ow = (H + 2 * padding - k) // stride + 1, (W + 2 * padding - k) // stride + 1
+        y = _empty((N, O, oh, ow))
+        bd = _c(bias.data).reshape(-1) if bias is not None else None
+        _call("pdn_conv2d_fwd", xd.ptr, wd.ptr, bd.ptr if bd is not None else None, y.ptr, N, Cin, H, W, O, k, stride, padding)
+
+    def backward(g):
+        g = _c(g)
+        dx = dw = db = None
+        if x.requires_grad:
+            dx = _empty(xd.shape)
+            _call("pdn_conv2d_bwd_data", g.ptr, wd.ptr, dx.ptr, N, Cin, H, W, O, k, stride, padding)
+        need_b = bias is not None and bias.requires_grad
+        if kernel.requires_grad or need_b:
+            dw = _empty(wd.shape) if kernel.requires_grad else None
+            db = _empty(bias.shape) if need_b else None
+            _call("pdn_conv2d_bwd_weight", xd.ptr, g.ptr, dw.ptr if dw is not None else None, db.ptr if db is not None else None, N, Cin, H,
+                  W, O, k, stride, padding)
+        return (dx, dw, db) if bias is not None else (dx, dw)
+
+    ins = (x, kernel) + ((bias, ) if bias is not None else ())
+    return _result(y, x.device, ins, backward, "conv2d")
+
+
+@fused_op
+def pool2d(x, k, stride, padding, mode):
+    """max / avg pooling as a direct window kernel; zero padding participates, tied maxima all receive the gradient
+    (reference functional.py:284-339, tensor.py:741-747)."""
+    m = 0 if mode == "max" else 1
+    with x.device:
+        xd = _c(x.data)
+        N, Cn, H, W = xd.shape
+        oh, ow = (H + 2 * padding - k) // stride + 1, (W + 2 * padding - k) // stride + 1
+        y = _empty((N, Cn, oh, ow))
+        _call("pdn_pool2d_fwd", xd.ptr, y.ptr, N, Cn, H, W, k, stride, padding, m)
+
+    def backward(g):
+        g = _c(g)
+        dx = _empty(xd.shape)
+        _call("pdn_pool2d_bwd", xd.ptr, y.ptr, g.ptr, dx.ptr, N, Cn, H, W, k, stride, padding, m)
+        return (dx, )
+
+    return _result(y, x.device, (x, ), backward, "pool2d")
+
+
+# ---------------------------------------------------------------------------------- feature-statistic norm ----
+@fused_op
+def feature_norm(mod, x, axes, keep):
+    """Training-mode forward of BatchNorm1d/2d and the reference's batch-statistic "LayerNorm" (norm.py:58-73, 132-147,
+    203-218) incl. the in-place running-stat update; 3 kernels forward, 3 backward instead of ~12 eager nodes."""
+    scale, shift = mod.scale, mod.shift
+    red = (axes, ) if isinstance(axes, int) else tuple(axes)
+    with x.device:
+        xd = _c(x.data)
+        nd = xd.ndim
+        if red == tuple(range(len(red))):  # leading axes reduced: [outer, C]
+            outer = int(np.prod(xd.shape[:len(red)], dtype=np.int64))
+            Cn, inner = xd.size // max(outer, 1), 1
+        elif red == (0, ) + tuple(range(2, nd)):  # channel axis 1: [N, C, inner]
+            outer, Cn, inner = xd.shape[0], xd.shape[1], int(np.prod(xd.shape[2:], dtype=np.int64))
+        else:
+            raise NotImplementedError(f"feature_norm over axes {red}")
+        stat_shape = scale.shape
+        mean, var = _empty((Cn, )), _empty((Cn, ))
+        _call("pdn_bnorm_stats", xd.ptr, mean.ptr, var.ptr, outer, Cn, inner)
+        y = _empty(xd.shape)
+        sc, sh = _c(scale.data).reshape(-1), _c(shift.data).reshape(-1)
+        _call("pdn_bnorm_apply", xd.ptr, mean.ptr, var.ptr, sc.ptr, sh.ptr, y.ptr, outer, Cn, inner, mod.eps)
+        rm, rv = mod.running_mean.data, mod.running_var.data
+        rm *= (1 - mod.momentum)
+        rm += (mean * mod.momentum).reshape(rm.shape)
+        rv *= (1 - mod.momentum)
+        rv += (var * mod.momentum).reshape(rv.shape)
+
+    def backward(g):
+        g = _c(g)
+        dx = _empty(xd.shape) if x.requires_grad else None
+        dsc, dsh = _empty((Cn, )), _empty((Cn, ))
+        _call("pdn_bnorm_bwd", xd.ptr, mean.ptr, var.ptr, sc.ptr, g.ptr, dx.ptr if dx is not None else None, dsc.ptr, dsh.ptr, outer, Cn, inner,
+              mod.eps)
+        return dx, dsc.reshape(stat_shape), dsh.reshape(stat_shape)
+
+    return _result(y, x.device, (x, scale, shift), backward, "feature_norm")
+
+
+# ---------------------------------------------------------------------------------- recurrent sequences ------
+def _seq_inputs(x):
+    """[T, B, I] device array (unbatched [T, I] gets B = 1) flattened to contiguous [T*B, I]."""
+    xd = x.data
+    if xd.ndim == 2:
+        xd = xd.reshape(xd.shape[0], 1, xd.shape[1])
+    T, B, I = xd.shape
+    return _c(xd).reshape(T * B, I), T, B, I
+
+
+def sequence(cell, x, state):
+    """Whole-sequence forward of one recurrent layer/direction as ONE tape entry (csrc/rnn.cu). Returns
+    ([state sequences], [last states]) like the per-step loop in nn/modules/rnn.py, or None when not applicable."""
+    from .modules.rnn import GRUCell, LSTMCell
+    if not _ENABLED or type(cell) not in (GRUCell, LSTMCell) or x.ndim not in (2, 3):
+        return None
+    tensors = [x] + list(state) + list(cell._parameters.values())
+    if not all(t.device.is_cuda and t.data.dtype == F32 for t in tensors):
+        return None
+    return _gru_sequence(cell, x, state[0]) if type(cell) is GRUCell else _lstm_sequence(cell, x, state[0], state[1])
+
+
+def _gru_sequence(cell, x, h0):
+    bk = _bk()
+    H = cell.hidden_size
+    Wx1, Wh1, Wx2, Wh2 = cell.Wx1, cell.Wh1, cell.Wx2, cell.Wh2
+    b1, b2 = (cell.bias1, cell.bias2) if cell.has_bias else (None, None)
+    unb = x.ndim == 2
+    with x.device:
+        x2, T, B, I = _seq_inputs(x)
+        h0d = _c(h0.data).reshape(B, H)
+        xp1 = bk.gemm_into(None, x2, Wx1.data, bias=_c(b1.data) if b1 is not None else None)  # hoisted over all T
+        xp2 = bk.gemm_into(None, x2, Wx2.data, bias=_c(b2.data) if b2 is not None else None)
+        hs, zr, nn_ = _empty((T, B, H)), _empty((T, B, 2 * H)), _empty((T, B, H))
+        w1, w2 = _c(Wh1.data), _c(Wh2.data)
+        _call("pdn_gru_seq_fwd", xp1.ptr, xp2.ptr, h0d.ptr, w1.ptr, w2.ptr, hs.ptr, zr.ptr, nn_.ptr, T, B, H)
+        del xp1, xp2
+
+    def backward(g):
+        g = _c(g.reshape(T, B, H))
+        dxp1, dxp2 = _empty((T * B, 2 * H)), _empty((T * B, H))
+        dh0, dW1, dW2 = _empty((B, H)), _empty((H, 2 * H)), _empty((H, H))
+        _call("pdn_gru_seq_bwd", g.ptr, h0d.ptr, hs.ptr, zr.ptr, nn_.ptr, w1.ptr, w2.ptr, dxp1.ptr, dxp2.ptr, dh0.ptr, dW1.ptr, dW2.ptr, T, B, H)
+        dx = None
+        if x.requires_grad:
+            dx = bk.gemm_into(None, dxp1, Wx1.data.swapaxes(0, 1))
+            bk.gemm_into(dx, dxp2, Wx2.data.swapaxes(0, 1), accumulate=True)
+            dx = dx.reshape(x.shape)
+        xt = x2.swapaxes(0, 1)
+        outs = [dx, dh0.reshape(h0.shape), bk.gemm_into(None, xt, dxp1), dW1, bk.gemm_into(None, xt, dxp2), dW2]
+        if b1 is not None:
+            outs += [dxp1.sum(axis=0), dxp2.sum(axis=0)]
+        return tuple(outs)
+
+    ins = (x, h0, Wx1, Wh1, Wx2, Wh2) + ((b1, b2) if b1 is not None else ())
+    seq = _result(hs.reshape(T, H) if unb else hs, x.device, ins, backward, "gru_sequence")
+    return [seq], [seq[T - 1:T]]
+
+
+def _lstm_sequence(cell, x, h0, c0):
+    bk = _bk()
+    H = cell.hidden_size
+    Wx, Wh = cell.Wx, cell.Wh
+    b = cell.bias if cell.has_bias else None
+    unb = x.ndim == 2
+    with x.device:
+        x2, T, B, I = _seq_inputs(x)
+        h0d, c0d = _c(h0.data).reshape(B, H), _c(c0.data).reshape(B, H)
+        xp = bk.gemm_into(None, x2, Wx.data, bias=_c(b.data) if b is not None else None)
+        hc, gates = _empty((2, T, B, H)), _empty((T, B, 4 * H))
+        wh = _c(Wh.data)
+        cs_ptr = hc.ptr + T * B * H * 4
+        _call("pdn_lstm_seq_fwd", xp.ptr, h0d.ptr, c0d.ptr, wh.ptr, hc.ptr, cs_ptr, gates.ptr, T, B, H)
+        del xp
+
+    def backward(g):
+        g = _c(g.reshape(2, T, B, H))
+        g_cT = _c(g[1, T - 1])  # only the final cell state is exposed by the module API
+        dxp, dh0, dc0, dWh = _empty((T * B, 4 * H)), _empty((B, H)), _empty((B, H)), _empty((H, 4 * H))
+        _call("pdn_lstm_seq_bwd", g.ptr, g_cT.ptr, h0d.ptr, c0d.ptr, hc.ptr, cs_ptr, gates.ptr, wh.ptr, dxp.ptr, dh0.ptr, dc0.ptr, dWh.ptr, T, B, H)
+        dx = bk.gemm_into(None, dxp, Wx.data.swapaxes(0, 1)).reshape(x.shape) if x.requires_grad else None
+        outs = [dx, dh0.reshape(h0.shape), dc0.reshape(c0.shape), bk.gemm_into(None, x2.swapaxes(0, 1), dxp), dWh]
+        if b is not None:
+            outs.append(dxp.sum(axis=0))
+        return tuple(outs)
+
+    ins = (x, h0, c0, Wx, Wh) + ((b, ) if b is not None else ())
+    both = _result(hc.reshape(2, T, H) if unb else hc, x.device, ins, backward, "lstm_sequence")
+    hs, cs = both[0], both[1]
+    return [hs, cs], [hs[T - 1:T], cs[T - 1:T]]
