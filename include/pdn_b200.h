@@ -150,6 +150,13 @@ int pdn_index_scatter(void* dst, int dtype, const void* values, int K, const voi
 int pdn_gemm(int dtype, const void* A, const void* B, void* C, int64_t M, int64_t N, int64_t K, int64_t a_rs,
              int64_t a_cs, int64_t b_rs, int64_t b_cs, int64_t ldc, const int64_t* nb, const int64_t* a_bs,
              const int64_t* b_bs, const int64_t* c_bs, const void* bias, int accumulate, int prec);
+/* Inference: pack a constant fp32 weight matrix B (K x N, element strides b_rs/b_cs) once into the tcgen05 operand format
+ * and reuse it: C[M,N] (+)= A[M,K] @ B (+ bias). The handle owns device memory until pdn_gemm_prepack_free. The caller
+ * must re-pack when the weight values change (pydynet_b200 tracks a per-buffer version for that). */
+int pdn_gemm_prepack(const float* B, int64_t K, int64_t N, int64_t b_rs, int64_t b_cs, void** handle);
+int pdn_gemm_prepacked(const float* A, void* handle, float* C, int64_t M, int64_t a_rs, int64_t a_cs, int64_t ldc,
+                       const float* bias, int accumulate);
+int pdn_gemm_prepack_free(void* handle);
 /* which path the last pdn_gemm call took: 0 = FFMA tiles, 1 = tcgen05, 2 = skinny (M<=16) */
 int pdn_gemm_last_path(void);
 
@@ -262,6 +269,13 @@ int pdn_adam_multi(int n_tensors, float* const* p, const float* const* grad, flo
  * [Bmax, S, H, D] at [b, pos0 + l] (model.py:105-107). */
 int pdn_rope_kv_append(float* q, float* k, const float* v, const float* cosT, const float* sinT, float* cache_k,
                        float* cache_v, int64_t B, int64_t L, int64_t H, int64_t D, int64_t S, int64_t pos0);
+/* Device-scalar variants for CUDA-graph replay of one decode step: the sequence position is read from device memory
+ * (pos_dev) instead of being baked into the launch; attention runs over Lk = *pos_dev + lk_add cached keys, no mask. */
+int pdn_rope_kv_append_dev(float* q, float* k, const float* v, const float* cosT, const float* sinT, float* cache_k,
+                           float* cache_v, int64_t B, int64_t L, int64_t H, int64_t D, int64_t S, const int64_t* pos_dev);
+int pdn_attention_fwd_dev(const float* q, const float* k, const float* v, float* out, int64_t B, int64_t H, int64_t Lq,
+                          int64_t D, const int64_t* q_str, const int64_t* k_str, const int64_t* v_str, float scale,
+                          const int64_t* pos_dev, int64_t lk_add);
 /* out = silu(gate) * up  (FeedForward.forward model.py:56-58), gate/up are the two halves [rows, F] */
 int pdn_swiglu(const float* gate, const float* up, float* out, int64_t n);
 int pdn_swiglu_bwd(const float* gate, const float* up, const float* g, float* dgate, float* dup, int64_t n);

@@ -42,13 +42,14 @@ def _arr(vals):
 
 class _Buffer:
     """Owns one allocation of the caching allocator; freed when the last view dies."""
-    __slots__ = ("ptr", "nbytes")
+    __slots__ = ("ptr", "nbytes", "version")
 
     def __init__(self, nbytes: int):
         p = C.c_void_p()
         L.call("pdn_malloc", C.byref(p), max(int(nbytes), 1))
         self.ptr = p.value or 0
         self.nbytes = nbytes
+        self.version = 0  # bumped by every in-place write; derived caches (pre-packed GEMM weights) key on it
 
     def __del__(self):
         try:
@@ -192,6 +193,7 @@ class ndarray:
     def _copy_into(self, dst: "ndarray"):
         """dst[...] = self (same shape), strided, with cast."""
         assert dst.shape == self.shape, (dst.shape, self.shape)
+        dst.buf.version += 1
         L.call("pdn_copy", self.ptr, _code(self.dtype), dst.ptr, _code(dst.dtype), len(self.shape), _arr(self.shape),
                _arr(self.estrides), _arr(dst.estrides))
 
@@ -212,6 +214,7 @@ class ndarray:
         return self if self.is_contiguous else self.copy()
 
     def fill(self, value):
+        self.buf.version += 1
         L.call("pdn_fill", self.ptr, _code(self.dtype), len(self.shape), _arr(self.shape), _arr(self.estrides), float(value))
 
     # ------------------------------------------------------------------ views -------------------
@@ -485,6 +488,7 @@ def _scatter(view: ndarray, adv, value, accumulate: bool):
     if value.shape != tshape:
         value = value.broadcast_to(tshape)
     value = value.ascontiguous()
+    view.buf.version += 1
     if value.size:
         L.call("pdn_index_scatter", view.ptr, _code(view.dtype), value.ptr, K, ptrs, _arr(dims), _arr(dst), J, len(os_), _arr(os_),
                _arr(ost), len(is_), _arr(is_), _arr(ist), 1 if accumulate else 0)
@@ -540,6 +544,7 @@ def _binary(op, a, b, out: ndarray | None = None, true_div: bool = False) -> nda
         if dt == np.bool_ and not cmp:
             dt = np.dtype(np.int64) if op in (L.ADD, L.SUB, L.MUL) else dt
         if out is not None:
+            out.buf.version += 1
             dt_c = out.dtype  # in-place ops compute in the destination dtype
             x = arr if arr.dtype == dt_c else arr.astype(dt_c)
             L.call("pdn_ew_binary_scalar", op, _code(dt_c), x.ptr, float(sc), rev, out.ptr, len(out.shape), _arr(out.shape),
@@ -561,6 +566,7 @@ def _binary(op, a, b, out: ndarray | None = None, true_div: bool = False) -> nda
         r = _binary(op, a.astype(np.int32), b.astype(np.int32))
         return r.astype(np.bool_)
     if out is not None:
+        out.buf.version += 1
         dt = out.dtype  # in-place ops compute in the destination dtype (same-kind casting)
         shape = out.shape
         if np.broadcast_shapes(a.shape, b.shape) != shape:

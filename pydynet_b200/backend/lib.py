@@ -71,6 +71,9 @@ _PROTOS = {
     "pdn_index_scatter": [vp, i32, vp, i32, C.POINTER(vp), pi64, pi64, i64, i32, pi64, pi64, i32, pi64, pi64, i32],
     "pdn_gemm": [i32, vp, vp, vp, i64, i64, i64, i64, i64, i64, i64, i64, pi64, pi64, pi64, pi64, vp, i32, i32],
     "pdn_gemm_last_path": [],
+    "pdn_gemm_prepack": [vp, i64, i64, i64, i64, C.POINTER(vp)],
+    "pdn_gemm_prepacked": [vp, vp, vp, i64, i64, i64, i64, vp, i32],
+    "pdn_gemm_prepack_free": [vp],
     "pdn_softmax_fwd": [i32, vp, vp, i64, i64, i32],
     "pdn_softmax_bwd": [i32, vp, vp, vp, i64, i64, i32],
     "pdn_rmsnorm_fwd": [vp, vp, vp, vp, i64, i64, f32],
@@ -94,6 +97,8 @@ _PROTOS = {
     "pdn_adam_step": [vp, vp, vp, vp, i64, f32, f32, f32, f32, f32, i32, f32],
     "pdn_adam_multi": [i32, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), pi64, f32, f32, f32, f32, f32, i32, f32],
     "pdn_rope_kv_append": [vp, vp, vp, vp, vp, vp, vp, i64, i64, i64, i64, i64, i64],
+    "pdn_rope_kv_append_dev": [vp, vp, vp, vp, vp, vp, vp, i64, i64, i64, i64, i64, vp],
+    "pdn_attention_fwd_dev": [vp, vp, vp, vp, i64, i64, i64, i64, pi64, pi64, pi64, f32, vp, i64],
     "pdn_swiglu": [vp, vp, vp, i64],
     "pdn_swiglu_bwd": [vp, vp, vp, vp, vp, i64],
     "pdn_nccl_unique_id": [C.c_char_p],

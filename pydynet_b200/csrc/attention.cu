@@ -22,6 +22,8 @@ struct AttArgs {
   int64_t qs[3], ks[3], vs[3];  // element strides: batch, head, row (D axis is unit stride)
   int64_t mask_bs, mask_qs;     // mask element strides for batch and query row (0 = broadcast); key axis unit stride
   float scale;
+  const int64_t* lk_dev;        // optional device scalar: Lk = *lk_dev + lk_add (CUDA-graph replay of the decode step)
+  int64_t lk_add;
 };
 
 __global__ void __launch_bounds__(128) k_attention_fwd(AttArgs a) {
@@ -32,6 +34,7 @@ __global__ void __launch_bounds__(128) k_attention_fwd(AttArgs a) {
   if (w >= total) return;
   const int64_t iq = w % a.Lq, h = (w / a.Lq) % a.H, b = w / (a.Lq * a.H);
   const int D = (int)a.D;
+  if (a.lk_dev) a.Lk = *a.lk_dev + a.lk_add;
   float* qsm = sm + wib * ATT_MAXD;
   const float* qrow = a.q + b * a.qs[0] + h * a.qs[1] + iq * a.qs[2];
   for (int d = lane; d < D; d += 32) qsm[d] = qrow[d] * a.scale;
@@ -174,7 +177,10 @@ __global__ void __launch_bounds__(128) k_attention_bwd(AttBwdArgs a) {
 // k (rotated) and v rows are also written into the caches [Bmax, S, H, D] at [b, pos0 + l].
 __global__ void __launch_bounds__(256) k_rope_kv_append(float* __restrict__ q, float* __restrict__ k, const float* __restrict__ v,
                                                         const float* __restrict__ cosT, const float* __restrict__ sinT, float* __restrict__ ck,
-                                                        float* __restrict__ cv, int64_t B, int64_t L, int64_t H, int64_t D, int64_t S, int64_t pos0) {
+                                                        float* __restrict__ cv, int64_t B, int64_t L, int64_t H, int64_t D, int64_t S, int64_t pos0,
+                                                        const int64_t* __restrict__ pos_dev) {
+  if (pos_dev) pos0 = *pos_dev;
+  if (pos0 < 0 || pos0 + L > S) return;  // out of the cache: the host-side check could not run for a device-side position
   const int64_t half = D / 2, total = B * L * H * half;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int64_t pi = i % half, hh = (i / half) % H, r = i / (half * H);
@@ -208,6 +214,8 @@ static int fill_att(AttArgs& a, const float* q, const float* k, const float* v, 
   a.mask_bs = mask && mask_str ? mask_str[0] : 0;
   a.mask_qs = mask && mask_str ? mask_str[1] : 0;
   a.scale = scale;
+  a.lk_dev = nullptr;
+  a.lk_add = 0;
   return 0;
 }
 
@@ -253,8 +261,36 @@ int pdn_rope_kv_append(float* q, float* k, const float* v, const float* cosT, co
             (long long)S);
   const int64_t total = B * L * H * (D / 2);
   if (total == 0) return 0;
-  k_rope_kv_append<<<grid_for(total, 256), 256, 0, stream()>>>(q, k, v, cosT, sinT, cache_k, cache_v, B, L, H, D, S, pos0);
+  k_rope_kv_append<<<grid_for(total, 256), 256, 0, stream()>>>(q, k, v, cosT, sinT, cache_k, cache_v, B, L, H, D, S, pos0, nullptr);
   PDN_LAUNCHED("rope_kv_append");
+  return 0;
+}
+
+/* Device-scalar variants used when one decode step is captured as a CUDA graph: the position lives in device memory
+ * (pos_dev), so the recorded launches stay valid while the sequence grows. */
+int pdn_rope_kv_append_dev(float* q, float* k, const float* v, const float* cosT, const float* sinT, float* cache_k, float* cache_v, int64_t B,
+                           int64_t L, int64_t H, int64_t D, int64_t S, const int64_t* pos_dev) {
+  PDN_TRY(ensure_init());
+  PDN_CHECK(D % 2 == 0 && pos_dev != nullptr, "rope_dev: bad arguments");
+  const int64_t total = B * L * H * (D / 2);
+  if (total == 0) return 0;
+  k_rope_kv_append<<<grid_for(total, 256), 256, 0, stream()>>>(q, k, v, cosT, sinT, cache_k, cache_v, B, L, H, D, S, 0, pos_dev);
+  PDN_LAUNCHED("rope_kv_append");
+  return 0;
+}
+
+int pdn_attention_fwd_dev(const float* q, const float* k, const float* v, float* out, int64_t B, int64_t H, int64_t Lq, int64_t D,
+                          const int64_t* q_str, const int64_t* k_str, const int64_t* v_str, float scale, const int64_t* pos_dev, int64_t lk_add) {
+  PDN_TRY(ensure_init());
+  PDN_CHECK(pos_dev != nullptr, "attention_dev: null position");
+  AttArgs a;
+  PDN_TRY(fill_att(a, q, k, v, nullptr, out, nullptr, B, H, Lq, 1, D, q_str, k_str, v_str, nullptr, scale));
+  a.lk_dev = pos_dev;
+  a.lk_add = lk_add;
+  const int64_t total = B * H * Lq;
+  if (total == 0) return 0;
+  k_attention_fwd<<<(unsigned)((total + 3) / 4), 128, 4 * ATT_MAXD * sizeof(float), stream()>>>(a);
+  PDN_LAUNCHED("attention_fwd");
   return 0;
 }
 

@@ -176,7 +176,7 @@ constexpr int TC_BK = 64;  // 64 bf16 = 128 B = one swizzle span
 template <int BN>
 struct TcCfg {
   static constexpr int kStageBytes = 2 * (TC_BM * TC_BK * 2) + 2 * (BN * TC_BK * 2);  // Ahi, Alo, Bhi, Blo
-  static constexpr int kStages = (BN == 128) ? 3 : 2;
+  static constexpr int kStages = (BN == 64) ? 4 : ((BN == 128) ? 3 : 2);
   static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
   static constexpr int kTmemCols = BN;  // fp32 accumulator columns (power of two >= 32)
 };
@@ -432,15 +432,22 @@ static int launch_tc(const CUtensorMap& mA, const CUtensorMap& mB, const TcArgs&
 // splits <= 0 picks a split-K factor that fills the SMs when the tile grid is small and K is long.
 int gemm_tc_packed(const PackedOperand& A, const PackedOperand& B, TcArgs t, int splits) {
   PDN_TRY(get_encode_fn());
-  const int BN = (t.N > 128 && getenv("PDN_TC_BN128") == nullptr) ? 256 : 128;
-  for (int i = 0; i < 3; ++i) { t.a_pbs[i] = A.pbs[i]; t.b_pbs[i] = B.pbs[i]; }
   const int64_t nbatch = t.nb[0] * t.nb[1] * t.nb[2];
-  const int64_t tiles = ((t.M + TC_BM - 1) / TC_BM) * ((t.N + BN - 1) / BN) * nbatch;
+  const int64_t m_tiles = (t.M + TC_BM - 1) / TC_BM;
+  auto tiles_for = [&](int bn) { return m_tiles * ((t.N + bn - 1) / bn) * nbatch; };
+  // widest N tile that still gives the grid enough CTAs; narrow tiles (and split-K below) for small problems
+  const int sms = sm_count();
+  int       BN = 64;
+  if (getenv("PDN_TC_BN128") != nullptr) BN = 128;
+  else if (t.N > 128 && tiles_for(256) >= (sms * 3) / 4) BN = 256;
+  else if (t.N > 64 && tiles_for(128) >= sms / 2) BN = 128;
+  for (int i = 0; i < 3; ++i) { t.a_pbs[i] = A.pbs[i]; t.b_pbs[i] = B.pbs[i]; }
+  const int64_t tiles = tiles_for(BN);
   const int     num_kb = (int)((t.K + TC_BK - 1) / TC_BK);
   if (splits <= 0) {
     splits = 1;
-    if (tiles < sm_count() / 2 && num_kb >= 8) {
-      int64_t want = (sm_count() + tiles - 1) / tiles;
+    if (tiles < sms / 2 && num_kb >= 8) {
+      int64_t want = (sms + tiles - 1) / tiles;
       int64_t cap = num_kb / 4;
       splits = (int)(want < cap ? want : cap);
       if (splits < 1) splits = 1;
@@ -463,7 +470,8 @@ int gemm_tc_packed(const PackedOperand& A, const PackedOperand& B, TcArgs t, int
   PDN_TRY(make_map(&mA, A.planes, A.R, A.K, A.Kp, A.nbatch, TC_BM));
   PDN_TRY(make_map(&mB, B.planes, B.R, B.K, B.Kp, B.nbatch, BN));
   if (BN == 256) return launch_tc<256>(mA, mB, t);
-  return launch_tc<128>(mA, mB, t);
+  if (BN == 128) return launch_tc<128>(mA, mB, t);
+  return launch_tc<64>(mA, mB, t);
 }
 
 int gemm_tc_launch(const GemmArgs& g) {
@@ -486,3 +494,51 @@ int gemm_tc_launch(const GemmArgs& g) {
 }
 
 }  // namespace pdn
+
+// ------------------------------------------------------------------ pre-packed weights -----------
+// Inference keeps a weight matrix's bf16 hi/lo planes resident (packed once) instead of re-packing 4 B/element on every
+// GEMM call — for Llama decode this removes one pack launch and one full weight read+write per Linear per token.
+namespace pdn {
+struct Prepacked {
+  Scratch       buf;
+  PackedOperand op;
+};
+}  // namespace pdn
+
+extern "C" {
+
+int pdn_gemm_prepack(const float* B, int64_t K, int64_t N, int64_t b_rs, int64_t b_cs, void** handle) {
+  PDN_TRY(pdn::ensure_init());
+  PDN_CHECK(K > 0 && N > 0, "prepack: empty matrix");
+  auto* h = new pdn::Prepacked();
+  const int64_t one[3] = {1, 1, 1}, zero[3] = {0, 0, 0};
+  int r = pdn::pack_operand_ex(B, N, K, b_cs, b_rs, 0, 0, one, zero, &h->buf, &h->op);
+  if (r) { delete h; return r; }
+  *handle = h;
+  return 0;
+}
+
+int pdn_gemm_prepacked(const float* A, void* handle, float* C, int64_t M, int64_t a_rs, int64_t a_cs, int64_t ldc, const float* bias,
+                       int accumulate) {
+  PDN_TRY(pdn::ensure_init());
+  auto* h = (pdn::Prepacked*)handle;
+  PDN_CHECK(h != nullptr, "prepacked: null handle");
+  if (M == 0) return 0;
+  pdn::Scratch       bufA;
+  pdn::PackedOperand Aop;
+  const int64_t one[3] = {1, 1, 1}, zero[3] = {0, 0, 0};
+  PDN_TRY(pdn::pack_operand_ex(A, M, h->op.K, a_rs, a_cs, 0, 0, one, zero, &bufA, &Aop));
+  pdn::TcArgs t;
+  t.C = C; t.bias = bias; t.M = M; t.N = h->op.R; t.K = h->op.K; t.ldc = ldc;
+  for (int i = 0; i < 3; ++i) { t.nb[i] = 1; t.c_bs[i] = 0; }
+  t.accumulate = accumulate; t.nchw_hw = 0; t.c_clear_bytes = 0;
+  return pdn::gemm_tc_packed(Aop, h->op, t, 0);
+}
+
+int pdn_gemm_prepack_free(void* handle) {
+  delete (pdn::Prepacked*)handle;
+  return 0;
+}
+
+}  // extern "C"
+

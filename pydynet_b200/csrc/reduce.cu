@@ -122,8 +122,10 @@ __global__ void __launch_bounds__(256) k_argreduce(const T* x, long long* out, R
     int64_t   base = off_of(d.nk, d.ks, d.kst, o);
     A         best = 0;
     long long bi = -1;
+    const bool    flat = d.nr == 1;  // one (collapsed) reduced axis: plain strided walk, no index decomposition
+    const int64_t rstride = d.rst[0];
     for (int64_t r = threadIdx.x; r < d.n_red; r += 256) {
-      A    v = ld<T>(x + base + off_of(d.nr, d.rs, d.rst, r));
+      A    v = ld<T>(x + base + (flat ? r * rstride : off_of(d.nr, d.rs, d.rst, r)));
       bool better;
       if (bi < 0) better = true;
       else if (best != best) better = false;  // first NaN wins (NumPy)

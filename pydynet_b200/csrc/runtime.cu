@@ -44,13 +44,24 @@ struct DevState {
   cudaStream_t comm = nullptr;
   int          sms = 0;
   // caching allocator: free blocks by size; live blocks by pointer
-  std::multimap<size_t, void*>      free_blocks;
-  std::unordered_map<void*, size_t> live;
+  struct Block {
+    size_t size;
+    int    graph;      // 0 = ordinary; else id of the CUDA graph whose kernels reference this block
+    bool   user_live;  // still owned by a caller (false: only the graph keeps it reserved)
+  };
+  std::multimap<size_t, void*>     free_blocks;
+  std::unordered_map<void*, Block> live;
+  std::multimap<size_t, void*>     capture_free;  // blocks freed DURING the active capture: reusable inside it only
   uint64_t in_use = 0, cached = 0, n_malloc = 0;
 };
 static DevState   g_dev[16];
 static std::mutex g_mu;
 static bool       g_capturing = false;
+static int        g_capture_id = 0;   // id of the graph being captured
+static int        g_next_graph_id = 1;
+static std::unordered_map<void*, int> g_exec_graph;  // cudaGraphExec_t -> graph id
+static std::unordered_map<void*, uint64_t> g_exec_kernels;  // kernels recorded in the graph (for the launch counter)
+static uint64_t g_capture_launch0 = 0;
 
 static DevState* cur() {
   int d = 0;
@@ -106,6 +117,16 @@ int dev_alloc(void** p, size_t bytes) {
   DevState* s = cur();
   size_t    want = round_size(bytes);
   std::lock_guard<std::mutex> lk(g_mu);
+  const int gid = g_capturing ? g_capture_id : 0;
+  if (g_capturing) {  // memory released earlier in this capture is ordered before us inside the graph: reuse it first
+    auto it = s->capture_free.lower_bound(want);
+    if (it != s->capture_free.end() && it->first <= want + want / 4) {
+      *p = it->second;
+      s->capture_free.erase(it);
+      s->live[*p].user_live = true;
+      return 0;
+    }
+  }
   auto it = s->free_blocks.lower_bound(want);
   // accept a cached block only if it wastes < 25 % (or is an exact granule match)
   if (it != s->free_blocks.end() && (it->first == want || it->first <= want + want / 4)) {
@@ -113,16 +134,13 @@ int dev_alloc(void** p, size_t bytes) {
     size_t got = it->first;
     s->free_blocks.erase(it);
     s->cached -= got;
-    s->live[*p] = got;
+    s->live[*p] = DevState::Block{got, gid, true};
     s->in_use += got;
     return 0;
   }
-  if (g_capturing) {
-    set_error("allocation of %zu bytes missed the cache during CUDA-graph capture (warm the step up first)", want);
-    return PDN_ERR_INVALID;
-  }
+  // (cudaMalloc is legal during a capture started in relaxed mode; it is not a stream operation)
   cudaError_t e = cudaMalloc(p, want);
-  if (e == cudaErrorMemoryAllocation) {
+  if (e == cudaErrorMemoryAllocation && !g_capturing) {
     cudaGetLastError();
     cudaStreamSynchronize(s->compute);
     release_cached(s);
@@ -133,9 +151,24 @@ int dev_alloc(void** p, size_t bytes) {
     return cuda_fail(e, "cudaMalloc", __FILE__, __LINE__);
   }
   s->n_malloc++;
-  s->live[*p] = want;
+  s->live[*p] = DevState::Block{want, gid, true};
   s->in_use += want;
   return 0;
+}
+
+static void free_in(DevState& d, std::unordered_map<void*, DevState::Block>::iterator it) {
+  void* p = it->first;
+  if (it->second.graph != 0) {
+    // referenced by a CUDA graph: never hand it to unrelated work while the graph exists
+    it->second.user_live = false;
+    if (g_capturing && it->second.graph == g_capture_id) d.capture_free.emplace(it->second.size, p);
+    return;
+  }
+  // single compute stream => a freed block can be handed out again immediately (stream order)
+  d.free_blocks.emplace(it->second.size, p);
+  d.cached += it->second.size;
+  d.in_use -= it->second.size;
+  d.live.erase(it);
 }
 
 void dev_free(void* p) {
@@ -144,24 +177,37 @@ void dev_free(void* p) {
   if (!s) return;
   std::lock_guard<std::mutex> lk(g_mu);
   auto it = s->live.find(p);
-  if (it == s->live.end()) {  // allocated on another device: search
-    for (auto& d : g_dev) {
-      auto jt = d.live.find(p);
-      if (jt != d.live.end()) {
-        d.free_blocks.emplace(jt->second, p);
-        d.cached += jt->second;
-        d.in_use -= jt->second;
-        d.live.erase(jt);
-        return;
-      }
-    }
+  if (it != s->live.end()) {
+    free_in(*s, it);
     return;
   }
-  // single compute stream => a freed block can be handed out again immediately (stream order)
-  s->free_blocks.emplace(it->second, p);
-  s->cached += it->second;
-  s->in_use -= it->second;
-  s->live.erase(it);
+  for (auto& d : g_dev) {  // allocated on another device
+    auto jt = d.live.find(p);
+    if (jt != d.live.end()) {
+      free_in(d, jt);
+      return;
+    }
+  }
+}
+
+// called when a graph is destroyed: blocks it kept reserved go back to the cache (or to their still-living owner)
+static void release_graph_blocks(int gid) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  for (auto& d : g_dev) {
+    for (auto it = d.live.begin(); it != d.live.end();) {
+      if (it->second.graph == gid) {
+        it->second.graph = 0;
+        if (!it->second.user_live) {
+          d.free_blocks.emplace(it->second.size, it->first);
+          d.cached += it->second.size;
+          d.in_use -= it->second.size;
+          it = d.live.erase(it);
+          continue;
+        }
+      }
+      ++it;
+    }
+  }
 }
 
 }  // namespace pdn
@@ -306,29 +352,61 @@ int pdn_event_elapsed_ms(void* start, void* stop, float* ms) {
 int pdn_graph_begin(void) {
   PDN_TRY(ensure_init());
   PDN_CHECK(!g_capturing, "graph capture already active");
-  PDN_CUDA(cudaStreamBeginCapture(stream(), cudaStreamCaptureModeThreadLocal));
+  PDN_CUDA(cudaStreamBeginCapture(stream(), cudaStreamCaptureModeRelaxed));
+  std::lock_guard<std::mutex> lk(g_mu);
   g_capturing = true;
+  g_capture_id = g_next_graph_id++;
+  g_capture_launch0 = g_launches;
   return 0;
 }
 int pdn_graph_end(void** graph_exec) {
   PDN_CHECK(g_capturing, "no graph capture active");
-  g_capturing = false;
+  int gid;
+  {
+    std::lock_guard<std::mutex> lk(g_mu);
+    g_capturing = false;
+    gid = g_capture_id;
+    g_capture_id = 0;
+    for (auto& d : g_dev) d.capture_free.clear();  // stay reserved for the graph (user_live == false)
+  }
   cudaGraph_t g;
-  PDN_CUDA(cudaStreamEndCapture(stream(), &g));
+  cudaError_t e = cudaStreamEndCapture(stream(), &g);
+  if (e != cudaSuccess) {
+    release_graph_blocks(gid);
+    return cuda_fail(e, "cudaStreamEndCapture", __FILE__, __LINE__);
+  }
   cudaGraphExec_t ge;
-  cudaError_t     e = cudaGraphInstantiate(&ge, g, 0);
+  e = cudaGraphInstantiate(&ge, g, 0);
   cudaGraphDestroy(g);
-  if (e != cudaSuccess) return cuda_fail(e, "cudaGraphInstantiate", __FILE__, __LINE__);
+  if (e != cudaSuccess) {
+    release_graph_blocks(gid);
+    return cuda_fail(e, "cudaGraphInstantiate", __FILE__, __LINE__);
+  }
+  {
+    std::lock_guard<std::mutex> lk(g_mu);
+    g_exec_graph[(void*)ge] = gid;
+    g_exec_kernels[(void*)ge] = g_launches - g_capture_launch0;
+    g_launches = g_capture_launch0;  // recording is not launching
+  }
   *graph_exec = (void*)ge;
   return 0;
 }
 int pdn_graph_launch(void* graph_exec) {
   PDN_CUDA(cudaGraphLaunch((cudaGraphExec_t)graph_exec, stream()));
-  ++g_launches;
+  auto it = g_exec_kernels.find(graph_exec);
+  g_launches += it != g_exec_kernels.end() ? it->second : 1;  // every kernel node of the replayed graph is one of ours
   return 0;
 }
 int pdn_graph_destroy(void* graph_exec) {
+  PDN_CUDA(cudaStreamSynchronize(stream()));
   PDN_CUDA(cudaGraphExecDestroy((cudaGraphExec_t)graph_exec));
+  int gid = 0;
+  {
+    std::lock_guard<std::mutex> lk(g_mu);
+    auto it = g_exec_graph.find(graph_exec);
+    if (it != g_exec_graph.end()) { gid = it->second; g_exec_graph.erase(it); }
+  }
+  if (gid) release_graph_blocks(gid);
   return 0;
 }
 

@@ -126,3 +126,38 @@ def _ensure_init(dev_id: int):
         if cur is not None and cur != dev_id and cur in _inited:
             _L.call("pdn_set_device", cur)
         _inited.add(dev_id)
+
+
+class Graph:
+    """CUDA-graph capture / replay of a launch sequence on the library's compute stream (pdn_graph_* in
+    include/pdn_b200.h). Memory allocated while capturing stays reserved for the graph until it is destroyed, so the
+    recorded kernels' buffers cannot be handed to unrelated work between replays.
+
+        g = Graph(); g.begin(); ...launch work...; g.end(); g.launch(); g.launch()
+    """
+
+    def __init__(self):
+        self._exec = None
+
+    def begin(self):
+        _L.call("pdn_graph_begin")
+
+    def end(self):
+        h = C.c_void_p()
+        _L.call("pdn_graph_end", C.byref(h))
+        self._exec = h
+
+    def launch(self):
+        _L.call("pdn_graph_launch", self._exec)
+
+    def destroy(self):
+        if self._exec is not None:
+            _L.call("pdn_graph_destroy", self._exec)
+            self._exec = None
+
+    def __del__(self):
+        try:
+            if _L._lib is not None:
+                self.destroy()
+        except Exception:
+            pass

@@ -61,17 +61,54 @@ def _needs(*ts):
 
 
 # ---------------------------------------------------------------------------------- linear -------------------
+class _PackedWeight:
+    """bf16 hi/lo operand planes of a constant weight matrix, owned by libpdn_b200 (pdn_gemm_prepack)."""
+    __slots__ = ("handle", "key")
+
+    def __init__(self, w):
+        h = C.c_void_p()
+        K, N = w.shape
+        _call("pdn_gemm_prepack", w.ptr, K, N, w.estrides[0], w.estrides[1], C.byref(h))
+        self.handle = h
+        self.key = (w.ptr, w.buf.version, w.shape, w.estrides)
+
+    def __del__(self):
+        try:
+            from ..backend import lib
+            if lib._lib is not None and self.handle:
+                lib._lib.pdn_gemm_prepack_free(self.handle)
+        except Exception:
+            pass
+
+
+def _packed(weight):
+    w = weight.data
+    pw = getattr(weight, "_pdn_packed", None)
+    if pw is None or pw.key != (w.ptr, w.buf.version, w.shape, w.estrides):
+        pw = _PackedWeight(w)
+        weight._pdn_packed = pw
+    return pw
+
+
 @fused_op
 def linear(x, weight, bias):
     """x @ W + b as one GEMM with the bias added in the epilogue (F.linear, reference functional.py:7-11); backward
-    contracts dW over all leading dims at once and reduces db with one column-sum."""
+    contracts dW over all leading dims at once and reduces db with one column-sum. Under no_grad (inference) the weight's
+    tcgen05 operand planes are packed once and cached until the weight buffer is written again."""
     bk = _bk()
     with x.device:
         xd = x.data
         lead = xd.shape[:-1]
         x2 = bk.ext._flat2d(xd) if xd.ndim != 2 else xd
-        out = bk.gemm_into(None, x2, weight.data, bias=_c(bias.data) if bias is not None else None)
-        data = out.reshape(lead + (weight.shape[1], )) if xd.ndim != 2 else out
+        M, N = x2.shape[0], weight.shape[1]
+        bd = _c(bias.data) if bias is not None else None
+        if not is_grad_enable() and M >= 32 and weight.data.ndim == 2:
+            out = _empty((M, N))
+            _call("pdn_gemm_prepacked", x2.ptr, _packed(weight).handle, out.ptr, M, x2.estrides[0], x2.estrides[1], N,
+                  bd.ptr if bd is not None else None, 0)
+        else:
+            out = bk.gemm_into(None, x2, weight.data, bias=bd)
+        data = out.reshape(lead + (N, )) if xd.ndim != 2 else out
 
     def backward(g):
         g2 = bk.ext._flat2d(g) if g.ndim != 2 else g
@@ -239,27 +276,42 @@ def attention(xq, xk, xv, mask, scale):
     return _result(out.reshape(B, Lq, H * D), xq.device, (xq, xk, xv), backward, "attention")
 
 
+class DevicePos:
+    """Sequence position of a decode step held in DEVICE memory (an int64 [1] tensor) so that a CUDA-graph recording of
+    the step stays valid while the position advances."""
+
+    def __init__(self, tensor):
+        self.tensor = tensor
+
+
 @fused_op
 def llama_cached_attention(att, xq, xk, xv, start_pos, mask, scale):
     """Inference step of the Llama attention block (reference llm/llama/model.py:101-121): interleaved-pair RoPE on q and k,
     append k/v to the per-layer KV cache at [start_pos, start_pos+L), attention of the new queries over cache[:start_pos+L].
-    Two kernels (rope_kv_append, attention_fwd) instead of ~40 eager nodes. Inference only (no tape)."""
+    Two kernels (rope_kv_append, attention_fwd) instead of ~40 eager nodes. Inference only (no tape). ``start_pos`` is a
+    host int, or a DevicePos while one decode step is being recorded into a CUDA graph."""
     assert not _needs(xq, xk, xv), "llama_cached_attention is the eval-mode path"
     model_cos, model_sin = att._rope_tables
     with xq.device:
-        q, k, v = _c(xq.data), _c(xk.data), _c(xv.data)
-        if q is xq.data and getattr(q, "buf", None) is not None:
-            pass  # projection outputs are fresh buffers; rotating them in place is safe
+        q, k, v = _c(xq.data), _c(xk.data), _c(xv.data)  # projection outputs are fresh buffers: rotated in place
         B, L, H, D = q.shape
         ck, cv = att.cache_k.data, att.cache_v.data
         S = ck.shape[1]
-        _call("pdn_rope_kv_append", q.ptr, k.ptr, v.ptr, model_cos.ptr, model_sin.ptr, ck.ptr, cv.ptr, B, L, H, D, S, int(start_pos))
-        Lk = int(start_pos) + L
         out = _empty((B, L, H, D))
-        keep, mptr, mstr = _mask_args(mask, B, H, L, Lk)
         cstr = _i64((ck.estrides[0], ck.estrides[2], ck.estrides[1]))
-        _call("pdn_attention_fwd", q.ptr, ck.ptr, cv.ptr, mptr, out.ptr, None, B, H, L, Lk, D, _bhl_strides(q), cstr, cstr, mstr, scale)
-        _ = keep
+        if isinstance(start_pos, DevicePos):
+            assert mask is None
+            pos_ptr = start_pos.tensor.data.ptr
+            _call("pdn_rope_kv_append_dev", q.ptr, k.ptr, v.ptr, model_cos.ptr, model_sin.ptr, ck.ptr, cv.ptr, B, L, H, D, S, pos_ptr)
+            _call("pdn_attention_fwd_dev", q.ptr, ck.ptr, cv.ptr, out.ptr, B, H, L, D, _bhl_strides(q), cstr, cstr, scale, pos_ptr, L)
+        else:
+            _call("pdn_rope_kv_append", q.ptr, k.ptr, v.ptr, model_cos.ptr, model_sin.ptr, ck.ptr, cv.ptr, B, L, H, D, S, int(start_pos))
+            Lk = int(start_pos) + L
+            keep, mptr, mstr = _mask_args(mask, B, H, L, Lk)
+            _call("pdn_attention_fwd", q.ptr, ck.ptr, cv.ptr, mptr, out.ptr, None, B, H, L, Lk, D, _bhl_strides(q), cstr, cstr, mstr, scale)
+            _ = keep
+        ck.buf.version += 1
+        cv.buf.version += 1
     return _result(out.reshape(B, L, H * D), xq.device, (), None, "llama_cached_attention")
 
 
@@ -335,7 +387,17 @@ def feature_norm(mod, x, axes, keep):
             raise NotImplementedError(f"feature_norm over axes {red}")
         stat_shape = scale.shape
         mean, var = _empty((Cn, )), _empty((Cn, ))
-        _call("pdn_bnorm_stats", xd.ptr, mean.ptr, var.ptr, outer, Cn, inner)
+        from .. import distributed as dist
+        sync = dist.sync_stats_enabled()
+        W = dist.get_world_size() if sync else 1
+        inv_mg = 1.0 / (outer * inner * W)  # 1 / (elements per feature in the GLOBAL batch)
+        if sync:  # partial sums pre-scaled by 1/m_global, summed across ranks on the compute stream
+            _call("pdn_bnorm_partial", xd.ptr, None, mean.ptr, outer, Cn, inner, 0, inv_mg)
+            dist.all_reduce_sum_(mean)
+            _call("pdn_bnorm_partial", xd.ptr, mean.ptr, var.ptr, outer, Cn, inner, 1, inv_mg)
+            dist.all_reduce_sum_(var)
+        else:
+            _call("pdn_bnorm_stats", xd.ptr, mean.ptr, var.ptr, outer, Cn, inner)
         y = _empty(xd.shape)
         sc, sh = _c(scale.data).reshape(-1), _c(shift.data).reshape(-1)
         _call("pdn_bnorm_apply", xd.ptr, mean.ptr, var.ptr, sc.ptr, sh.ptr, y.ptr, outer, Cn, inner, mod.eps)
@@ -349,8 +411,17 @@ def feature_norm(mod, x, axes, keep):
         g = _c(g)
         dx = _empty(xd.shape) if x.requires_grad else None
         dsc, dsh = _empty((Cn, )), _empty((Cn, ))
-        _call("pdn_bnorm_bwd", xd.ptr, mean.ptr, var.ptr, sc.ptr, g.ptr, dx.ptr if dx is not None else None, dsc.ptr, dsh.ptr, outer, Cn, inner,
-              mod.eps)
+        if sync:
+            mg, mgx = _empty((Cn, )), _empty((Cn, ))
+            _call("pdn_bnorm_bwd_reduce", xd.ptr, mean.ptr, var.ptr, g.ptr, mg.ptr, mgx.ptr, outer, Cn, inner, mod.eps, inv_mg)
+            dsh, dsc = mg * (1.0 / inv_mg), mgx * (1.0 / inv_mg)  # this rank's share of dshift / dscale
+            dist.all_reduce_sum_(mg)
+            dist.all_reduce_sum_(mgx)
+            if dx is not None:
+                _call("pdn_bnorm_bwd_dx", xd.ptr, mean.ptr, var.ptr, sc.ptr, g.ptr, mg.ptr, mgx.ptr, dx.ptr, outer, Cn, inner, mod.eps)
+        else:
+            _call("pdn_bnorm_bwd", xd.ptr, mean.ptr, var.ptr, sc.ptr, g.ptr, dx.ptr if dx is not None else None, dsc.ptr, dsh.ptr, outer, Cn,
+                  inner, mod.eps)
         return dx, dsc.reshape(stat_shape), dsh.reshape(stat_shape)
 
     return _result(y, x.device, (x, scale, shift), backward, "feature_norm")

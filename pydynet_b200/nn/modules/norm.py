@@ -38,9 +38,15 @@ class _FeatureStatNorm(Module):
         axes, keep = self._axes(x)
         if F._fused.usable(x, self.scale, self.shift, op='feature_norm'):
             return F._fused.feature_norm(self, x, axes, keep)
+        from ... import distributed as dist
+        sync = dist.sync_stats_enabled()  # data parallel: statistics of the GLOBAL batch (equal shards)
         mean = x.mean(axes, keepdims=keep)
+        if sync:
+            mean = dist.dist_mean(mean)
         centered = x - mean
         var = core.mean(core.square(centered), axes, keepdims=keep)
+        if sync:
+            var = dist.dist_mean(var)
         out = centered / core.sqrt(var + self.eps)
         self.running_mean *= (1 - self.momentum)
         self.running_mean += self.momentum * mean

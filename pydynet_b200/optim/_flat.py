@@ -59,5 +59,6 @@ class FlatAdamState:
     def step(self, lr, b1, b2, eps, wd, t, grad_scale):
         with self.device:
             self._settle_grads()
+            self.flat_p.buf.version += 1
             L.call("pdn_adam_step", self.flat_p.ptr, self.flat_g.ptr, self.flat_m.ptr, self.flat_v.ptr, self.total, lr, b1, b2, eps,
                    wd, t, grad_scale)

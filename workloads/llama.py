@@ -7,6 +7,7 @@ position L+i-1 with start_pos = L+i (model.py:258-267), so one zero KV slot sits
 attention over the strided cache view, SwiGLU, RMSNorm, skinny GEMMs) instead of ~490 eager nodes per token.
 """
 import math
+import os
 
 import numpy as np
 
@@ -123,10 +124,13 @@ class Llama(nn.Module):
         self.norm = nn.RMSNorm(embed_dim, dtype=dtype)
         self.lm_head = nn.Linear(embed_dim, vocab_size, dtype=dtype)
 
-    def _forward_hidden(self, input_ids, start_pos: int):
+    def _forward_hidden(self, input_ids, start_pos):
         L = input_ids.shape[-1]
         h = self.tok_embedding(input_ids)
-        cos, sin = self.freqs_cos[start_pos:start_pos + L], self.freqs_sin[start_pos:start_pos + L]
+        if isinstance(start_pos, _fused.DevicePos):  # graph-recorded decode step: the fused kernels index the RoPE tables
+            cos = sin = None
+        else:
+            cos, sin = self.freqs_cos[start_pos:start_pos + L], self.freqs_sin[start_pos:start_pos + L]
         mask = None
         if L > 1:  # causal mask over [cached positions | new positions], built on the host like the reference
             mask = np.concatenate([np.zeros((L, start_pos)), np.triu(np.full((L, L), float("-inf")), k=1)], axis=1)
@@ -157,14 +161,51 @@ class Llama(nn.Module):
         optimizer.step()
         return loss.item()
 
-    def forward(self, input_ids, start_pos: int):
-        return self.lm_head(self._forward_hidden(input_ids, start_pos)[:, [-1], :])
+    def forward(self, input_ids, start_pos):
+        h = self._forward_hidden(input_ids, start_pos)
+        return self.lm_head(h if h.shape[1] == 1 else h[:, [-1], :])  # logits of the last position, [B, 1, V]
+
+    def _graph_decode_ok(self, ids) -> bool:
+        return (os.environ.get("PDN_DECODE_GRAPH", "1") != "0" and ids.device.is_cuda and not self._train
+                and not pdn.autograd.is_grad_enable() and self.freqs_cos.dtype == np.float32
+                and _fused.usable(self.freqs_cos, op="llama_cached_attention"))
 
     def generate(self, input_ids, max_new_tokens: int):
-        """Greedy decoding; yields one (B, 1) id tensor per step until the total length reaches max_new_tokens."""
+        """Greedy decoding; yields one (B, 1) id tensor per step until the total length reaches max_new_tokens
+        (reference llm/llama/model.py:258-269, including its position bookkeeping: decode step i feeds the token produced
+        at step i-1 with start_pos = L + i).
+
+        On a cuda device the decode step is recorded ONCE as a CUDA graph (position and current ids live in device
+        memory) and replayed for every further token: one graph launch per token instead of ~130 kernel launches driven
+        from Python."""
         _, L = input_ids.shape
-        next_id = None
-        for i, curr_pos in enumerate(range(L, max_new_tokens)):
-            logits = self(input_ids, 0) if i == 0 else self(next_id, curr_pos)
-            next_id = logits[:, -1, :].argmax(-1, True)
-            yield next_id
+        next_id, graph, ids_buf, pos = None, None, None, None
+        try:
+            for i, curr_pos in enumerate(range(L, max_new_tokens)):
+                if i == 0:  # prefill
+                    next_id = self(input_ids, 0)[:, -1, :].argmax(-1, True)
+                elif i == 1 or not self._graph_decode_ok(next_id):  # eager decode step (also warms caches for the capture)
+                    next_id = self(next_id, curr_pos)[:, -1, :].argmax(-1, True)
+                else:
+                    assert curr_pos + 1 <= self.max_seq_len, "generation runs past the KV cache"
+                    if graph is None:
+                        with next_id.device:
+                            ids_buf = pdn.Tensor(next_id.data, dtype=np.int64, device=next_id.device, copy=True)
+                            pos = _fused.DevicePos(pdn.Tensor(np.array([curr_pos], dtype=np.int64), device=next_id.device))
+                            graph = pdn.cuda.Graph()
+                            graph.begin()
+                            try:
+                                nid = self(ids_buf, pos)[:, -1, :].argmax(-1, True)
+                                ids_buf[...] = nid  # feeds the next replay
+                                pos.tensor += 1
+                            finally:
+                                graph.end()
+                            del nid
+                    with next_id.device:
+                        graph.launch()
+                        next_id = pdn.Tensor(ids_buf.data, dtype=np.int64, device=ids_buf.device, copy=True)
+                yield next_id
+        finally:
+            if graph is not None:
+                with ids_buf.device:
+                    graph.destroy()
