@@ -112,6 +112,8 @@ class KernelTimer:
     def __init__(self, lib, entry, predicate):
         self.lib, self.entry, self.pred, self.pairs, self.on = lib, entry, predicate, [], False
         self.pool = []
+        import pydynet_b200.cuda as cuda
+        self.cuda = cuda
 
     def install(self):
         import ctypes as C
@@ -120,7 +122,7 @@ class KernelTimer:
         timer = self
 
         def call(name, *args):
-            if timer.on and name == timer.entry and timer.pred(args):
+            if timer.on and name == timer.entry and timer.pred(args) and not timer.cuda.is_capturing():
                 if timer.pool:
                     e0, e1 = timer.pool.pop()
                 else:

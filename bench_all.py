@@ -1,0 +1,174 @@
+"""bench_all.py — the other BASELINE configs and the micro-benchmarks of SURVEY.md §8(d), one JSON line each.
+
+(bench.py carries the headline metric; this script produces the per-config numbers quoted in README.md / profiles/.)
+  C1 matmul fwd+bwd (512^3 literal + size sweep)      C2 LeNet b256 train step        C4 Transformer encoder train step
+  C5 GRU T=1024 train step                            micro: Conv2d fwd+bwd, attention core fwd+bwd, GEMM fwd
+Usage: python bench_all.py [--only c1,c2,...] [--steps K] [--small]
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+import pydynet_b200 as pdn  # noqa: E402
+import pydynet_b200.nn as nn  # noqa: E402
+import pydynet_b200.nn.functional as F  # noqa: E402
+from pydynet_b200.backend import lib  # noqa: E402
+from pydynet_b200.optim import Adam  # noqa: E402
+
+DEV = "cuda:0"
+f32 = np.float32
+PEAK_BF16 = 1362.4e12
+PEAK_HBM = 6552.6e9
+try:
+    _p = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    PEAK_BF16, PEAK_HBM = _p.get("bf16_tflops_sustained", _p["bf16_tflops"]) * 1e12, _p["hbm_gbs"] * 1e9
+except Exception:
+    pass
+
+
+def timed(fn, steps, warmup=3):
+    for _ in range(warmup):
+        fn()
+    pdn.cuda.synchronize()
+    e0, e1 = C.c_void_p(), C.c_void_p()
+    lib.call("pdn_event_create", C.byref(e0))
+    lib.call("pdn_event_create", C.byref(e1))
+    lib.reset_launch_count()
+    lib.call("pdn_event_record", e0)
+    for _ in range(steps):
+        fn()
+    lib.call("pdn_event_record", e1)
+    ms = C.c_float()
+    lib.load().pdn_event_elapsed_ms(e0, e1, C.byref(ms))
+    return ms.value / steps / 1e3, lib.launch_count() // steps
+
+
+def emit(name, sec, flops=None, nbytes=None, launches=None, **extra):
+    r = {"config": name, "ms_per_step": sec * 1e3, "launches_per_step": launches}
+    if flops:
+        r["tflops_alg"] = flops / sec / 1e12
+        r["frac_of_bf16_peak"] = flops / sec / PEAK_BF16
+        r["frac_of_bf16x3_ceiling"] = 3 * flops / sec / PEAK_BF16
+    if nbytes:
+        r["gbs_alg"] = nbytes / sec / 1e9
+        r["frac_of_hbm_peak"] = nbytes / sec / PEAK_HBM
+    r.update(extra)
+    print(json.dumps(r), flush=True)
+    return r
+
+
+def T(a, rg=False):
+    return pdn.Tensor(a, dtype=a.dtype, device=DEV, requires_grad=rg)
+
+
+def c1(args):
+    rng = np.random.default_rng(0)
+    for n in ([512] if args.small else [512, 1024, 2048, 4096, 8192]):
+        A, B = rng.standard_normal((n, n)).astype(f32), rng.standard_normal((n, n)).astype(f32)
+        x, w = T(A, True), T(B, True)
+
+        def step():
+            x.zero_grad(); w.zero_grad()
+            pdn.matmul(x, w).sum().backward()
+
+        sec, nl = timed(step, args.steps if n < 8192 else max(2, args.steps // 2))
+        cpu = None
+        if n == 512:
+            t0 = time.perf_counter()
+            for _ in range(5):
+                ones = np.ones((n, n), f32)
+                _ = A @ B; _ = ones @ B.T; _ = A.T @ ones
+            cpu = (time.perf_counter() - t0) / 5
+        emit(f"C1 matmul fwd+bwd {n}^3 fp32 (matmul(x,w).sum().backward())", sec, flops=6.0 * n**3, nbytes=9 * 4.0 * n * n, launches=nl,
+             cpu_numpy_3_sgemms_ms=cpu * 1e3 if cpu else None)
+    for n in ([] if args.small else [4096, 8192]):
+        a, b = pdn.backend.array(rng.standard_normal((n, n)).astype(f32)), pdn.backend.array(rng.standard_normal((n, n)).astype(f32))
+        out = pdn.backend.empty((n, n), f32)
+        sec, nl = timed(lambda: pdn.backend.gemm_into(out, a, b), args.steps)
+        emit(f"micro GEMM fwd {n}^3 fp32 (pack + tcgen05 BF16x3)", sec, flops=2.0 * n**3, launches=nl)
+
+
+def c2(args):
+    from workloads.lenet import ConvNet, train_step
+    np.random.seed(42)
+    net = ConvNet().to(DEV)
+    opt = Adam(net.parameters(), lr=1e-4)
+    B = 256
+    X, y = T(np.random.rand(B, 1, 28, 28).astype(f32)), T(np.random.randint(0, 10, B))
+    net.train()
+    sec, nl = timed(lambda: train_step(net, opt, X, y), args.steps)
+    emit("C2 LeNet b256 train step (CE, backward, Adam)", sec, flops=4_743_290_880, nbytes=170e6, launches=nl, images_per_s=B / sec)
+
+
+def c4(args):
+    from workloads.encoder import Transformer, train_step
+    np.random.seed(0)
+    B, S, V = (16, 128, 1000) if args.small else (128, 512, 8192)
+    net = Transformer(512, 1, 8, 3, 0.05, V, S)
+    net.word_embedding.reset_parameters()
+    net.to(DEV)
+    opt = Adam(net.parameters(), lr=5e-4)
+    X, y = T(np.random.randint(1, V, (B, S))), T(np.random.choice([-1, 1], B).astype(f32))
+    net.train()
+    sec, nl = timed(lambda: train_step(net, opt, X, y, None), max(2, args.steps // 2), warmup=2)
+    fl = 3 * (2.0 * B * S * 512 * 512 * 4 + 4.0 * B * 8 * S * S * 64 + 2.0 * B * S * 512 * 1536 * 2)
+    emit(f"C4 Transformer encoder d512 h8 S{S} B{B} train step", sec, flops=fl, launches=nl, tokens_per_s=B * S / sec)
+
+
+def c5(args):
+    from workloads.gru import GRURegressor, train_step
+    np.random.seed(0)
+    B, Tn = (64, 128) if args.small else (256, 1024)
+    net = GRURegressor(512, 512).to(DEV)
+    opt = Adam(net.parameters(), lr=0.01)
+    X, Y = T(np.random.randn(B, Tn, 512).astype(f32)), T(np.random.randn(B, 1).astype(f32))
+    sec, nl = timed(lambda: train_step(net, opt, X, Y), max(2, args.steps // 3), warmup=2)
+    emit(f"C5 GRU in512 h512 T{Tn} B{B} train step", sec, flops=2_013_265_920.0 * Tn * B / 256, launches=nl, us_per_time_step=sec / Tn * 1e6)
+
+
+def micro(args):
+    rng = np.random.default_rng(1)
+    for (N, Ci, O, HW) in ([(32, 20, 50, 14)] if args.small else [(256, 20, 50, 14), (128, 64, 128, 56)]):
+        conv = nn.Conv2d(Ci, O, 3, 1, 1, dtype=f32).to(DEV)
+        x = T(rng.standard_normal((N, Ci, HW, HW)).astype(f32), True)
+
+        def step():
+            x.zero_grad(); conv.weight.zero_grad(); conv.bias.zero_grad()
+            conv(x).sum().backward()
+
+        sec, nl = timed(step, args.steps)
+        emit(f"micro Conv2d {Ci}->{O} {HW}x{HW} k3p1 b{N} fwd+bwd", sec, flops=3 * 2.0 * N * HW * HW * Ci * 9 * O, launches=nl)
+    B, H, S, D = (8, 8, 128, 64) if args.small else (128, 8, 512, 64)
+    q, k, v = (T(rng.standard_normal((B, S, H, D)).astype(f32), True) for _ in range(3))
+
+    def att():
+        for t in (q, k, v):
+            t.zero_grad()
+        s = q.transpose(0, 2, 1, 3) @ k.transpose(0, 2, 3, 1) / D**.5
+        (F.softmax(s, axis=-1) @ v.transpose(0, 2, 1, 3)).sum().backward()
+
+    sec, nl = timed(att, max(2, args.steps // 2), warmup=2)
+    emit(f"micro attention core B{B} H{H} S{S} hd{D} fwd+bwd (tcgen05 GEMM -> fused softmax -> GEMM)", sec, flops=3 * 4.0 * B * H * S * S * D, launches=nl)
+
+
+if __name__ == "__main__":
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--only", default="c1,c2,c4,c5,micro")
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--small", action="store_true")
+    args = ap.parse_args()
+    for name in args.only.split(","):
+        try:
+            {"c1": c1, "c2": c2, "c4": c4, "c5": c5, "micro": micro}[name](args)
+        except Exception as e:  # keep going: one config must not hide the others
+            import traceback
+            traceback.print_exc()
+            print(json.dumps({"config": name, "error": repr(e)[:300]}), flush=True)
+        pdn.autograd.set_grad_enabled(True)

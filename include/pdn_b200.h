@@ -268,16 +268,21 @@ int pdn_adam_multi(int n_tensors, float* const* p, const float* const* grad, flo
  * cos/sin [max_seq, D/2] at positions pos0 + (row % L) ; then k,v rows appended to the KV cache
  * [Bmax, S, H, D] at [b, pos0 + l] (model.py:105-107). */
 int pdn_rope_kv_append(float* q, float* k, const float* v, const float* cosT, const float* sinT, float* cache_k,
-                       float* cache_v, int64_t B, int64_t L, int64_t H, int64_t D, int64_t S, int64_t pos0);
+                       float* cache_v, int64_t B, int64_t L, int64_t H, int64_t D, int64_t S, int64_t pos0, int64_t ld);
+/* ld = elements between consecutive q/k/v rows: H*D for separate projections (0 selects it), 3*H*D when q, k, v are the
+ * three column blocks of one fused QKV projection output. */
 /* Device-scalar variants for CUDA-graph replay of one decode step: the sequence position is read from device memory
  * (pos_dev) instead of being baked into the launch; attention runs over Lk = *pos_dev + lk_add cached keys, no mask. */
 int pdn_rope_kv_append_dev(float* q, float* k, const float* v, const float* cosT, const float* sinT, float* cache_k,
-                           float* cache_v, int64_t B, int64_t L, int64_t H, int64_t D, int64_t S, const int64_t* pos_dev);
+                           float* cache_v, int64_t B, int64_t L, int64_t H, int64_t D, int64_t S, const int64_t* pos_dev,
+                           int64_t ld);
 int pdn_attention_fwd_dev(const float* q, const float* k, const float* v, float* out, int64_t B, int64_t H, int64_t Lq,
                           int64_t D, const int64_t* q_str, const int64_t* k_str, const int64_t* v_str, float scale,
                           const int64_t* pos_dev, int64_t lk_add);
 /* out = silu(gate) * up  (FeedForward.forward model.py:56-58), gate/up are the two halves [rows, F] */
 int pdn_swiglu(const float* gate, const float* up, float* out, int64_t n);
+/* same on the [rows, 2F] output of a fused gate|up projection: out[r, j] = silu(gu[r, j]) * gu[r, F + j] */
+int pdn_swiglu_rows(const float* gu, float* out, int64_t rows, int64_t F);
 int pdn_swiglu_bwd(const float* gate, const float* up, const float* g, float* dgate, float* dup, int64_t n);
 
 /* ---------------------------------------------------------------- data-parallel comm -------- */

@@ -96,8 +96,9 @@ _PROTOS = {
     "pdn_ce_loss_bwd": [vp, vp, vp, vp, vp, i64, i64, i32],
     "pdn_adam_step": [vp, vp, vp, vp, i64, f32, f32, f32, f32, f32, i32, f32],
     "pdn_adam_multi": [i32, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), pi64, f32, f32, f32, f32, f32, i32, f32],
-    "pdn_rope_kv_append": [vp, vp, vp, vp, vp, vp, vp, i64, i64, i64, i64, i64, i64],
-    "pdn_rope_kv_append_dev": [vp, vp, vp, vp, vp, vp, vp, i64, i64, i64, i64, i64, vp],
+    "pdn_rope_kv_append": [vp, vp, vp, vp, vp, vp, vp, i64, i64, i64, i64, i64, i64, i64],
+    "pdn_rope_kv_append_dev": [vp, vp, vp, vp, vp, vp, vp, i64, i64, i64, i64, i64, vp, i64],
+    "pdn_swiglu_rows": [vp, vp, i64, i64],
     "pdn_attention_fwd_dev": [vp, vp, vp, vp, i64, i64, i64, i64, pi64, pi64, pi64, f32, vp, i64],
     "pdn_swiglu": [vp, vp, vp, i64],
     "pdn_swiglu_bwd": [vp, vp, vp, vp, vp, i64],

@@ -173,12 +173,12 @@ __global__ void __launch_bounds__(128) k_attention_bwd(AttBwdArgs a) {
 }
 
 // ---------------------------------------------------------------- RoPE + KV append -------------------------------
-// q,k: [B*L, H, D] contiguous rows (row r = b*L + l, position pos0 + l); pairs (2i, 2i+1) rotated by angle[pos][i].
+// q,k,v: rows r = b*L + l of [H, D] values, `ld` elements apart (position pos0 + l); pairs (2i, 2i+1) rotated by angle[pos][i].
 // k (rotated) and v rows are also written into the caches [Bmax, S, H, D] at [b, pos0 + l].
 __global__ void __launch_bounds__(256) k_rope_kv_append(float* __restrict__ q, float* __restrict__ k, const float* __restrict__ v,
                                                         const float* __restrict__ cosT, const float* __restrict__ sinT, float* __restrict__ ck,
                                                         float* __restrict__ cv, int64_t B, int64_t L, int64_t H, int64_t D, int64_t S, int64_t pos0,
-                                                        const int64_t* __restrict__ pos_dev) {
+                                                        const int64_t* __restrict__ pos_dev, int64_t ld) {
   if (pos_dev) pos0 = *pos_dev;
   if (pos0 < 0 || pos0 + L > S) return;  // out of the cache: the host-side check could not run for a device-side position
   const int64_t half = D / 2, total = B * L * H * half;
@@ -186,7 +186,7 @@ __global__ void __launch_bounds__(256) k_rope_kv_append(float* __restrict__ q, f
     const int64_t pi = i % half, hh = (i / half) % H, r = i / (half * H);
     const int64_t b = r / L, l = r % L, pos = pos0 + l;
     const float c = cosT[pos * half + pi], s = sinT[pos * half + pi];
-    const int64_t e = (r * H + hh) * D + 2 * pi;
+    const int64_t e = r * ld + hh * D + 2 * pi;  // ld = elements between consecutive rows (H*D, or 3*H*D inside a fused QKV buffer)
     float2 qq = *reinterpret_cast<float2*>(q + e);
     *reinterpret_cast<float2*>(q + e) = make_float2(qq.x * c - qq.y * s, qq.x * s + qq.y * c);
     float2 kk = *reinterpret_cast<float2*>(k + e);
@@ -254,14 +254,14 @@ int pdn_attention_bwd(const float* q, const float* k, const float* v, const floa
 }
 
 int pdn_rope_kv_append(float* q, float* k, const float* v, const float* cosT, const float* sinT, float* cache_k, float* cache_v, int64_t B,
-                       int64_t L, int64_t H, int64_t D, int64_t S, int64_t pos0) {
+                       int64_t L, int64_t H, int64_t D, int64_t S, int64_t pos0, int64_t ld) {
   PDN_TRY(ensure_init());
   PDN_CHECK(D % 2 == 0, "rope: head dim must be even");
   PDN_CHECK(!cache_k || pos0 + L <= S, "rope_kv_append: positions [%lld, %lld) exceed the cache length %lld", (long long)pos0, (long long)(pos0 + L),
             (long long)S);
   const int64_t total = B * L * H * (D / 2);
   if (total == 0) return 0;
-  k_rope_kv_append<<<grid_for(total, 256), 256, 0, stream()>>>(q, k, v, cosT, sinT, cache_k, cache_v, B, L, H, D, S, pos0, nullptr);
+  k_rope_kv_append<<<grid_for(total, 256), 256, 0, stream()>>>(q, k, v, cosT, sinT, cache_k, cache_v, B, L, H, D, S, pos0, nullptr, ld > 0 ? ld : H * D);
   PDN_LAUNCHED("rope_kv_append");
   return 0;
 }
@@ -269,12 +269,12 @@ int pdn_rope_kv_append(float* q, float* k, const float* v, const float* cosT, co
 /* Device-scalar variants used when one decode step is captured as a CUDA graph: the position lives in device memory
  * (pos_dev), so the recorded launches stay valid while the sequence grows. */
 int pdn_rope_kv_append_dev(float* q, float* k, const float* v, const float* cosT, const float* sinT, float* cache_k, float* cache_v, int64_t B,
-                           int64_t L, int64_t H, int64_t D, int64_t S, const int64_t* pos_dev) {
+                           int64_t L, int64_t H, int64_t D, int64_t S, const int64_t* pos_dev, int64_t ld) {
   PDN_TRY(ensure_init());
   PDN_CHECK(D % 2 == 0 && pos_dev != nullptr, "rope_dev: bad arguments");
   const int64_t total = B * L * H * (D / 2);
   if (total == 0) return 0;
-  k_rope_kv_append<<<grid_for(total, 256), 256, 0, stream()>>>(q, k, v, cosT, sinT, cache_k, cache_v, B, L, H, D, S, 0, pos_dev);
+  k_rope_kv_append<<<grid_for(total, 256), 256, 0, stream()>>>(q, k, v, cosT, sinT, cache_k, cache_v, B, L, H, D, S, 0, pos_dev, ld > 0 ? ld : H * D);
   PDN_LAUNCHED("rope_kv_append");
   return 0;
 }

@@ -226,6 +226,13 @@ __global__ void __launch_bounds__(256) k_swiglu(const float4* gate, const float4
   if (blockIdx.x == 0)
     for (int64_t i = n4 * 4 + threadIdx.x; i < n; i += blockDim.x) out_s[i] = silu_f(gate_s[i]) * up_s[i];
 }
+// fused gate|up projection output [rows, 2F]: out[r, j] = silu(gu[r, j]) * gu[r, F + j]
+__global__ void __launch_bounds__(256) k_swiglu_rows(const float* __restrict__ gu, float* __restrict__ out, int64_t rows, int64_t F) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < rows * F; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / F, j = i - r * F;
+    out[i] = silu_f(gu[r * 2 * F + j]) * gu[r * 2 * F + F + j];
+  }
+}
 // dgate = g * up * silu'(gate), dup = g * silu(gate); silu'(x) = s + x*s*(1-s), s = sigmoid(x)
 __global__ void __launch_bounds__(256) k_swiglu_bwd(const float* __restrict__ gate, const float* __restrict__ up, const float* __restrict__ g,
                                                     float* __restrict__ dgate, float* __restrict__ dup, int64_t n) {
@@ -360,6 +367,14 @@ int pdn_swiglu(const float* gate, const float* up, float* out, int64_t n) {
   int64_t n4 = al ? n / 4 : 0;
   k_swiglu<<<grid_for(n4 > 0 ? n4 : 1, 256), 256, 0, stream()>>>((const float4*)gate, (const float4*)up, (float4*)out, n4, gate, up, out, n);
   PDN_LAUNCHED("swiglu");
+  return 0;
+}
+
+int pdn_swiglu_rows(const float* gu, float* out, int64_t rows, int64_t F) {
+  PDN_TRY(ensure_init());
+  if (rows * F == 0) return 0;
+  k_swiglu_rows<<<grid_for(rows * F, 256), 256, 0, stream()>>>(gu, out, rows, F);
+  PDN_LAUNCHED("swiglu_rows");
   return 0;
 }
 

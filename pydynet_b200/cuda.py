@@ -128,6 +128,14 @@ def _ensure_init(dev_id: int):
         _inited.add(dev_id)
 
 
+_capturing = False
+
+
+def is_capturing() -> bool:
+    """True while launches on the library stream are being recorded into a CUDA graph instead of executed."""
+    return _capturing
+
+
 class Graph:
     """CUDA-graph capture / replay of a launch sequence on the library's compute stream (pdn_graph_* in
     include/pdn_b200.h). Memory allocated while capturing stays reserved for the graph until it is destroyed, so the
@@ -140,9 +148,13 @@ class Graph:
         self._exec = None
 
     def begin(self):
+        global _capturing
         _L.call("pdn_graph_begin")
+        _capturing = True
 
     def end(self):
+        global _capturing
+        _capturing = False
         h = C.c_void_p()
         _L.call("pdn_graph_end", C.byref(h))
         self._exec = h

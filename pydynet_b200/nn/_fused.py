@@ -284,16 +284,79 @@ class DevicePos:
         self.tensor = tensor
 
 
+def _cat_packed(owner, key, weights):
+    """Pre-packed operand planes of [W0 | W1 | ...] (column-wise concatenation), cached on ``owner`` until any of the
+    weight buffers is written again."""
+    sig = tuple((w.data.ptr, w.data.buf.version, w.data.shape) for w in weights)
+    ent = getattr(owner, key, None)
+    if ent is None or ent[0] != sig:
+        bk = _bk()
+        cat = bk.concatenate([w.data for w in weights], axis=1)
+        ent = (sig, _PackedWeight(cat), cat.shape[1])
+        setattr(owner, key, ent)
+    return ent[1], ent[2]
+
+
+def linear_cat(owner, key, x, weights):
+    """x @ [W0 | W1 | ...] as ONE GEMM (inference): the Q/K/V projections, or gate|up of the SwiGLU block, share their
+    input, so their weight planes are concatenated once and a single launch produces all outputs side by side."""
+    bk = _bk()
+    with x.device:
+        xd = x.data
+        x2 = bk.ext._flat2d(xd) if xd.ndim != 2 else xd
+        pw, N = _cat_packed(owner, key, weights)
+        out = _empty((x2.shape[0], N))
+        _call("pdn_gemm_prepacked", x2.ptr, pw.handle, out.ptr, x2.shape[0], x2.estrides[0], x2.estrides[1], N, None, 0)
+    return _result(out.reshape(xd.shape[:-1] + (N, )), x.device, (), None, "linear_cat")
+
+
+def linear_residual_(a, weight, res):
+    """res += a @ W, accumulated in the GEMM epilogue INTO res's buffer (inference only: the residual stream is not
+    needed in its old state). Returns res."""
+    bk = _bk()
+    with a.device:
+        ad = a.data
+        a2 = bk.ext._flat2d(ad) if ad.ndim != 2 else ad
+        rd = res.data
+        assert rd.is_contiguous and rd.dtype == F32
+        N = weight.shape[1]
+        rd.buf.version += 1
+        _call("pdn_gemm_prepacked", a2.ptr, _packed(weight).handle, rd.ptr, a2.shape[0], a2.estrides[0], a2.estrides[1], N, None, 1)
+    return res
+
+
+def swiglu_rows(gu, F_):
+    """silu(gu[..., :F]) * gu[..., F:] on the fused gate|up projection output."""
+    with gu.device:
+        g = _c(gu.data)
+        rows = g.size // (2 * F_)
+        out = _empty(g.shape[:-1] + (F_, ))
+        _call("pdn_swiglu_rows", g.ptr, out.ptr, rows, F_)
+    return _result(out, gu.device, (), None, "swiglu_rows")
+
+
+class DevicePos:
+    """Sequence position of a decode step held in DEVICE memory (an int64 [1] tensor) so that a CUDA-graph recording of
+    the step stays valid while the position advances."""
+
+    def __init__(self, tensor):
+        self.tensor = tensor
+
+
 @fused_op
-def llama_cached_attention(att, xq, xk, xv, start_pos, mask, scale):
+def llama_cached_attention(att, xq, xk, xv, start_pos, mask, scale, ld=0):
     """Inference step of the Llama attention block (reference llm/llama/model.py:101-121): interleaved-pair RoPE on q and k,
     append k/v to the per-layer KV cache at [start_pos, start_pos+L), attention of the new queries over cache[:start_pos+L].
     Two kernels (rope_kv_append, attention_fwd) instead of ~40 eager nodes. Inference only (no tape). ``start_pos`` is a
-    host int, or a DevicePos while one decode step is being recorded into a CUDA graph."""
+    host int, or a DevicePos while one decode step is being recorded into a CUDA graph. q/k/v are [B, L, H, D] arrays with
+    unit-stride D and a common row stride ``ld`` (0: contiguous H*D; 3*H*D: column blocks of a fused QKV projection)."""
     assert not _needs(xq, xk, xv), "llama_cached_attention is the eval-mode path"
     model_cos, model_sin = att._rope_tables
     with xq.device:
-        q, k, v = _c(xq.data), _c(xk.data), _c(xv.data)  # projection outputs are fresh buffers: rotated in place
+        if ld:
+            q, k, v = xq.data, xk.data, xv.data  # strided views of one fresh QKV buffer: rotated in place
+        else:
+            q, k, v = _c(xq.data), _c(xk.data), _c(xv.data)  # projection outputs are fresh buffers: rotated in place
         B, L, H, D = q.shape
         ck, cv = att.cache_k.data, att.cache_v.data
         S = ck.shape[1]
@@ -302,10 +365,10 @@ def llama_cached_attention(att, xq, xk, xv, start_pos, mask, scale):
         if isinstance(start_pos, DevicePos):
             assert mask is None
             pos_ptr = start_pos.tensor.data.ptr
-            _call("pdn_rope_kv_append_dev", q.ptr, k.ptr, v.ptr, model_cos.ptr, model_sin.ptr, ck.ptr, cv.ptr, B, L, H, D, S, pos_ptr)
+            _call("pdn_rope_kv_append_dev", q.ptr, k.ptr, v.ptr, model_cos.ptr, model_sin.ptr, ck.ptr, cv.ptr, B, L, H, D, S, pos_ptr, ld)
             _call("pdn_attention_fwd_dev", q.ptr, ck.ptr, cv.ptr, out.ptr, B, H, L, D, _bhl_strides(q), cstr, cstr, scale, pos_ptr, L)
         else:
-            _call("pdn_rope_kv_append", q.ptr, k.ptr, v.ptr, model_cos.ptr, model_sin.ptr, ck.ptr, cv.ptr, B, L, H, D, S, int(start_pos))
+            _call("pdn_rope_kv_append", q.ptr, k.ptr, v.ptr, model_cos.ptr, model_sin.ptr, ck.ptr, cv.ptr, B, L, H, D, S, int(start_pos), ld)
             Lk = int(start_pos) + L
             keep, mptr, mstr = _mask_args(mask, B, H, L, Lk)
             _call("pdn_attention_fwd", q.ptr, ck.ptr, cv.ptr, mptr, out.ptr, None, B, H, L, Lk, D, _bhl_strides(q), cstr, cstr, mstr, scale)

@@ -51,6 +51,12 @@ class FeedForward(nn.Module):
             return self.down(_fused.swiglu(self.gate(x), self.up(x)))
         return self.down(F.silu(self.gate(x)) * self.up(x))
 
+    def hidden_fast(self, x):
+        """Inference: gate|up as one GEMM on concatenated weight planes, then SwiGLU; the down projection is applied by the
+        block together with the residual add."""
+        gu = _fused.linear_cat(self, "_pdn_gate_up", x, (self.gate.weight, self.up.weight))
+        return _fused.swiglu_rows(gu, self.up_dim)
+
 
 class Attention(nn.Module):
 
@@ -101,9 +107,31 @@ class TransformerBlock(nn.Module):
         self.input_norm = nn.RMSNorm(dim, dtype=dtype)
         self.post_attn_norm = nn.RMSNorm(dim, dtype=dtype)
 
-    def forward(self, x, start_pos: int, mask, freqs_cos, freqs_sin):
+    def _fast_ok(self, x) -> bool:
+        return (os.environ.get("PDN_LLAMA_FAST", "1") != "0" and not self._train and not pdn.autograd.is_grad_enable()
+                and x.shape[0] * x.shape[1] >= 32 and _fused.usable(x, self.attention.Q.weight, op="llama_cached_attention"))
+
+    def forward(self, x, start_pos, mask, freqs_cos, freqs_sin):
+        if self._fast_ok(x):
+            return self._forward_inference(x, start_pos, mask)
         z = x + self.attention(self.input_norm(x), start_pos, mask, freqs_cos, freqs_sin)
         return z + self.ffn(self.post_attn_norm(z))
+
+    def _forward_inference(self, x, start_pos, mask):
+        """Same block (reference llm/llama/model.py:142-150) with 9 launches instead of 22: fused QKV GEMM, RoPE + cache
+        append, cached attention, O-projection accumulating onto the residual stream in its epilogue, fused gate|up GEMM,
+        SwiGLU, down-projection accumulating onto the residual stream. ``x``'s buffer becomes the block output."""
+        att = self.attention
+        B, L, dim = x.shape
+        H, D = att.n_heads, att.head_dim
+        qkv = _fused.linear_cat(att, "_pdn_qkv", self.input_norm(x), (att.Q.weight, att.K.weight, att.V.weight))
+        with x.device:
+            q3 = qkv.data.reshape(B, L, 3, H, D)
+        att._rope_tables = att._rope_src()
+        parts = [pdn.Tensor(q3[:, :, j], dtype=np.float32, copy=None, device=x.device) for j in range(3)]
+        o = _fused.llama_cached_attention(att, parts[0], parts[1], parts[2], start_pos, mask, 1.0 / math.sqrt(D), ld=3 * dim)
+        z = _fused.linear_residual_(o, att.O.weight, x)
+        return _fused.linear_residual_(self.ffn.hidden_fast(self.post_attn_norm(z)), self.ffn.down.weight, z)
 
 
 class Llama(nn.Module):
