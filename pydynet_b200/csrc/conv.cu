@@ -20,50 +20,94 @@ struct ConvGeom {
 
 // MODE 0: im2col of x — row m = (n, oy, ox), column kk = (c, ky, kx)
 // MODE 1: transposed-conv gather of g — row m = (n, y, x) of the INPUT grid, column kk = (o, ky, kx)
+// The row index is decomposed once per thread (it is fixed across the tile's columns); columns cost three small
+// 32-bit divisions each.
+struct RowPos { int64_t base; int y, x; bool ok; };  // base = element offset of (n, channel 0, 0, 0) in the source
+
 template <int MODE>
-__device__ __forceinline__ float conv_fetch(const float* __restrict__ src, const ConvGeom& g, int64_t m, int64_t kk, int64_t Mtot, int64_t Ktot) {
-  if (m >= Mtot || kk >= Ktot) return 0.f;
-  const int kx = (int)(kk % g.k), ky = (int)((kk / g.k) % g.k);
-  const int64_t ch = kk / ((int64_t)g.k * g.k);
+__device__ __forceinline__ RowPos conv_row(const ConvGeom& g, int64_t m, int64_t Mtot) {
+  RowPos r;
+  r.ok = m < Mtot;
+  if (!r.ok) { r.base = 0; r.y = r.x = 0; return r; }
   if (MODE == 0) {
-    const int64_t ox = m % g.ow, oy = (m / g.ow) % g.oh, n = m / (g.ow * g.oh);
-    const int64_t iy = oy * g.stride + ky - g.pad, ix = ox * g.stride + kx - g.pad;
-    if (iy < 0 || iy >= g.H || ix < 0 || ix >= g.W) return 0.f;
-    return __ldg(src + ((n * g.C + ch) * g.H + iy) * g.W + ix);
+    const int64_t hw = g.oh * g.ow, n = m / hw;
+    const int pix = (int)(m - n * hw);
+    r.y = (pix / (int)g.ow) * g.stride - g.pad;   // top-left input coordinate of the window
+    r.x = (pix % (int)g.ow) * g.stride - g.pad;
+    r.base = n * g.C * g.H * g.W;
   } else {
-    const int64_t x = m % g.W, y = (m / g.W) % g.H, n = m / (g.W * g.H);
-    const int64_t ty = y + g.pad - ky, tx = x + g.pad - kx;
-    if (ty < 0 || tx < 0 || ty % g.stride || tx % g.stride) return 0.f;
-    const int64_t oy = ty / g.stride, ox = tx / g.stride;
-    if (oy >= g.oh || ox >= g.ow) return 0.f;
-    return __ldg(src + ((n * g.O + ch) * g.oh + oy) * g.ow + ox);
+    const int64_t hw = g.H * g.W, n = m / hw;
+    const int pix = (int)(m - n * hw);
+    r.y = pix / (int)g.W + g.pad;
+    r.x = pix % (int)g.W + g.pad;
+    r.base = n * g.O * g.oh * g.ow;
+  }
+  return r;
+}
+
+template <int MODE>
+__device__ __forceinline__ float conv_fetch(const float* __restrict__ src, const ConvGeom& g, const RowPos& r, int kk, int Ktot) {
+  if (!r.ok || kk >= Ktot) return 0.f;
+  const int kx = kk % g.k, t = kk / g.k, ky = t % g.k, ch = t / g.k;
+  if (MODE == 0) {
+    const int iy = r.y + ky, ix = r.x + kx;
+    if (iy < 0 || iy >= (int)g.H || ix < 0 || ix >= (int)g.W) return 0.f;
+    return __ldg(src + r.base + ((int64_t)ch * g.H + iy) * g.W + ix);
+  } else {
+    const int ty = r.y - ky, tx = r.x - kx;
+    if (ty < 0 || tx < 0) return 0.f;
+    int oy = ty, ox = tx;
+    if (g.stride != 1) {
+      if (ty % g.stride || tx % g.stride) return 0.f;
+      oy = ty / g.stride; ox = tx / g.stride;
+    }
+    if (oy >= (int)g.oh || ox >= (int)g.ow) return 0.f;
+    return __ldg(src + r.base + ((int64_t)ch * g.oh + oy) * g.ow + ox);
   }
 }
 
-// Writes planes [2][R][Kp]: ROWS_M ? (R = Mtot, k index = kk) : (R = Ktot, k index = m). 32x32 tile through smem so that
-// both the gather (along m = consecutive pixels) and the plane stores (along the plane's k axis) are coalesced.
+// Writes planes [2][R][Kp]: ROWS_M ? (R = Mtot, k index = kk) : (R = Ktot, k index = m). 32(m) x 64(kk) tile through smem so
+// that both the gather (along m = consecutive pixels) and the plane stores (along the plane's k axis) are coalesced.
 template <int MODE, bool ROWS_M>
 __global__ void __launch_bounds__(256) k_conv_pack(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, ConvGeom g, int64_t Mtot,
                                                    int64_t Ktot, int64_t Kp) {
-  __shared__ float tile[32][33];
+  __shared__ float tile[64][33];
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-  const int64_t m0 = (int64_t)blockIdx.x * 32, kk0 = (int64_t)blockIdx.y * 32;
+  const int64_t m0 = (int64_t)blockIdx.x * 32;
+  const int kk0 = blockIdx.y * 64;
+  const RowPos rp = conv_row<MODE>(g, m0 + tx, Mtot);
 #pragma unroll
-  for (int i = 0; i < 4; ++i) tile[ty + i * 8][tx] = conv_fetch<MODE>(src, g, m0 + tx, kk0 + ty + i * 8, Mtot, Ktot);
+  for (int i = 0; i < 8; ++i) tile[ty + i * 8][tx] = conv_fetch<MODE>(src, g, rp, kk0 + ty + i * 8, (int)Ktot);
   __syncthreads();
   const int64_t R = ROWS_M ? Mtot : Ktot;
   __nv_bfloat16* hi = dst;
   __nv_bfloat16* lo = dst + (size_t)R * Kp;
+  if (ROWS_M) {  // rows = m: each warp writes 64 consecutive k (one bf16x2 per lane) of one row
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    int64_t row, col;
-    float   v;
-    if (ROWS_M) { row = m0 + ty + i * 8; col = kk0 + tx; v = tile[tx][ty + i * 8]; }
-    else        { row = kk0 + ty + i * 8; col = m0 + tx; v = tile[ty + i * 8][tx]; }
-    if (row < R && col < Kp) {
-      __nv_bfloat16 h = __float2bfloat16_rn(v);
-      hi[row * Kp + col] = h;
-      lo[row * Kp + col] = __float2bfloat16_rn(v - __bfloat162float(h));
+    for (int i = 0; i < 4; ++i) {
+      const int     rl = ty + i * 8;
+      const int64_t row = m0 + rl, col = kk0 + 2 * tx;
+      if (row < R && col < Kp) {  // Kp is even
+        const float v0 = tile[2 * tx][rl], v1 = tile[2 * tx + 1][rl];
+        const __nv_bfloat16 h0 = __float2bfloat16_rn(v0), h1 = __float2bfloat16_rn(v1);
+        __nv_bfloat162 H2, L2;
+        H2.x = h0; H2.y = h1;
+        L2.x = __float2bfloat16_rn(v0 - __bfloat162float(h0));
+        L2.y = __float2bfloat16_rn(v1 - __bfloat162float(h1));
+        *reinterpret_cast<__nv_bfloat162*>(hi + row * Kp + col) = H2;
+        *reinterpret_cast<__nv_bfloat162*>(lo + row * Kp + col) = L2;
+      }
+    }
+  } else {  // rows = kk, k axis = m
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int64_t row = kk0 + ty + i * 8, col = m0 + tx;
+      if (row < R && col < Kp) {
+        const float v = tile[ty + i * 8][tx];
+        const __nv_bfloat16 h = __float2bfloat16_rn(v);
+        hi[row * Kp + col] = h;
+        lo[row * Kp + col] = __float2bfloat16_rn(v - __bfloat162float(h));
+      }
     }
   }
 }
@@ -75,7 +119,7 @@ static int conv_pack(const float* src, const ConvGeom& g, int64_t Mtot, int64_t 
   PDN_TRY(buf->alloc((size_t)2 * R * Kp * sizeof(__nv_bfloat16)));
   // the grid walks (m tiles, kk tiles); pad columns [K, Kp) are covered because conv_fetch returns 0 out of range
   const int64_t m_ext = ROWS_M ? Mtot : Kp, kk_ext = ROWS_M ? Kp : Ktot;
-  dim3 grd((unsigned)((m_ext + 31) / 32), (unsigned)((kk_ext + 31) / 32));
+  dim3 grd((unsigned)((m_ext + 31) / 32), (unsigned)((kk_ext + 63) / 64));
   PDN_CHECK(grd.y <= 65535, "conv: C*k*k too large for the pack grid");
   k_conv_pack<MODE, ROWS_M><<<grd, 256, 0, stream()>>>(src, (__nv_bfloat16*)buf->p, g, Mtot, Ktot, Kp);
   PDN_LAUNCHED("conv_pack");
@@ -87,6 +131,7 @@ static int conv_pack(const float* src, const ConvGeom& g, int64_t Mtot, int64_t 
 static int make_geom(ConvGeom& g, int64_t N, int64_t C, int64_t H, int64_t W, int64_t O, int k, int stride, int pad) {
   PDN_CHECK(k >= 1 && stride >= 1 && pad >= 0, "conv: bad kernel/stride/pad");
   PDN_CHECK(H + 2 * pad >= k && W + 2 * pad >= k, "conv: kernel larger than the padded input");
+  PDN_CHECK(C * k * k <= 0x7fffffff && O * k * k <= 0x7fffffff && H * W <= 0x7fffffff, "conv: dimension too large");
   g.N = N; g.C = C; g.H = H; g.W = W; g.O = O; g.k = k; g.stride = stride; g.pad = pad;
   g.oh = (H + 2 * pad - k) / stride + 1;
   g.ow = (W + 2 * pad - k) / stride + 1;
