@@ -95,6 +95,47 @@ def c1(args):
         emit(f"micro GEMM fwd {n}^3 fp32 (pack + tcgen05 BF16x3)", sec, flops=2.0 * n**3, launches=nl)
 
 
+def gemm(args):
+    """Single large fp32 GEMM (the ncu --set full target for the tcgen05 kernel)."""
+    rng = np.random.default_rng(0)
+    n = 2048 if args.small else 8192
+    a, b = pdn.backend.array(rng.standard_normal((n, n)).astype(f32)), pdn.backend.array(rng.standard_normal((n, n)).astype(f32))
+    out = pdn.backend.empty((n, n), f32)
+    sec, nl = timed(lambda: pdn.backend.gemm_into(out, a, b), args.steps)
+    emit(f"micro GEMM fwd {n}^3 fp32 (pack + tcgen05 BF16x3)", sec, flops=2.0 * n**3, launches=nl)
+
+
+def rows(args):
+    """HBM-bound row kernels at encoder-like sizes: softmax, feature norm, Adam (ncu --set full targets)."""
+    rng = np.random.default_rng(0)
+    R, Cn = (4096, 512) if args.small else (65536, 512)
+    x = T(rng.standard_normal((R, Cn)).astype(f32))
+    with pdn.no_grad():
+        sec, nl = timed(lambda: F.softmax(x, axis=-1), args.steps)
+    emit(f"micro softmax fwd [{R},{Cn}] fp32", sec, nbytes=8.0 * R * Cn, launches=nl)
+    ln = nn.LayerNorm(Cn, dtype=f32).to(DEV)
+    ln.train()
+    xg = T(rng.standard_normal((R, Cn)).astype(f32), True)
+
+    def lnstep():
+        xg.zero_grad(); ln.scale.zero_grad(); ln.shift.zero_grad()
+        ln(xg).sum().backward()
+
+    sec, nl = timed(lnstep, args.steps)
+    emit(f"micro batch-statistic LayerNorm fwd+bwd [{R},{Cn}] fp32", sec, nbytes=4.0 * R * Cn * (4 + 5), launches=nl)
+    n = 1 << 20 if args.small else 1 << 26
+    p = T(rng.standard_normal(n).astype(f32), True)
+    opt = Adam([p], lr=1e-3)
+    p.grad[...] = 0.5
+
+    def adam():
+        p._grad_stale = False
+        opt.step()
+
+    sec, nl = timed(adam, args.steps)
+    emit(f"micro Adam step {n} params fp32 (one fused kernel)", sec, nbytes=28.0 * n, launches=nl)
+
+
 def c2(args):
     from workloads.lenet import ConvNet, train_step
     np.random.seed(42)
@@ -166,7 +207,7 @@ if __name__ == "__main__":
     args = ap.parse_args()
     for name in args.only.split(","):
         try:
-            {"c1": c1, "c2": c2, "c4": c4, "c5": c5, "micro": micro}[name](args)
+            {"c1": c1, "c2": c2, "c4": c4, "c5": c5, "micro": micro, "gemm": gemm, "rows": rows}[name](args)
         except Exception as e:  # keep going: one config must not hide the others
             import traceback
             traceback.print_exc()

@@ -156,6 +156,14 @@ int pdn_gemm(int dtype, const void* A, const void* B, void* C, int64_t M, int64_
 int pdn_gemm_prepack(const float* B, int64_t K, int64_t N, int64_t b_rs, int64_t b_cs, void** handle);
 int pdn_gemm_prepacked(const float* A, void* handle, float* C, int64_t M, int64_t a_rs, int64_t a_cs, int64_t ldc,
                        const float* bias, int accumulate);
+/* same with the A operand already emitted as bf16 hi/lo planes [2][M][Kp] by a producer kernel (pdn_rmsnorm_planes,
+ * pdn_swiglu_rows_planes, pdn_attention_fwd* with out_planes): no fp32 round trip, no pack launch. */
+int pdn_gemm_prepacked_planes(const void* A_planes, int64_t M, int64_t Kp, void* handle, float* C, int64_t ldc,
+                              const float* bias, int accumulate);
+/* greedy decoding: out_idx[m] = argmax_n (A @ B + bias)[m, n] (first occurrence), computed in the GEMM epilogue + a tiny
+ * second stage; the [M, N] logits are never written (reference llm/llama/model.py:268: logits[:, -1, :].argmax(-1)) */
+int pdn_gemm_prepacked_planes_argmax(const void* A_planes, int64_t M, int64_t Kp, void* handle, const float* bias,
+                                     int64_t* out_idx);
 int pdn_gemm_prepack_free(void* handle);
 /* which path the last pdn_gemm call took: 0 = FFMA tiles, 1 = tcgen05, 2 = skinny (M<=16) */
 int pdn_gemm_last_path(void);
@@ -171,6 +179,8 @@ int pdn_softmax_bwd(int dtype, const void* y, const void* g, void* dx, int64_t r
 /* RMSNorm over the last axis (norm.py:245-248): y = x / sqrt(mean(x^2) + eps) * w ; rstd[rows] saved */
 int pdn_rmsnorm_fwd(const float* x, const float* w, float* y, float* rstd, int64_t rows, int64_t n, float eps);
 /* dx (nullable) and dw[n] (nullable; zeroed here, accumulated with atomics) of the composite */
+/* inference: y emitted directly as GEMM operand planes [2][rows][Kp] (pad columns zero) */
+int pdn_rmsnorm_planes(const float* x, const float* w, void* planes, int64_t rows, int64_t n, int64_t Kp, float eps);
 int pdn_rmsnorm_bwd(const float* x, const float* w, const float* rstd, const float* g, float* dx, float* dw, int64_t rows,
                     int64_t n);
 
@@ -223,7 +233,9 @@ int pdn_pool2d_bwd(const float* x, const float* y, const float* g, float* dx, in
  * lse [B,H,Lq] saved for backward. D <= 128. */
 int pdn_attention_fwd(const float* q, const float* k, const float* v, const float* mask, float* out, float* lse,
                       int64_t B, int64_t H, int64_t Lq, int64_t Lk, int64_t D, const int64_t* q_str,
-                      const int64_t* k_str, const int64_t* v_str, const int64_t* mask_str, float scale);
+                      const int64_t* k_str, const int64_t* v_str, const int64_t* mask_str, float scale,
+                      void* out_planes, int64_t planes_kp);
+/* (out_planes != NULL: instead of fp32 `out`, write the [B*Lq, H*D] result as GEMM operand planes [2][B*Lq][planes_kp]) */
 /* dq [B,Lq,H,D], dk/dv [B,Lk,H,D] contiguous (each nullable; dk/dv are zeroed here and accumulated atomically) */
 int pdn_attention_bwd(const float* q, const float* k, const float* v, const float* mask, const float* out,
                       const float* lse, const float* g_out, float* dq, float* dk, float* dv, int64_t B, int64_t H,
@@ -278,11 +290,12 @@ int pdn_rope_kv_append_dev(float* q, float* k, const float* v, const float* cosT
                            int64_t ld);
 int pdn_attention_fwd_dev(const float* q, const float* k, const float* v, float* out, int64_t B, int64_t H, int64_t Lq,
                           int64_t D, const int64_t* q_str, const int64_t* k_str, const int64_t* v_str, float scale,
-                          const int64_t* pos_dev, int64_t lk_add);
+                          const int64_t* pos_dev, int64_t lk_add, void* out_planes, int64_t planes_kp);
 /* out = silu(gate) * up  (FeedForward.forward model.py:56-58), gate/up are the two halves [rows, F] */
 int pdn_swiglu(const float* gate, const float* up, float* out, int64_t n);
 /* same on the [rows, 2F] output of a fused gate|up projection: out[r, j] = silu(gu[r, j]) * gu[r, F + j] */
 int pdn_swiglu_rows(const float* gu, float* out, int64_t rows, int64_t F);
+int pdn_swiglu_rows_planes(const float* gu, void* planes, int64_t rows, int64_t F, int64_t Kp);
 int pdn_swiglu_bwd(const float* gate, const float* up, const float* g, float* dgate, float* dup, int64_t n);
 
 /* ---------------------------------------------------------------- data-parallel comm -------- */

@@ -86,7 +86,7 @@ _PROTOS = {
     "pdn_conv2d_bwd_weight": [vp, vp, vp, vp, i64, i64, i64, i64, i64, i32, i32, i32],
     "pdn_pool2d_fwd": [vp, vp, i64, i64, i64, i64, i32, i32, i32, i32],
     "pdn_pool2d_bwd": [vp, vp, vp, vp, i64, i64, i64, i64, i32, i32, i32, i32],
-    "pdn_attention_fwd": [vp, vp, vp, vp, vp, vp, i64, i64, i64, i64, i64, pi64, pi64, pi64, pi64, f32],
+    "pdn_attention_fwd": [vp, vp, vp, vp, vp, vp, i64, i64, i64, i64, i64, pi64, pi64, pi64, pi64, f32, vp, i64],
     "pdn_attention_bwd": [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i64, i64, i64, i64, i64, pi64, pi64, pi64, pi64, f32],
     "pdn_gru_seq_fwd": [vp, vp, vp, vp, vp, vp, vp, vp, i64, i64, i64],
     "pdn_gru_seq_bwd": [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i64, i64, i64],
@@ -99,7 +99,11 @@ _PROTOS = {
     "pdn_rope_kv_append": [vp, vp, vp, vp, vp, vp, vp, i64, i64, i64, i64, i64, i64, i64],
     "pdn_rope_kv_append_dev": [vp, vp, vp, vp, vp, vp, vp, i64, i64, i64, i64, i64, vp, i64],
     "pdn_swiglu_rows": [vp, vp, i64, i64],
-    "pdn_attention_fwd_dev": [vp, vp, vp, vp, i64, i64, i64, i64, pi64, pi64, pi64, f32, vp, i64],
+    "pdn_attention_fwd_dev": [vp, vp, vp, vp, i64, i64, i64, i64, pi64, pi64, pi64, f32, vp, i64, vp, i64],
+    "pdn_rmsnorm_planes": [vp, vp, vp, i64, i64, i64, f32],
+    "pdn_swiglu_rows_planes": [vp, vp, i64, i64, i64],
+    "pdn_gemm_prepacked_planes": [vp, i64, i64, vp, vp, i64, vp, i32],
+    "pdn_gemm_prepacked_planes_argmax": [vp, i64, i64, vp, vp, vp],
     "pdn_swiglu": [vp, vp, vp, i64],
     "pdn_swiglu_bwd": [vp, vp, vp, vp, vp, i64],
     "pdn_nccl_unique_id": [C.c_char_p],

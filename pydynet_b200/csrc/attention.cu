@@ -24,6 +24,8 @@ struct AttArgs {
   float scale;
   const int64_t* lk_dev;        // optional device scalar: Lk = *lk_dev + lk_add (CUDA-graph replay of the decode step)
   int64_t lk_add;
+  __nv_bfloat16* out_planes;    // optional: emit [B*Lq, H*D] as bf16 hi/lo operand planes [2][B*Lq][planes_kp] instead of fp32 out
+  int64_t planes_kp;
 };
 
 __global__ void __launch_bounds__(128) k_attention_fwd(AttArgs a) {
@@ -85,11 +87,26 @@ __global__ void __launch_bounds__(128) k_attention_fwd(AttArgs a) {
     }
   }
   const float inv = 1.f / l;
-  float* orow = a.out + ((b * a.Lq + iq) * a.H + h) * a.D;
+  if (a.out_planes) {  // the O-projection GEMM consumes this directly (no fp32 round trip, no pack launch)
+    const int64_t rows = a.B * a.Lq, r = b * a.Lq + iq;
+    __nv_bfloat16 *hi = a.out_planes + r * a.planes_kp + h * a.D, *lo = hi + rows * a.planes_kp;
 #pragma unroll
-  for (int i = 0; i < ATT_DPL; ++i) {
-    int d = lane + i * 32;
-    if (d < D) orow[d] = acc[i] * inv;
+    for (int i = 0; i < ATT_DPL; ++i) {
+      int d = lane + i * 32;
+      if (d < D) {
+        const float v = acc[i] * inv;
+        const __nv_bfloat16 hv = __float2bfloat16_rn(v);
+        hi[d] = hv;
+        lo[d] = __float2bfloat16_rn(v - __bfloat162float(hv));
+      }
+    }
+  } else {
+    float* orow = a.out + ((b * a.Lq + iq) * a.H + h) * a.D;
+#pragma unroll
+    for (int i = 0; i < ATT_DPL; ++i) {
+      int d = lane + i * 32;
+      if (d < D) orow[d] = acc[i] * inv;
+    }
   }
   if (lane == 0 && a.lse) a.lse[(b * a.H + h) * a.Lq + iq] = m + logf(l);
 }
@@ -216,6 +233,8 @@ static int fill_att(AttArgs& a, const float* q, const float* k, const float* v, 
   a.scale = scale;
   a.lk_dev = nullptr;
   a.lk_add = 0;
+  a.out_planes = nullptr;
+  a.planes_kp = 0;
   return 0;
 }
 
@@ -223,10 +242,13 @@ extern "C" {
 
 int pdn_attention_fwd(const float* q, const float* k, const float* v, const float* mask, float* out, float* lse, int64_t B, int64_t H, int64_t Lq,
                       int64_t Lk, int64_t D, const int64_t* q_str, const int64_t* k_str, const int64_t* v_str, const int64_t* mask_str,
-                      float scale) {
+                      float scale, void* out_planes, int64_t planes_kp) {
   PDN_TRY(ensure_init());
   AttArgs a;
   PDN_TRY(fill_att(a, q, k, v, mask, out, lse, B, H, Lq, Lk, D, q_str, k_str, v_str, mask_str, scale));
+  PDN_CHECK(!out_planes || (planes_kp >= H * D && (planes_kp & 7) == 0), "attention: bad planes padding");
+  a.out_planes = (__nv_bfloat16*)out_planes;
+  a.planes_kp = planes_kp;
   const int64_t total = B * H * Lq;
   if (total == 0) return 0;
   PDN_CHECK(Lk > 0, "attention: no keys");
@@ -280,11 +302,15 @@ int pdn_rope_kv_append_dev(float* q, float* k, const float* v, const float* cosT
 }
 
 int pdn_attention_fwd_dev(const float* q, const float* k, const float* v, float* out, int64_t B, int64_t H, int64_t Lq, int64_t D,
-                          const int64_t* q_str, const int64_t* k_str, const int64_t* v_str, float scale, const int64_t* pos_dev, int64_t lk_add) {
+                          const int64_t* q_str, const int64_t* k_str, const int64_t* v_str, float scale, const int64_t* pos_dev, int64_t lk_add,
+                          void* out_planes, int64_t planes_kp) {
   PDN_TRY(ensure_init());
   PDN_CHECK(pos_dev != nullptr, "attention_dev: null position");
   AttArgs a;
   PDN_TRY(fill_att(a, q, k, v, nullptr, out, nullptr, B, H, Lq, 1, D, q_str, k_str, v_str, nullptr, scale));
+  PDN_CHECK(!out_planes || (planes_kp >= H * D && (planes_kp & 7) == 0), "attention: bad planes padding");
+  a.out_planes = (__nv_bfloat16*)out_planes;
+  a.planes_kp = planes_kp;
   a.lk_dev = pos_dev;
   a.lk_add = lk_add;
   const int64_t total = B * H * Lq;

@@ -140,7 +140,7 @@ static int make_geom(ConvGeom& g, int64_t N, int64_t C, int64_t H, int64_t W, in
 
 static void tc_defaults(TcArgs& t) {
   for (int i = 0; i < 3; ++i) { t.nb[i] = 1; t.c_bs[i] = 0; t.a_pbs[i] = 0; t.b_pbs[i] = 0; }
-  t.bias = nullptr; t.accumulate = 0; t.splits = 1; t.nchw_hw = 0; t.c_clear_bytes = 0;
+  t.bias = nullptr; t.accumulate = 0; t.splits = 1; t.nchw_hw = 0; t.c_clear_bytes = 0; t.amax_val = nullptr; t.amax_idx = nullptr;
 }
 
 // per-output-channel sum of an NCHW tensor: dbias[o] = Σ_{n,pix} g[n,o,pix]

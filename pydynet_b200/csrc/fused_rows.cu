@@ -140,6 +140,29 @@ __global__ void __launch_bounds__(256) k_rmsnorm_fwd(const float* __restrict__ x
   for (int j = lane; j < n; j += 32) yr[j] = xr[j] * r * __ldg(w + j);
 }
 
+// Same normalisation, but the result is emitted directly as the next GEMM's A operand: K-major bf16 hi/lo planes
+// [2][rows][Kp] (x = hi + lo), skipping the fp32 round trip and the separate pack launch.
+__device__ __forceinline__ void put_pair(__nv_bfloat16* hi, __nv_bfloat16* lo, int64_t idx, float v) {
+  __nv_bfloat16 h = __float2bfloat16_rn(v);
+  hi[idx] = h;
+  lo[idx] = __float2bfloat16_rn(v - __bfloat162float(h));
+}
+__global__ void __launch_bounds__(256) k_rmsnorm_planes(const float* __restrict__ x, const float* __restrict__ w, __nv_bfloat16* __restrict__ planes,
+                                                        int64_t rows, int n, int64_t Kp, float eps) {
+  const int lane = threadIdx.x & 31;
+  const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const float* xr = x + row * n;
+  float ss = 0.f;
+  for (int j = lane; j < n; j += 32) { float v = xr[j]; ss += v * v; }
+  ss = warp_sum(ss);
+  const float r = 1.f / sqrtf(ss / (float)n + eps);
+  __nv_bfloat16 *hi = planes, *lo = planes + rows * Kp;
+  for (int j = lane; j < Kp; j += 32) put_pair(hi, lo, row * Kp + j, j < n ? xr[j] * r * __ldg(w + j) : 0.f);
+}
+__global__ void __launch_bounds__(256) k_swiglu_rows_planes(const float* __restrict__ gu, __nv_bfloat16* __restrict__ planes, int64_t rows,
+                                                            int64_t F, int64_t Kp);
+
 // dx = r*w*g - x * r^3 * mean(g*w*x) ; dw[j] += sum_rows g*x*r   (per-warp register partials, then atomics)
 template <int MAXJ>
 __global__ void __launch_bounds__(256) k_rmsnorm_bwd(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ rstd,
@@ -233,6 +256,14 @@ __global__ void __launch_bounds__(256) k_swiglu_rows(const float* __restrict__ g
     out[i] = silu_f(gu[r * 2 * F + j]) * gu[r * 2 * F + F + j];
   }
 }
+__global__ void __launch_bounds__(256) k_swiglu_rows_planes(const float* __restrict__ gu, __nv_bfloat16* __restrict__ planes, int64_t rows,
+                                                            int64_t F, int64_t Kp) {
+  __nv_bfloat16 *hi = planes, *lo = planes + rows * Kp;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < rows * Kp; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / Kp, j = i - r * Kp;
+    put_pair(hi, lo, i, j < F ? silu_f(gu[r * 2 * F + j]) * gu[r * 2 * F + F + j] : 0.f);
+  }
+}
 // dgate = g * up * silu'(gate), dup = g * silu(gate); silu'(x) = s + x*s*(1-s), s = sigmoid(x)
 __global__ void __launch_bounds__(256) k_swiglu_bwd(const float* __restrict__ gate, const float* __restrict__ up, const float* __restrict__ g,
                                                     float* __restrict__ dgate, float* __restrict__ dup, int64_t n) {
@@ -324,6 +355,24 @@ int pdn_rmsnorm_fwd(const float* x, const float* w, float* y, float* rstd, int64
   PDN_CHECK(n <= 0x7fffffff, "rmsnorm: row too long");
   k_rmsnorm_fwd<<<rows_grid(rows, 8), 256, 0, stream()>>>(x, w, y, rstd, rows, (int)n, eps);
   PDN_LAUNCHED("rmsnorm_fwd");
+  return 0;
+}
+
+int pdn_rmsnorm_planes(const float* x, const float* w, void* planes, int64_t rows, int64_t n, int64_t Kp, float eps) {
+  PDN_TRY(ensure_init());
+  if (rows == 0 || n == 0) return 0;
+  PDN_CHECK(n <= 0x7fffffff && Kp >= n && (Kp & 7) == 0, "rmsnorm_planes: bad K padding");
+  k_rmsnorm_planes<<<rows_grid(rows, 8), 256, 0, stream()>>>(x, w, (__nv_bfloat16*)planes, rows, (int)n, Kp, eps);
+  PDN_LAUNCHED("rmsnorm_planes");
+  return 0;
+}
+
+int pdn_swiglu_rows_planes(const float* gu, void* planes, int64_t rows, int64_t F, int64_t Kp) {
+  PDN_TRY(ensure_init());
+  if (rows * F == 0) return 0;
+  PDN_CHECK(Kp >= F && (Kp & 7) == 0, "swiglu_rows_planes: bad K padding");
+  k_swiglu_rows_planes<<<grid_for(rows * Kp, 256), 256, 0, stream()>>>(gu, (__nv_bfloat16*)planes, rows, F, Kp);
+  PDN_LAUNCHED("swiglu_rows_planes");
   return 0;
 }
 

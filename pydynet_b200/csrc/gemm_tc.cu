@@ -283,61 +283,111 @@ __global__ void __launch_bounds__(256, 1) k_gemm_tc(const __grid_constant__ CUte
     if (g.nchw_hw > 0) { img = row / g.nchw_hw; pix = row - img * g.nchw_hw; }
     const bool atomic = g.splits > 1;
     const bool add_bias = g.bias != nullptr && split == 0;
-    const bool vec_ok = !atomic && g.nchw_hw == 0 && ((g.ldc & 3) == 0) && ((((uintptr_t)g.C) & 15) == 0) &&
-                        (((g.c_bs[0] | g.c_bs[1] | g.c_bs[2]) & 3) == 0);
     if (num_kb > 0 || (!atomic && !g.accumulate)) {
+      const int64_t row0 = (int64_t)m_blk * TC_BM + q * 32;
+      float*        stg = reinterpret_cast<float*>(smem) + (warp - 4) * (32 * 33);  // pipeline stages are idle by now
+      float         best_v = -INFINITY;
+      long long     best_i = (long long)n_blk * BN;
 #pragma unroll 1
-    for (int c0 = 0; c0 < BN; c0 += 32) {
-      float v[32];
-      if (num_kb > 0) {
-        tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
-        tmem_ld_wait();
-      } else {
+      for (int c0 = 0; c0 < BN; c0 += 32) {
+        const int64_t col0 = (int64_t)n_blk * BN + c0;
+        if (col0 >= g.N) break;  // uniform across the CTA
+        float v[32];
+        if (num_kb > 0) {
+          tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
+          tmem_ld_wait();
+        } else {
 #pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = 0.f;
-      }
-      const int64_t col0 = (int64_t)n_blk * BN + c0;
-      if (row < g.M && col0 < g.N) {
+          for (int j = 0; j < 32; ++j) v[j] = 0.f;
+        }
         if (add_bias) {
 #pragma unroll
           for (int j = 0; j < 32; ++j)
             if (col0 + j < g.N) v[j] += __ldg(g.bias + col0 + j);
         }
-        if (g.nchw_hw > 0) {
-          float* p0 = cbase + img * g.N * g.nchw_hw + pix;
+        if (g.amax_val) {
+          // running (max, first column) of this row over the tile's columns; nothing is stored to C
 #pragma unroll
           for (int j = 0; j < 32; ++j)
-            if (col0 + j < g.N) {
-              float* p = p0 + (col0 + j) * g.nchw_hw;
-              if (atomic) atomicAdd(p, v[j]);
-              else *p = g.accumulate ? *p + v[j] : v[j];
-            }
-        } else if (vec_ok && col0 + 32 <= g.N) {
-          float4* c4 = reinterpret_cast<float4*>(crow + col0);
+            if (col0 + j < g.N && v[j] > best_v) { best_v = v[j]; best_i = col0 + j; }
+        } else if (g.nchw_hw > 0) {
+          // NCHW scatter: for a fixed column (channel) consecutive lanes hold consecutive pixels -> coalesced
+          if (row < g.M) {
+            float* p0 = cbase + img * g.N * g.nchw_hw + pix;
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            float4 o = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-            if (g.accumulate) {
-              float4 p = c4[j];
-              o.x += p.x; o.y += p.y; o.z += p.z; o.w += p.w;
-            }
-            c4[j] = o;
+            for (int j = 0; j < 32; ++j)
+              if (col0 + j < g.N) {
+                float* p = p0 + (col0 + j) * g.nchw_hw;
+                if (atomic) atomicAdd(p, v[j]);
+                else *p = g.accumulate ? *p + v[j] : v[j];
+              }
+          }
+        } else if (atomic) {
+          if (row < g.M) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (col0 + j < g.N) atomicAdd(crow + col0 + j, v[j]);
           }
         } else {
+          // row-major C: transpose the 32x32 chunk through shared memory so that every store instruction writes one
+          // 128-byte row segment (a thread owns a ROW of the accumulator, which would otherwise give 32 scattered 4-byte
+          // or 16-byte stores per instruction)
 #pragma unroll
-          for (int j = 0; j < 32; ++j)
-            if (col0 + j < g.N) {
-              if (atomic) atomicAdd(crow + col0 + j, v[j]);
-              else crow[col0 + j] = g.accumulate ? crow[col0 + j] + v[j] : v[j];
+          for (int j = 0; j < 32; ++j) stg[lane * 33 + j] = v[j];
+          __syncwarp();
+          const int64_t col = col0 + lane;
+          if (col < g.N) {
+            float* p = cbase + row0 * g.ldc + col;
+            if (g.accumulate) {
+              // all 32 loads of the old C values are issued before the first store: a load-add-store loop would serialise
+              // 32 memory round trips (the compiler must assume the stores alias the next loads)
+              float old[32];
+#pragma unroll
+              for (int r = 0; r < 32; ++r) old[r] = (row0 + r < g.M) ? __ldcg(p + r * g.ldc) : 0.f;
+#pragma unroll
+              for (int r = 0; r < 32; ++r)
+                if (row0 + r < g.M) p[r * g.ldc] = old[r] + stg[r * 33 + lane];
+            } else {
+#pragma unroll
+              for (int r = 0; r < 32; ++r)
+                if (row0 + r < g.M) p[r * g.ldc] = stg[r * 33 + lane];
             }
+          }
+          __syncwarp();
         }
       }
-    }
+      if (g.amax_val && row < g.M) {
+        g.amax_val[row * gridDim.x + n_blk] = best_v;
+        g.amax_idx[row * gridDim.x + n_blk] = best_i;
+      }
     }
   }
   tc_fence_before();
   __syncthreads();
   if (warp == 2) tmem_dealloc(tmem_base, Cfg::kTmemCols);
+}
+
+// second stage of the fused GEMM + argmax: one warp per row over the per-tile partials (tiles are in column order, so the
+// smallest tile index wins ties = NumPy's first-occurrence rule)
+__global__ void __launch_bounds__(256) k_argmax_partials(const float* __restrict__ val, const long long* __restrict__ idx, long long* __restrict__ out,
+                                                         int64_t M, int nt) {
+  const int lane = threadIdx.x & 31;
+  const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= M) return;
+  float     bv = -INFINITY;
+  long long bi = 0x7fffffffffffffffLL;
+  for (int t = lane; t < nt; t += 32) {
+    float v = val[row * nt + t];
+    long long i = idx[row * nt + t];
+    if (v > bv || (v == bv && i < bi)) { bv = v; bi = i; }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    float     ov = __shfl_xor_sync(0xffffffffu, bv, o);
+    long long oi = __shfl_xor_sync(0xffffffffu, bi, o);
+    if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+  }
+  if (lane == 0) out[row] = bi;
 }
 
 // ------------------------------------------------------------------ host side ------------------
@@ -430,7 +480,7 @@ static int launch_tc(const CUtensorMap& mA, const CUtensorMap& mB, const TcArgs&
 
 // C (+)= A·Bᵀ on pre-packed bf16 hi/lo planes. `t` carries C, bias, M/N/K, ldc, batches, accumulate, nchw_hw;
 // splits <= 0 picks a split-K factor that fills the SMs when the tile grid is small and K is long.
-int gemm_tc_packed(const PackedOperand& A, const PackedOperand& B, TcArgs t, int splits) {
+int gemm_tc_packed(const PackedOperand& A, const PackedOperand& B, TcArgs t, int splits, int* n_tiles_out) {
   PDN_TRY(get_encode_fn());
   const int64_t nbatch = t.nb[0] * t.nb[1] * t.nb[2];
   const int64_t m_tiles = (t.M + TC_BM - 1) / TC_BM;
@@ -466,6 +516,7 @@ int gemm_tc_packed(const PackedOperand& A, const PackedOperand& B, TcArgs t, int
       PDN_CUDA(cudaMemset2DAsync(t.C, (size_t)t.ldc * sizeof(float), 0, (size_t)t.N * sizeof(float), (size_t)t.M, stream()));
     }
   }
+  if (n_tiles_out) *n_tiles_out = (int)((t.N + BN - 1) / BN);
   CUtensorMap mA, mB;
   PDN_TRY(make_map(&mA, A.planes, A.R, A.K, A.Kp, A.nbatch, TC_BM));
   PDN_TRY(make_map(&mB, B.planes, B.R, B.K, B.Kp, B.nbatch, BN));
@@ -489,6 +540,7 @@ int gemm_tc_launch(const GemmArgs& g) {
   t.accumulate = g.accumulate;
   t.nchw_hw = 0;
   t.c_clear_bytes = 0;
+  t.amax_val = nullptr; t.amax_idx = nullptr;
   // split-K only for single-batch products (batched ones already fill the grid or have strided C)
   return gemm_tc_packed(A, B, t, nbatch > 1 ? 1 : 0);
 }
@@ -532,7 +584,54 @@ int pdn_gemm_prepacked(const float* A, void* handle, float* C, int64_t M, int64_
   t.C = C; t.bias = bias; t.M = M; t.N = h->op.R; t.K = h->op.K; t.ldc = ldc;
   for (int i = 0; i < 3; ++i) { t.nb[i] = 1; t.c_bs[i] = 0; }
   t.accumulate = accumulate; t.nchw_hw = 0; t.c_clear_bytes = 0;
+  t.amax_val = nullptr; t.amax_idx = nullptr;
   return pdn::gemm_tc_packed(Aop, h->op, t, 0);
+}
+
+// A operand already in plane format [2][M][Kp] (emitted by k_rmsnorm_planes / k_swiglu_rows_planes / k_attention_fwd)
+int pdn_gemm_prepacked_planes(const void* A_planes, int64_t M, int64_t Kp, void* handle, float* C, int64_t ldc, const float* bias,
+                              int accumulate) {
+  PDN_TRY(pdn::ensure_init());
+  auto* h = (pdn::Prepacked*)handle;
+  PDN_CHECK(h != nullptr && A_planes != nullptr, "prepacked_planes: null operand");
+  PDN_CHECK(Kp >= h->op.K && (Kp & 7) == 0, "prepacked_planes: K padding %lld does not cover K=%lld", (long long)Kp, (long long)h->op.K);
+  if (M == 0) return 0;
+  pdn::PackedOperand Aop;
+  Aop.planes = const_cast<void*>(A_planes); Aop.R = M; Aop.K = h->op.K; Aop.Kp = Kp; Aop.nbatch = 1;
+  Aop.pbs[0] = Aop.pbs[1] = Aop.pbs[2] = 0;
+  pdn::TcArgs t;
+  t.C = C; t.bias = bias; t.M = M; t.N = h->op.R; t.K = h->op.K; t.ldc = ldc;
+  for (int i = 0; i < 3; ++i) { t.nb[i] = 1; t.c_bs[i] = 0; }
+  t.accumulate = accumulate; t.nchw_hw = 0; t.c_clear_bytes = 0;
+  t.amax_val = nullptr; t.amax_idx = nullptr;
+  return pdn::gemm_tc_packed(Aop, h->op, t, 0);
+}
+
+// out_idx[m] = argmax_n (A·B + bias)[m, n] without materialising the [M, N] product (greedy decoding over the vocabulary)
+int pdn_gemm_prepacked_planes_argmax(const void* A_planes, int64_t M, int64_t Kp, void* handle, const float* bias, int64_t* out_idx) {
+  PDN_TRY(pdn::ensure_init());
+  auto* h = (pdn::Prepacked*)handle;
+  PDN_CHECK(h != nullptr && A_planes != nullptr, "prepacked_argmax: null operand");
+  PDN_CHECK(Kp >= h->op.K && (Kp & 7) == 0, "prepacked_argmax: bad K padding");
+  if (M == 0) return 0;
+  const int64_t N = h->op.R;
+  const int64_t nt_max = (N + 63) / 64;  // upper bound on N tiles whatever BN the launcher picks
+  pdn::Scratch sv, si;
+  PDN_TRY(sv.alloc((size_t)M * nt_max * sizeof(float)));
+  PDN_TRY(si.alloc((size_t)M * nt_max * sizeof(long long)));
+  pdn::PackedOperand Aop;
+  Aop.planes = const_cast<void*>(A_planes); Aop.R = M; Aop.K = h->op.K; Aop.Kp = Kp; Aop.nbatch = 1;
+  Aop.pbs[0] = Aop.pbs[1] = Aop.pbs[2] = 0;
+  pdn::TcArgs t;
+  t.C = nullptr; t.bias = bias; t.M = M; t.N = N; t.K = h->op.K; t.ldc = N;
+  for (int i = 0; i < 3; ++i) { t.nb[i] = 1; t.c_bs[i] = 0; }
+  t.accumulate = 0; t.nchw_hw = 0; t.c_clear_bytes = 0;
+  t.amax_val = (float*)sv.p; t.amax_idx = (long long*)si.p;
+  int n_tiles = 0;
+  PDN_TRY(pdn::gemm_tc_packed(Aop, h->op, t, 1, &n_tiles));
+  pdn::k_argmax_partials<<<(unsigned)((M + 7) / 8), 256, 0, pdn::stream()>>>((const float*)sv.p, (const long long*)si.p, (long long*)out_idx, M, n_tiles);
+  PDN_LAUNCHED("argmax_partials");
+  return 0;
 }
 
 int pdn_gemm_prepack_free(void* handle) {

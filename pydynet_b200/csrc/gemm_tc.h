@@ -20,10 +20,13 @@ struct TcArgs {
   int splits;       // split-K factor; > 1 => epilogue accumulates with atomics
   int64_t nchw_hw;  // 0: C row-major [M, N] (ldc). > 0: row m = (img, pix) of an NCHW tensor: C[img][col][pix], hw = nchw_hw
   size_t c_clear_bytes;  // extent of C to clear before a split-K launch when C is not a plain [M, N] matrix
+  // greedy-decode epilogue: instead of storing C, keep per (row, N-tile) the maximum of (A·B + bias) and its column
+  float*     amax_val;   // [M][n_tiles] (nullptr = normal store epilogue)
+  long long* amax_idx;   // [M][n_tiles]
 };
 
 int pack_operand_ex(const float* src, int64_t R, int64_t K, int64_t r_stride, int64_t k_stride, int64_t k_inner, int64_t k_outer_stride,
                     const int64_t* nb, const int64_t* bs, Scratch* buf, PackedOperand* out);
-int gemm_tc_packed(const PackedOperand& A, const PackedOperand& B, TcArgs t, int splits);
+int gemm_tc_packed(const PackedOperand& A, const PackedOperand& B, TcArgs t, int splits, int* n_tiles_out = nullptr);
 
 }  // namespace pdn

@@ -142,7 +142,7 @@ static inline int64_t kpad(int64_t k) { return (k + 7) & ~(int64_t)7; }
 
 static void tc_init(TcArgs& t, float* C, int64_t M, int64_t N, int64_t K, int accumulate) {
   for (int i = 0; i < 3; ++i) { t.nb[i] = 1; t.c_bs[i] = 0; t.a_pbs[i] = 0; t.b_pbs[i] = 0; }
-  t.C = C; t.bias = nullptr; t.M = M; t.N = N; t.K = K; t.ldc = N; t.accumulate = accumulate; t.splits = 1; t.nchw_hw = 0; t.c_clear_bytes = 0;
+  t.C = C; t.bias = nullptr; t.M = M; t.N = N; t.K = K; t.ldc = N; t.accumulate = accumulate; t.splits = 1; t.nchw_hw = 0; t.c_clear_bytes = 0; t.amax_val = nullptr; t.amax_idx = nullptr;
 }
 
 static int alloc_planes(Scratch* s, PackedOperand* op, int64_t rows, int64_t K) {

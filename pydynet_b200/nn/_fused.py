@@ -260,7 +260,7 @@ def attention(xq, xk, xv, mask, scale):
         out, lse = _empty((B, Lq, H, D)), _empty((B, H, Lq))
         keep, mptr, mstr = _mask_args(mask, B, H, Lq, Lk)
         _call("pdn_attention_fwd", q.ptr, k.ptr, v.ptr, mptr, out.ptr, lse.ptr, B, H, Lq, Lk, D, _bhl_strides(q), _bhl_strides(k),
-              _bhl_strides(v), mstr, scale)
+              _bhl_strides(v), mstr, scale, None, 0)
 
     def backward(g):
         g = _c(g.reshape(B, Lq, H, D))
@@ -284,6 +284,40 @@ class DevicePos:
         self.tensor = tensor
 
 
+class Planes:
+    """A GEMM A-operand already in tensor-core format: bf16 hi/lo planes [2][M][Kp] written by a producer kernel."""
+    __slots__ = ("buf", "M", "K", "Kp", "lead", "device")
+
+    def __init__(self, lead, K, device):
+        from ..backend.array import ndarray
+        self.lead, self.K, self.device = tuple(lead), K, device
+        self.M = int(np.prod(lead, dtype=np.int64)) if lead else 1
+        self.Kp = (K + 7) // 8 * 8
+        self.buf = ndarray.empty((4 * self.M * self.Kp, ), np.uint8)
+
+    @property
+    def ptr(self):
+        return self.buf.ptr
+
+
+def rmsnorm_planes(x, weight, eps):
+    """RMSNorm whose result feeds only GEMMs: emitted directly as operand planes (inference)."""
+    with x.device:
+        xd, w = _c(x.data), _c(weight.data)
+        n = xd.shape[-1]
+        pl = Planes(xd.shape[:-1], n, x.device)
+        _call("pdn_rmsnorm_planes", xd.ptr, w.ptr, pl.ptr, pl.M, n, pl.Kp, eps)
+    return pl
+
+
+def swiglu_rows_planes(gu, F_):
+    with gu.device:
+        g = _c(gu.data)
+        pl = Planes(g.shape[:-1], F_, gu.device)
+        _call("pdn_swiglu_rows_planes", g.ptr, pl.ptr, pl.M, F_, pl.Kp)
+    return pl
+
+
 def _cat_packed(owner, key, weights):
     """Pre-packed operand planes of [W0 | W1 | ...] (column-wise concatenation), cached on ``owner`` until any of the
     weight buffers is written again."""
@@ -302,9 +336,13 @@ def linear_cat(owner, key, x, weights):
     input, so their weight planes are concatenated once and a single launch produces all outputs side by side."""
     bk = _bk()
     with x.device:
+        pw, N = _cat_packed(owner, key, weights)
+        if isinstance(x, Planes):
+            out = _empty((x.M, N))
+            _call("pdn_gemm_prepacked_planes", x.ptr, x.M, x.Kp, pw.handle, out.ptr, N, None, 0)
+            return _result(out.reshape(x.lead + (N, )), x.device, (), None, "linear_cat")
         xd = x.data
         x2 = bk.ext._flat2d(xd) if xd.ndim != 2 else xd
-        pw, N = _cat_packed(owner, key, weights)
         out = _empty((x2.shape[0], N))
         _call("pdn_gemm_prepacked", x2.ptr, pw.handle, out.ptr, x2.shape[0], x2.estrides[0], x2.estrides[1], N, None, 0)
     return _result(out.reshape(xd.shape[:-1] + (N, )), x.device, (), None, "linear_cat")
@@ -315,14 +353,28 @@ def linear_residual_(a, weight, res):
     needed in its old state). Returns res."""
     bk = _bk()
     with a.device:
-        ad = a.data
-        a2 = bk.ext._flat2d(ad) if ad.ndim != 2 else ad
         rd = res.data
         assert rd.is_contiguous and rd.dtype == F32
         N = weight.shape[1]
         rd.buf.version += 1
+        if isinstance(a, Planes):
+            _call("pdn_gemm_prepacked_planes", a.ptr, a.M, a.Kp, _packed(weight).handle, rd.ptr, N, None, 1)
+            return res
+        ad = a.data
+        a2 = bk.ext._flat2d(ad) if ad.ndim != 2 else ad
         _call("pdn_gemm_prepacked", a2.ptr, _packed(weight).handle, rd.ptr, a2.shape[0], a2.estrides[0], a2.estrides[1], N, None, 1)
     return res
+
+
+def lm_head_argmax(pl, weight, bias):
+    """argmax over the vocabulary of (h @ W + b) for greedy decoding, fused into the GEMM epilogue: the [B, V] logits are
+    never written to HBM (reference llm/llama/model.py:254-256, 268). Returns int64 ids [B, 1]."""
+    from ..backend.array import ndarray
+    with pl.device:
+        out = ndarray.empty((pl.M, 1), np.int64)
+        bd = _c(bias.data) if bias is not None else None
+        _call("pdn_gemm_prepacked_planes_argmax", pl.ptr, pl.M, pl.Kp, _packed(weight).handle, bd.ptr if bd is not None else None, out.ptr)
+    return _result(out, pl.device, (), None, "lm_head_argmax")
 
 
 def swiglu_rows(gu, F_):
@@ -344,7 +396,7 @@ class DevicePos:
 
 
 @fused_op
-def llama_cached_attention(att, xq, xk, xv, start_pos, mask, scale, ld=0):
+def llama_cached_attention(att, xq, xk, xv, start_pos, mask, scale, ld=0, as_planes=False):
     """Inference step of the Llama attention block (reference llm/llama/model.py:101-121): interleaved-pair RoPE on q and k,
     append k/v to the per-layer KV cache at [start_pos, start_pos+L), attention of the new queries over cache[:start_pos+L].
     Two kernels (rope_kv_append, attention_fwd) instead of ~40 eager nodes. Inference only (no tape). ``start_pos`` is a
@@ -360,21 +412,29 @@ def llama_cached_attention(att, xq, xk, xv, start_pos, mask, scale, ld=0):
         B, L, H, D = q.shape
         ck, cv = att.cache_k.data, att.cache_v.data
         S = ck.shape[1]
-        out = _empty((B, L, H, D))
+        if as_planes:  # the O-projection consumes the result as operand planes: skip the fp32 output and its pack
+            pl = Planes((B, L), H * D, xq.device)
+            out, optr, pptr, pkp = None, None, pl.ptr, pl.Kp
+        else:
+            out = _empty((B, L, H, D))
+            optr, pptr, pkp = out.ptr, None, 0
         cstr = _i64((ck.estrides[0], ck.estrides[2], ck.estrides[1]))
         if isinstance(start_pos, DevicePos):
             assert mask is None
             pos_ptr = start_pos.tensor.data.ptr
             _call("pdn_rope_kv_append_dev", q.ptr, k.ptr, v.ptr, model_cos.ptr, model_sin.ptr, ck.ptr, cv.ptr, B, L, H, D, S, pos_ptr, ld)
-            _call("pdn_attention_fwd_dev", q.ptr, ck.ptr, cv.ptr, out.ptr, B, H, L, D, _bhl_strides(q), cstr, cstr, scale, pos_ptr, L)
+            _call("pdn_attention_fwd_dev", q.ptr, ck.ptr, cv.ptr, optr, B, H, L, D, _bhl_strides(q), cstr, cstr, scale, pos_ptr, L, pptr, pkp)
         else:
             _call("pdn_rope_kv_append", q.ptr, k.ptr, v.ptr, model_cos.ptr, model_sin.ptr, ck.ptr, cv.ptr, B, L, H, D, S, int(start_pos), ld)
             Lk = int(start_pos) + L
             keep, mptr, mstr = _mask_args(mask, B, H, L, Lk)
-            _call("pdn_attention_fwd", q.ptr, ck.ptr, cv.ptr, mptr, out.ptr, None, B, H, L, Lk, D, _bhl_strides(q), cstr, cstr, mstr, scale)
+            _call("pdn_attention_fwd", q.ptr, ck.ptr, cv.ptr, mptr, optr, None, B, H, L, Lk, D, _bhl_strides(q), cstr, cstr, mstr, scale, pptr,
+                  pkp)
             _ = keep
         ck.buf.version += 1
         cv.buf.version += 1
+    if as_planes:
+        return pl
     return _result(out.reshape(B, L, H * D), xq.device, (), None, "llama_cached_attention")
 
 

@@ -55,7 +55,7 @@ class FeedForward(nn.Module):
         """Inference: gate|up as one GEMM on concatenated weight planes, then SwiGLU; the down projection is applied by the
         block together with the residual add."""
         gu = _fused.linear_cat(self, "_pdn_gate_up", x, (self.gate.weight, self.up.weight))
-        return _fused.swiglu_rows(gu, self.up_dim)
+        return _fused.swiglu_rows_planes(gu, self.up_dim)
 
 
 class Attention(nn.Module):
@@ -107,31 +107,35 @@ class TransformerBlock(nn.Module):
         self.input_norm = nn.RMSNorm(dim, dtype=dtype)
         self.post_attn_norm = nn.RMSNorm(dim, dtype=dtype)
 
-    def _fast_ok(self, x) -> bool:
+    def _fast_ok(self, x, rows) -> bool:
+        """Inference fast path applies: eval mode, no tape, fp32 cuda tensors, at least 32 token rows (below that the
+        skinny FFMA GEMM of the generic path is the better kernel)."""
         return (os.environ.get("PDN_LLAMA_FAST", "1") != "0" and not self._train and not pdn.autograd.is_grad_enable()
-                and x.shape[0] * x.shape[1] >= 32 and _fused.usable(x, self.attention.Q.weight, op="llama_cached_attention"))
+                and rows >= 32 and _fused.usable(x, self.attention.Q.weight, op="llama_cached_attention"))
 
     def forward(self, x, start_pos, mask, freqs_cos, freqs_sin):
-        if self._fast_ok(x):
+        if self._fast_ok(x, x.shape[0] * x.shape[1]):
             return self._forward_inference(x, start_pos, mask)
         z = x + self.attention(self.input_norm(x), start_pos, mask, freqs_cos, freqs_sin)
         return z + self.ffn(self.post_attn_norm(z))
 
     def _forward_inference(self, x, start_pos, mask):
-        """Same block (reference llm/llama/model.py:142-150) with 9 launches instead of 22: fused QKV GEMM, RoPE + cache
-        append, cached attention, O-projection accumulating onto the residual stream in its epilogue, fused gate|up GEMM,
-        SwiGLU, down-projection accumulating onto the residual stream. ``x``'s buffer becomes the block output."""
+        """Same block (reference llm/llama/model.py:142-150) with 9 launches instead of 22: RMSNorm emitting GEMM operand
+        planes, fused QKV GEMM, RoPE + cache append, cached attention emitting operand planes, O-projection accumulating
+        onto the residual stream in its epilogue, RMSNorm -> planes, fused gate|up GEMM, SwiGLU -> planes, down-projection
+        accumulating onto the residual stream. ``x``'s buffer becomes the block output."""
         att = self.attention
         B, L, dim = x.shape
         H, D = att.n_heads, att.head_dim
-        qkv = _fused.linear_cat(att, "_pdn_qkv", self.input_norm(x), (att.Q.weight, att.K.weight, att.V.weight))
+        norm_in, norm_post = self.input_norm, self.post_attn_norm
+        qkv = _fused.linear_cat(att, "_pdn_qkv", _fused.rmsnorm_planes(x, norm_in.weight, norm_in.eps), (att.Q.weight, att.K.weight, att.V.weight))
         with x.device:
             q3 = qkv.data.reshape(B, L, 3, H, D)
         att._rope_tables = att._rope_src()
         parts = [pdn.Tensor(q3[:, :, j], dtype=np.float32, copy=None, device=x.device) for j in range(3)]
-        o = _fused.llama_cached_attention(att, parts[0], parts[1], parts[2], start_pos, mask, 1.0 / math.sqrt(D), ld=3 * dim)
+        o = _fused.llama_cached_attention(att, parts[0], parts[1], parts[2], start_pos, mask, 1.0 / math.sqrt(D), ld=3 * dim, as_planes=True)
         z = _fused.linear_residual_(o, att.O.weight, x)
-        return _fused.linear_residual_(self.ffn.hidden_fast(self.post_attn_norm(z)), self.ffn.down.weight, z)
+        return _fused.linear_residual_(self.ffn.hidden_fast(_fused.rmsnorm_planes(z, norm_post.weight, norm_post.eps)), self.ffn.down.weight, z)
 
 
 class Llama(nn.Module):
@@ -152,7 +156,7 @@ class Llama(nn.Module):
         self.norm = nn.RMSNorm(embed_dim, dtype=dtype)
         self.lm_head = nn.Linear(embed_dim, vocab_size, dtype=dtype)
 
-    def _forward_hidden(self, input_ids, start_pos):
+    def _forward_hidden(self, input_ids, start_pos, final_norm=True):
         L = input_ids.shape[-1]
         h = self.tok_embedding(input_ids)
         if isinstance(start_pos, _fused.DevicePos):  # graph-recorded decode step: the fused kernels index the RoPE tables
@@ -165,7 +169,7 @@ class Llama(nn.Module):
             mask = pdn.Tensor(mask, device=h.device, dtype=h.dtype)
         for layer in self.layers:
             h = layer(h, start_pos, mask, cos, sin)
-        return self.norm(h)
+        return self.norm(h) if final_norm else h
 
     def forward_logits(self, input_ids, start_pos: int = 0):
         return self.lm_head(self._forward_hidden(input_ids, start_pos))
@@ -193,6 +197,18 @@ class Llama(nn.Module):
         h = self._forward_hidden(input_ids, start_pos)
         return self.lm_head(h if h.shape[1] == 1 else h[:, [-1], :])  # logits of the last position, [B, 1, V]
 
+    def _next_ids(self, input_ids, start_pos):
+        """Greedy next token ids [B, 1] = argmax of the last position's logits (reference model.py:266-268). Inference fast
+        path: final RMSNorm emitted as GEMM operand planes and the vocabulary argmax taken in the lm_head GEMM epilogue, so
+        the [B, 32000] logits never reach HBM."""
+        B = input_ids.shape[0]
+        if self.layers[0]._fast_ok(self.norm.weight, input_ids.size) and os.environ.get("PDN_LM_HEAD_ARGMAX", "1") != "0":
+            h = self._forward_hidden(input_ids, start_pos, final_norm=False)
+            last = h if h.shape[1] == 1 else h[:, -1, :]
+            pl = _fused.rmsnorm_planes(last, self.norm.weight, self.norm.eps)
+            return _fused.lm_head_argmax(pl, self.lm_head.weight, self.lm_head.bias)
+        return self(input_ids, start_pos)[:, -1, :].argmax(-1, True)
+
     def _graph_decode_ok(self, ids) -> bool:
         return (os.environ.get("PDN_DECODE_GRAPH", "1") != "0" and ids.device.is_cuda and not self._train
                 and not pdn.autograd.is_grad_enable() and self.freqs_cos.dtype == np.float32
@@ -211,9 +227,9 @@ class Llama(nn.Module):
         try:
             for i, curr_pos in enumerate(range(L, max_new_tokens)):
                 if i == 0:  # prefill
-                    next_id = self(input_ids, 0)[:, -1, :].argmax(-1, True)
+                    next_id = self._next_ids(input_ids, 0)
                 elif i == 1 or not self._graph_decode_ok(next_id):  # eager decode step (also warms caches for the capture)
-                    next_id = self(next_id, curr_pos)[:, -1, :].argmax(-1, True)
+                    next_id = self._next_ids(next_id, curr_pos)
                 else:
                     assert curr_pos + 1 <= self.max_seq_len, "generation runs past the KV cache"
                     if graph is None:
@@ -223,7 +239,7 @@ class Llama(nn.Module):
                             graph = pdn.cuda.Graph()
                             graph.begin()
                             try:
-                                nid = self(ids_buf, pos)[:, -1, :].argmax(-1, True)
+                                nid = self._next_ids(ids_buf, pos)
                                 ids_buf[...] = nid  # feeds the next replay
                                 pos.tensor += 1
                             finally:
