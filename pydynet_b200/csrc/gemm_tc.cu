@@ -177,35 +177,33 @@ template <int BN>
 struct TcCfg {
   static constexpr int kStageBytes = 2 * (TC_BM * TC_BK * 2) + 2 * (BN * TC_BK * 2);  // Ahi, Alo, Bhi, Blo
   static constexpr int kStages = (BN == 64) ? 4 : ((BN == 128) ? 3 : 2);
-  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
-  static constexpr int kTmemCols = BN;  // fp32 accumulator columns (power of two >= 32)
+  static constexpr int kEpiBytes = 4 * 32 * 33 * 4;  // per-epilogue-warp 32x33 fp32 transpose tile
+  static constexpr int kSmemBytes = kStages * kStageBytes + kEpiBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int kTmemCols = 2 * BN;  // two fp32 accumulators: the epilogue of tile i overlaps the MMAs of tile i+1
 };
 
-
+// Persistent kernel: each CTA walks output tiles t = blockIdx.x, blockIdx.x + gridDim.x, ...; tile index decodes to
+// (n_blk fastest, m_blk, batch/split) so CTAs running at the same time share A rows in L2.
+//   warp 0     TMA producer   (smem ring: full/empty mbarriers, runs ahead across tile boundaries)
+//   warp 1     MMA issuer     (one elected lane; accumulator ping-pong in TMEM: tmem_full/tmem_empty mbarriers)
+//   warp 2     TMEM allocator
+//   warps 4-7  epilogue       (tcgen05.ld -> +bias -> smem transpose -> coalesced stores | NCHW scatter | split-K atomics | argmax)
 template <int BN>
 __global__ void __launch_bounds__(256, 1) k_gemm_tc(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
-                                                   TcArgs g) {
+                                                   TcArgs g, int n_tiles_n, int n_tiles_m, long long total_tiles) {
   using Cfg = TcCfg<BN>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t*  smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-  uint64_t* full_bar = (uint64_t*)(smem + Cfg::kStages * Cfg::kStageBytes);
+  float*    epi_smem = (float*)(smem + Cfg::kStages * Cfg::kStageBytes);
+  uint64_t* full_bar = (uint64_t*)(smem + Cfg::kStages * Cfg::kStageBytes + Cfg::kEpiBytes);
   uint64_t* empty_bar = full_bar + Cfg::kStages;
-  uint64_t* accum_bar = empty_bar + Cfg::kStages;
-  uint32_t* tmem_slot = (uint32_t*)(accum_bar + 1);
+  uint64_t* tfull_bar = empty_bar + Cfg::kStages;  // [2] accumulator ready for the epilogue
+  uint64_t* tempty_bar = tfull_bar + 2;            // [2] accumulator drained by the epilogue
+  uint32_t* tmem_slot = (uint32_t*)(tempty_bar + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int n_blk = blockIdx.x, m_blk = blockIdx.y;
-  int64_t   z = blockIdx.z;
-  const int split = (int)(z % g.splits); z /= g.splits;
-  const int64_t i2 = z % g.nb[2]; z /= g.nb[2];
-  const int64_t i1 = z % g.nb[1]; z /= g.nb[1];
-  const int64_t i0 = z;
-  const int     a_batch = (int)(i0 * g.a_pbs[0] + i1 * g.a_pbs[1] + i2 * g.a_pbs[2]);
-  const int     b_batch = (int)(i0 * g.b_pbs[0] + i1 * g.b_pbs[1] + i2 * g.b_pbs[2]);
-  const int     all_kb = (int)((g.K + TC_BK - 1) / TC_BK);
-  const int     kb_per = (all_kb + g.splits - 1) / g.splits;
-  const int     kb_begin = split * kb_per;
-  const int     num_kb = max(0, min(all_kb, kb_begin + kb_per) - kb_begin);  // may be 0 for trailing splits
+  const int all_kb = (int)((g.K + TC_BK - 1) / TC_BK);
+  const int kb_per = (all_kb + g.splits - 1) / g.splits;  // the host guarantees every split owns >= 1 k-block
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&mapA);
@@ -216,7 +214,10 @@ __global__ void __launch_bounds__(256, 1) k_gemm_tc(const __grid_constant__ CUte
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
     }
-    mbar_init(accum_bar, 1);
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&tfull_bar[a], 1);
+      mbar_init(&tempty_bar[a], 4);  // one arrival per epilogue warp
+    }
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc(tmem_slot, Cfg::kTmemCols);
@@ -225,80 +226,112 @@ __global__ void __launch_bounds__(256, 1) k_gemm_tc(const __grid_constant__ CUte
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
+  // tile -> coordinates
+  auto decode = [&](long long t, int& n_blk, int& m_blk, int& split, int64_t& i0, int64_t& i1, int64_t& i2) {
+    n_blk = (int)(t % n_tiles_n); t /= n_tiles_n;
+    m_blk = (int)(t % n_tiles_m); t /= n_tiles_m;
+    split = (int)(t % g.splits); t /= g.splits;
+    i2 = t % g.nb[2]; t /= g.nb[2];
+    i1 = t % g.nb[1]; t /= g.nb[1];
+    i0 = t;
+  };
+
   if (warp == 0) {
     // ===== TMA producer =====
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int kb = 0; kb < num_kb; ++kb) {
-        mbar_wait(&empty_bar[stage], phase ^ 1);
-        uint8_t* st = smem + stage * Cfg::kStageBytes;
-        mbar_expect_tx(&full_bar[stage], Cfg::kStageBytes);
-        const int k = (kb_begin + kb) * TC_BK;
-        tma_load_4d(&mapA, &full_bar[stage], st, k, m_blk * TC_BM, 0, a_batch);
-        tma_load_4d(&mapA, &full_bar[stage], st + TC_BM * TC_BK * 2, k, m_blk * TC_BM, 1, a_batch);
-        tma_load_4d(&mapB, &full_bar[stage], st + 2 * TC_BM * TC_BK * 2, k, n_blk * BN, 0, b_batch);
-        tma_load_4d(&mapB, &full_bar[stage], st + 2 * TC_BM * TC_BK * 2 + BN * TC_BK * 2, k, n_blk * BN, 1, b_batch);
-        if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
+      for (long long t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+        int n_blk, m_blk, split; int64_t i0, i1, i2;
+        decode(t, n_blk, m_blk, split, i0, i1, i2);
+        const int a_batch = (int)(i0 * g.a_pbs[0] + i1 * g.a_pbs[1] + i2 * g.a_pbs[2]);
+        const int b_batch = (int)(i0 * g.b_pbs[0] + i1 * g.b_pbs[1] + i2 * g.b_pbs[2]);
+        const int kb_begin = split * kb_per;
+        const int num_kb = min(all_kb, kb_begin + kb_per) - kb_begin;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* st = smem + stage * Cfg::kStageBytes;
+          mbar_expect_tx(&full_bar[stage], Cfg::kStageBytes);
+          const int k = (kb_begin + kb) * TC_BK;
+          tma_load_4d(&mapA, &full_bar[stage], st, k, m_blk * TC_BM, 0, a_batch);
+          tma_load_4d(&mapA, &full_bar[stage], st + TC_BM * TC_BK * 2, k, m_blk * TC_BM, 1, a_batch);
+          tma_load_4d(&mapB, &full_bar[stage], st + 2 * TC_BM * TC_BK * 2, k, n_blk * BN, 0, b_batch);
+          tma_load_4d(&mapB, &full_bar[stage], st + 2 * TC_BM * TC_BK * 2 + BN * TC_BK * 2, k, n_blk * BN, 1, b_batch);
+          if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
+        }
       }
     }
   } else if (warp == 1) {
     // ===== MMA issuer (single elected lane) =====
     if (lane == 0) {
       constexpr uint32_t idesc = make_idesc_bf16(TC_BM, BN);
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int kb = 0; kb < num_kb; ++kb) {
-        mbar_wait(&full_bar[stage], phase);
+      int stage = 0, acc = 0;
+      uint32_t phase = 0, acc_phase = 0;
+      for (long long t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+        int n_blk, m_blk, split; int64_t i0, i1, i2;
+        decode(t, n_blk, m_blk, split, i0, i1, i2);
+        const int kb_begin = split * kb_per;
+        const int num_kb = min(all_kb, kb_begin + kb_per) - kb_begin;
+        mbar_wait(&tempty_bar[acc], acc_phase ^ 1);  // the epilogue has drained this accumulator (passes on first use)
         tc_fence_after();
-        const uint32_t sa = smem_u32(smem + stage * Cfg::kStageBytes);
-        const uint64_t d_ahi = make_smem_desc_sw128(sa);
-        const uint64_t d_alo = make_smem_desc_sw128(sa + TC_BM * TC_BK * 2);
-        const uint64_t d_bhi = make_smem_desc_sw128(sa + 2 * TC_BM * TC_BK * 2);
-        const uint64_t d_blo = make_smem_desc_sw128(sa + 2 * TC_BM * TC_BK * 2 + BN * TC_BK * 2);
+        const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BN);
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * Cfg::kStageBytes);
+          const uint64_t d_ahi = make_smem_desc_sw128(sa);
+          const uint64_t d_alo = make_smem_desc_sw128(sa + TC_BM * TC_BK * 2);
+          const uint64_t d_bhi = make_smem_desc_sw128(sa + 2 * TC_BM * TC_BK * 2);
+          const uint64_t d_blo = make_smem_desc_sw128(sa + 2 * TC_BM * TC_BK * 2 + BN * TC_BK * 2);
 #pragma unroll
-        for (int k = 0; k < TC_BK / 16; ++k) {
-          const uint64_t adv = (uint64_t)((k * 16 * 2) >> 4);  // 32 B per UMMA_K step inside the swizzle span
-          // small cross terms first, then the leading term
-          umma_bf16(tmem_base, d_alo + adv, d_bhi + adv, idesc, (kb | k) ? 1u : 0u);
-          umma_bf16(tmem_base, d_ahi + adv, d_blo + adv, idesc, 1u);
-          umma_bf16(tmem_base, d_ahi + adv, d_bhi + adv, idesc, 1u);
+          for (int k = 0; k < TC_BK / 16; ++k) {
+            const uint64_t adv = (uint64_t)((k * 16 * 2) >> 4);  // 32 B per UMMA_K step inside the swizzle span
+            // small cross terms first, then the leading term
+            umma_bf16(tmem_d, d_alo + adv, d_bhi + adv, idesc, (kb | k) ? 1u : 0u);
+            umma_bf16(tmem_d, d_ahi + adv, d_blo + adv, idesc, 1u);
+            umma_bf16(tmem_d, d_ahi + adv, d_bhi + adv, idesc, 1u);
+          }
+          umma_commit(&empty_bar[stage]);  // frees this smem stage once the MMAs above have read it
+          if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
         }
-        umma_commit(&empty_bar[stage]);  // frees this smem stage once the MMAs above have read it
-        if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
+        umma_commit(&tfull_bar[acc]);  // accumulator complete
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
-      if (num_kb > 0) umma_commit(accum_bar);  // accumulator complete
     }
   } else if (warp >= 4) {
     // ===== epilogue: TMEM -> registers -> (+bias, +C) -> global =====
     const int q = warp & 3;  // TMEM lane quarter this warp may access
-    if (num_kb > 0) {
-      mbar_wait(accum_bar, 0);
-      tc_fence_after();
-    }
-    const int64_t row = (int64_t)m_blk * TC_BM + q * 32 + lane;
-    float*        cbase = g.C + i0 * g.c_bs[0] + i1 * g.c_bs[1] + i2 * g.c_bs[2];
-    float*        crow = cbase + row * g.ldc;
-    int64_t       img = 0, pix = 0;
-    if (g.nchw_hw > 0) { img = row / g.nchw_hw; pix = row - img * g.nchw_hw; }
+    float*    stg = epi_smem + q * (32 * 33);
+    int       acc = 0;
+    uint32_t  acc_phase = 0;
     const bool atomic = g.splits > 1;
-    const bool add_bias = g.bias != nullptr && split == 0;
-    if (num_kb > 0 || (!atomic && !g.accumulate)) {
+    for (long long t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+      int n_blk, m_blk, split; int64_t i0, i1, i2;
+      decode(t, n_blk, m_blk, split, i0, i1, i2);
+      mbar_wait(&tfull_bar[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BN) + ((uint32_t)(q * 32) << 16);
       const int64_t row0 = (int64_t)m_blk * TC_BM + q * 32;
-      float*        stg = reinterpret_cast<float*>(smem) + (warp - 4) * (32 * 33);  // pipeline stages are idle by now
-      float         best_v = -INFINITY;
-      long long     best_i = (long long)n_blk * BN;
+      const int64_t row = row0 + lane;
+      float*        cbase = g.C + i0 * g.c_bs[0] + i1 * g.c_bs[1] + i2 * g.c_bs[2];
+      float*        crow = cbase + row * g.ldc;
+      int64_t       img = 0, pix = 0;
+      if (g.nchw_hw > 0) { img = row / g.nchw_hw; pix = row - img * g.nchw_hw; }
+      const bool add_bias = g.bias != nullptr && split == 0;
+      float      best_v = -INFINITY;
+      long long  best_i = (long long)n_blk * BN;
 #pragma unroll 1
       for (int c0 = 0; c0 < BN; c0 += 32) {
         const int64_t col0 = (int64_t)n_blk * BN + c0;
         if (col0 >= g.N) break;  // uniform across the CTA
         float v[32];
-        if (num_kb > 0) {
-          tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
-          tmem_ld_wait();
-        } else {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = 0.f;
+        tmem_ld_32x32(tmem_d + (uint32_t)c0, v);
+        tmem_ld_wait();
+        if (c0 + 32 >= BN || col0 + 32 >= g.N) {
+          // last chunk of this tile is in registers: hand the accumulator back to the MMA warp
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tempty_bar[acc]);
         }
         if (add_bias) {
 #pragma unroll
@@ -330,8 +363,7 @@ __global__ void __launch_bounds__(256, 1) k_gemm_tc(const __grid_constant__ CUte
           }
         } else {
           // row-major C: transpose the 32x32 chunk through shared memory so that every store instruction writes one
-          // 128-byte row segment (a thread owns a ROW of the accumulator, which would otherwise give 32 scattered 4-byte
-          // or 16-byte stores per instruction)
+          // 128-byte row segment (a thread owns a ROW of the accumulator, which would otherwise give 32 scattered stores)
 #pragma unroll
           for (int j = 0; j < 32; ++j) stg[lane * 33 + j] = v[j];
           __syncwarp();
@@ -357,9 +389,10 @@ __global__ void __launch_bounds__(256, 1) k_gemm_tc(const __grid_constant__ CUte
         }
       }
       if (g.amax_val && row < g.M) {
-        g.amax_val[row * gridDim.x + n_blk] = best_v;
-        g.amax_idx[row * gridDim.x + n_blk] = best_i;
+        g.amax_val[row * n_tiles_n + n_blk] = best_v;
+        g.amax_idx[row * n_tiles_n + n_blk] = best_i;
       }
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
   }
   tc_fence_before();
@@ -470,10 +503,11 @@ static int launch_tc(const CUtensorMap& mA, const CUtensorMap& mB, const TcArgs&
     PDN_CUDA(cudaFuncSetAttribute(k_gemm_tc<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
     attr_set = true;
   }
-  int64_t nbatch = t.nb[0] * t.nb[1] * t.nb[2] * t.splits;
-  PDN_CHECK(nbatch <= 65535, "gemm_tc: batch x split count %lld exceeds the grid", (long long)nbatch);
-  dim3    grd((unsigned)((t.N + BN - 1) / BN), (unsigned)((t.M + TC_BM - 1) / TC_BM), (unsigned)nbatch);
-  k_gemm_tc<BN><<<grd, 256, Cfg::kSmemBytes, stream()>>>(mA, mB, t);
+  const int64_t n_tiles_n = (t.N + BN - 1) / BN, n_tiles_m = (t.M + TC_BM - 1) / TC_BM;
+  const int64_t total = n_tiles_n * n_tiles_m * t.nb[0] * t.nb[1] * t.nb[2] * t.splits;
+  PDN_CHECK(n_tiles_n <= 0x7fffffff && n_tiles_m <= 0x7fffffff, "gemm_tc: too many tiles");
+  const int64_t ctas = total < sm_count() ? total : sm_count();  // persistent: one CTA per SM walks the tile list
+  k_gemm_tc<BN><<<(unsigned)ctas, 256, Cfg::kSmemBytes, stream()>>>(mA, mB, t, (int)n_tiles_n, (int)n_tiles_m, (long long)total);
   PDN_LAUNCHED("gemm_tc");
   return 0;
 }
@@ -482,6 +516,7 @@ static int launch_tc(const CUtensorMap& mA, const CUtensorMap& mB, const TcArgs&
 // splits <= 0 picks a split-K factor that fills the SMs when the tile grid is small and K is long.
 int gemm_tc_packed(const PackedOperand& A, const PackedOperand& B, TcArgs t, int splits, int* n_tiles_out) {
   PDN_TRY(get_encode_fn());
+  PDN_CHECK(t.K > 0 && t.M > 0 && t.N > 0, "gemm_tc: empty product (M=%lld N=%lld K=%lld)", (long long)t.M, (long long)t.N, (long long)t.K);
   const int64_t nbatch = t.nb[0] * t.nb[1] * t.nb[2];
   const int64_t m_tiles = (t.M + TC_BM - 1) / TC_BM;
   auto tiles_for = [&](int bn) { return m_tiles * ((t.N + bn - 1) / bn) * nbatch; };
@@ -501,8 +536,11 @@ int gemm_tc_packed(const PackedOperand& A, const PackedOperand& B, TcArgs t, int
       int64_t cap = num_kb / 4;
       splits = (int)(want < cap ? want : cap);
       if (splits < 1) splits = 1;
-      if (nbatch * splits > 65535) splits = 1;
     }
+  }
+  if (splits > 1) {  // every split must own at least one k-block (the kernel's barriers assume it)
+    const int kb_per = (num_kb + splits - 1) / splits;
+    splits = (num_kb + kb_per - 1) / kb_per;
   }
   t.splits = splits;
   if (splits > 1 && !t.accumulate) {
