@@ -1,0 +1,426 @@
+// attention_tc.cu — softmax(q kᵀ·scale + mask)·v forward AND backward on the Blackwell tensor cores, scores never in HBM.
+//
+// The reference materialises the [B,H,Lq,Lk] score tensor and ≥5 same-sized temporaries (llm/llama/model.py:112-121,
+// examples/pydynet/transformer.py:93-104: 1.07 GB each at BASELINE config 4). Here one kernel template serves five passes
+// that all have the same shape — "score MMA(s) into TMEM → element-wise in registers → one bf16 hi/lo operand tile into
+// swizzled shared memory → accumulate MMA into TMEM":
+//     LSE  rows = queries   S = Q·Kᵀ                      row-wise log-sum-exp (online), nothing accumulated
+//     FWD  rows = queries   S = Q·Kᵀ                      P = exp(S − lse)              O  += P · V
+//     DQ   rows = queries   S = Q·Kᵀ, dP = dO·Vᵀ          dS = P∘(dP − Δ)·scale         dQ += dS · K
+//     DV   rows = keys      Sᵀ = K·Qᵀ                     Pᵀ = exp(Sᵀ − lse)            dV += Pᵀ · dO
+//     DK   rows = keys      Sᵀ = K·Qᵀ, dPᵀ = V·dOᵀ        dSᵀ = Pᵀ∘(dPᵀ − Δ)·scale      dK += dSᵀ · Q
+// Because lse is known before P is formed (LSE pass first), no accumulator is ever rescaled; the price is recomputing S.
+// Every MMA operand is K-major: the transposed operands (Vᵀ, Kᵀ, Qᵀ, dOᵀ as [d][seq]) come from the strided pack kernel,
+// and P / dS are written by the softmax warps directly in the 128-byte-swizzled layout tcgen05 expects. fp32 parity comes
+// from the same BF16x3 split as the GEMM (hi·hi + hi·lo + lo·hi), applied to P/dS as well.
+//
+// CTA = one 128-row tile of one (batch, head); warp 0 TMA producer (2-stage ring over 64-column tiles), warp 1 MMA issuer,
+// warp 2 TMEM allocator, warps 4-7 = 128 softmax threads (one row each: row max / sum need no shuffles at all).
+#include "common.cuh"
+#include "gemm_tc.h"
+#include "tc_ptx.cuh"
+#include <cudaTypedefs.h>
+#include <math.h>
+
+namespace pdn {
+
+enum { AT_LSE = 0, AT_FWD = 1, AT_DQ = 2, AT_DV = 3, AT_DK = 4 };
+constexpr int AT_R = 128;  // row tile
+constexpr int AT_C = 64;   // column tile
+constexpr int AT_KA = 2 * AT_R * 64 * 2;  // resident row operand, hi + lo: 32 KB
+constexpr int AT_KB = 2 * AT_C * 64 * 2;  // one column-tile operand, hi + lo: 16 KB
+constexpr int AT_KP = 2 * AT_R * AT_C * 2;  // P / dS tile, hi + lo: 32 KB
+
+struct AtArgs {
+  int64_t rows, cols;  // (Lq, Lk) in the query-row passes, (Lk, Lq) in the key-row passes
+  int64_t H;
+  int     D;           // real head dim (<= 64)
+  float   scale;
+  const float* mask;   // additive, element (b, query, key) at b*mask_bs + query*mask_qs + key ; nullptr = none
+  int64_t mask_bs, mask_qs;
+  const float* lse;    // [BH][Lq] (input of FWD / DQ / DV / DK)
+  const float* delta;  // [BH][Lq] Σ_d dO·O (DQ, DK)
+  float* lse_out;      // [BH][Lq] (LSE)
+  float* out;          // [B, rows, H, D] fp32 (FWD: O, DQ: dQ, DV: dV, DK: dK)
+  int ncol_tiles;
+};
+
+template <int MODE>
+struct AtCfg {
+  static constexpr bool TWO = (MODE == AT_DQ || MODE == AT_DK);
+  static constexpr bool ACC = (MODE != AT_LSE);
+  static constexpr bool TRANS = (MODE == AT_DV || MODE == AT_DK);
+  static constexpr int  kStage = AT_KB * (1 + (TWO ? 1 : 0) + (ACC ? 1 : 0));
+  static constexpr int  kOffStages = AT_KA * (TWO ? 2 : 1);
+  static constexpr int  kOffP = kOffStages + 2 * kStage;
+  static constexpr int  kOffBars = kOffP + (ACC ? 2 * AT_KP : 0);
+  static constexpr int  kSmem = kOffBars + 256 + 1024;
+};
+
+// 16-byte chunk c (8 bf16) of row r in a K-major [rows x 64] bf16 tile with 128-byte swizzle (what TMA writes / UMMA reads)
+__device__ __forceinline__ uint32_t sw128_off(int r, int c) { return (uint32_t)((r >> 3) * 1024 + (r & 7) * 128 + ((c ^ (r & 7)) << 4)); }
+
+__device__ __forceinline__ void umma3(uint32_t d, uint64_t ahi, uint64_t alo, uint64_t bhi, uint64_t blo, uint32_t idesc, bool first_clears) {
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const uint64_t adv = (uint64_t)((k * 16 * 2) >> 4);
+    umma_bf16(d, alo + adv, bhi + adv, idesc, (first_clears && k == 0) ? 0u : 1u);
+    umma_bf16(d, ahi + adv, blo + adv, idesc, 1u);
+    umma_bf16(d, ahi + adv, bhi + adv, idesc, 1u);
+  }
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(256, 1)
+k_attn_tc(const __grid_constant__ CUtensorMap mA1, const __grid_constant__ CUtensorMap mA2, const __grid_constant__ CUtensorMap mB1,
+          const __grid_constant__ CUtensorMap mB2, const __grid_constant__ CUtensorMap mB3, AtArgs a) {
+  using Cfg = AtCfg<MODE>;
+  constexpr bool TWO = Cfg::TWO, ACC = Cfg::ACC, TRANS = Cfg::TRANS;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t*  smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint64_t* bars = (uint64_t*)(smem + Cfg::kOffBars);
+  uint64_t *a_full = bars, *b_full = bars + 1, *b_empty = bars + 3, *s_full = bars + 5, *s_empty = bars + 7, *p_full = bars + 9,
+           *p_empty = bars + 11, *acc_full = bars + 13;
+  uint32_t* tmem_slot = (uint32_t*)(bars + 14);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int bh = blockIdx.y;
+  const int64_t row0 = (int64_t)blockIdx.x * AT_R;
+  const int n = a.ncol_tiles;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&mA1);
+    tma_prefetch_desc(&mB1);
+    if (TWO) { tma_prefetch_desc(&mA2); tma_prefetch_desc(&mB2); }
+    if (ACC) tma_prefetch_desc(&mB3);
+  }
+  if (warp == 1 && lane == 0) {
+    mbar_init(a_full, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&b_full[i], 1);
+      mbar_init(&b_empty[i], 1);
+      mbar_init(&s_full[i], 1);
+      mbar_init(&s_empty[i], 4);
+      mbar_init(&p_full[i], 4);
+      mbar_init(&p_empty[i], 1);
+    }
+    mbar_init(acc_full, 1);
+    fence_barrier_init();
+  }
+  constexpr uint32_t kTmemCols = ACC ? 512u : 128u;  // LSE needs only the two score buffers (lets several CTAs share an SM)
+  if (warp == 2) tmem_alloc(tmem_slot, kTmemCols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  // TMEM columns: S1[2] at 0/64, S2[2] at 128/192, accumulator at 256
+  auto tmS1 = [&](int i) { return tmem_base + (uint32_t)(i * 64); };
+  auto tmS2 = [&](int i) { return tmem_base + (uint32_t)(128 + i * 64); };
+  const uint32_t tmACC = tmem_base + 256u;
+
+  if (warp == 0) {
+    // ===== TMA producer =====
+    if (lane == 0) {
+      mbar_expect_tx(a_full, AT_KA * (TWO ? 2 : 1));
+      tma_load_4d(&mA1, a_full, smem, 0, (int)row0, 0, bh);
+      tma_load_4d(&mA1, a_full, smem + AT_KA / 2, 0, (int)row0, 1, bh);
+      if (TWO) {
+        tma_load_4d(&mA2, a_full, smem + AT_KA, 0, (int)row0, 0, bh);
+        tma_load_4d(&mA2, a_full, smem + AT_KA + AT_KA / 2, 0, (int)row0, 1, bh);
+      }
+      for (int j = 0; j < n; ++j) {
+        const int st = j & 1;
+        mbar_wait(&b_empty[st], (uint32_t)(((j >> 1) & 1) ^ 1));
+        uint8_t* sb = smem + Cfg::kOffStages + st * Cfg::kStage;
+        mbar_expect_tx(&b_full[st], Cfg::kStage);
+        const int col0 = j * AT_C;
+        tma_load_4d(&mB1, &b_full[st], sb, 0, col0, 0, bh);
+        tma_load_4d(&mB1, &b_full[st], sb + AT_KB / 2, 0, col0, 1, bh);
+        int off = AT_KB;
+        if (TWO) {
+          tma_load_4d(&mB2, &b_full[st], sb + off, 0, col0, 0, bh);
+          tma_load_4d(&mB2, &b_full[st], sb + off + AT_KB / 2, 0, col0, 1, bh);
+          off += AT_KB;
+        }
+        if (ACC) {  // [d rows][column items along k]
+          tma_load_4d(&mB3, &b_full[st], sb + off, col0, 0, 0, bh);
+          tma_load_4d(&mB3, &b_full[st], sb + off + AT_KB / 2, col0, 0, 1, bh);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer =====
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(AT_R, AT_C);  // M = 128, N = 64 for the score and the accumulate MMAs alike
+      mbar_wait(a_full, 0);
+      tc_fence_after();
+      const uint32_t sA = smem_u32(smem);
+      const uint64_t a1hi = make_smem_desc_sw128(sA), a1lo = make_smem_desc_sw128(sA + AT_KA / 2);
+      const uint64_t a2hi = make_smem_desc_sw128(sA + AT_KA), a2lo = make_smem_desc_sw128(sA + AT_KA + AT_KA / 2);
+      auto score = [&](int j) {
+        const int st = j & 1, sb = j & 1;
+        mbar_wait(&b_full[st], (uint32_t)((j >> 1) & 1));
+        mbar_wait(&s_empty[sb], (uint32_t)(((j >> 1) & 1) ^ 1));
+        tc_fence_after();
+        const uint32_t sB = smem_u32(smem + Cfg::kOffStages + st * Cfg::kStage);
+        umma3(tmS1(sb), a1hi, a1lo, make_smem_desc_sw128(sB), make_smem_desc_sw128(sB + AT_KB / 2), idesc, true);
+        if (TWO) umma3(tmS2(sb), a2hi, a2lo, make_smem_desc_sw128(sB + AT_KB), make_smem_desc_sw128(sB + AT_KB + AT_KB / 2), idesc, true);
+        umma_commit(&s_full[sb]);
+        if (!ACC) umma_commit(&b_empty[st]);
+      };
+      auto accumulate = [&](int j) {
+        const int st = j & 1, pb = j & 1;
+        mbar_wait(&p_full[pb], (uint32_t)((j >> 1) & 1));
+        tc_fence_after();
+        const uint32_t sP = smem_u32(smem + Cfg::kOffP + pb * AT_KP);
+        const uint32_t sB3 = smem_u32(smem + Cfg::kOffStages + st * Cfg::kStage + AT_KB * (TWO ? 2 : 1));
+        umma3(tmACC, make_smem_desc_sw128(sP), make_smem_desc_sw128(sP + AT_KP / 2), make_smem_desc_sw128(sB3),
+              make_smem_desc_sw128(sB3 + AT_KB / 2), idesc, j == 0);
+        umma_commit(&p_empty[pb]);
+        umma_commit(&b_empty[st]);
+      };
+      if (n > 0) score(0);
+      for (int j = 0; j < n; ++j) {
+        if (j + 1 < n) score(j + 1);
+        if (ACC) accumulate(j);
+      }
+      if (ACC) umma_commit(acc_full);
+    }
+  } else if (warp >= 4) {
+    // ===== softmax / epilogue: thread = one row of the tile =====
+    const int q = warp & 3, r = q * 32 + lane;
+    const int64_t gr = row0 + r;
+    const bool    row_ok = gr < a.rows;
+    const int64_t b = bh / a.H, h = bh % a.H;
+    const uint32_t lane_sel = (uint32_t)(q * 32) << 16;
+    const int64_t Lq = TRANS ? a.cols : a.rows;
+    float lse_r = 0.f, delta_r = 0.f;
+    if (!TRANS && MODE != AT_LSE && row_ok) {
+      lse_r = a.lse[(int64_t)bh * Lq + gr];
+      if (TWO) delta_r = a.delta[(int64_t)bh * Lq + gr];
+    }
+    float m_run = -INFINITY, l_run = 0.f;
+    for (int j = 0; j < n; ++j) {
+      const int sb = j & 1;
+      mbar_wait(&s_full[sb], (uint32_t)((j >> 1) & 1));
+      tc_fence_after();
+      float s[64], dp[TWO ? 64 : 1];
+      tmem_ld_32x32(tmS1(sb) + lane_sel, s);
+      tmem_ld_32x32(tmS1(sb) + lane_sel + 32u, s + 32);
+      if (TWO) {
+        tmem_ld_32x32(tmS2(sb) + lane_sel, dp);
+        tmem_ld_32x32(tmS2(sb) + lane_sel + 32u, dp + 32);
+      }
+      tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&s_empty[sb]);
+      const int64_t col0 = (int64_t)j * AT_C;
+      // x = s*scale + mask ; invalid columns -> -inf
+#pragma unroll
+      for (int e = 0; e < 64; ++e) {
+        const int64_t c = col0 + e;
+        float x = s[e] * a.scale;
+        if (a.mask) {
+          const int64_t qi = TRANS ? c : gr, ki = TRANS ? gr : c;
+          if (c < a.cols && row_ok) x += __ldg(a.mask + b * a.mask_bs + qi * a.mask_qs + ki);
+        }
+        s[e] = (c < a.cols) ? x : -INFINITY;
+      }
+      if (MODE == AT_LSE) {
+        float tm = -INFINITY;
+#pragma unroll
+        for (int e = 0; e < 64; ++e) tm = fmaxf(tm, s[e]);
+        const float mn = fmaxf(m_run, tm);
+        if (mn != -INFINITY) {
+          float sum = 0.f;
+#pragma unroll
+          for (int e = 0; e < 64; ++e) sum += __expf(s[e] - mn);
+          l_run = l_run * __expf(m_run - mn) + sum;
+          m_run = mn;
+        }
+      } else {
+        // value that becomes the A operand of the accumulate MMA
+#pragma unroll
+        for (int e = 0; e < 64; ++e) {
+          const int64_t c = col0 + e;
+          float lse_e = lse_r, delta_e = delta_r;
+          if (TRANS) {
+            const int64_t ci = c < a.cols ? c : 0;
+            lse_e = __ldg(a.lse + (int64_t)bh * Lq + ci);
+            if (TWO) delta_e = __ldg(a.delta + (int64_t)bh * Lq + ci);
+          }
+          float p = (s[e] == -INFINITY || !row_ok) ? 0.f : __expf(s[e] - lse_e);
+          if (TWO) p = p * (dp[e] - delta_e) * a.scale;
+          s[e] = p;
+        }
+        const int pb = j & 1;
+        mbar_wait(&p_empty[pb], (uint32_t)(((j >> 1) & 1) ^ 1));
+        uint8_t* ph = smem + Cfg::kOffP + pb * AT_KP;
+        uint8_t* pl = ph + AT_KP / 2;
+#pragma unroll
+        for (int c8 = 0; c8 < 8; ++c8) {
+          uint32_t hw[4], lw[4];
+#pragma unroll
+          for (int t = 0; t < 4; ++t) {
+            const float v0 = s[c8 * 8 + 2 * t], v1 = s[c8 * 8 + 2 * t + 1];
+            const __nv_bfloat16 h0 = __float2bfloat16_rn(v0), h1 = __float2bfloat16_rn(v1);
+            const __nv_bfloat16 l0 = __float2bfloat16_rn(v0 - __bfloat162float(h0)), l1 = __float2bfloat16_rn(v1 - __bfloat162float(h1));
+            hw[t] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+            lw[t] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+          }
+          const uint32_t off = sw128_off(r, c8);
+          *reinterpret_cast<uint4*>(ph + off) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+          *reinterpret_cast<uint4*>(pl + off) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+        }
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&p_full[pb]);
+      }
+    }
+    if (MODE == AT_LSE) {
+      if (row_ok) a.lse_out[(int64_t)bh * a.rows + gr] = m_run + logf(l_run);
+    } else {
+      mbar_wait(acc_full, 0);
+      tc_fence_after();
+      float o[64];
+      tmem_ld_32x32(tmACC + lane_sel, o);
+      tmem_ld_32x32(tmACC + lane_sel + 32u, o + 32);
+      tmem_ld_wait();
+      if (row_ok) {
+        float* dst = a.out + ((b * a.rows + gr) * a.H + h) * a.D;
+#pragma unroll
+        for (int d = 0; d < 64; ++d)
+          if (d < a.D) dst[d] = o[d];
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc(tmem_base, kTmemCols);
+}
+
+// Δ[bh][q] = Σ_d dO·O over [B, Lq, H, D] contiguous tensors
+__global__ void __launch_bounds__(256) k_attn_delta(const float* __restrict__ g, const float* __restrict__ o, float* __restrict__ delta, int64_t B,
+                                                    int64_t Lq, int64_t H, int D) {
+  const int64_t total = B * Lq * H;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t h = i % H, q = (i / H) % Lq, b = i / (H * Lq);
+    const float *gp = g + i * D, *op = o + i * D;
+    float s = 0.f;
+    for (int d = 0; d < D; ++d) s += gp[d] * op[d];
+    delta[(b * H + h) * Lq + q] = s;
+  }
+}
+
+struct AtOperand {
+  Scratch       buf;
+  PackedOperand op;
+  CUtensorMap   map;
+};
+
+// rows x K fp32 view of a [B, L, H, D]-style tensor given (batch, head, row) strides -> planes [B*H][2][R][Kp] + TMA map
+static int at_pack(AtOperand* o, const float* src, int64_t B, int64_t H, int64_t R, int64_t K, int64_t r_stride, int64_t k_stride, int64_t bs,
+                   int64_t hs, int box_rows) {
+  const int64_t nb[3] = {1, B, H}, st[3] = {0, bs, hs};
+  PDN_TRY(pack_operand_ex(src, R, K, r_stride, k_stride, 0, 0, nb, st, &o->buf, &o->op));
+  // a degenerate batch dimension (B*H == 1) or broadcast strides would collapse the packed batch count; attention always
+  // has distinct (b, h) slices, so the packed batch index is b*H + h whenever the strides are non-zero
+  return tc_make_map(&o->map, o->op.planes, R, K, o->op.Kp, o->op.nbatch, box_rows);
+}
+
+template <int MODE>
+static int at_launch(const CUtensorMap& A1, const CUtensorMap& A2, const CUtensorMap& B1, const CUtensorMap& B2, const CUtensorMap& B3,
+                     const AtArgs& a, int64_t BH) {
+  using Cfg = AtCfg<MODE>;
+  static bool attr = false;
+  if (!attr) {
+    PDN_CUDA(cudaFuncSetAttribute(k_attn_tc<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmem));
+    attr = true;
+  }
+  dim3 grd((unsigned)((a.rows + AT_R - 1) / AT_R), (unsigned)BH);
+  k_attn_tc<MODE><<<grd, 256, Cfg::kSmem, stream()>>>(A1, A2, B1, B2, B3, a);
+  PDN_LAUNCHED("attn_tc");
+  return 0;
+}
+
+static int at_check(int64_t B, int64_t H, int64_t Lq, int64_t Lk, int64_t D, const int64_t* q_str, const int64_t* k_str, const int64_t* v_str) {
+  PDN_CHECK(D >= 1 && D <= 64, "attention_tc: head dim %lld > 64", (long long)D);
+  PDN_CHECK(B * H >= 1 && B * H <= 65535, "attention_tc: batch*heads out of range");
+  PDN_CHECK(Lq >= 1 && Lk >= 1 && Lq <= 0x7fffffff && Lk <= 0x7fffffff, "attention_tc: bad sequence lengths");
+  for (int i = 0; i < 3; ++i) PDN_CHECK(q_str[i] != 0 || (i < 2 && (i == 0 ? B : H) == 1), "attention_tc: broadcast q strides are not supported");
+  (void)k_str; (void)v_str;
+  return 0;
+}
+
+}  // namespace pdn
+
+using namespace pdn;
+
+extern "C" {
+
+int pdn_attention_tc_fwd(const float* q, const float* k, const float* v, const float* mask, float* out, float* lse, int64_t B, int64_t H, int64_t Lq,
+                         int64_t Lk, int64_t D, const int64_t* q_str, const int64_t* k_str, const int64_t* v_str, const int64_t* mask_str,
+                         float scale) {
+  PDN_TRY(ensure_init());
+  PDN_TRY(at_check(B, H, Lq, Lk, D, q_str, k_str, v_str));
+  AtOperand Qp, Kp, Vt;
+  PDN_TRY(at_pack(&Qp, q, B, H, Lq, D, q_str[2], 1, q_str[0], q_str[1], AT_R));
+  PDN_TRY(at_pack(&Kp, k, B, H, Lk, D, k_str[2], 1, k_str[0], k_str[1], AT_C));
+  PDN_TRY(at_pack(&Vt, v, B, H, D, Lk, 1, v_str[2], v_str[0], v_str[1], AT_C));
+  AtArgs a;
+  a.rows = Lq; a.cols = Lk; a.H = H; a.D = (int)D; a.scale = scale;
+  a.mask = mask; a.mask_bs = mask && mask_str ? mask_str[0] : 0; a.mask_qs = mask && mask_str ? mask_str[1] : 0;
+  a.lse = lse; a.delta = nullptr; a.lse_out = lse; a.out = out;
+  a.ncol_tiles = (int)((Lk + AT_C - 1) / AT_C);
+  PDN_TRY((at_launch<AT_LSE>(Qp.map, Qp.map, Kp.map, Kp.map, Kp.map, a, B * H)));
+  PDN_TRY((at_launch<AT_FWD>(Qp.map, Qp.map, Kp.map, Kp.map, Vt.map, a, B * H)));
+  return 0;
+}
+
+int pdn_attention_tc_bwd(const float* q, const float* k, const float* v, const float* mask, const float* out, const float* lse, const float* g_out,
+                         float* dq, float* dk, float* dv, int64_t B, int64_t H, int64_t Lq, int64_t Lk, int64_t D, const int64_t* q_str,
+                         const int64_t* k_str, const int64_t* v_str, const int64_t* mask_str, float scale) {
+  PDN_TRY(ensure_init());
+  PDN_TRY(at_check(B, H, Lq, Lk, D, q_str, k_str, v_str));
+  Scratch sdelta;
+  PDN_TRY(sdelta.alloc((size_t)B * H * Lq * sizeof(float)));
+  k_attn_delta<<<grid_for(B * Lq * H, 256), 256, 0, stream()>>>(g_out, out, (float*)sdelta.p, B, Lq, H, (int)D);
+  PDN_LAUNCHED("attn_delta");
+  const int64_t g_str[3] = {Lq * H * D, D, H * D};  // g_out is [B, Lq, H, D] contiguous
+  AtArgs a;
+  a.H = H; a.D = (int)D; a.scale = scale;
+  a.mask = mask; a.mask_bs = mask && mask_str ? mask_str[0] : 0; a.mask_qs = mask && mask_str ? mask_str[1] : 0;
+  a.lse = lse; a.delta = (const float*)sdelta.p; a.lse_out = nullptr;
+  if (dq) {
+    AtOperand Qp, Kp, dOp, Vp, Kt;
+    PDN_TRY(at_pack(&Qp, q, B, H, Lq, D, q_str[2], 1, q_str[0], q_str[1], AT_R));
+    PDN_TRY(at_pack(&dOp, g_out, B, H, Lq, D, g_str[2], 1, g_str[0], g_str[1], AT_R));
+    PDN_TRY(at_pack(&Kp, k, B, H, Lk, D, k_str[2], 1, k_str[0], k_str[1], AT_C));
+    PDN_TRY(at_pack(&Vp, v, B, H, Lk, D, v_str[2], 1, v_str[0], v_str[1], AT_C));
+    PDN_TRY(at_pack(&Kt, k, B, H, D, Lk, 1, k_str[2], k_str[0], k_str[1], AT_C));
+    a.rows = Lq; a.cols = Lk; a.out = dq; a.ncol_tiles = (int)((Lk + AT_C - 1) / AT_C);
+    PDN_TRY((at_launch<AT_DQ>(Qp.map, dOp.map, Kp.map, Vp.map, Kt.map, a, B * H)));
+  }
+  if (dk || dv) {
+    AtOperand Kp, Qp, Vp, dOp, dOt, Qt;
+    PDN_TRY(at_pack(&Kp, k, B, H, Lk, D, k_str[2], 1, k_str[0], k_str[1], AT_R));
+    PDN_TRY(at_pack(&Qp, q, B, H, Lq, D, q_str[2], 1, q_str[0], q_str[1], AT_C));
+    a.rows = Lk; a.cols = Lq; a.ncol_tiles = (int)((Lq + AT_C - 1) / AT_C);
+    if (dv) {
+      PDN_TRY(at_pack(&dOt, g_out, B, H, D, Lq, 1, g_str[2], g_str[0], g_str[1], AT_C));
+      a.out = dv;
+      PDN_TRY((at_launch<AT_DV>(Kp.map, Kp.map, Qp.map, Qp.map, dOt.map, a, B * H)));
+    }
+    if (dk) {
+      PDN_TRY(at_pack(&Vp, v, B, H, Lk, D, v_str[2], 1, v_str[0], v_str[1], AT_R));
+      PDN_TRY(at_pack(&dOp, g_out, B, H, Lq, D, g_str[2], 1, g_str[0], g_str[1], AT_C));
+      PDN_TRY(at_pack(&Qt, q, B, H, D, Lq, 1, q_str[2], q_str[0], q_str[1], AT_C));
+      a.out = dk;
+      PDN_TRY((at_launch<AT_DK>(Kp.map, Vp.map, Qp.map, dOp.map, Qt.map, a, B * H)));
+    }
+  }
+  return 0;
+}
+
+}  // extern "C"

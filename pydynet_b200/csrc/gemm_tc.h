@@ -2,6 +2,7 @@
 // (conv.cu's im2col gather writes the bf16 hi/lo planes directly instead of materialising an fp32 column matrix).
 #pragma once
 #include "common.cuh"
+#include <cuda.h>
 namespace pdn {
 
 // K-major bf16 planes [nbatch][2 (hi, lo)][R][Kp]; pbs = packed-batch index stride per GEMM batch dim (0 = broadcast)
@@ -27,6 +28,8 @@ struct TcArgs {
 
 int pack_operand_ex(const float* src, int64_t R, int64_t K, int64_t r_stride, int64_t k_stride, int64_t k_inner, int64_t k_outer_stride,
                     const int64_t* nb, const int64_t* bs, Scratch* buf, PackedOperand* out);
+// 4-D TMA map over operand planes [batch][2][R][Kp] (bf16), box = 64 (k) x box_rows x 1 x 1, 128-byte swizzle
+int tc_make_map(CUtensorMap* map, const void* base, int64_t R, int64_t K, int64_t Kp, int64_t nbatch, int box_rows);
 int gemm_tc_packed(const PackedOperand& A, const PackedOperand& B, TcArgs t, int splits, int* n_tiles_out = nullptr);
 
 }  // namespace pdn

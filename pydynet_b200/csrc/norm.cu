@@ -63,31 +63,85 @@ __global__ void __launch_bounds__(256) k_feat_reduce_chan(const float* __restric
   }
 }
 
+// Element-wise passes. The channel of a flat element index needs a division; it is done once per FOUR elements (float4,
+// C*inner and inner are multiples of 4 on this path) and in 32-bit arithmetic (64-bit div/mod made these kernels ALU-bound:
+// 23 % of HBM peak in the first ncu capture, profiles/r1_ncu_summary.md).
+__device__ __forceinline__ uint32_t feat_channel(uint32_t e, uint32_t C, uint32_t inner) { return inner == 1 ? e % C : (e / inner) % C; }
+
+template <bool VEC>
 __global__ void __launch_bounds__(256) k_feat_apply(const float* __restrict__ x, const float* __restrict__ mean, const float* __restrict__ var,
                                                     const float* __restrict__ scale, const float* __restrict__ shift, float* __restrict__ y,
-                                                    int64_t total, int64_t C, int64_t inner, float eps) {
-  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t c = (e / inner) % C;
-    y[e] = (x[e] - mean[c]) * rsqrtf(var[c] + eps) * scale[c] + shift[c];
+                                                    int64_t total, uint32_t C, uint32_t inner, float eps) {
+  if (VEC) {
+    const int64_t n4 = total >> 2;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+      const uint32_t e = (uint32_t)((i << 2) % ((int64_t)C * inner));  // offset inside one [C, inner] slab (< 2^32 checked on the host)
+      const float4   xv = __ldg(reinterpret_cast<const float4*>(x) + i);
+      float4 o;
+      if (inner == 1) {
+        const uint32_t c = e;  // 4 consecutive channels (per-channel vectors are L1-resident: scalar loads, no alignment demand)
+        o.x = (xv.x - mean[c]) * rsqrtf(var[c] + eps) * scale[c] + shift[c];
+        o.y = (xv.y - mean[c + 1]) * rsqrtf(var[c + 1] + eps) * scale[c + 1] + shift[c + 1];
+        o.z = (xv.z - mean[c + 2]) * rsqrtf(var[c + 2] + eps) * scale[c + 2] + shift[c + 2];
+        o.w = (xv.w - mean[c + 3]) * rsqrtf(var[c + 3] + eps) * scale[c + 3] + shift[c + 3];
+      } else {
+        const uint32_t c = e / inner;  // all four elements share a channel (inner % 4 == 0)
+        const float mu = mean[c], rs = rsqrtf(var[c] + eps) * scale[c], sh = shift[c];
+        o.x = (xv.x - mu) * rs + sh; o.y = (xv.y - mu) * rs + sh; o.z = (xv.z - mu) * rs + sh; o.w = (xv.w - mu) * rs + sh;
+      }
+      reinterpret_cast<float4*>(y)[i] = o;
+    }
+  } else {
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+      const int64_t c = (e / inner) % C;
+      y[e] = (x[e] - mean[c]) * rsqrtf(var[c] + eps) * scale[c] + shift[c];
+    }
   }
 }
 
 // dx = scale * rstd * (g - mean(g) - xhat * mean(g * xhat)); mg / mgx arrive already divided by m
+template <bool VEC>
 __global__ void __launch_bounds__(256) k_feat_bwd_dx(const float* __restrict__ x, const float* __restrict__ g, const float* __restrict__ mean,
                                                      const float* __restrict__ var, const float* __restrict__ scale, const float* __restrict__ mg,
-                                                     const float* __restrict__ mgx, float* __restrict__ dx, int64_t total, int64_t C, int64_t inner,
+                                                     const float* __restrict__ mgx, float* __restrict__ dx, int64_t total, uint32_t C, uint32_t inner,
                                                      float eps) {
-  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t c = (e / inner) % C;
-    const float rs = rsqrtf(var[c] + eps);
-    const float xhat = (x[e] - mean[c]) * rs;
-    dx[e] = scale[c] * rs * (g[e] - mg[c] - xhat * mgx[c]);
+  if (VEC) {
+    const int64_t n4 = total >> 2;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+      const uint32_t e = (uint32_t)((i << 2) % ((int64_t)C * inner));
+      const float4   xv = __ldg(reinterpret_cast<const float4*>(x) + i), gv = __ldg(reinterpret_cast<const float4*>(g) + i);
+      const float xs[4] = {xv.x, xv.y, xv.z, xv.w}, gs[4] = {gv.x, gv.y, gv.z, gv.w};
+      float o[4];
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        const uint32_t c = inner == 1 ? e + t : e / inner;
+        const float rs = rsqrtf(var[c] + eps);
+        const float xhat = (xs[t] - mean[c]) * rs;
+        o[t] = scale[c] * rs * (gs[t] - mg[c] - xhat * mgx[c]);
+      }
+      reinterpret_cast<float4*>(dx)[i] = make_float4(o[0], o[1], o[2], o[3]);
+    }
+  } else {
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+      const int64_t c = (e / inner) % C;
+      const float rs = rsqrtf(var[c] + eps);
+      const float xhat = (x[e] - mean[c]) * rs;
+      dx[e] = scale[c] * rs * (g[e] - mg[c] - xhat * mgx[c]);
+    }
   }
 }
 
 __global__ void k_scale_vec(float* a, float* b, float s, int64_t n) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) { a[i] *= s; if (b) b[i] *= s; }
+}
+
+// float4 path: 16-byte aligned tensors, 4 elements never straddle a channel boundary (inner == 1: C % 4 == 0 and the stats
+// vectors are read as float4; inner > 1: inner % 4 == 0), one [C, inner] slab addressable in 32 bits
+static bool feat_vec_ok(const float* a, const float* b, int64_t C, int64_t inner) {
+  if ((((uintptr_t)a) | ((uintptr_t)b)) & 15) return false;
+  if (C * inner >= 0xffffffffLL || C > 0x7fffffff || inner > 0x7fffffff) return false;
+  return inner == 1 ? (C % 4 == 0) : (inner % 4 == 0);
 }
 
 template <int MODE>
@@ -156,7 +210,10 @@ int pdn_bnorm_bwd_dx(const float* x, const float* mean, const float* var, const 
   PDN_TRY(ensure_init());
   const int64_t total = outer * C * inner;
   if (total == 0 || !dx) return 0;
-  k_feat_bwd_dx<<<grid_for(total, 256), 256, 0, stream()>>>(x, g, mean, var, scale, mg, mgx, dx, total, C, inner, eps);
+  if (feat_vec_ok(x, dx, C, inner) && (((uintptr_t)g) & 15) == 0)
+    k_feat_bwd_dx<true><<<grid_for(total / 4, 256), 256, 0, stream()>>>(x, g, mean, var, scale, mg, mgx, dx, total, (uint32_t)C, (uint32_t)inner, eps);
+  else
+    k_feat_bwd_dx<false><<<grid_for(total, 256), 256, 0, stream()>>>(x, g, mean, var, scale, mg, mgx, dx, total, (uint32_t)C, (uint32_t)inner, eps);
   PDN_LAUNCHED("feat_bwd_dx");
   return 0;
 }
@@ -166,7 +223,8 @@ int pdn_bnorm_apply(const float* x, const float* mean, const float* var, const f
   PDN_TRY(ensure_init());
   const int64_t total = outer * C * inner;
   if (total == 0) return 0;
-  k_feat_apply<<<grid_for(total, 256), 256, 0, stream()>>>(x, mean, var, scale, shift, y, total, C, inner, eps);
+  if (feat_vec_ok(x, y, C, inner)) k_feat_apply<true><<<grid_for(total / 4, 256), 256, 0, stream()>>>(x, mean, var, scale, shift, y, total, (uint32_t)C, (uint32_t)inner, eps);
+  else k_feat_apply<false><<<grid_for(total, 256), 256, 0, stream()>>>(x, mean, var, scale, shift, y, total, (uint32_t)C, (uint32_t)inner, eps);
   PDN_LAUNCHED("feat_apply");
   return 0;
 }
@@ -180,7 +238,10 @@ int pdn_bnorm_bwd(const float* x, const float* mean, const float* var, const flo
   // dshift <- mean(g), dscale <- mean(g * xhat) (scaled by 1/m inside the reduction), used by dx, then rescaled to sums
   PDN_TRY((feat_reduce<2>(x, g, mean, var, eps, dshift, dscale, outer, C, inner, 1.f / m)));
   if (dx) {
-    k_feat_bwd_dx<<<grid_for(total, 256), 256, 0, stream()>>>(x, g, mean, var, scale, dshift, dscale, dx, total, C, inner, eps);
+    if (feat_vec_ok(x, dx, C, inner) && (((uintptr_t)g) & 15) == 0)
+      k_feat_bwd_dx<true><<<grid_for(total / 4, 256), 256, 0, stream()>>>(x, g, mean, var, scale, dshift, dscale, dx, total, (uint32_t)C, (uint32_t)inner, eps);
+    else
+      k_feat_bwd_dx<false><<<grid_for(total, 256), 256, 0, stream()>>>(x, g, mean, var, scale, dshift, dscale, dx, total, (uint32_t)C, (uint32_t)inner, eps);
     PDN_LAUNCHED("feat_bwd_dx");
   }
   k_scale_vec<<<(unsigned)((C + 255) / 256), 256, 0, stream()>>>(dshift, dscale, m, C);

@@ -218,9 +218,27 @@ def cross_entropy(logits, target, reduction):
 _ATT_FFMA_LIMIT = 1 << 29  # B*H*Lq*Lk*D multiply-adds served by the one-warp-per-query kernel; larger -> GEMM path
 
 
+_ATT_TC_MIN = 1 << 22  # below this many multiply-adds the warp-per-query kernel's single launch wins
+
+
+def _attention_impl(B, H, Lq, Lk, D) -> str:
+    """'tc' (tcgen05 flash kernels, D <= 64), 'ffma' (warp-per-query kernel, D <= 128) or '' (neither: composite path)."""
+    forced = os.environ.get("PDN_ATTN", "")
+    work = B * H * Lq * Lk * D
+    if forced == "tc" and D <= 64:
+        return "tc"
+    if forced == "ffma" and D <= 128:
+        return "ffma"
+    if D <= 64 and work >= _ATT_TC_MIN and B * H <= 65535:
+        return "tc"
+    if D <= 128 and work <= _ATT_FFMA_LIMIT:
+        return "ffma"
+    return ""
+
+
 def attention_fits(xq, xk) -> bool:
     B, Lq, H, D = xq.shape
-    return D <= 128 and B * H * Lq * xk.shape[1] * D <= _ATT_FFMA_LIMIT
+    return _attention_impl(B, H, Lq, xk.shape[1], D) != ""
 
 
 def _i64(vals):
@@ -252,36 +270,35 @@ def _unit_last(a):
 @fused_op
 def attention(xq, xk, xv, mask, scale):
     """softmax(q kᵀ·scale + mask) v for [B, L, H, D] head-split views; returns [B, Lq, H*D]
-    (llm/llama/model.py:112-121, examples/pydynet/transformer.py:93-104). One kernel forward, one backward."""
+    (llm/llama/model.py:112-121, examples/pydynet/transformer.py:93-104). One fused operator forward, one backward;
+    training-sized problems run on the tensor cores (csrc/attention_tc.cu), small ones on the warp-per-query kernel."""
     with xq.device:
         q, k, v = _unit_last(xq.data), _unit_last(xk.data), _unit_last(xv.data)
         B, Lq, H, D = q.shape
         Lk = k.shape[1]
+        impl = _attention_impl(B, H, Lq, Lk, D)
+        assert impl, "attention: shape not supported by the fused kernels (check attention_fits first)"
         out, lse = _empty((B, Lq, H, D)), _empty((B, H, Lq))
         keep, mptr, mstr = _mask_args(mask, B, H, Lq, Lk)
-        _call("pdn_attention_fwd", q.ptr, k.ptr, v.ptr, mptr, out.ptr, lse.ptr, B, H, Lq, Lk, D, _bhl_strides(q), _bhl_strides(k),
-              _bhl_strides(v), mstr, scale, None, 0)
+        if impl == "tc":
+            _call("pdn_attention_tc_fwd", q.ptr, k.ptr, v.ptr, mptr, out.ptr, lse.ptr, B, H, Lq, Lk, D, _bhl_strides(q), _bhl_strides(k),
+                  _bhl_strides(v), mstr, scale)
+        else:
+            _call("pdn_attention_fwd", q.ptr, k.ptr, v.ptr, mptr, out.ptr, lse.ptr, B, H, Lq, Lk, D, _bhl_strides(q), _bhl_strides(k),
+                  _bhl_strides(v), mstr, scale, None, 0)
 
     def backward(g):
         g = _c(g.reshape(B, Lq, H, D))
         dq = _empty((B, Lq, H, D)) if xq.requires_grad else None
         dk = _empty((B, Lk, H, D)) if xk.requires_grad else None
         dv = _empty((B, Lk, H, D)) if xv.requires_grad else None
-        _call("pdn_attention_bwd", q.ptr, k.ptr, v.ptr, mptr, out.ptr, lse.ptr, g.ptr, dq.ptr if dq is not None else None,
-              dk.ptr if dk is not None else None, dv.ptr if dv is not None else None, B, H, Lq, Lk, D, _bhl_strides(q), _bhl_strides(k),
-              _bhl_strides(v), mstr, scale)
+        _call("pdn_attention_tc_bwd" if impl == "tc" else "pdn_attention_bwd", q.ptr, k.ptr, v.ptr, mptr, out.ptr, lse.ptr, g.ptr,
+              dq.ptr if dq is not None else None, dk.ptr if dk is not None else None, dv.ptr if dv is not None else None, B, H, Lq, Lk, D,
+              _bhl_strides(q), _bhl_strides(k), _bhl_strides(v), mstr, scale)
         _ = keep
         return dq, dk, dv
 
     return _result(out.reshape(B, Lq, H * D), xq.device, (xq, xk, xv), backward, "attention")
-
-
-class DevicePos:
-    """Sequence position of a decode step held in DEVICE memory (an int64 [1] tensor) so that a CUDA-graph recording of
-    the step stays valid while the position advances."""
-
-    def __init__(self, tensor):
-        self.tensor = tensor
 
 
 class Planes:

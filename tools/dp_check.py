@@ -91,7 +91,7 @@ def main():
         step()
     pdn.cuda.synchronize()
     dt = (time.perf_counter() - t0) / 5
-    res = {"rank": rank, "world": world, "dp_vs_single_gpu_param_rel_err_max": worst, "losses_dp_rank": losses, "losses_single": ref_losses,
+    res = {"rank": rank, "world": world, "dp_vs_single_gpu_param_rel_err_max": float(worst), "losses_dp_rank": losses, "losses_single": ref_losses,
            "c4_dp_step_ms_per_gpu_batch%d" % B: dt * 1e3, "tokens_per_s_all_ranks": world * B * 512 / dt}
     print(json.dumps(res), flush=True)
     assert worst < 2e-3, worst
