@@ -174,9 +174,13 @@ def c5(args):
     emit(f"C5 GRU in512 h512 T{Tn} B{B} train step", sec, flops=2_013_265_920.0 * Tn * B / 256, launches=nl, us_per_time_step=sec / Tn * 1e6)
 
 
-def micro(args):
+def micro_att(args):
+    micro(args, conv=False)
+
+
+def micro(args, conv=True):
     rng = np.random.default_rng(1)
-    for (N, Ci, O, HW) in ([(32, 20, 50, 14)] if args.small else [(256, 20, 50, 14), (128, 64, 128, 56)]):
+    for (N, Ci, O, HW) in [] if not conv else ([(32, 20, 50, 14)] if args.small else [(256, 20, 50, 14), (128, 64, 128, 56)]):
         conv = nn.Conv2d(Ci, O, 3, 1, 1, dtype=f32).to(DEV)
         x = T(rng.standard_normal((N, Ci, HW, HW)).astype(f32), True)
 
@@ -208,7 +212,7 @@ if __name__ == "__main__":
     args = ap.parse_args()
     for name in args.only.split(","):
         try:
-            {"c1": c1, "c2": c2, "c4": c4, "c5": c5, "micro": micro, "gemm": gemm, "rows": rows}[name](args)
+            {"c1": c1, "c2": c2, "c4": c4, "c5": c5, "micro": micro, "micro_att": micro_att, "gemm": gemm, "rows": rows}[name](args)
         except Exception as e:  # keep going: one config must not hide the others
             import traceback
             traceback.print_exc()

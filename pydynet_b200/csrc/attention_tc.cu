@@ -71,7 +71,7 @@ __device__ __forceinline__ void umma3(uint32_t d, uint64_t ahi, uint64_t alo, ui
 }
 
 template <int MODE>
-__global__ void __launch_bounds__(256, 1)
+__global__ void __launch_bounds__(384, 1)
 k_attn_tc(const __grid_constant__ CUtensorMap mA1, const __grid_constant__ CUtensorMap mA2, const __grid_constant__ CUtensorMap mB1,
           const __grid_constant__ CUtensorMap mB2, const __grid_constant__ CUtensorMap mB3, AtArgs a) {
   using Cfg = AtCfg<MODE>;
@@ -100,8 +100,8 @@ k_attn_tc(const __grid_constant__ CUtensorMap mA1, const __grid_constant__ CUten
       mbar_init(&b_full[i], 1);
       mbar_init(&b_empty[i], 1);
       mbar_init(&s_full[i], 1);
-      mbar_init(&s_empty[i], 4);
-      mbar_init(&p_full[i], 4);
+      mbar_init(&s_empty[i], 8);  // one arrival per softmax warp
+      mbar_init(&p_full[i], 8);
       mbar_init(&p_empty[i], 1);
     }
     mbar_init(acc_full, 1);
@@ -187,12 +187,12 @@ k_attn_tc(const __grid_constant__ CUtensorMap mA1, const __grid_constant__ CUten
       if (ACC) umma_commit(acc_full);
     }
   } else if (warp >= 4) {
-    // ===== softmax / epilogue: thread = one row of the tile =====
-    const int q = warp & 3, r = q * 32 + lane;
+    // ===== softmax / epilogue: two threads per row (8 warps): warp w owns TMEM lane quarter w%4 and column half (w-4)/4 =====
+    const int q = warp & 3, half = (warp - 4) >> 2, r = q * 32 + lane;
     const int64_t gr = row0 + r;
     const bool    row_ok = gr < a.rows;
     const int64_t b = bh / a.H, h = bh % a.H;
-    const uint32_t lane_sel = (uint32_t)(q * 32) << 16;
+    const uint32_t lane_sel = ((uint32_t)(q * 32) << 16) + (uint32_t)(half * 32);
     const int64_t Lq = TRANS ? a.cols : a.rows;
     float lse_r = 0.f, delta_r = 0.f;
     if (!TRANS && MODE != AT_LSE && row_ok) {
@@ -204,21 +204,17 @@ k_attn_tc(const __grid_constant__ CUtensorMap mA1, const __grid_constant__ CUten
       const int sb = j & 1;
       mbar_wait(&s_full[sb], (uint32_t)((j >> 1) & 1));
       tc_fence_after();
-      float s[64], dp[TWO ? 64 : 1];
+      float s[32], dp[TWO ? 32 : 1];
       tmem_ld_32x32(tmS1(sb) + lane_sel, s);
-      tmem_ld_32x32(tmS1(sb) + lane_sel + 32u, s + 32);
-      if (TWO) {
-        tmem_ld_32x32(tmS2(sb) + lane_sel, dp);
-        tmem_ld_32x32(tmS2(sb) + lane_sel + 32u, dp + 32);
-      }
+      if (TWO) tmem_ld_32x32(tmS2(sb) + lane_sel, dp);
       tmem_ld_wait();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&s_empty[sb]);
-      const int64_t col0 = (int64_t)j * AT_C;
+      const int64_t col0 = (int64_t)j * AT_C + half * 32;
       // x = s*scale + mask ; invalid columns -> -inf
 #pragma unroll
-      for (int e = 0; e < 64; ++e) {
+      for (int e = 0; e < 32; ++e) {
         const int64_t c = col0 + e;
         float x = s[e] * a.scale;
         if (a.mask) {
@@ -230,28 +226,45 @@ k_attn_tc(const __grid_constant__ CUtensorMap mA1, const __grid_constant__ CUten
       if (MODE == AT_LSE) {
         float tm = -INFINITY;
 #pragma unroll
-        for (int e = 0; e < 64; ++e) tm = fmaxf(tm, s[e]);
+        for (int e = 0; e < 32; ++e) tm = fmaxf(tm, s[e]);
         const float mn = fmaxf(m_run, tm);
         if (mn != -INFINITY) {
           float sum = 0.f;
 #pragma unroll
-          for (int e = 0; e < 64; ++e) sum += __expf(s[e] - mn);
+          for (int e = 0; e < 32; ++e) sum += __expf(s[e] - mn);
           l_run = l_run * __expf(m_run - mn) + sum;
           m_run = mn;
         }
       } else {
         // value that becomes the A operand of the accumulate MMA
+        float cl[TRANS ? 32 : 1], cd[(TRANS && TWO) ? 32 : 1];
+        if (TRANS) {  // per-column statistics of this tile half (L1-resident; 128-bit loads when aligned)
+          const float* lp = a.lse + (int64_t)bh * Lq + col0;
+          const float* dpn = TWO ? a.delta + (int64_t)bh * Lq + col0 : nullptr;
+          if (col0 + 32 <= a.cols && (Lq & 3) == 0) {
 #pragma unroll
-        for (int e = 0; e < 64; ++e) {
-          const int64_t c = col0 + e;
-          float lse_e = lse_r, delta_e = delta_r;
-          if (TRANS) {
-            const int64_t ci = c < a.cols ? c : 0;
-            lse_e = __ldg(a.lse + (int64_t)bh * Lq + ci);
-            if (TWO) delta_e = __ldg(a.delta + (int64_t)bh * Lq + ci);
+            for (int e4 = 0; e4 < 8; ++e4) {
+              const float4 t = __ldg(reinterpret_cast<const float4*>(lp) + e4);
+              cl[e4 * 4] = t.x; cl[e4 * 4 + 1] = t.y; cl[e4 * 4 + 2] = t.z; cl[e4 * 4 + 3] = t.w;
+              if (TWO) {
+                const float4 u = __ldg(reinterpret_cast<const float4*>(dpn) + e4);
+                cd[e4 * 4] = u.x; cd[e4 * 4 + 1] = u.y; cd[e4 * 4 + 2] = u.z; cd[e4 * 4 + 3] = u.w;
+              }
+            }
+          } else {
+#pragma unroll
+            for (int e = 0; e < 32; ++e) {
+              const bool ok = col0 + e < a.cols;
+              cl[e] = ok ? __ldg(lp + e) : 0.f;
+              if (TWO) cd[e] = ok ? __ldg(dpn + e) : 0.f;
+            }
           }
+        }
+#pragma unroll
+        for (int e = 0; e < 32; ++e) {
+          const float lse_e = TRANS ? cl[e] : lse_r;
           float p = (s[e] == -INFINITY || !row_ok) ? 0.f : __expf(s[e] - lse_e);
-          if (TWO) p = p * (dp[e] - delta_e) * a.scale;
+          if (TWO) p = p * (dp[e] - ((TRANS && TWO) ? cd[e] : delta_r)) * a.scale;
           s[e] = p;
         }
         const int pb = j & 1;
@@ -259,7 +272,7 @@ k_attn_tc(const __grid_constant__ CUtensorMap mA1, const __grid_constant__ CUten
         uint8_t* ph = smem + Cfg::kOffP + pb * AT_KP;
         uint8_t* pl = ph + AT_KP / 2;
 #pragma unroll
-        for (int c8 = 0; c8 < 8; ++c8) {
+        for (int c8 = 0; c8 < 4; ++c8) {
           uint32_t hw[4], lw[4];
 #pragma unroll
           for (int t = 0; t < 4; ++t) {
@@ -269,7 +282,7 @@ k_attn_tc(const __grid_constant__ CUtensorMap mA1, const __grid_constant__ CUten
             hw[t] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
             lw[t] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
           }
-          const uint32_t off = sw128_off(r, c8);
+          const uint32_t off = sw128_off(r, half * 4 + c8);
           *reinterpret_cast<uint4*>(ph + off) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
           *reinterpret_cast<uint4*>(pl + off) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
         }
@@ -279,19 +292,27 @@ k_attn_tc(const __grid_constant__ CUtensorMap mA1, const __grid_constant__ CUten
       }
     }
     if (MODE == AT_LSE) {
-      if (row_ok) a.lse_out[(int64_t)bh * a.rows + gr] = m_run + logf(l_run);
+      // combine the two column halves of every row through shared memory (the operand stages are idle by now)
+      float* comb = reinterpret_cast<float*>(smem + Cfg::kOffStages);
+      if (half == 1) { comb[r] = m_run; comb[128 + r] = l_run; }
+      asm volatile("bar.sync 1, 256;" ::: "memory");  // the 8 softmax warps only
+      if (half == 0 && row_ok) {
+        const float m2 = comb[r], l2 = comb[128 + r];
+        const float mn = fmaxf(m_run, m2);
+        const float l = (mn == -INFINITY) ? 0.f : l_run * __expf(m_run - mn) + l2 * __expf(m2 - mn);
+        a.lse_out[(int64_t)bh * a.rows + gr] = mn + logf(l);
+      }
     } else {
       mbar_wait(acc_full, 0);
       tc_fence_after();
-      float o[64];
+      float o[32];
       tmem_ld_32x32(tmACC + lane_sel, o);
-      tmem_ld_32x32(tmACC + lane_sel + 32u, o + 32);
       tmem_ld_wait();
       if (row_ok) {
-        float* dst = a.out + ((b * a.rows + gr) * a.H + h) * a.D;
+        float* dst = a.out + ((b * a.rows + gr) * a.H + h) * a.D + half * 32;
 #pragma unroll
-        for (int d = 0; d < 64; ++d)
-          if (d < a.D) dst[d] = o[d];
+        for (int d = 0; d < 32; ++d)
+          if (half * 32 + d < a.D) dst[d] = o[d];
       }
     }
   }
@@ -300,16 +321,18 @@ k_attn_tc(const __grid_constant__ CUtensorMap mA1, const __grid_constant__ CUten
   if (warp == 2) tmem_dealloc(tmem_base, kTmemCols);
 }
 
-// Δ[bh][q] = Σ_d dO·O over [B, Lq, H, D] contiguous tensors
+// Δ[bh][q] = Σ_d dO·O over [B, Lq, H, D] contiguous tensors; one warp per (b, q, h) row, lanes across d (coalesced)
 __global__ void __launch_bounds__(256) k_attn_delta(const float* __restrict__ g, const float* __restrict__ o, float* __restrict__ delta, int64_t B,
                                                     int64_t Lq, int64_t H, int D) {
+  const int lane = threadIdx.x & 31;
   const int64_t total = B * Lq * H;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+  for (int64_t i = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); i < total; i += (int64_t)gridDim.x * (blockDim.x >> 5)) {
     const int64_t h = i % H, q = (i / H) % Lq, b = i / (H * Lq);
     const float *gp = g + i * D, *op = o + i * D;
     float s = 0.f;
-    for (int d = 0; d < D; ++d) s += gp[d] * op[d];
-    delta[(b * H + h) * Lq + q] = s;
+    for (int d = lane; d < D; d += 32) s += gp[d] * op[d];
+    s = warp_sum(s);
+    if (lane == 0) delta[(b * H + h) * Lq + q] = s;
   }
 }
 
@@ -339,7 +362,7 @@ static int at_launch(const CUtensorMap& A1, const CUtensorMap& A2, const CUtenso
     attr = true;
   }
   dim3 grd((unsigned)((a.rows + AT_R - 1) / AT_R), (unsigned)BH);
-  k_attn_tc<MODE><<<grd, 256, Cfg::kSmem, stream()>>>(A1, A2, B1, B2, B3, a);
+  k_attn_tc<MODE><<<grd, 384, Cfg::kSmem, stream()>>>(A1, A2, B1, B2, B3, a);
   PDN_LAUNCHED("attn_tc");
   return 0;
 }
@@ -385,39 +408,40 @@ int pdn_attention_tc_bwd(const float* q, const float* k, const float* v, const f
   PDN_TRY(at_check(B, H, Lq, Lk, D, q_str, k_str, v_str));
   Scratch sdelta;
   PDN_TRY(sdelta.alloc((size_t)B * H * Lq * sizeof(float)));
-  k_attn_delta<<<grid_for(B * Lq * H, 256), 256, 0, stream()>>>(g_out, out, (float*)sdelta.p, B, Lq, H, (int)D);
+  k_attn_delta<<<grid_for(B * Lq * H, 8), 256, 0, stream()>>>(g_out, out, (float*)sdelta.p, B, Lq, H, (int)D);
   PDN_LAUNCHED("attn_delta");
   const int64_t g_str[3] = {Lq * H * D, D, H * D};  // g_out is [B, Lq, H, D] contiguous
   AtArgs a;
   a.H = H; a.D = (int)D; a.scale = scale;
   a.mask = mask; a.mask_bs = mask && mask_str ? mask_str[0] : 0; a.mask_qs = mask && mask_str ? mask_str[1] : 0;
   a.lse = lse; a.delta = (const float*)sdelta.p; a.lse_out = nullptr;
+  // every tensor is packed ONCE per layout; the row-operand (box 128) and column-operand (box 64) TMA maps share the planes
+  AtOperand Qp, Kp, Vp, dOp, Kt, Qt, dOt;
+  CUtensorMap Qp64, Kp128, Vp128, dOp64;
+  PDN_TRY(at_pack(&Qp, q, B, H, Lq, D, q_str[2], 1, q_str[0], q_str[1], AT_R));
+  PDN_TRY(at_pack(&Kp, k, B, H, Lk, D, k_str[2], 1, k_str[0], k_str[1], AT_C));
+  PDN_TRY(at_pack(&dOp, g_out, B, H, Lq, D, g_str[2], 1, g_str[0], g_str[1], AT_R));
+  PDN_TRY(at_pack(&Vp, v, B, H, Lk, D, v_str[2], 1, v_str[0], v_str[1], AT_C));
+  PDN_TRY(tc_make_map(&Qp64, Qp.op.planes, Lq, D, Qp.op.Kp, Qp.op.nbatch, AT_C));
+  PDN_TRY(tc_make_map(&dOp64, dOp.op.planes, Lq, D, dOp.op.Kp, dOp.op.nbatch, AT_C));
+  PDN_TRY(tc_make_map(&Kp128, Kp.op.planes, Lk, D, Kp.op.Kp, Kp.op.nbatch, AT_R));
+  PDN_TRY(tc_make_map(&Vp128, Vp.op.planes, Lk, D, Vp.op.Kp, Vp.op.nbatch, AT_R));
   if (dq) {
-    AtOperand Qp, Kp, dOp, Vp, Kt;
-    PDN_TRY(at_pack(&Qp, q, B, H, Lq, D, q_str[2], 1, q_str[0], q_str[1], AT_R));
-    PDN_TRY(at_pack(&dOp, g_out, B, H, Lq, D, g_str[2], 1, g_str[0], g_str[1], AT_R));
-    PDN_TRY(at_pack(&Kp, k, B, H, Lk, D, k_str[2], 1, k_str[0], k_str[1], AT_C));
-    PDN_TRY(at_pack(&Vp, v, B, H, Lk, D, v_str[2], 1, v_str[0], v_str[1], AT_C));
     PDN_TRY(at_pack(&Kt, k, B, H, D, Lk, 1, k_str[2], k_str[0], k_str[1], AT_C));
     a.rows = Lq; a.cols = Lk; a.out = dq; a.ncol_tiles = (int)((Lk + AT_C - 1) / AT_C);
     PDN_TRY((at_launch<AT_DQ>(Qp.map, dOp.map, Kp.map, Vp.map, Kt.map, a, B * H)));
   }
   if (dk || dv) {
-    AtOperand Kp, Qp, Vp, dOp, dOt, Qt;
-    PDN_TRY(at_pack(&Kp, k, B, H, Lk, D, k_str[2], 1, k_str[0], k_str[1], AT_R));
-    PDN_TRY(at_pack(&Qp, q, B, H, Lq, D, q_str[2], 1, q_str[0], q_str[1], AT_C));
     a.rows = Lk; a.cols = Lq; a.ncol_tiles = (int)((Lq + AT_C - 1) / AT_C);
     if (dv) {
       PDN_TRY(at_pack(&dOt, g_out, B, H, D, Lq, 1, g_str[2], g_str[0], g_str[1], AT_C));
       a.out = dv;
-      PDN_TRY((at_launch<AT_DV>(Kp.map, Kp.map, Qp.map, Qp.map, dOt.map, a, B * H)));
+      PDN_TRY((at_launch<AT_DV>(Kp128, Kp128, Qp64, Qp64, dOt.map, a, B * H)));
     }
     if (dk) {
-      PDN_TRY(at_pack(&Vp, v, B, H, Lk, D, v_str[2], 1, v_str[0], v_str[1], AT_R));
-      PDN_TRY(at_pack(&dOp, g_out, B, H, Lq, D, g_str[2], 1, g_str[0], g_str[1], AT_C));
       PDN_TRY(at_pack(&Qt, q, B, H, D, Lq, 1, q_str[2], q_str[0], q_str[1], AT_C));
       a.out = dk;
-      PDN_TRY((at_launch<AT_DK>(Kp.map, Vp.map, Qp.map, dOp.map, Qt.map, a, B * H)));
+      PDN_TRY((at_launch<AT_DK>(Kp128, Vp128, Qp64, dOp64, Qt.map, a, B * H)));
     }
   }
   return 0;

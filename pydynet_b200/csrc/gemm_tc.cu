@@ -33,7 +33,9 @@ struct PackArgs {
 };
 
 __global__ void __launch_bounds__(256) k_pack_split(PackArgs p) {
-  __shared__ float tile[32][33];
+  // 32 (rows) x 64 (k) tile through shared memory: global reads follow the source's unit-stride axis, plane writes are
+  // bf16x2 along k (one 128-byte segment per warp and row)
+  __shared__ float tile[32][65];
   // blockIdx.z enumerates the operand's own distinct batches
   int64_t z = blockIdx.z, off = 0;
   {
@@ -47,32 +49,41 @@ __global__ void __launch_bounds__(256) k_pack_split(PackArgs p) {
   const float* src = p.src + off;
   __nv_bfloat16* hi = p.dst + (size_t)z * 2 * p.R * p.Kp;
   __nv_bfloat16* lo = hi + (size_t)p.R * p.Kp;
-  const int64_t r0 = (int64_t)blockIdx.y * 32, k0 = (int64_t)blockIdx.x * 32;
+  const int64_t r0 = (int64_t)blockIdx.y * 32, k0 = (int64_t)blockIdx.x * 64;
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
   const bool k_fast = (p.k_stride == 1) || (p.r_stride != 1);
-  auto koff = [&](int64_t k) { return (k / p.k_inner) * p.k_outer_stride + (k % p.k_inner) * p.k_stride; };
+  const bool flat_k = p.k_inner >= p.K;
+  auto koff = [&](int64_t k) { return flat_k ? k * p.k_stride : (k / p.k_inner) * p.k_outer_stride + (k % p.k_inner) * p.k_stride; };
   if (k_fast) {
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-      int64_t r = r0 + ty + i * 8, k = k0 + tx;
-      tile[ty + i * 8][tx] = (r < p.R && k < p.K) ? src[r * p.r_stride + koff(k)] : 0.f;
+      const int64_t r = r0 + ty + i * 8;
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int64_t k = k0 + tx + h * 32;
+        tile[ty + i * 8][tx + h * 32] = (r < p.R && k < p.K) ? src[r * p.r_stride + koff(k)] : 0.f;
+      }
     }
   } else {  // rows are the unit-stride axis of the source: read along rows, transpose through smem
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      int64_t r = r0 + tx, k = k0 + ty + i * 8;
+    for (int i = 0; i < 8; ++i) {
+      const int64_t r = r0 + tx, k = k0 + ty + i * 8;
       tile[tx][ty + i * 8] = (r < p.R && k < p.K) ? src[r * p.r_stride + koff(k)] : 0.f;
     }
   }
   __syncthreads();
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
-    int64_t r = r0 + ty + i * 8, k = k0 + tx;
-    if (r < p.R && k < p.Kp) {
-      float         x = tile[ty + i * 8][tx];
-      __nv_bfloat16 h = __float2bfloat16_rn(x);
-      hi[r * p.Kp + k] = h;
-      lo[r * p.Kp + k] = __float2bfloat16_rn(x - __bfloat162float(h));
+    const int64_t r = r0 + ty + i * 8, k = k0 + 2 * tx;
+    if (r < p.R && k < p.Kp) {  // Kp is even
+      const float x0 = tile[ty + i * 8][2 * tx], x1 = tile[ty + i * 8][2 * tx + 1];
+      const __nv_bfloat16 h0 = __float2bfloat16_rn(x0), h1 = __float2bfloat16_rn(x1);
+      __nv_bfloat162 H2, L2;
+      H2.x = h0; H2.y = h1;
+      L2.x = __float2bfloat16_rn(x0 - __bfloat162float(h0));
+      L2.y = __float2bfloat16_rn(x1 - __bfloat162float(h1));
+      *reinterpret_cast<__nv_bfloat162*>(hi + r * p.Kp + k) = H2;
+      *reinterpret_cast<__nv_bfloat162*>(lo + r * p.Kp + k) = L2;
     }
   }
 }
@@ -400,7 +411,7 @@ int pack_operand_ex(const float* src, int64_t R, int64_t K, int64_t r_stride, in
   p.r_stride = r_stride; p.k_stride = k_stride;
   p.k_inner = k_inner > 0 ? k_inner : (K > 0 ? K : 1);
   p.k_outer_stride = k_outer_stride;
-  dim3 grd((unsigned)((Kp + 31) / 32), (unsigned)((R + 31) / 32), (unsigned)pb);
+  dim3 grd((unsigned)((Kp + 63) / 64), (unsigned)((R + 31) / 32), (unsigned)pb);
   PDN_CHECK(grd.y <= 65535, "gemm_tc: operand has too many rows for the pack grid");
   k_pack_split<<<grd, 256, 0, stream()>>>(p);
   PDN_LAUNCHED("pack_split");
