@@ -111,6 +111,103 @@ __global__ void __launch_bounds__(128) k_attention_fwd(AttArgs a) {
   if (lane == 0 && a.lse) a.lse[(b * a.H + h) * a.Lq + iq] = m + logf(l);
 }
 
+// Decode form (few query rows, long key range): one CTA per (batch, head, query row), its 4 warps take interleaved
+// 32-key chunks (flash-decoding inside the block) and merge their (max, sum, partial output) through shared memory.
+// 4x more warps in flight than the warp-per-row kernel at the same batch: the first ncu capture of the decode step showed
+// that kernel latency-bound at 29 % of HBM peak with 31 % occupancy (profiles/r1_ncu_summary.md).
+__global__ void __launch_bounds__(128) k_attention_decode(AttArgs a) {
+  __shared__ float qsm[ATT_MAXD];
+  __shared__ float red_m[4], red_l[4];
+  __shared__ float red_acc[4][ATT_MAXD];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const int64_t w = blockIdx.x;
+  const int64_t iq = w % a.Lq, h = (w / a.Lq) % a.H, b = w / (a.Lq * a.H);
+  const int D = (int)a.D;
+  if (a.lk_dev) a.Lk = *a.lk_dev + a.lk_add;
+  const float* qrow = a.q + b * a.qs[0] + h * a.qs[1] + iq * a.qs[2];
+  for (int d = threadIdx.x; d < D; d += 128) qsm[d] = qrow[d] * a.scale;
+  __syncthreads();
+  const float* kb = a.k + b * a.ks[0] + h * a.ks[1];
+  const float* vb = a.v + b * a.vs[0] + h * a.vs[1];
+  const float* mrow = a.mask ? a.mask + b * a.mask_bs + iq * a.mask_qs : nullptr;
+  float m = -INFINITY, l = 0.f;
+  float acc[ATT_DPL];
+#pragma unroll
+  for (int i = 0; i < ATT_DPL; ++i) acc[i] = 0.f;
+  const bool vec = (D % 4 == 0) && ((a.ks[2] & 3) == 0) && ((((uintptr_t)kb) & 15) == 0);
+  for (int64_t j0 = (int64_t)wib * 32; j0 < a.Lk; j0 += 128) {
+    const int64_t j = j0 + lane;
+    float s = -INFINITY;
+    if (j < a.Lk) {
+      const float* kr = kb + j * a.ks[2];
+      float dot = 0.f;
+      if (vec) {
+        for (int d = 0; d < D; d += 4) {
+          float4 kk = *reinterpret_cast<const float4*>(kr + d);
+          dot += qsm[d] * kk.x + qsm[d + 1] * kk.y + qsm[d + 2] * kk.z + qsm[d + 3] * kk.w;
+        }
+      } else {
+        for (int d = 0; d < D; ++d) dot += qsm[d] * kr[d];
+      }
+      s = dot;
+      if (mrow) s += mrow[j];
+    }
+    const float cm = warp_max(s);
+    const float mn = fmaxf(m, cm);
+    const float corr = (mn == -INFINITY) ? 1.f : __expf(m - mn);
+    const float p = (s == -INFINITY) ? 0.f : __expf(s - mn);
+    l = l * corr + warp_sum(p);
+    m = mn;
+#pragma unroll
+    for (int i = 0; i < ATT_DPL; ++i) acc[i] *= corr;
+    const int cnt = (int)((a.Lk - j0) < 32 ? (a.Lk - j0) : 32);
+    for (int t = 0; t < cnt; ++t) {
+      const float pt = __shfl_sync(0xffffffffu, p, t);
+      const float* vr = vb + (j0 + t) * a.vs[2];
+#pragma unroll
+      for (int i = 0; i < ATT_DPL; ++i) {
+        int d = lane + i * 32;
+        if (d < D) acc[i] += pt * vr[d];
+      }
+    }
+  }
+  // merge the 4 warps
+  if (lane == 0) { red_m[wib] = m; red_l[wib] = l; }
+#pragma unroll
+  for (int i = 0; i < ATT_DPL; ++i) {
+    int d = lane + i * 32;
+    if (d < D) red_acc[wib][d] = acc[i];
+  }
+  __syncthreads();
+  if (wib == 0) {
+    const float mt = fmaxf(fmaxf(red_m[0], red_m[1]), fmaxf(red_m[2], red_m[3]));
+    float lt = 0.f, sc[4];
+#pragma unroll
+    for (int ww = 0; ww < 4; ++ww) {
+      sc[ww] = (red_m[ww] == -INFINITY) ? 0.f : __expf(red_m[ww] - mt);
+      lt += red_l[ww] * sc[ww];
+    }
+    const float inv = 1.f / lt;
+    const int64_t rows = a.B * a.Lq, r = b * a.Lq + iq;
+#pragma unroll
+    for (int i = 0; i < ATT_DPL; ++i) {
+      int d = lane + i * 32;
+      if (d < D) {
+        const float v = (red_acc[0][d] * sc[0] + red_acc[1][d] * sc[1] + red_acc[2][d] * sc[2] + red_acc[3][d] * sc[3]) * inv;
+        if (a.out_planes) {
+          __nv_bfloat16 *hi = a.out_planes + r * a.planes_kp + h * a.D, *lo = hi + rows * a.planes_kp;
+          const __nv_bfloat16 hv = __float2bfloat16_rn(v);
+          hi[d] = hv;
+          lo[d] = __float2bfloat16_rn(v - __bfloat162float(hv));
+        } else {
+          a.out[((b * a.Lq + iq) * a.H + h) * a.D + d] = v;
+        }
+      }
+    }
+    if (lane == 0 && a.lse) a.lse[(b * a.H + h) * a.Lq + iq] = mt + logf(lt);
+  }
+}
+
 struct AttBwdArgs {
   AttArgs f;
   const float* g;  // grad of out, [B, Lq, H, D] contiguous
@@ -253,6 +350,11 @@ int pdn_attention_fwd(const float* q, const float* k, const float* v, const floa
   if (total == 0) return 0;
   PDN_CHECK(Lk > 0, "attention: no keys");
   PDN_CHECK((total + 3) / 4 <= 0x7fffffff, "attention: too many query rows");
+  if (Lq <= 4 && Lk >= 64 && total <= 0x7fffffff) {  // decode: split the keys of each row over a whole CTA
+    k_attention_decode<<<(unsigned)total, 128, 0, stream()>>>(a);
+    PDN_LAUNCHED("attention_decode");
+    return 0;
+  }
   k_attention_fwd<<<(unsigned)((total + 3) / 4), 128, 4 * ATT_MAXD * sizeof(float), stream()>>>(a);
   PDN_LAUNCHED("attention_fwd");
   return 0;
@@ -315,6 +417,11 @@ int pdn_attention_fwd_dev(const float* q, const float* k, const float* v, float*
   a.lk_add = lk_add;
   const int64_t total = B * H * Lq;
   if (total == 0) return 0;
+  if (Lq <= 4 && total <= 0x7fffffff) {  // graph-replayed decode step: the key count is only known on the device
+    k_attention_decode<<<(unsigned)total, 128, 0, stream()>>>(a);
+    PDN_LAUNCHED("attention_decode");
+    return 0;
+  }
   k_attention_fwd<<<(unsigned)((total + 3) / 4), 128, 4 * ATT_MAXD * sizeof(float), stream()>>>(a);
   PDN_LAUNCHED("attention_fwd");
   return 0;

@@ -60,6 +60,12 @@ struct AtCfg {
 // 16-byte chunk c (8 bf16) of row r in a K-major [rows x 64] bf16 tile with 128-byte swizzle (what TMA writes / UMMA reads)
 __device__ __forceinline__ uint32_t sw128_off(int r, int c) { return (uint32_t)((r >> 3) * 1024 + (r & 7) * 128 + ((c ^ (r & 7)) << 4)); }
 
+__device__ __forceinline__ float ex2f(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
 __device__ __forceinline__ void umma3(uint32_t d, uint64_t ahi, uint64_t alo, uint64_t bhi, uint64_t blo, uint32_t idesc, bool first_clears) {
 #pragma unroll
   for (int k = 0; k < 4; ++k) {
@@ -211,17 +217,30 @@ k_attn_tc(const __grid_constant__ CUtensorMap mA1, const __grid_constant__ CUten
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&s_empty[sb]);
-      const int64_t col0 = (int64_t)j * AT_C + half * 32;
-      // x = s*scale + mask ; invalid columns -> -inf
+      const int col0 = j * AT_C + half * 32;
+      const int ncols = (int)a.cols;
+      // Everything below works in the log2 domain: t = (s*scale + mask) * log2(e), so that exp(x - lse) is ONE ex2.approx of
+      // one FFMA result. Column validity only matters in the last tile (uniform branch); masks take the slower path.
+      const float c1 = a.scale * 1.4426950408889634f;
+      if (a.mask) {
 #pragma unroll
-      for (int e = 0; e < 32; ++e) {
-        const int64_t c = col0 + e;
-        float x = s[e] * a.scale;
-        if (a.mask) {
-          const int64_t qi = TRANS ? c : gr, ki = TRANS ? gr : c;
-          if (c < a.cols && row_ok) x += __ldg(a.mask + b * a.mask_bs + qi * a.mask_qs + ki);
+        for (int e = 0; e < 32; ++e) {
+          const int c = col0 + e;
+          float mk = 0.f;
+          if (c < ncols && row_ok) {
+            const int64_t qi = TRANS ? c : gr, ki = TRANS ? gr : c;
+            mk = __ldg(a.mask + b * a.mask_bs + qi * a.mask_qs + ki);
+          }
+          s[e] = fmaf(s[e], c1, mk * 1.4426950408889634f);
         }
-        s[e] = (c < a.cols) ? x : -INFINITY;
+      } else {
+#pragma unroll
+        for (int e = 0; e < 32; ++e) s[e] *= c1;
+      }
+      if (col0 + 32 > ncols) {
+#pragma unroll
+        for (int e = 0; e < 32; ++e)
+          if (col0 + e >= ncols) s[e] = -INFINITY;
       }
       if (MODE == AT_LSE) {
         float tm = -INFINITY;
@@ -231,17 +250,17 @@ k_attn_tc(const __grid_constant__ CUtensorMap mA1, const __grid_constant__ CUten
         if (mn != -INFINITY) {
           float sum = 0.f;
 #pragma unroll
-          for (int e = 0; e < 32; ++e) sum += __expf(s[e] - mn);
-          l_run = l_run * __expf(m_run - mn) + sum;
+          for (int e = 0; e < 32; ++e) sum += ex2f(s[e] - mn);
+          l_run = l_run * ex2f(m_run - mn) + sum;
           m_run = mn;
         }
       } else {
-        // value that becomes the A operand of the accumulate MMA
-        float cl[TRANS ? 32 : 1], cd[(TRANS && TWO) ? 32 : 1];
+        // value that becomes the A operand of the accumulate MMA: P = 2^(t - lse2) [ * (dP - delta) * scale ]
         if (TRANS) {  // per-column statistics of this tile half (L1-resident; 128-bit loads when aligned)
           const float* lp = a.lse + (int64_t)bh * Lq + col0;
           const float* dpn = TWO ? a.delta + (int64_t)bh * Lq + col0 : nullptr;
-          if (col0 + 32 <= a.cols && (Lq & 3) == 0) {
+          float cl[32], cd[TWO ? 32 : 1];
+          if (col0 + 32 <= ncols && (Lq & 3) == 0) {
 #pragma unroll
             for (int e4 = 0; e4 < 8; ++e4) {
               const float4 t = __ldg(reinterpret_cast<const float4*>(lp) + e4);
@@ -254,18 +273,25 @@ k_attn_tc(const __grid_constant__ CUtensorMap mA1, const __grid_constant__ CUten
           } else {
 #pragma unroll
             for (int e = 0; e < 32; ++e) {
-              const bool ok = col0 + e < a.cols;
+              const bool ok = col0 + e < ncols;
               cl[e] = ok ? __ldg(lp + e) : 0.f;
               if (TWO) cd[e] = ok ? __ldg(dpn + e) : 0.f;
             }
           }
-        }
 #pragma unroll
-        for (int e = 0; e < 32; ++e) {
-          const float lse_e = TRANS ? cl[e] : lse_r;
-          float p = (s[e] == -INFINITY || !row_ok) ? 0.f : __expf(s[e] - lse_e);
-          if (TWO) p = p * (dp[e] - ((TRANS && TWO) ? cd[e] : delta_r)) * a.scale;
-          s[e] = p;
+          for (int e = 0; e < 32; ++e) {
+            float p = ex2f(fmaf(cl[e], -1.4426950408889634f, s[e]));
+            if (TWO) p = p * (dp[e] - cd[e]) * a.scale;
+            s[e] = p;
+          }
+        } else {
+          const float lse2 = lse_r * 1.4426950408889634f;
+#pragma unroll
+          for (int e = 0; e < 32; ++e) {
+            float p = ex2f(s[e] - lse2);
+            if (TWO) p = p * (dp[e] - delta_r) * a.scale;
+            s[e] = p;
+          }
         }
         const int pb = j & 1;
         mbar_wait(&p_empty[pb], (uint32_t)(((j >> 1) & 1) ^ 1));
@@ -277,10 +303,11 @@ k_attn_tc(const __grid_constant__ CUtensorMap mA1, const __grid_constant__ CUten
 #pragma unroll
           for (int t = 0; t < 4; ++t) {
             const float v0 = s[c8 * 8 + 2 * t], v1 = s[c8 * 8 + 2 * t + 1];
-            const __nv_bfloat16 h0 = __float2bfloat16_rn(v0), h1 = __float2bfloat16_rn(v1);
-            const __nv_bfloat16 l0 = __float2bfloat16_rn(v0 - __bfloat162float(h0)), l1 = __float2bfloat16_rn(v1 - __bfloat162float(h1));
-            hw[t] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
-            lw[t] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+            const __nv_bfloat162 hh = __floats2bfloat162_rn(v0, v1);   // one packed convert for two elements
+            const float2         hf = __bfloat1622float2(hh);
+            const __nv_bfloat162 ll = __floats2bfloat162_rn(v0 - hf.x, v1 - hf.y);
+            hw[t] = *reinterpret_cast<const uint32_t*>(&hh);
+            lw[t] = *reinterpret_cast<const uint32_t*>(&ll);
           }
           const uint32_t off = sw128_off(r, half * 4 + c8);
           *reinterpret_cast<uint4*>(ph + off) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
@@ -298,9 +325,9 @@ k_attn_tc(const __grid_constant__ CUtensorMap mA1, const __grid_constant__ CUten
       asm volatile("bar.sync 1, 256;" ::: "memory");  // the 8 softmax warps only
       if (half == 0 && row_ok) {
         const float m2 = comb[r], l2 = comb[128 + r];
-        const float mn = fmaxf(m_run, m2);
-        const float l = (mn == -INFINITY) ? 0.f : l_run * __expf(m_run - mn) + l2 * __expf(m2 - mn);
-        a.lse_out[(int64_t)bh * a.rows + gr] = mn + logf(l);
+        const float mn = fmaxf(m_run, m2);  // running maxima are in the log2 domain
+        const float l = (mn == -INFINITY) ? 0.f : l_run * ex2f(m_run - mn) + l2 * ex2f(m2 - mn);
+        a.lse_out[(int64_t)bh * a.rows + gr] = mn * 0.6931471805599453f + logf(l);
       }
     } else {
       mbar_wait(acc_full, 0);

@@ -8,7 +8,7 @@ mkdir -p build
 pids=()
 for f in *.cu; do
   o=build/${f%.cu}.o
-  if [ ! -f "$o" ] || [ "$f" -nt "$o" ] || [ common.cuh -nt "$o" ] || [ ../../include/pdn_b200.h -nt "$o" ] || [ gemm_args.h -nt "$o" ] || [ gemm_tc.h -nt "$o" ] || [ tc_ptx.cuh -nt "$o" ]; then
+  if [ ! -f "$o" ] || [ "$f" -nt "$o" ] || [ common.cuh -nt "$o" ] || [ ../../include/pdn_b200.h -nt "$o" ] || [ gemm_args.h -nt "$o" ] || [ gemm_tc.h -nt "$o" ] || [ tc_ptx.cuh -nt "$o" ] || [ conv_gather.cuh -nt "$o" ]; then
     $NVCC $FLAGS $EXTRA -c "$f" -o "$o" &
     pids+=($!)
   fi

@@ -10,61 +10,10 @@
 // Pooling is a direct window kernel (the reference runs it through the same im2col + max/mean + add.at).
 #include "common.cuh"
 #include "gemm_tc.h"
+#include "conv_gather.cuh"
+#include <stdlib.h>
 
 namespace pdn {
-
-struct ConvGeom {
-  int64_t N, C, H, W, O, oh, ow;
-  int     k, stride, pad;
-};
-
-// MODE 0: im2col of x — row m = (n, oy, ox), column kk = (c, ky, kx)
-// MODE 1: transposed-conv gather of g — row m = (n, y, x) of the INPUT grid, column kk = (o, ky, kx)
-// The row index is decomposed once per thread (it is fixed across the tile's columns); columns cost three small
-// 32-bit divisions each.
-struct RowPos { int64_t base; int y, x; bool ok; };  // base = element offset of (n, channel 0, 0, 0) in the source
-
-template <int MODE>
-__device__ __forceinline__ RowPos conv_row(const ConvGeom& g, int64_t m, int64_t Mtot) {
-  RowPos r;
-  r.ok = m < Mtot;
-  if (!r.ok) { r.base = 0; r.y = r.x = 0; return r; }
-  if (MODE == 0) {
-    const int64_t hw = g.oh * g.ow, n = m / hw;
-    const int pix = (int)(m - n * hw);
-    r.y = (pix / (int)g.ow) * g.stride - g.pad;   // top-left input coordinate of the window
-    r.x = (pix % (int)g.ow) * g.stride - g.pad;
-    r.base = n * g.C * g.H * g.W;
-  } else {
-    const int64_t hw = g.H * g.W, n = m / hw;
-    const int pix = (int)(m - n * hw);
-    r.y = pix / (int)g.W + g.pad;
-    r.x = pix % (int)g.W + g.pad;
-    r.base = n * g.O * g.oh * g.ow;
-  }
-  return r;
-}
-
-template <int MODE>
-__device__ __forceinline__ float conv_fetch(const float* __restrict__ src, const ConvGeom& g, const RowPos& r, int kk, int Ktot) {
-  if (!r.ok || kk >= Ktot) return 0.f;
-  const int kx = kk % g.k, t = kk / g.k, ky = t % g.k, ch = t / g.k;
-  if (MODE == 0) {
-    const int iy = r.y + ky, ix = r.x + kx;
-    if (iy < 0 || iy >= (int)g.H || ix < 0 || ix >= (int)g.W) return 0.f;
-    return __ldg(src + r.base + ((int64_t)ch * g.H + iy) * g.W + ix);
-  } else {
-    const int ty = r.y - ky, tx = r.x - kx;
-    if (ty < 0 || tx < 0) return 0.f;
-    int oy = ty, ox = tx;
-    if (g.stride != 1) {
-      if (ty % g.stride || tx % g.stride) return 0.f;
-      oy = ty / g.stride; ox = tx / g.stride;
-    }
-    if (oy >= (int)g.oh || ox >= (int)g.ow) return 0.f;
-    return __ldg(src + r.base + ((int64_t)ch * g.oh + oy) * g.ow + ox);
-  }
-}
 
 // Writes planes [2][R][Kp]: ROWS_M ? (R = Mtot, k index = kk) : (R = Ktot, k index = m). 32(m) x 64(kk) tile through smem so
 // that both the gather (along m = consecutive pixels) and the plane stores (along the plane's k axis) are coalesced.
@@ -223,7 +172,6 @@ int pdn_conv2d_fwd(const float* x, const float* w, const float* bias, float* y, 
   if (M == 0 || O == 0) return 0;
   Scratch       bufA, bufB;
   PackedOperand A, B;
-  PDN_TRY((conv_pack<0, true>(x, g, M, K, &bufA, &A)));
   const int64_t one[3] = {1, 1, 1}, zero[3] = {0, 0, 0};
   PDN_TRY(pack_operand_ex(w, O, K, K, 1, 0, 0, one, zero, &bufB, &B));
   TcArgs t;
@@ -231,6 +179,8 @@ int pdn_conv2d_fwd(const float* x, const float* w, const float* bias, float* y, 
   t.C = y; t.bias = bias; t.M = M; t.N = O; t.K = K; t.ldc = O;
   t.nchw_hw = g.oh * g.ow;
   t.c_clear_bytes = (size_t)M * O * sizeof(float);
+  if (!getenv("PDN_CONV_EXPLICIT")) return gemm_tc_conv(x, g, 1, M, (int)K, B, t);  // implicit GEMM: no column matrix in HBM
+  PDN_TRY((conv_pack<0, true>(x, g, M, K, &bufA, &A)));
   return gemm_tc_packed(A, B, t, 1);
 }
 
@@ -243,7 +193,6 @@ int pdn_conv2d_bwd_data(const float* gy, const float* w, float* dx, int64_t N, i
   if (M == 0 || C == 0) return 0;
   Scratch       bufA, bufB;
   PackedOperand A, B;
-  PDN_TRY((conv_pack<1, true>(gy, g, M, K, &bufA, &A)));
   // B rows = input channel c; k index (o, ky, kx) -> W[o, c, ky, kx]
   const int64_t one[3] = {1, 1, 1}, zero[3] = {0, 0, 0};
   PDN_TRY(pack_operand_ex(w, C, K, (int64_t)k * k, 1, (int64_t)k * k, C * (int64_t)k * k, one, zero, &bufB, &B));
@@ -252,6 +201,8 @@ int pdn_conv2d_bwd_data(const float* gy, const float* w, float* dx, int64_t N, i
   t.C = dx; t.M = M; t.N = C; t.K = K; t.ldc = C;
   t.nchw_hw = H * W;
   t.c_clear_bytes = (size_t)M * C * sizeof(float);
+  if (!getenv("PDN_CONV_EXPLICIT")) return gemm_tc_conv(gy, g, 2, M, (int)K, B, t);
+  PDN_TRY((conv_pack<1, true>(gy, g, M, K, &bufA, &A)));
   return gemm_tc_packed(A, B, t, 1);
 }
 

@@ -15,6 +15,7 @@
 #include "gemm_args.h"
 #include "gemm_tc.h"
 #include "tc_ptx.cuh"
+#include "conv_gather.cuh"
 #include <cuda.h>
 #include <cudaTypedefs.h>
 #include <stdlib.h>
@@ -107,9 +108,20 @@ struct TcCfg {
 //   warp 1     MMA issuer     (one elected lane; accumulator ping-pong in TMEM: tmem_full/tmem_empty mbarriers)
 //   warp 2     TMEM allocator
 //   warps 4-7  epilogue       (tcgen05.ld -> +bias -> smem transpose -> coalesced stores | NCHW scatter | split-K atomics | argmax)
-template <int BN>
-__global__ void __launch_bounds__(256, 1) k_gemm_tc(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
-                                                   TcArgs g, int n_tiles_n, int n_tiles_m, long long total_tiles) {
+// GATHER = 0: A tiles arrive by TMA from packed planes. GATHER = 1 / 2: implicit-GEMM convolution — 8 extra producer warps
+// gather the im2col (1) or transposed-conv (2) rows of the A tile straight from the fp32 NCHW tensor, split them into bf16
+// hi/lo and write them in the swizzled layout the MMA expects; the column matrix never exists in HBM.
+struct GatherArgs {
+  const float* src;
+  ConvGeom     geom;
+  int64_t      Mtot;
+  int          Ktot;
+};
+
+template <int BN, int GATHER>
+__global__ void __launch_bounds__(GATHER ? 512 : 256, 1)
+k_gemm_tc(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, TcArgs g, int n_tiles_n, int n_tiles_m,
+          long long total_tiles, GatherArgs ga) {
   using Cfg = TcCfg<BN>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t*  smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -125,12 +137,12 @@ __global__ void __launch_bounds__(256, 1) k_gemm_tc(const __grid_constant__ CUte
   const int kb_per = (all_kb + g.splits - 1) / g.splits;  // the host guarantees every split owns >= 1 k-block
 
   if (warp == 0 && lane == 0) {
-    tma_prefetch_desc(&mapA);
+    if (!GATHER) tma_prefetch_desc(&mapA);
     tma_prefetch_desc(&mapB);
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < Cfg::kStages; ++s) {
-      mbar_init(&full_bar[s], 1);
+      mbar_init(&full_bar[s], GATHER ? 9 : 1);  // TMA producer (+ 8 gather warps)
       mbar_init(&empty_bar[s], 1);
     }
     for (int a = 0; a < 2; ++a) {
@@ -170,10 +182,12 @@ __global__ void __launch_bounds__(256, 1) k_gemm_tc(const __grid_constant__ CUte
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* st = smem + stage * Cfg::kStageBytes;
-          mbar_expect_tx(&full_bar[stage], Cfg::kStageBytes);
+          mbar_expect_tx(&full_bar[stage], GATHER ? 2 * (BN * TC_BK * 2) : Cfg::kStageBytes);
           const int k = (kb_begin + kb) * TC_BK;
-          tma_load_4d(&mapA, &full_bar[stage], st, k, m_blk * TC_BM, 0, a_batch);
-          tma_load_4d(&mapA, &full_bar[stage], st + TC_BM * TC_BK * 2, k, m_blk * TC_BM, 1, a_batch);
+          if (!GATHER) {
+            tma_load_4d(&mapA, &full_bar[stage], st, k, m_blk * TC_BM, 0, a_batch);
+            tma_load_4d(&mapA, &full_bar[stage], st + TC_BM * TC_BK * 2, k, m_blk * TC_BM, 1, a_batch);
+          }
           tma_load_4d(&mapB, &full_bar[stage], st + 2 * TC_BM * TC_BK * 2, k, n_blk * BN, 0, b_batch);
           tma_load_4d(&mapB, &full_bar[stage], st + 2 * TC_BM * TC_BK * 2 + BN * TC_BK * 2, k, n_blk * BN, 1, b_batch);
           if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
@@ -217,7 +231,7 @@ __global__ void __launch_bounds__(256, 1) k_gemm_tc(const __grid_constant__ CUte
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
     }
-  } else if (warp >= 4) {
+  } else if (warp >= 4 && warp < 8) {
     // ===== epilogue: TMEM -> registers -> (+bias, +C) -> global =====
     const int q = warp & 3;  // TMEM lane quarter this warp may access
     float*    stg = epi_smem + q * (32 * 33);
@@ -312,6 +326,72 @@ __global__ void __launch_bounds__(256, 1) k_gemm_tc(const __grid_constant__ CUte
         g.amax_idx[row * n_tiles_n + n_blk] = best_i;
       }
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+  if (GATHER && warp >= 8) {
+    // ===== implicit-GEMM A producer: thread = (tile row r, 32-column half of the 64-wide k-block) =====
+    const int gw = warp - 8, r = (gw & 3) * 32 + lane, half = gw >> 2;
+    const int kk2 = ga.geom.k * ga.geom.k;
+    int stage = 0;
+    uint32_t phase = 0;
+    for (long long t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+      int n_blk, m_blk, split; int64_t i0, i1, i2;
+      decode(t, n_blk, m_blk, split, i0, i1, i2);
+      const int kb_begin = split * kb_per;
+      const int num_kb = min(all_kb, kb_begin + kb_per) - kb_begin;
+      const RowPos rp = (GATHER == 1) ? conv_row<0>(ga.geom, (int64_t)m_blk * TC_BM + r, ga.Mtot) : conv_row<1>(ga.geom, (int64_t)m_blk * TC_BM + r, ga.Mtot);
+      for (int kb = 0; kb < num_kb; ++kb) {
+        const int kk0 = (kb_begin + kb) * TC_BK + half * 32;
+        // all 32 loads are issued before the first conversion (one warp per scheduler: ILP hides the latency)
+        float v[32];
+        int ch = kk0 / kk2, rem = kk0 - ch * kk2, ky = rem / ga.geom.k, kx = rem - ky * ga.geom.k;
+#pragma unroll
+        for (int e = 0; e < 32; ++e) {
+          float x = 0.f;
+          if (rp.ok && kk0 + e < ga.Ktot) {
+            if (GATHER == 1) {
+              const int iy = rp.y + ky, ix = rp.x + kx;
+              if (iy >= 0 && iy < (int)ga.geom.H && ix >= 0 && ix < (int)ga.geom.W) x = __ldg(ga.src + rp.base + ((int64_t)ch * ga.geom.H + iy) * ga.geom.W + ix);
+            } else {
+              const int ty = rp.y - ky, tx = rp.x - kx;
+              if (ty >= 0 && tx >= 0) {
+                int oy = ty, ox = tx;
+                bool ok = true;
+                if (ga.geom.stride != 1) {
+                  ok = (ty % ga.geom.stride == 0) && (tx % ga.geom.stride == 0);
+                  oy = ty / ga.geom.stride; ox = tx / ga.geom.stride;
+                }
+                if (ok && oy < (int)ga.geom.oh && ox < (int)ga.geom.ow) x = __ldg(ga.src + rp.base + ((int64_t)ch * ga.geom.oh + oy) * ga.geom.ow + ox);
+              }
+            }
+          }
+          v[e] = x;
+          if (++kx == ga.geom.k) { kx = 0; if (++ky == ga.geom.k) { ky = 0; ++ch; } }
+        }
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        uint8_t* ah = smem + stage * Cfg::kStageBytes;
+        uint8_t* al = ah + TC_BM * TC_BK * 2;
+#pragma unroll
+        for (int c8 = 0; c8 < 4; ++c8) {
+          uint32_t hw[4], lw[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const float v0 = v[c8 * 8 + 2 * u], v1 = v[c8 * 8 + 2 * u + 1];
+            const __nv_bfloat16 h0 = __float2bfloat16_rn(v0), h1 = __float2bfloat16_rn(v1);
+            const __nv_bfloat16 l0 = __float2bfloat16_rn(v0 - __bfloat162float(h0)), l1 = __float2bfloat16_rn(v1 - __bfloat162float(h1));
+            hw[u] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+            lw[u] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+          }
+          const int      c = half * 4 + c8;
+          const uint32_t off = (uint32_t)((r >> 3) * 1024 + (r & 7) * 128 + ((c ^ (r & 7)) << 4));  // 128-byte swizzle, K-major
+          *reinterpret_cast<uint4*>(ah + off) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+          *reinterpret_cast<uint4*>(al + off) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+        }
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&full_bar[stage]);
+        if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
+      }
     }
   }
   tc_fence_before();
@@ -419,21 +499,29 @@ int pack_operand_ex(const float* src, int64_t R, int64_t K, int64_t r_stride, in
   return 0;
 }
 
-template <int BN>
-static int launch_tc(const CUtensorMap& mA, const CUtensorMap& mB, const TcArgs& t) {
+template <int BN, int GATHER>
+static int launch_tc(const CUtensorMap& mA, const CUtensorMap& mB, const TcArgs& t, const GatherArgs& ga) {
   using Cfg = TcCfg<BN>;
   static bool attr_set = false;
   if (!attr_set) {
-    PDN_CUDA(cudaFuncSetAttribute(k_gemm_tc<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    PDN_CUDA(cudaFuncSetAttribute(k_gemm_tc<BN, GATHER>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
     attr_set = true;
   }
   const int64_t n_tiles_n = (t.N + BN - 1) / BN, n_tiles_m = (t.M + TC_BM - 1) / TC_BM;
   const int64_t total = n_tiles_n * n_tiles_m * t.nb[0] * t.nb[1] * t.nb[2] * t.splits;
   PDN_CHECK(n_tiles_n <= 0x7fffffff && n_tiles_m <= 0x7fffffff, "gemm_tc: too many tiles");
   const int64_t ctas = total < sm_count() ? total : sm_count();  // persistent: one CTA per SM walks the tile list
-  k_gemm_tc<BN><<<(unsigned)ctas, 256, Cfg::kSmemBytes, stream()>>>(mA, mB, t, (int)n_tiles_n, (int)n_tiles_m, (long long)total);
-  PDN_LAUNCHED("gemm_tc");
+  k_gemm_tc<BN, GATHER><<<(unsigned)ctas, GATHER ? 512 : 256, Cfg::kSmemBytes, stream()>>>(mA, mB, t, (int)n_tiles_n, (int)n_tiles_m,
+                                                                                             (long long)total, ga);
+  PDN_LAUNCHED(GATHER ? "conv_gemm_tc" : "gemm_tc");
   return 0;
+}
+
+template <int GATHER>
+static int launch_bn(int BN, const CUtensorMap& mA, const CUtensorMap& mB, const TcArgs& t, const GatherArgs& ga) {
+  if (BN == 256) return launch_tc<256, GATHER>(mA, mB, t, ga);
+  if (BN == 128) return launch_tc<128, GATHER>(mA, mB, t, ga);
+  return launch_tc<64, GATHER>(mA, mB, t, ga);
 }
 
 // C (+)= A·Bᵀ on pre-packed bf16 hi/lo planes. `t` carries C, bias, M/N/K, ldc, batches, accumulate, nchw_hw;
@@ -482,9 +570,27 @@ int gemm_tc_packed(const PackedOperand& A, const PackedOperand& B, TcArgs t, int
   CUtensorMap mA, mB;
   PDN_TRY(make_map(&mA, A.planes, A.R, A.K, A.Kp, A.nbatch, TC_BM));
   PDN_TRY(make_map(&mB, B.planes, B.R, B.K, B.Kp, B.nbatch, BN));
-  if (BN == 256) return launch_tc<256>(mA, mB, t);
-  if (BN == 128) return launch_tc<128>(mA, mB, t);
-  return launch_tc<64>(mA, mB, t);
+  GatherArgs none{};
+  return launch_bn<0>(BN, mA, mB, t, none);
+}
+
+// Implicit-GEMM convolution: C[(n,pix), o] = Σ_kk gather(src)[(n,pix), kk] · B[o, kk]; mode 1 = im2col of x (forward),
+// mode 2 = transposed-conv gather of the output gradient (backward-data). B = pre-packed planes [rows = N][K].
+int gemm_tc_conv(const float* src, const ConvGeom& geom, int mode, int64_t Mtot, int Ktot, const PackedOperand& B, TcArgs t) {
+  PDN_TRY(get_encode_fn());
+  PDN_CHECK(t.K > 0 && t.M > 0 && t.N > 0 && (mode == 1 || mode == 2), "conv_gemm_tc: bad arguments");
+  const int64_t m_tiles = (t.M + TC_BM - 1) / TC_BM;
+  const int sms = sm_count();
+  int BN = 64;
+  if (t.N > 128 && m_tiles * ((t.N + 255) / 256) >= (sms * 3) / 4) BN = 256;
+  else if (t.N > 64 && m_tiles * ((t.N + 127) / 128) >= sms / 2) BN = 128;
+  for (int i = 0; i < 3; ++i) { t.nb[i] = 1; t.a_pbs[i] = 0; t.b_pbs[i] = B.pbs[i]; }
+  t.splits = 1;
+  CUtensorMap mB;
+  PDN_TRY(make_map(&mB, B.planes, B.R, B.K, B.Kp, B.nbatch, BN));
+  GatherArgs ga;
+  ga.src = src; ga.geom = geom; ga.Mtot = Mtot; ga.Ktot = Ktot;
+  return mode == 1 ? launch_bn<1>(BN, mB, mB, t, ga) : launch_bn<2>(BN, mB, mB, t, ga);
 }
 
 int gemm_tc_launch(const GemmArgs& g) {

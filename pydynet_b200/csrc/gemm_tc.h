@@ -30,6 +30,8 @@ int pack_operand_ex(const float* src, int64_t R, int64_t K, int64_t r_stride, in
                     const int64_t* nb, const int64_t* bs, Scratch* buf, PackedOperand* out);
 // 4-D TMA map over operand planes [batch][2][R][Kp] (bf16), box = 64 (k) x box_rows x 1 x 1, 128-byte swizzle
 int tc_make_map(CUtensorMap* map, const void* base, int64_t R, int64_t K, int64_t Kp, int64_t nbatch, int box_rows);
+struct ConvGeom;
+int gemm_tc_conv(const float* src, const ConvGeom& geom, int mode, int64_t Mtot, int Ktot, const PackedOperand& B, TcArgs t);
 int gemm_tc_packed(const PackedOperand& A, const PackedOperand& B, TcArgs t, int splits, int* n_tiles_out = nullptr);
 
 }  // namespace pdn
