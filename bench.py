@@ -239,9 +239,15 @@ def run_ours(args):
                 "d2h_bytes_per_step": int(B * (TOTAL_LEN - PROMPT_LEN) * 8)},
         "gpu_launches": int(launches),
         "wall_ms_per_step": wall / args.steps * 1e3,
-        "roofline": {"kernel": "lm_head GEMM + argmax: k_gemm_tc<256> (tcgen05 BF16x3, argmax epilogue) + k_argmax_partials on cached weight planes", "bound": "hbm", "achieved": alg_bytes / max(k_avg_s, 1e-12) / 1e9,
-                     "peak": hbm, "unit": "GB/s", "frac": alg_bytes / max(k_avg_s, 1e-12) / 1e9 / hbm, "traffic": None, "peak_source": which,
-                     "launch_us": k_avg_s * 1e6, "launches_timed": k_n, "tensor_tflops_alg": alg_flops / max(k_avg_s, 1e-12) / 1e12},
+        "roofline": {"kernel": "k_gemm_tc<256> with argmax epilogue (lm_head [B,288]x[288,32000] on cached bf16 hi/lo weight planes, tcgen05 BF16x3) "
+                               "+ k_argmax_partials — the longest launch of the dominant kernel family of the decode step",
+                     "bound": "tensor", "achieved": alg_flops / max(k_avg_s, 1e-12) / 1e12, "peak": tf, "unit": "TFLOP/s",
+                     "frac": alg_flops / max(k_avg_s, 1e-12) / 1e12 / tf, "traffic": 37.7e6 if B == 512 else None, "peak_source": which,
+                     "note": "achieved = algorithmic fp32 FLOPs (2*B*288*32000) / CUDA-event time; every product costs 3 BF16 MMAs (fp32 parity), "
+                             "so the MMA-issue fraction is 3x frac; traffic = ncu dram bytes per launch at B=512 (profiles/r1_ncu_extract.txt)",
+                     "frac_of_bf16x3_ceiling": 3 * alg_flops / max(k_avg_s, 1e-12) / 1e12 / tf,
+                     "hbm_gbs_alg": alg_bytes / max(k_avg_s, 1e-12) / 1e9, "hbm_frac": alg_bytes / max(k_avg_s, 1e-12) / 1e9 / hbm,
+                     "launch_us": k_avg_s * 1e6, "launches_timed": k_n},
         "clocks": clk.summary(),
     }
     if rank == 0:
@@ -303,9 +309,9 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--batch", type=int, default=int(os.environ.get("PDN_BENCH_BATCH", 128)))
-    ap.add_argument("--cpu-batch", type=int, default=128)
-    ap.add_argument("--cpu-total-len", type=int, default=24)
+    ap.add_argument("--batch", type=int, default=int(os.environ.get("PDN_BENCH_BATCH", 1024)))
+    ap.add_argument("--cpu-batch", type=int, default=int(os.environ.get("PDN_BENCH_BATCH", 1024)))
+    ap.add_argument("--cpu-total-len", type=int, default=12)
     ap.add_argument("--no-cpu-baseline", dest="cpu_baseline", action="store_false")
     args = ap.parse_args()
     if args.impl == "reference":

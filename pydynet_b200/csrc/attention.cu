@@ -350,7 +350,7 @@ int pdn_attention_fwd(const float* q, const float* k, const float* v, const floa
   if (total == 0) return 0;
   PDN_CHECK(Lk > 0, "attention: no keys");
   PDN_CHECK((total + 3) / 4 <= 0x7fffffff, "attention: too many query rows");
-  if (Lq <= 4 && Lk >= 64 && total <= 0x7fffffff) {  // decode: split the keys of each row over a whole CTA
+  if (Lq <= 4 && Lk >= 64 && total < (int64_t)sm_count() * 16) {  // decode with few rows: split the keys of each row over a whole CTA
     k_attention_decode<<<(unsigned)total, 128, 0, stream()>>>(a);
     PDN_LAUNCHED("attention_decode");
     return 0;
@@ -417,7 +417,7 @@ int pdn_attention_fwd_dev(const float* q, const float* k, const float* v, float*
   a.lk_add = lk_add;
   const int64_t total = B * H * Lq;
   if (total == 0) return 0;
-  if (Lq <= 4 && total <= 0x7fffffff) {  // graph-replayed decode step: the key count is only known on the device
+  if (Lq <= 4 && total < (int64_t)sm_count() * 16) {  // graph-replayed decode step with few rows (key count only known on the device)
     k_attention_decode<<<(unsigned)total, 128, 0, stream()>>>(a);
     PDN_LAUNCHED("attention_decode");
     return 0;

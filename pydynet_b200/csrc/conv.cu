@@ -92,17 +92,17 @@ static void tc_defaults(TcArgs& t) {
   t.bias = nullptr; t.accumulate = 0; t.splits = 1; t.nchw_hw = 0; t.c_clear_bytes = 0; t.amax_val = nullptr; t.amax_idx = nullptr;
 }
 
-// per-output-channel sum of an NCHW tensor: dbias[o] = Σ_{n,pix} g[n,o,pix]
+// per-output-channel sum of an NCHW tensor: dbias[o] = Σ_{n,pix} g[n,o,pix]; grid (O, image chunks), atomics into a zeroed vector
 __global__ void __launch_bounds__(256) k_channel_sum(const float* __restrict__ g, float* __restrict__ out, int64_t N, int64_t O, int64_t hw) {
   __shared__ float red[32];
   const int64_t o = blockIdx.x;
   float s = 0.f;
-  for (int64_t i = threadIdx.x; i < N * hw; i += blockDim.x) {
-    int64_t n = i / hw, p = i - n * hw;
-    s += g[(n * O + o) * hw + p];
+  for (int64_t n = blockIdx.y; n < N; n += gridDim.y) {
+    const float* p = g + (n * O + o) * hw;
+    for (int64_t i = threadIdx.x; i < hw; i += blockDim.x) s += p[i];
   }
   s = block_sum<float>(s, red);
-  if (threadIdx.x == 0) out[o] = s;
+  if (threadIdx.x == 0) atomicAdd(out + o, s);
 }
 
 // ---------------------------------------------------------------- pooling ----------------------------------------
@@ -213,7 +213,11 @@ int pdn_conv2d_bwd_weight(const float* x, const float* gy, float* dw, float* dbi
   PDN_TRY(make_geom(g, N, C, H, W, O, k, stride, pad));
   const int64_t hw = g.oh * g.ow, M = N * hw, K = C * k * k;
   if (dbias && O > 0) {
-    k_channel_sum<<<(unsigned)O, 256, 0, stream()>>>(gy, dbias, N, O, hw);
+    PDN_CUDA(cudaMemsetAsync(dbias, 0, (size_t)O * sizeof(float), stream()));
+    int64_t chunks = (sm_count() * 8 + O - 1) / O;
+    if (chunks > N) chunks = N;
+    if (chunks < 1) chunks = 1;
+    k_channel_sum<<<dim3((unsigned)O, (unsigned)chunks), 256, 0, stream()>>>(gy, dbias, N, O, hw);
     PDN_LAUNCHED("channel_sum");
   }
   if (!dw || O == 0 || K == 0) return 0;

@@ -116,7 +116,17 @@ struct GatherArgs {
   ConvGeom     geom;
   int64_t      Mtot;
   int          Ktot;
+  const int2*  tab;  // per column kk of the im2col matrix: {channel * plane_size, (ky << 16) | kx}, built once per call
 };
+
+// kk -> (channel plane offset, window offsets): hoists three divisions out of the gather loop (the first ncu capture of the
+// producer warps showed ~70 instructions per gathered element and instruction-fetch stalls, profiles/r1_ncu_summary.md)
+__global__ void k_conv_table(int2* tab, int Kpad, int Ktot, int k, int plane) {
+  const int kk = blockIdx.x * blockDim.x + threadIdx.x;
+  if (kk >= Kpad) return;
+  const int kx = kk % k, t = kk / k, ky = t % k, ch = t / k;
+  tab[kk] = kk < Ktot ? make_int2(ch * plane, (ky << 16) | kx) : make_int2(0, 0x7fff7fff);  // out of range -> fails the bounds test
+}
 
 template <int BN, int GATHER>
 __global__ void __launch_bounds__(GATHER ? 512 : 256, 1)
@@ -331,7 +341,6 @@ k_gemm_tc(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUte
   if (GATHER && warp >= 8) {
     // ===== implicit-GEMM A producer: thread = (tile row r, 32-column half of the 64-wide k-block) =====
     const int gw = warp - 8, r = (gw & 3) * 32 + lane, half = gw >> 2;
-    const int kk2 = ga.geom.k * ga.geom.k;
     int stage = 0;
     uint32_t phase = 0;
     for (long long t = blockIdx.x; t < total_tiles; t += gridDim.x) {
@@ -342,31 +351,29 @@ k_gemm_tc(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUte
       const RowPos rp = (GATHER == 1) ? conv_row<0>(ga.geom, (int64_t)m_blk * TC_BM + r, ga.Mtot) : conv_row<1>(ga.geom, (int64_t)m_blk * TC_BM + r, ga.Mtot);
       for (int kb = 0; kb < num_kb; ++kb) {
         const int kk0 = (kb_begin + kb) * TC_BK + half * 32;
-        // all 32 loads are issued before the first conversion (one warp per scheduler: ILP hides the latency)
+        // all 32 loads are issued before the first conversion (ILP hides the latency); per element: one broadcast table read,
+        // two unsigned bounds tests, one 32-bit offset
         float v[32];
-        int ch = kk0 / kk2, rem = kk0 - ch * kk2, ky = rem / ga.geom.k, kx = rem - ky * ga.geom.k;
+        const float* base = ga.src + rp.base;
+        const int2*  tb = ga.tab + kk0;
+        const int    Hs = (GATHER == 1) ? (int)ga.geom.H : (int)ga.geom.oh, Ws = (GATHER == 1) ? (int)ga.geom.W : (int)ga.geom.ow;
 #pragma unroll
         for (int e = 0; e < 32; ++e) {
-          float x = 0.f;
-          if (rp.ok && kk0 + e < ga.Ktot) {
-            if (GATHER == 1) {
-              const int iy = rp.y + ky, ix = rp.x + kx;
-              if (iy >= 0 && iy < (int)ga.geom.H && ix >= 0 && ix < (int)ga.geom.W) x = __ldg(ga.src + rp.base + ((int64_t)ch * ga.geom.H + iy) * ga.geom.W + ix);
-            } else {
-              const int ty = rp.y - ky, tx = rp.x - kx;
-              if (ty >= 0 && tx >= 0) {
-                int oy = ty, ox = tx;
-                bool ok = true;
-                if (ga.geom.stride != 1) {
-                  ok = (ty % ga.geom.stride == 0) && (tx % ga.geom.stride == 0);
-                  oy = ty / ga.geom.stride; ox = tx / ga.geom.stride;
-                }
-                if (ok && oy < (int)ga.geom.oh && ox < (int)ga.geom.ow) x = __ldg(ga.src + rp.base + ((int64_t)ch * ga.geom.oh + oy) * ga.geom.ow + ox);
-              }
+          const int2 te = __ldg(tb + e);
+          const int  ky = te.y >> 16, kx = te.y & 0xffff;
+          int yy, xx;
+          bool ok = rp.ok;
+          if (GATHER == 1) {
+            yy = rp.y + ky; xx = rp.x + kx;
+          } else {
+            yy = rp.y - ky; xx = rp.x - kx;
+            if (ga.geom.stride != 1) {
+              ok = ok && yy >= 0 && xx >= 0 && (yy % ga.geom.stride == 0) && (xx % ga.geom.stride == 0);
+              yy /= ga.geom.stride; xx /= ga.geom.stride;
             }
           }
-          v[e] = x;
-          if (++kx == ga.geom.k) { kx = 0; if (++ky == ga.geom.k) { ky = 0; ++ch; } }
+          ok = ok && (unsigned)yy < (unsigned)Hs && (unsigned)xx < (unsigned)Ws;
+          v[e] = ok ? __ldg(base + (te.x + yy * Ws + xx)) : 0.f;
         }
         mbar_wait(&empty_bar[stage], phase ^ 1);
         uint8_t* ah = smem + stage * Cfg::kStageBytes;
@@ -590,6 +597,14 @@ int gemm_tc_conv(const float* src, const ConvGeom& geom, int mode, int64_t Mtot,
   PDN_TRY(make_map(&mB, B.planes, B.R, B.K, B.Kp, B.nbatch, BN));
   GatherArgs ga;
   ga.src = src; ga.geom = geom; ga.Mtot = Mtot; ga.Ktot = Ktot;
+  Scratch   stab;
+  const int Kpad = ((Ktot + TC_BK - 1) / TC_BK) * TC_BK;
+  PDN_TRY(stab.alloc((size_t)Kpad * sizeof(int2)));
+  const int64_t plane = mode == 1 ? geom.H * geom.W : geom.oh * geom.ow;
+  PDN_CHECK(plane * (mode == 1 ? geom.C : geom.O) < 0x7fffffff && geom.k < 0x7fff, "conv_gemm_tc: image too large for 32-bit offsets");
+  k_conv_table<<<(Kpad + 255) / 256, 256, 0, stream()>>>((int2*)stab.p, Kpad, Ktot, geom.k, (int)plane);
+  PDN_LAUNCHED("conv_table");
+  ga.tab = (const int2*)stab.p;
   return mode == 1 ? launch_bn<1>(BN, mB, mB, t, ga) : launch_bn<2>(BN, mB, mB, t, ga);
 }
 

@@ -74,8 +74,12 @@ __global__ void __launch_bounds__(256) k_feat_apply(const float* __restrict__ x,
                                                     int64_t total, uint32_t C, uint32_t inner, float eps) {
   if (VEC) {
     const int64_t n4 = total >> 2;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
-      const uint32_t e = (uint32_t)((i << 2) % ((int64_t)C * inner));  // offset inside one [C, inner] slab (< 2^32 checked on the host)
+    // offset inside one [C, inner] slab, advanced incrementally (no division in the loop; slab < 2^31 checked on the host)
+    const uint32_t slab = C * inner;
+    const int64_t  i0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, di = (int64_t)gridDim.x * blockDim.x;
+    uint32_t       e = (uint32_t)((i0 << 2) % slab);
+    const uint32_t de = (uint32_t)((di << 2) % slab);
+    for (int64_t i = i0; i < n4; i += di, e = (e + de >= slab) ? e + de - slab : e + de) {
       const float4   xv = __ldg(reinterpret_cast<const float4*>(x) + i);
       float4 o;
       if (inner == 1) {
@@ -107,8 +111,11 @@ __global__ void __launch_bounds__(256) k_feat_bwd_dx(const float* __restrict__ x
                                                      float eps) {
   if (VEC) {
     const int64_t n4 = total >> 2;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
-      const uint32_t e = (uint32_t)((i << 2) % ((int64_t)C * inner));
+    const uint32_t slab = C * inner;
+    const int64_t  i0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, di = (int64_t)gridDim.x * blockDim.x;
+    uint32_t       e = (uint32_t)((i0 << 2) % slab);
+    const uint32_t de = (uint32_t)((di << 2) % slab);
+    for (int64_t i = i0; i < n4; i += di, e = (e + de >= slab) ? e + de - slab : e + de) {
       const float4   xv = __ldg(reinterpret_cast<const float4*>(x) + i), gv = __ldg(reinterpret_cast<const float4*>(g) + i);
       const float xs[4] = {xv.x, xv.y, xv.z, xv.w}, gs[4] = {gv.x, gv.y, gv.z, gv.w};
       float o[4];
@@ -140,7 +147,7 @@ __global__ void k_scale_vec(float* a, float* b, float s, int64_t n) {
 // vectors are read as float4; inner > 1: inner % 4 == 0), one [C, inner] slab addressable in 32 bits
 static bool feat_vec_ok(const float* a, const float* b, int64_t C, int64_t inner) {
   if ((((uintptr_t)a) | ((uintptr_t)b)) & 15) return false;
-  if (C * inner >= 0xffffffffLL || C > 0x7fffffff || inner > 0x7fffffff) return false;
+  if (C * inner >= 0x7fffffffLL) return false;
   return inner == 1 ? (C % 4 == 0) : (inner % 4 == 0);
 }
 
