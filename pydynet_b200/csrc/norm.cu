@@ -37,6 +37,52 @@ __global__ void __launch_bounds__(256) k_feat_reduce_rows(const float* __restric
   }
 }
 
+// inner == 1, C % 4 == 0: same reduction with 128-bit loads — block = 32 column-quads (128 channels) x 8 row-lanes
+template <int MODE>
+__global__ void __launch_bounds__(256) k_feat_reduce_rows4(const float* __restrict__ x, const float* __restrict__ g, const float* __restrict__ mean,
+                                                           const float* __restrict__ var, float eps, float* __restrict__ s1, float* __restrict__ s2,
+                                                           int64_t rows, int64_t C, float inv_m) {
+  __shared__ float4 r1[8][33], r2[8][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int64_t c = ((int64_t)blockIdx.x * 32 + tx) * 4;
+  float4 a1 = make_float4(0.f, 0.f, 0.f, 0.f), a2 = a1;
+  if (c < C) {
+    float4 mu = a1, rs = a1;
+    if (MODE >= 1) mu = *reinterpret_cast<const float4*>(mean + c);
+    if (MODE == 2) {
+      const float4 vv = *reinterpret_cast<const float4*>(var + c);
+      rs = make_float4(rsqrtf(vv.x + eps), rsqrtf(vv.y + eps), rsqrtf(vv.z + eps), rsqrtf(vv.w + eps));
+    }
+    for (int64_t r = (int64_t)blockIdx.y * 8 + ty; r < rows; r += (int64_t)gridDim.y * 8) {
+      const float4 xv = __ldg(reinterpret_cast<const float4*>(x + r * C + c));
+      if (MODE == 0) { a1.x += xv.x; a1.y += xv.y; a1.z += xv.z; a1.w += xv.w; }
+      else if (MODE == 1) {
+        const float dx = xv.x - mu.x, dy = xv.y - mu.y, dz = xv.z - mu.z, dw = xv.w - mu.w;
+        a1.x += dx * dx; a1.y += dy * dy; a1.z += dz * dz; a1.w += dw * dw;
+      } else {
+        const float4 gv = __ldg(reinterpret_cast<const float4*>(g + r * C + c));
+        a1.x += gv.x; a1.y += gv.y; a1.z += gv.z; a1.w += gv.w;
+        a2.x += gv.x * (xv.x - mu.x) * rs.x; a2.y += gv.y * (xv.y - mu.y) * rs.y;
+        a2.z += gv.z * (xv.z - mu.z) * rs.z; a2.w += gv.w * (xv.w - mu.w) * rs.w;
+      }
+    }
+  }
+  r1[ty][tx] = a1; r2[ty][tx] = a2;
+  __syncthreads();
+  if (ty == 0 && c < C) {
+#pragma unroll
+    for (int i = 1; i < 8; ++i) {
+      const float4 b1 = r1[i][tx], b2 = r2[i][tx];
+      a1.x += b1.x; a1.y += b1.y; a1.z += b1.z; a1.w += b1.w;
+      a2.x += b2.x; a2.y += b2.y; a2.z += b2.z; a2.w += b2.w;
+    }
+    atomicAdd(s1 + c, a1.x * inv_m); atomicAdd(s1 + c + 1, a1.y * inv_m); atomicAdd(s1 + c + 2, a1.z * inv_m); atomicAdd(s1 + c + 3, a1.w * inv_m);
+    if (MODE == 2) {
+      atomicAdd(s2 + c, a2.x * inv_m); atomicAdd(s2 + c + 1, a2.y * inv_m); atomicAdd(s2 + c + 2, a2.z * inv_m); atomicAdd(s2 + c + 3, a2.w * inv_m);
+    }
+  }
+}
+
 // inner > 1 : block = (channel, chunk); threads walk j = (o, i) with i fastest (coalesced along inner)
 template <int MODE>
 __global__ void __launch_bounds__(256) k_feat_reduce_chan(const float* __restrict__ x, const float* __restrict__ g, const float* __restrict__ mean,
@@ -157,7 +203,15 @@ static int feat_reduce(const float* x, const float* g, const float* mean, const 
   PDN_CUDA(cudaMemsetAsync(s1, 0, (size_t)C * sizeof(float), stream()));
   if (s2) PDN_CUDA(cudaMemsetAsync(s2, 0, (size_t)C * sizeof(float), stream()));
   const int sms = sm_count();
-  if (inner == 1) {
+  const bool al16 = ((((uintptr_t)x) | ((uintptr_t)g) | ((uintptr_t)mean) | ((uintptr_t)var)) & 15) == 0;
+  if (inner == 1 && (C & 3) == 0 && al16) {
+    int64_t gx = (C / 4 + 31) / 32;
+    int64_t gy = (sms * 8 + gx - 1) / gx;
+    if (gy > (outer + 7) / 8) gy = (outer + 7) / 8;
+    if (gy < 1) gy = 1;
+    if (gy > 65535) gy = 65535;
+    k_feat_reduce_rows4<MODE><<<dim3((unsigned)gx, (unsigned)gy), 256, 0, stream()>>>(x, g, mean, var, eps, s1, s2, outer, C, inv_m);
+  } else if (inner == 1) {
     int64_t gx = (C + 31) / 32;
     int64_t gy = (sms * 4 + gx - 1) / gx;
     if (gy > (outer + 7) / 8) gy = (outer + 7) / 8;
