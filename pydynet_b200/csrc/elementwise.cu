@@ -151,6 +151,37 @@ __global__ void __launch_bounds__(256) k_binary_dense_f32(int op, const float4* 
     out[i] = r;
   }
 }
+// dense fp32 operands where any input may instead be ONE broadcast element (a 0-d / size-1 device array — what the reference's
+// scalar wrapping produces, tensor.py:488-493: relu = maximum(Tensor(0.), x)); avoids the generic strided walk
+__global__ void __launch_bounds__(256) k_binary_mixed_f32(int op, const float* __restrict__ a, const float* __restrict__ b, float4* __restrict__ out,
+                                                         int64_t n4, int a_one, int b_one) {
+  const float a0 = a_one ? __ldg(a) : 0.f, b0 = b_one ? __ldg(b) : 0.f;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+    const float4 x = a_one ? make_float4(a0, a0, a0, a0) : __ldg(reinterpret_cast<const float4*>(a) + i);
+    const float4 y = b_one ? make_float4(b0, b0, b0, b0) : __ldg(reinterpret_cast<const float4*>(b) + i);
+    float4 r;
+    r.x = binary_arith<float>(op, x.x, y.x);
+    r.y = binary_arith<float>(op, x.y, y.y);
+    r.z = binary_arith<float>(op, x.z, y.z);
+    r.w = binary_arith<float>(op, x.w, y.w);
+    out[i] = r;
+  }
+}
+__global__ void __launch_bounds__(256) k_ternary_mixed_f32(int op, const float* __restrict__ a, const float* __restrict__ b, const float* __restrict__ c,
+                                                          float4* __restrict__ out, int64_t n4, int a_one, int b_one, int c_one) {
+  const float a0 = a_one ? __ldg(a) : 0.f, b0 = b_one ? __ldg(b) : 0.f, c0 = c_one ? __ldg(c) : 0.f;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+    const float4 x = a_one ? make_float4(a0, a0, a0, a0) : __ldg(reinterpret_cast<const float4*>(a) + i);
+    const float4 y = b_one ? make_float4(b0, b0, b0, b0) : __ldg(reinterpret_cast<const float4*>(b) + i);
+    const float4 z = c_one ? make_float4(c0, c0, c0, c0) : __ldg(reinterpret_cast<const float4*>(c) + i);
+    float4 r;
+    r.x = ternary_float<float>(op, x.x, y.x, z.x);
+    r.y = ternary_float<float>(op, x.y, y.y, z.y);
+    r.z = ternary_float<float>(op, x.z, y.z, z.z);
+    r.w = ternary_float<float>(op, x.w, y.w, z.w);
+    out[i] = r;
+  }
+}
 // dense rows + broadcast vector over the last dim (bias add, scale mul): a[r, c] op b[c]
 __global__ void __launch_bounds__(256) k_binary_rowvec_f32(int op, const float4* __restrict__ a, const float4* __restrict__ b,
                                                           float4* __restrict__ out, int64_t n4, int cols4, int b_left) {
@@ -345,6 +376,15 @@ int pdn_ew_binary(int op, int dtype, const void* a, const void* b, void* out, in
       PDN_LAUNCHED("binary_dense_f32");
       return 0;
     }
+    {  // every input dense or a single broadcast element, output dense
+      auto one = [&](int o) { return d.ndim == 0 || (d.ndim == 1 && d.s[o][0] == 0); };
+      if (desc_dense(d, 2) && d.n % 4 == 0 && d.ndim <= 1 && (desc_dense(d, 0) || one(0)) && (desc_dense(d, 1) || one(1))) {
+        k_binary_mixed_f32<<<grid_for(d.n / 4, 256, 2), 256, 0, stream()>>>(op, (const float*)a, (const float*)b, (float4*)out, d.n / 4,
+                                                                           one(0) && !desc_dense(d, 0), one(1) && !desc_dense(d, 1));
+        PDN_LAUNCHED("binary_mixed_f32");
+        return 0;
+      }
+    }
     // [rows, cols] op [cols] with dense rows (bias / scale vectors)
     if (d.ndim == 2 && d.s[2][1] == 1 && d.s[2][0] == d.shape[1] && d.shape[1] % 4 == 0) {
       bool a_full = d.s[0][1] == 1 && d.s[0][0] == d.shape[1], b_full = d.s[1][1] == 1 && d.s[1][0] == d.shape[1];
@@ -420,6 +460,16 @@ int pdn_ew_ternary(int op, int dtype, const void* a, const void* b, const void* 
   const int64_t* st[4] = {sa, sb, sc, so};
   PDN_TRY(make_desc(ndim, shape, 4, st, &d));
   if (d.n == 0) return 0;
+  if (dtype == PDN_F32 && d.ndim <= 1 && d.n % 4 == 0 && desc_dense(d, 3) && aligned16(a) && aligned16(b) && aligned16(c) && aligned16(out)) {
+    auto one = [&](int o) { return d.ndim == 0 || (d.ndim == 1 && d.s[o][0] == 0); };
+    if ((desc_dense(d, 0) || one(0)) && (desc_dense(d, 1) || one(1)) && (desc_dense(d, 2) || one(2))) {
+      k_ternary_mixed_f32<<<grid_for(d.n / 4, 256, 2), 256, 0, stream()>>>(op, (const float*)a, (const float*)b, (const float*)c, (float4*)out,
+                                                                          d.n / 4, one(0) && !desc_dense(d, 0), one(1) && !desc_dense(d, 1),
+                                                                          one(2) && !desc_dense(d, 2));
+      PDN_LAUNCHED("ternary_mixed_f32");
+      return 0;
+    }
+  }
   int g = grid_for(d.n, 256, 2);
   switch (dtype) {
     case PDN_F32: k_ternary_strided<float><<<g, 256, 0, stream()>>>(op, (const float*)a, (const float*)b, (const float*)c, (float*)out, d); break;

@@ -55,7 +55,18 @@ __global__ void __launch_bounds__(256) k_pack_split(PackArgs p) {
   const bool k_fast = (p.k_stride == 1) || (p.r_stride != 1);
   const bool flat_k = p.k_inner >= p.K;
   auto koff = [&](int64_t k) { return flat_k ? k * p.k_stride : (k / p.k_inner) * p.k_outer_stride + (k % p.k_inner) * p.k_stride; };
-  if (k_fast) {
+  if (p.k_stride == 1 && flat_k && (p.r_stride & 3) == 0 && ((((uintptr_t)src) & 15) == 0) && k0 + 64 <= p.K) {
+    // contiguous k: the 32 x 64 tile is 32 rows of 16 float4 — half a warp per row, 128-bit loads
+    const int c4 = threadIdx.x & 15, rr = threadIdx.x >> 4;  // 16 x 16
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const int64_t r = r0 + rr + i * 16;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (r < p.R) v = __ldg(reinterpret_cast<const float4*>(src + r * p.r_stride + k0) + c4);
+      float* t = &tile[rr + i * 16][c4 * 4];
+      t[0] = v.x; t[1] = v.y; t[2] = v.z; t[3] = v.w;
+    }
+  } else if (k_fast) {
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       const int64_t r = r0 + ty + i * 8;
@@ -545,6 +556,7 @@ int gemm_tc_packed(const PackedOperand& A, const PackedOperand& B, TcArgs t, int
   if (getenv("PDN_TC_BN128") != nullptr) BN = 128;
   else if (t.N > 128 && tiles_for(256) >= (sms * 3) / 4) BN = 256;
   else if (t.N > 64 && tiles_for(128) >= sms / 2) BN = 128;
+  else if (splits <= 0 && (t.K + TC_BK - 1) / TC_BK >= 16 && t.N > 64) BN = t.N > 128 ? 256 : 128;  // long K: wide tiles, split-K fills the SMs
   for (int i = 0; i < 3; ++i) { t.a_pbs[i] = A.pbs[i]; t.b_pbs[i] = B.pbs[i]; }
   const int64_t tiles = tiles_for(BN);
   const int     num_kb = (int)((t.K + TC_BK - 1) / TC_BK);

@@ -1,0 +1,80 @@
+"""The reference's OWN model files run unchanged on this package (drop-in check of the Python surface): its Llama
+(llm/llama/model.py) and example ConvNet / Transformer / GRU classes are exec'd with ``pydynet`` aliased to ``pydynet_b200``
+and must reproduce the golden vectors that the unmodified reference produced. Runs on the cpu device; skipped where
+/root/reference is not mounted (the GPU box) — nothing here is needed at run time by the product."""
+import importlib
+import os
+import sys
+
+import numpy as np
+import pytest
+
+REF = "/root/reference"
+pytestmark = pytest.mark.skipif(not os.path.isdir(REF), reason="reference sources not mounted")
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+@pytest.fixture()
+def aliased():
+    import pydynet_b200 as pdn
+    names = {"pydynet": pdn, "pydynet.core": pdn.core, "pydynet.core.tensor": importlib.import_module("pydynet_b200.core.tensor"),
+             "pydynet.nn": pdn.nn, "pydynet.nn.functional": pdn.nn.functional, "pydynet.nn.parameter": importlib.import_module("pydynet_b200.nn.parameter"),
+             "pydynet.special": pdn.special, "pydynet.optim": pdn.optim, "pydynet.autograd": pdn.autograd, "pydynet.cuda": pdn.cuda}
+    saved = {k: sys.modules.get(k) for k in names}
+    sys.modules.update(names)
+    try:
+        yield pdn
+    finally:
+        for k, v in saved.items():
+            if v is None:
+                sys.modules.pop(k, None)
+            else:
+                sys.modules[k] = v
+        pdn.autograd.set_grad_enabled(True)
+
+
+def _exec(path, start=None, end=None, extra=None):
+    src = open(path).read().splitlines()
+    ns = {"__name__": "ref_model_on_b200"}
+    ns.update(extra or {})
+    exec(compile("\n".join(src[start:end]), path, "exec"), ns)
+    return ns
+
+
+def test_reference_llama_file_runs_unchanged(aliased):
+    pdn = aliased
+    ns = _exec(os.path.join(REF, "llm/llama/model.py"))
+    g = np.load(os.path.join(GOLD, "llama.npz"))
+    V, D, H, FF, S, B, L = (int(v) for v in g["cfg"])
+    net = ns["Llama"](V, D, H, FF, S, B, L, np.float32)
+    for name, p in net._parameters.items():
+        if "p." + name in g.files:
+            p.data[...] = g["p." + name]
+    net.eval()
+    with pdn.no_grad():
+        toks = np.concatenate([t.numpy() for t in net.generate(pdn.Tensor(g["gen.prompt"]), 40)], axis=1)
+    np.testing.assert_array_equal(toks, g["gen.tokens"])
+
+
+def test_reference_example_models_run_unchanged(aliased):
+    pdn = aliased
+    import pydynet_b200.nn as nn
+    import pydynet_b200.nn.functional as F
+    extra = {"np": np, "pdn": pdn, "nn": nn, "F": F, "DTYPE": np.float32}
+    ConvNet = _exec(os.path.join(REF, "examples/pydynet/mnist.py"), 81, 98, extra)["ConvNet"]
+    g = np.load(os.path.join(GOLD, "lenet.npz"))
+    net = ConvNet()
+    for name, p in net._parameters.items():
+        p.data[...] = g["p0." + name]
+    out = net(pdn.Tensor(g["X"], dtype=np.float32))
+    np.testing.assert_allclose(out.numpy(), g["logits0"], rtol=1e-4, atol=1e-5)
+    ns = _exec(os.path.join(REF, "examples/pydynet/transformer.py"), 52, 192, extra)
+    g = np.load(os.path.join(GOLD, "transformer.npz"))
+    net = ns["Transformer"](32, 1, 4, 3, 0.05, 40, 12)
+    for name, p in net._parameters.items():
+        if "p0." + name in g.files:
+            p.data[...] = g["p0." + name]
+    net.train()
+    X = pdn.Tensor(g["X"])
+    out = net(X, ns["construct_mask"](X))
+    np.testing.assert_allclose(out.numpy(), g["out0"], rtol=1e-4, atol=1e-5)
