@@ -77,8 +77,7 @@ class ClockSampler:
 # ------------------------------------------------------------------------------------------------- our arm
 def build_model(B, device):
     import pydynet_b200 as pdn
-    from oracle.pdn_oracle import synthetic_llama_params  # weight generator only (shared with the CPU arm)
-    from workloads.llama import Llama
+    from workloads.llama import Llama, synthetic_llama_params
     params = synthetic_llama_params(CFG["V"], CFG["D"], CFG["H"], CFG["FF"], CFG["L"], seed=0, std=0.05)
     net = Llama(CFG["V"], CFG["D"], CFG["H"], CFG["FF"], CFG["S"], B, CFG["L"], np.float32).to(device)
     for name, p in net._parameters.items():

@@ -24,6 +24,25 @@ def compute_cos_sin_cache(head_dim: int, max_seq_len: int, base: int = 10000, dt
     return Tensor(np.cos(freqs)), Tensor(np.sin(freqs))
 
 
+def synthetic_llama_params(V, D, H, FF, n_layers, seed=0, std=0.05, dtype=np.float32):
+    """Random-init weights of the BASELINE config-3 architecture keyed by the reference's ``_parameters`` names
+    (llm/llama/model.py:216): matrices N(0, std), norm weights 1, lm_head bias N(0, std) — SURVEY.md §8(d) C3. Draw order is
+    part of the contract (tests compare against the oracle's own generator bit for bit)."""
+    rng = np.random.default_rng(seed)
+    draw = lambda *shape: (rng.standard_normal(shape) * std).astype(dtype)
+    out = {"tok_embedding.weight": draw(V, D), "norm.weight": np.ones(D, dtype), "lm_head.weight": draw(D, V), "lm_head.bias": draw(V)}
+    for i in range(n_layers):
+        pre = f"layers.{i}."
+        for nm in "QKVO":
+            out[pre + f"attention.{nm}.weight"] = draw(D, D)
+        out[pre + "ffn.up.weight"] = draw(D, FF)
+        out[pre + "ffn.gate.weight"] = draw(D, FF)
+        out[pre + "ffn.down.weight"] = draw(FF, D)
+        out[pre + "input_norm.weight"] = np.ones(D, dtype)
+        out[pre + "post_attn_norm.weight"] = np.ones(D, dtype)
+    return out
+
+
 def apply_rotary_emb(xq, xk, freqs_cos, freqs_sin):
     """Rotates consecutive (even, odd) feature pairs of every head by the position angle."""
     cos, sin = pdn.unsqueeze(freqs_cos, axis=-2), pdn.unsqueeze(freqs_sin, axis=-2)
