@@ -24,6 +24,8 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 CFG = dict(V=32000, D=288, H=6, FF=768, S=1024, L=6)
+# dram__bytes_read.sum + dram__bytes_write.sum of ONE k_attention_rows launch from `ncu --set full`, keyed by (batch, keys)
+ATT_NCU_TRAFFIC = {}
 PROMPT_LEN, TOTAL_LEN = 4, int(os.environ.get("PDN_BENCH_TOTAL_LEN", 256))  # the env override exists for short ncu captures only
 
 
@@ -106,10 +108,15 @@ def generate_e2e(net, prompt_host, device, pinned):
 
 class KernelTimer:
     """CUDA-event bracket around every launch of one entry point inside the timed region (events are recorded on the
-    library's compute stream, the stream the kernel is launched on)."""
+    library's compute stream, the stream the kernel is launched on).
 
-    def __init__(self, lib, entry, predicate):
-        self.lib, self.entry, self.pred, self.pairs, self.on = lib, entry, predicate, [], False
+    in_graph=False: brackets eager launches. in_graph=True: brackets the launches made while a decode step is being RECORDED
+    into a CUDA graph — the two cudaEventRecord calls become event-record nodes of that graph, so every replay re-stamps them
+    and, once the pass has finished, the pair holds the device time of the kernel in the LAST replayed decode step (context =
+    total length). No host hook runs between kernels of a replay."""
+
+    def __init__(self, lib, entry, predicate, in_graph=False):
+        self.lib, self.entry, self.pred, self.pairs, self.on, self.in_graph = lib, entry, predicate, [], False, in_graph
         self.pool = []
         import pydynet_b200.cuda as cuda
         self.cuda = cuda
@@ -121,7 +128,7 @@ class KernelTimer:
         timer = self
 
         def call(name, *args):
-            if timer.on and name == timer.entry and timer.pred(args) and not timer.cuda.is_capturing():
+            if timer.on and name == timer.entry and timer.pred(args) and timer.cuda.is_capturing() == timer.in_graph:
                 if timer.pool:
                     e0, e1 = timer.pool.pop()
                 else:
@@ -142,7 +149,7 @@ class KernelTimer:
         ms = C.c_float()
         tot, n = 0.0, 0
         for e0, e1 in self.pairs:
-            self.lib.load().pdn_event_elapsed_ms(e0, e1, C.byref(ms))
+            self.lib.call("pdn_event_elapsed_ms", e0, e1, C.byref(ms))
             tot += ms.value
             n += 1
         self.pool.extend(self.pairs)
@@ -173,9 +180,20 @@ def run_ours(args):
         if dist is not None:
             dist.barrier()
 
-    # dominant kernel of a decode step (profiles/): the lm_head GEMM [B,288] x [288,32000] on pre-packed weight planes.
-    # Decode steps 2.. are CUDA-graph replays (no host hook between kernels), so the CUDA-event bracket catches the launches
-    # made eagerly inside the timed region: the first decode step of every pass (same kernel, same shapes, same stream).
+    # Dominant kernel of a decode step at this batch (profiles/r1d_launches_b1024.csv): the KV-cache attention, one launch per
+    # layer, HBM-bound (every cached K and V row of the batch is read once per layer and step). Decode steps 2.. are CUDA-graph
+    # replays, so its CUDA-event bracket is recorded INTO the graph (KernelTimer, in_graph=True) and read after each pass: the
+    # samples are the 6 layers' launches of the last decode step of every timed pass (context = TOTAL_LEN keys).
+    seen = [0]
+
+    def first_layer_only(a):  # layer 0's launch of each recorded decode step: two event nodes per graph, not twelve
+        seen[0] += 1
+        return seen[0] % CFG["L"] == 1
+
+    att_timer = KernelTimer(lib, "pdn_attention_fwd_dev", first_layer_only if os.environ.get("PDN_BENCH_ATT_ALL") is None else (lambda a: True), in_graph=True)
+    att_timer.install()
+    # Second view: the longest launch of the GEMM family, lm_head [B,288]x[288,32000] with the argmax epilogue, bracketed where it
+    # is launched eagerly inside the timed region (the first decode step of every pass: same kernel, same shapes, same stream).
     timer = KernelTimer(lib, "pdn_gemm_prepacked_planes_argmax", lambda a: int(a[1]) == B)
     timer.install()
     with pdn.no_grad():
@@ -187,6 +205,7 @@ def run_ours(args):
         lib.call("pdn_event_create", C.byref(ev1))
         lib.reset_launch_count()
         timer.on = True
+        att_timer.on = os.environ.get("PDN_BENCH_NO_ATT_TIMER") is None
         with ClockSampler(local) as clk:
             t0 = time.perf_counter()
             lib.call("pdn_event_record", ev0)
@@ -195,11 +214,12 @@ def run_ours(args):
             lib.call("pdn_event_record", ev1)
             barrier()
             wall = time.perf_counter() - t0
-        timer.on = False
+        timer.on = att_timer.on = False
         ms = C.c_float()
         lib.load().pdn_event_elapsed_ms(ev0, ev1, C.byref(ms))
         launches = lib.launch_count()
         k_ms, k_n = timer.collect()
+        a_ms, a_n = att_timer.collect()
         dev_s = max(ms.value / 1e3, 1e-9)
         # end-to-end arm: host prompt in, every id read back to the host (reference infer.py loop)
         for _ in range(2):
@@ -221,8 +241,13 @@ def run_ours(args):
         launches = int(lt[0])
     tokens = world * B * TOTAL_LEN * args.steps
     hbm, tf, which = _peaks()
-    # lm_head GEMM fused with the greedy argmax: algorithmic bytes per launch = A [B,288] + W [288,32000] + bias (fp32-sized
-    # operands, 4 B/element as bf16 hi+lo planes) + B int64 ids out; the [B,32000] logits never touch HBM
+    # KV-cache attention of one layer in the last decode step: algorithmic bytes per launch = every cached K and V row of the
+    # batch once (Lk = TOTAL_LEN keys x H*D fp32) + the query rows in + the output operand planes out (bf16 hi/lo = 4 B/element)
+    HD = CFG["D"]
+    att_bytes = 2.0 * B * TOTAL_LEN * HD * 4 + B * HD * 4 + B * HD * 4
+    a_avg_s = (a_ms / a_n) / 1e3 if a_n else float("nan")
+    # lm_head GEMM fused with the greedy argmax: A [B,288] + W [288,32000] + bias (fp32-sized operands, 4 B/element as bf16 hi+lo
+    # planes) + B int64 ids out; the [B,32000] logits never touch HBM
     alg_bytes = 4.0 * (B * CFG["D"] + CFG["D"] * CFG["V"] + CFG["V"]) + 8.0 * B
     alg_flops = 2.0 * B * CFG["D"] * CFG["V"]
     k_avg_s = (k_ms / k_n) / 1e3 if k_n else float("nan")
@@ -238,15 +263,24 @@ def run_ours(args):
                 "d2h_bytes_per_step": int(B * (TOTAL_LEN - PROMPT_LEN) * 8)},
         "gpu_launches": int(launches),
         "wall_ms_per_step": wall / args.steps * 1e3,
-        "roofline": {"kernel": "k_gemm_tc<256> with argmax epilogue (lm_head [B,288]x[288,32000] on cached bf16 hi/lo weight planes, tcgen05 BF16x3) "
-                               "+ k_argmax_partials — the longest launch of the dominant kernel family of the decode step",
-                     "bound": "tensor", "achieved": alg_flops / max(k_avg_s, 1e-12) / 1e12, "peak": tf, "unit": "TFLOP/s",
-                     "frac": alg_flops / max(k_avg_s, 1e-12) / 1e12 / tf, "traffic": 37.7e6 if B == 512 else None, "peak_source": which,
-                     "note": "achieved = algorithmic fp32 FLOPs (2*B*288*32000) / CUDA-event time; every product costs 3 BF16 MMAs (fp32 parity), "
-                             "so the MMA-issue fraction is 3x frac; traffic = ncu dram bytes per launch at B=512 (profiles/r1_ncu_extract.txt)",
-                     "frac_of_bf16x3_ceiling": 3 * alg_flops / max(k_avg_s, 1e-12) / 1e12 / tf,
-                     "hbm_gbs_alg": alg_bytes / max(k_avg_s, 1e-12) / 1e9, "hbm_frac": alg_bytes / max(k_avg_s, 1e-12) / 1e9 / hbm,
-                     "launch_us": k_avg_s * 1e6, "launches_timed": k_n},
+        "roofline": {"kernel": "k_attention_rows<16,4,4,8> (KV-cache decode attention, one launch per layer: q [B,1,6,48] over cache[:, :Lk] of "
+                               "[B,1024,6,48] fp32, output as GEMM operand planes) - the top kernel of the decode step at this batch "
+                               "(profiles/r1e_launches_b1024.csv)",
+                     "bound": "hbm", "achieved": att_bytes / max(a_avg_s, 1e-12) / 1e9, "peak": hbm, "unit": "GB/s",
+                     "frac": att_bytes / max(a_avg_s, 1e-12) / 1e9 / hbm, "traffic": ATT_NCU_TRAFFIC.get((B, TOTAL_LEN)), "peak_source": which,
+                     "launch_us": a_avg_s * 1e6, "launches_timed": a_n,
+                     "note": "achieved = algorithmic bytes (K and V rows of the batch once at Lk = total length, + q in + planes out) / CUDA-event "
+                             "time of the launch, bracketed by event-record nodes inside the replayed CUDA graph (last decode step of every "
+                             "timed pass, all 6 layers); traffic = ncu dram bytes of one launch at the same shape (profiles/), null if that "
+                             "shape was not captured",
+                     "gemm_view": {"kernel": "k_gemm_tc<256> with argmax epilogue (lm_head [B,288]x[288,32000] on cached bf16 hi/lo weight planes, "
+                                             "tcgen05 BF16x3) - the longest launch of the GEMM family", "bound": "tensor",
+                                   "achieved": alg_flops / max(k_avg_s, 1e-12) / 1e12, "peak": tf, "unit": "TFLOP/s",
+                                   "frac": alg_flops / max(k_avg_s, 1e-12) / 1e12 / tf,
+                                   "frac_of_bf16x3_ceiling": 3 * alg_flops / max(k_avg_s, 1e-12) / 1e12 / tf,
+                                   "note": "algorithmic fp32 FLOPs (2*B*288*32000) / CUDA-event time; every product costs 3 BF16 MMAs (fp32 parity), "
+                                           "so the MMA-issue fraction is 3x frac",
+                                   "hbm_gbs_alg": alg_bytes / max(k_avg_s, 1e-12) / 1e9, "launch_us": k_avg_s * 1e6, "launches_timed": k_n}},
         "clocks": clk.summary(),
     }
     if rank == 0:

@@ -174,6 +174,48 @@ def c5(args):
     emit(f"C5 GRU in512 h512 T{Tn} B{B} train step", sec, flops=2_013_265_920.0 * Tn * B / 256, launches=nl, us_per_time_step=sec / Tn * 1e6)
 
 
+def decode(args):
+    """Decode-step micro-benchmarks at BASELINE config-3 shapes (batch 1024 sequences): the KV-cache attention of one layer at
+    a context of 130 keys (HBM-bound: K and V rows once) and the four per-layer GEMMs + lm_head on cached weight planes."""
+    from pydynet_b200.nn import _fused
+    from pydynet_b200.backend.array import ndarray
+    rng = np.random.default_rng(2)
+    B, H, D, S, Lk = (64 if args.small else 1024), 6, 48, 1024, 130
+    for Bv in ([B] if args.small else [B, 128]):
+        q = T(rng.standard_normal((Bv, 1, H, D)).astype(f32))
+        # several cache pairs so that consecutive launches do not find their K/V rows in the 126 MB L2
+        n_caches = 1 if args.small else max(2, int(400e6 / (2 * Bv * Lk * H * D * 4)) + 1)
+        caches = [(T(rng.standard_normal((Bv, S, H, D)).astype(f32)), T(rng.standard_normal((Bv, S, H, D)).astype(f32))) for _ in range(min(n_caches, 6))]
+        it = [0]
+        out = ndarray.empty((Bv, 1, H, D), f32)
+        qs = _fused._bhl_strides(q.data)
+        views = [(ck.data[:, :Lk], cv.data[:, :Lk]) for ck, cv in caches]
+        cs = _fused._bhl_strides(views[0][0])
+
+        def att():  # straight through the C ABI: the Python operator wrapper costs more than this kernel
+            kv, vv = views[it[0] % len(views)]
+            it[0] += 1
+            lib.call("pdn_attention_fwd", q.data.ptr, kv.ptr, vv.ptr, None, out.ptr, None, Bv, H, 1, Lk, D, qs, cs, cs, None, 1.0 / D**.5, None, 0)
+
+        os.environ["PDN_ATTN"] = "ffma"
+        sec, nl = timed(att, 50)
+        os.environ.pop("PDN_ATTN", None)
+        emit(f"micro decode attention B{Bv} H{H} hd{D} ctx{Lk} (one layer, KV cache [B,{S},H,D] fp32, {len(caches)} rotating caches)", sec,
+             nbytes=2.0 * Bv * Lk * H * D * 4 + 2.0 * Bv * H * D * 4, launches=nl)
+    for (K, N) in [(288, 864), (288, 288), (288, 1536), (768, 288), (288, 32000)]:
+        w = nn.Parameter(T(rng.standard_normal((K, N)).astype(f32) * 0.05))
+        x = T(rng.standard_normal((B, K)).astype(f32))
+        pl = _fused.rmsnorm_planes(x, T(np.ones(K, f32)), 1e-5)
+        out = ndarray.empty((B, N), f32)
+        handle = _fused._packed(w).handle
+
+        def mm():
+            lib.call("pdn_gemm_prepacked_planes", pl.ptr, pl.M, pl.Kp, handle, out.ptr, N, None, 0)
+
+        sec, nl = timed(mm, 100)
+        emit(f"micro decode GEMM [{B},{K}]x[{K},{N}] on cached planes (back-to-back launches)", sec, flops=2.0 * B * K * N, launches=nl)
+
+
 def micro_att(args):
     micro(args, conv=False)
 
@@ -212,7 +254,7 @@ if __name__ == "__main__":
     args = ap.parse_args()
     for name in args.only.split(","):
         try:
-            {"c1": c1, "c2": c2, "c4": c4, "c5": c5, "micro": micro, "micro_att": micro_att, "gemm": gemm, "rows": rows}[name](args)
+            {"c1": c1, "c2": c2, "c4": c4, "c5": c5, "micro": micro, "micro_att": micro_att, "gemm": gemm, "rows": rows, "decode": decode}[name](args)
         except Exception as e:  # keep going: one config must not hide the others
             import traceback
             traceback.print_exc()

@@ -340,7 +340,9 @@ int pdn_event_destroy(void* ev) {
 }
 int pdn_event_record(void* ev) {
   PDN_TRY(ensure_init());
-  PDN_CUDA(cudaEventRecord((cudaEvent_t)ev, stream()));
+  // while a CUDA graph is being recorded the event becomes an event-record NODE of the graph (cudaEventRecordExternal): every
+  // replay stamps it, so a kernel inside a replayed graph can be timed with an ordinary event pair
+  PDN_CUDA(cudaEventRecordWithFlags((cudaEvent_t)ev, stream(), g_capturing ? cudaEventRecordExternal : cudaEventRecordDefault));
   return 0;
 }
 int pdn_event_elapsed_ms(void* start, void* stop, float* ms) {

@@ -72,3 +72,49 @@ def test_attention_fwd_bwd(impl, case):
         assert np.isfinite(a).all(), name
         e = _err(a, b)
         assert e < 1e-4, f"{impl} {case} {name}: normwise rel err {e:.3e}"
+
+
+ROW_CASES = [  # B, H, Lq, Lk, D, mask kind, cache length S (K/V are [:, :Lk] views of a [B, S, H, D] cache)
+    (3, 6, 1, 130, 48, None, 256), (2, 4, 4, 37, 64, "causal", 37), (1, 2, 2, 300, 128, None, 512), (5, 3, 1, 9, 32, "pad", 16),
+    (420, 6, 1, 70, 48, None, 96), (2, 2, 16, 16, 24, "causal", 16), (400, 8, 1, 33, 20, "pad", 40)
+]
+
+
+@pytest.mark.parametrize("case", ROW_CASES)
+def test_attention_rows_decode_shapes(case):
+    """The coalesced float4 row kernel (k_attention_rows: decode and short prefill over strided KV-cache views) — forward
+    against the fp64 chain, and backward (lse it wrote feeds k_attention_bwd) as well."""
+    import pydynet_b200 as pdn
+    from pydynet_b200.nn import _fused
+    B, H, Lq, Lk, D, mk, S = case
+    rng = np.random.default_rng(7 + Lk)
+    q = rng.standard_normal((B, Lq, H, D)).astype(np.float32)
+    ck, cv = (rng.standard_normal((B, S, H, D)).astype(np.float32) for _ in range(2))
+    g = rng.standard_normal((B, Lq, H * D)).astype(np.float32)
+    mask = None
+    if mk == "causal":
+        mask = np.triu(np.full((Lq, Lk), -np.inf, np.float32), k=1 + max(0, Lk - Lq))
+    elif mk == "pad":
+        mask = np.zeros((B, 1, 1, Lk), np.float32)
+        mask[0, ..., Lk - 5:] = -np.inf
+        mask[B - 1, ..., :2] = -np.inf
+    scale = 1.0 / np.sqrt(D)
+    k, v = ck[:, :Lk], cv[:, :Lk]
+    ref = _ref(q.astype(np.float64), k.astype(np.float64), v.astype(np.float64), None if mask is None else mask.astype(np.float64), scale,
+               g.astype(np.float64))
+    os.environ["PDN_ATTN"] = "ffma"
+    try:
+        dev = "cuda:0"
+        tq = pdn.Tensor(q, dtype=np.float32, device=dev, requires_grad=True)
+        tck, tcv = (pdn.Tensor(t, dtype=np.float32, device=dev, requires_grad=True) for t in (ck, cv))
+        tm = pdn.Tensor(mask, dtype=np.float32, device=dev) if mask is not None else None
+        out = _fused.attention(tq, tck[:, :Lk], tcv[:, :Lk], tm, float(scale))
+        (out * pdn.Tensor(g, dtype=np.float32, device=dev)).sum().backward()
+        got = (out.numpy(), tq.grad.get(), tck.grad.get()[:, :Lk], tcv.grad.get()[:, :Lk])
+    finally:
+        os.environ.pop("PDN_ATTN", None)
+    for name, a, b in zip(("out", "dq", "dk", "dv"), got, ref):
+        assert a.shape == b.shape, name
+        assert np.isfinite(a).all(), name
+        e = _err(a, b)
+        assert e < 1e-4, f"rows {case} {name}: normwise rel err {e:.3e}"
