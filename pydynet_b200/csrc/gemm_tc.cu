@@ -108,7 +108,7 @@ template <int BN>
 struct TcCfg {
   static constexpr int kStageBytes = 2 * (TC_BM * TC_BK * 2) + 2 * (BN * TC_BK * 2);  // Ahi, Alo, Bhi, Blo
   static constexpr int kStages = (BN == 64) ? 4 : ((BN == 128) ? 3 : 2);
-  static constexpr int kEpiBytes = 4 * 32 * 33 * 4;  // per-epilogue-warp 32x33 fp32 transpose tile
+  static constexpr int kEpiBytes = 4 * 32 * 32 * 4;  // per-epilogue-warp 32x32 fp32 transpose tile (XOR-swizzled float4 chunks)
   static constexpr int kSmemBytes = kStages * kStageBytes + kEpiBytes + 1024 /*align slack*/ + 256 /*barriers*/;
   static constexpr int kTmemCols = 2 * BN;  // two fp32 accumulators: the epilogue of tile i overlaps the MMAs of tile i+1
 };
@@ -154,6 +154,9 @@ k_gemm_tc(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUte
   uint32_t* tmem_slot = (uint32_t*)(tempty_bar + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const bool tr = g.trace != nullptr && blockIdx.x == 0 && lane == 0;
+#define TC_STAMP(i) do { if (tr) g.trace[i] = clock64(); } while (0)
+  if (warp == 0) TC_STAMP(0);
   const int all_kb = (int)((g.K + TC_BK - 1) / TC_BK);
   const int kb_per = (all_kb + g.splits - 1) / g.splits;  // the host guarantees every split owns >= 1 k-block
 
@@ -177,15 +180,23 @@ k_gemm_tc(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUte
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  if (warp == 0) TC_STAMP(1);
 
   // tile -> coordinates
-  auto decode = [&](long long t, int& n_blk, int& m_blk, int& split, int64_t& i0, int64_t& i1, int64_t& i2) {
-    n_blk = (int)(t % n_tiles_n); t /= n_tiles_n;
-    m_blk = (int)(t % n_tiles_m); t /= n_tiles_m;
-    split = (int)(t % g.splits); t /= g.splits;
-    i2 = t % g.nb[2]; t /= g.nb[2];
-    i1 = t % g.nb[1]; t /= g.nb[1];
-    i0 = t;
+  // 32-bit arithmetic (the host guarantees total_tiles < 2^31): 64-bit divisions cost the producer ~2000 cycles before its first TMA
+  auto decode = [&](uint32_t t, int& n_blk, int& m_blk, int& split, int64_t& i0, int64_t& i1, int64_t& i2) {
+    const uint32_t tn = (uint32_t)n_tiles_n, tm = (uint32_t)n_tiles_m;
+    uint32_t r = t / tn;
+    n_blk = (int)(t - r * tn);
+    t = r; r = t / tm;
+    m_blk = (int)(t - r * tm);
+    t = r;
+    if (g.splits > 1) { r = t / (uint32_t)g.splits; split = (int)(t - r * (uint32_t)g.splits); t = r; } else split = 0;
+    if (t == 0) { i0 = i1 = i2 = 0; return; }
+    const uint32_t n2 = (uint32_t)g.nb[2], n1 = (uint32_t)g.nb[1];
+    r = t / n2; i2 = t - r * n2; t = r;
+    r = t / n1; i1 = t - r * n1;
+    i0 = r;
   };
 
   if (warp == 0) {
@@ -193,7 +204,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUte
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (long long t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+      for (uint32_t t = blockIdx.x; t < (uint32_t)total_tiles; t += gridDim.x) {
         int n_blk, m_blk, split; int64_t i0, i1, i2;
         decode(t, n_blk, m_blk, split, i0, i1, i2);
         const int a_batch = (int)(i0 * g.a_pbs[0] + i1 * g.a_pbs[1] + i2 * g.a_pbs[2]);
@@ -211,6 +222,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUte
           }
           tma_load_4d(&mapB, &full_bar[stage], st + 2 * TC_BM * TC_BK * 2, k, n_blk * BN, 0, b_batch);
           tma_load_4d(&mapB, &full_bar[stage], st + 2 * TC_BM * TC_BK * 2 + BN * TC_BK * 2, k, n_blk * BN, 1, b_batch);
+          if (kb == 0 && t == blockIdx.x) TC_STAMP(2);
           if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
         }
       }
@@ -221,7 +233,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUte
       constexpr uint32_t idesc = make_idesc_bf16(TC_BM, BN);
       int stage = 0, acc = 0;
       uint32_t phase = 0, acc_phase = 0;
-      for (long long t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+      for (uint32_t t = blockIdx.x; t < (uint32_t)total_tiles; t += gridDim.x) {
         int n_blk, m_blk, split; int64_t i0, i1, i2;
         decode(t, n_blk, m_blk, split, i0, i1, i2);
         const int kb_begin = split * kb_per;
@@ -232,6 +244,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUte
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
+          if (kb == 0 && t == blockIdx.x) TC_STAMP(3);
           const uint32_t sa = smem_u32(smem + stage * Cfg::kStageBytes);
           const uint64_t d_ahi = make_smem_desc_sw128(sa);
           const uint64_t d_alo = make_smem_desc_sw128(sa + TC_BM * TC_BK * 2);
@@ -249,103 +262,154 @@ k_gemm_tc(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUte
           if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
         }
         umma_commit(&tfull_bar[acc]);  // accumulator complete
+        if (t == blockIdx.x) TC_STAMP(4);
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
     }
   } else if (warp >= 4 && warp < 8) {
-    // ===== epilogue: TMEM -> registers -> (+bias, +C) -> global =====
+    // ===== epilogue: TMEM -> registers -> (+bias) -> {swizzled smem transpose -> 128-bit coalesced stores | NCHW | argmax} =====
+    // Everything per element is 32-bit and predicate-free on full 32-column chunks; the first timeline trace of this kernel
+    // (PDN_TC_TRACE) showed the previous scalar epilogue at ~2100 cycles per 32-column chunk — more than the MMAs of a K = 288 tile.
     const int q = warp & 3;  // TMEM lane quarter this warp may access
-    float*    stg = epi_smem + q * (32 * 33);
+    float*    stg = epi_smem + q * (32 * 32);  // 32 rows x 32 floats, float4 chunk c of row r at r*32 + ((c ^ (r & 7)) << 2)
     int       acc = 0;
     uint32_t  acc_phase = 0;
     const bool atomic = g.splits > 1;
-    for (long long t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+    const int  N = (int)g.N;
+    const bool bias_vec = (((uintptr_t)g.bias) & 15) == 0;
+    for (uint32_t t = blockIdx.x; t < (uint32_t)total_tiles; t += gridDim.x) {
       int n_blk, m_blk, split; int64_t i0, i1, i2;
       decode(t, n_blk, m_blk, split, i0, i1, i2);
-      mbar_wait(&tfull_bar[acc], acc_phase);
-      tc_fence_after();
       const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BN) + ((uint32_t)(q * 32) << 16);
       const int64_t row0 = (int64_t)m_blk * TC_BM + q * 32;
-      const int64_t row = row0 + lane;
+      const int     m_rem = (int)((g.M - row0) < 32 ? (g.M - row0) : 32);  // valid rows of this warp's quarter (may be <= 0)
       float*        cbase = g.C + i0 * g.c_bs[0] + i1 * g.c_bs[1] + i2 * g.c_bs[2];
-      float*        crow = cbase + row * g.ldc;
-      int64_t       img = 0, pix = 0;
-      if (g.nchw_hw > 0) { img = row / g.nchw_hw; pix = row - img * g.nchw_hw; }
-      const bool add_bias = g.bias != nullptr && split == 0;
-      float      best_v = -INFINITY;
-      long long  best_i = (long long)n_blk * BN;
+      const bool    c_vec = ((g.ldc & 3) == 0) && ((((uintptr_t)cbase) & 15) == 0);
+      const bool    add_bias = g.bias != nullptr && split == 0;
+      float*        nchw_p0 = nullptr;
+      if (g.nchw_hw > 0 && lane < m_rem) {
+        const int64_t row = row0 + lane, img = row / g.nchw_hw;
+        nchw_p0 = cbase + img * g.N * g.nchw_hw + (row - img * g.nchw_hw);
+      }
+      float best_v = -INFINITY;
+      int   best_i = n_blk * BN;
+      mbar_wait(&tfull_bar[acc], acc_phase);
+      tc_fence_after();
+      if (warp == 4 && t == blockIdx.x) TC_STAMP(5);
 #pragma unroll 1
       for (int c0 = 0; c0 < BN; c0 += 32) {
-        const int64_t col0 = (int64_t)n_blk * BN + c0;
-        if (col0 >= g.N) break;  // uniform across the CTA
+        const int col0 = n_blk * BN + c0;
+        if (col0 >= N) break;  // uniform across the CTA
+        const int ncol = (N - col0) < 32 ? (N - col0) : 32;
         float v[32];
+        const bool tr0 = warp == 4 && t == blockIdx.x && c0 == 0;
+        if (tr0) TC_STAMP(9);
         tmem_ld_32x32(tmem_d + (uint32_t)c0, v);
         tmem_ld_wait();
-        if (c0 + 32 >= BN || col0 + 32 >= g.N) {
+        if (tr0) TC_STAMP(10);
+        if (c0 + 32 >= BN || col0 + 32 >= N) {
           // last chunk of this tile is in registers: hand the accumulator back to the MMA warp
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(&tempty_bar[acc]);
         }
         if (add_bias) {
+          if (ncol == 32 && bias_vec) {  // col0 is a multiple of 32: 8 broadcast 128-bit loads
 #pragma unroll
-          for (int j = 0; j < 32; ++j)
-            if (col0 + j < g.N) v[j] += __ldg(g.bias + col0 + j);
+            for (int c = 0; c < 8; ++c) {
+              const float4 b4 = __ldg(reinterpret_cast<const float4*>(g.bias + col0) + c);
+              v[4 * c] += b4.x; v[4 * c + 1] += b4.y; v[4 * c + 2] += b4.z; v[4 * c + 3] += b4.w;
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (j < ncol) v[j] += __ldg(g.bias + col0 + j);
+          }
         }
         if (g.amax_val) {
           // running (max, first column) of this row over the tile's columns; nothing is stored to C
+          if (ncol == 32) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j)
-            if (col0 + j < g.N && v[j] > best_v) { best_v = v[j]; best_i = col0 + j; }
+            for (int j = 0; j < 32; ++j)
+              if (v[j] > best_v) { best_v = v[j]; best_i = col0 + j; }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (j < ncol && v[j] > best_v) { best_v = v[j]; best_i = col0 + j; }
+          }
         } else if (g.nchw_hw > 0) {
           // NCHW scatter: for a fixed column (channel) consecutive lanes hold consecutive pixels -> coalesced
-          if (row < g.M) {
-            float* p0 = cbase + img * g.N * g.nchw_hw + pix;
+          if (nchw_p0) {
+            float* p = nchw_p0 + (int64_t)col0 * g.nchw_hw;
+            if (atomic) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (col0 + j < g.N) {
-                float* p = p0 + (col0 + j) * g.nchw_hw;
-                if (atomic) atomicAdd(p, v[j]);
-                else *p = g.accumulate ? *p + v[j] : v[j];
-              }
-          }
-        } else if (atomic) {
-          if (row < g.M) {
+              for (int j = 0; j < 32; ++j)
+                if (j < ncol) atomicAdd(p + (int64_t)j * g.nchw_hw, v[j]);
+            } else if (g.accumulate) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (col0 + j < g.N) atomicAdd(crow + col0 + j, v[j]);
-          }
-        } else {
-          // row-major C: transpose the 32x32 chunk through shared memory so that every store instruction writes one
-          // 128-byte row segment (a thread owns a ROW of the accumulator, which would otherwise give 32 scattered stores)
-#pragma unroll
-          for (int j = 0; j < 32; ++j) stg[lane * 33 + j] = v[j];
-          __syncwarp();
-          const int64_t col = col0 + lane;
-          if (col < g.N) {
-            float* p = cbase + row0 * g.ldc + col;
-            if (g.accumulate) {
-              // all 32 loads of the old C values are issued before the first store: a load-add-store loop would serialise
-              // 32 memory round trips (the compiler must assume the stores alias the next loads)
-              float old[32];
-#pragma unroll
-              for (int r = 0; r < 32; ++r) old[r] = (row0 + r < g.M) ? __ldcg(p + r * g.ldc) : 0.f;
-#pragma unroll
-              for (int r = 0; r < 32; ++r)
-                if (row0 + r < g.M) p[r * g.ldc] = old[r] + stg[r * 33 + lane];
+              for (int j = 0; j < 32; ++j)
+                if (j < ncol) p[(int64_t)j * g.nchw_hw] += v[j];
             } else {
 #pragma unroll
-              for (int r = 0; r < 32; ++r)
-                if (row0 + r < g.M) p[r * g.ldc] = stg[r * 33 + lane];
+              for (int j = 0; j < 32; ++j)
+                if (j < ncol) p[(int64_t)j * g.nchw_hw] = v[j];
+            }
+          }
+        } else {
+          // row-major C: a thread owns a ROW of the accumulator; transpose the 32x32 chunk through XOR-swizzled shared memory
+          // (8 conflict-free 128-bit stores) so that every global access is a 128-bit piece of a fully covered 128-byte row segment
+#pragma unroll
+          for (int c = 0; c < 8; ++c)
+            *reinterpret_cast<float4*>(stg + lane * 32 + ((c ^ (lane & 7)) << 2)) = make_float4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
+          __syncwarp();
+          if (tr0) TC_STAMP(11);
+          if (ncol == 32 && c_vec) {
+            const int c = lane & 7, rs = lane >> 3;  // lane -> (float4 column chunk, row within a group of 4 rows)
+            float*    p = cbase + (row0 + rs) * g.ldc + col0 + 4 * c;
+            const int64_t step = 4 * g.ldc;
+            float4    x[8];
+#pragma unroll
+            for (int it = 0; it < 8; ++it) {
+              const int r = it * 4 + rs;
+              x[it] = *reinterpret_cast<const float4*>(stg + r * 32 + ((c ^ (r & 7)) << 2));
+            }
+            if (atomic) {
+#pragma unroll
+              for (int it = 0; it < 8; ++it)
+                if (it * 4 + rs < m_rem) atomicAdd(reinterpret_cast<float4*>(p + it * step), x[it]);
+            } else {
+              if (g.accumulate) {  // all loads of the old C values are issued before the first store
+                float4 o[8];
+#pragma unroll
+                for (int it = 0; it < 8; ++it)
+                  o[it] = (it * 4 + rs < m_rem) ? __ldcg(reinterpret_cast<const float4*>(p + it * step)) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                for (int it = 0; it < 8; ++it) { x[it].x += o[it].x; x[it].y += o[it].y; x[it].z += o[it].z; x[it].w += o[it].w; }
+              }
+#pragma unroll
+              for (int it = 0; it < 8; ++it)
+                if (it * 4 + rs < m_rem) *reinterpret_cast<float4*>(p + it * step) = x[it];
+            }
+          } else if (lane < ncol) {  // edge chunk or unaligned C: scalar, lane = column
+            float* p = cbase + row0 * g.ldc + col0 + lane;
+            const int sw = lane >> 2, lo = lane & 3;
+#pragma unroll 4
+            for (int r = 0; r < m_rem; ++r) {
+              const float x = stg[r * 32 + ((sw ^ (r & 7)) << 2) + lo];
+              if (atomic) atomicAdd(p + (int64_t)r * g.ldc, x);
+              else if (g.accumulate) p[(int64_t)r * g.ldc] += x;
+              else p[(int64_t)r * g.ldc] = x;
             }
           }
           __syncwarp();
         }
+        if (tr0) TC_STAMP(12);
       }
-      if (g.amax_val && row < g.M) {
-        g.amax_val[row * n_tiles_n + n_blk] = best_v;
-        g.amax_idx[row * n_tiles_n + n_blk] = best_i;
+      if (g.amax_val && lane < m_rem) {
+        g.amax_val[(row0 + lane) * n_tiles_n + n_blk] = best_v;
+        g.amax_idx[(row0 + lane) * n_tiles_n + n_blk] = (long long)best_i;
       }
+      if (warp == 4 && t == blockIdx.x) TC_STAMP(6);
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
   }
@@ -354,7 +418,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUte
     const int gw = warp - 8, r = (gw & 3) * 32 + lane, half = gw >> 2;
     int stage = 0;
     uint32_t phase = 0;
-    for (long long t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+    for (uint32_t t = blockIdx.x; t < (uint32_t)total_tiles; t += gridDim.x) {
       int n_blk, m_blk, split; int64_t i0, i1, i2;
       decode(t, n_blk, m_blk, split, i0, i1, i2);
       const int kb_begin = split * kb_per;
@@ -414,7 +478,10 @@ k_gemm_tc(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUte
   }
   tc_fence_before();
   __syncthreads();
+  if (warp == 0) TC_STAMP(7);
   if (warp == 2) tmem_dealloc(tmem_base, Cfg::kTmemCols);
+  if (warp == 2) TC_STAMP(8);
+#undef TC_STAMP
 }
 
 // second stage of the fused GEMM + argmax: one warp per row over the per-tile partials (tiles are in column order, so the
@@ -527,11 +594,29 @@ static int launch_tc(const CUtensorMap& mA, const CUtensorMap& mB, const TcArgs&
   }
   const int64_t n_tiles_n = (t.N + BN - 1) / BN, n_tiles_m = (t.M + TC_BM - 1) / TC_BM;
   const int64_t total = n_tiles_n * n_tiles_m * t.nb[0] * t.nb[1] * t.nb[2] * t.splits;
-  PDN_CHECK(n_tiles_n <= 0x7fffffff && n_tiles_m <= 0x7fffffff, "gemm_tc: too many tiles");
+  PDN_CHECK(n_tiles_n <= 0x7fffffff && n_tiles_m <= 0x7fffffff && total < 0x7fffffff, "gemm_tc: too many tiles");
   const int64_t ctas = total < sm_count() ? total : sm_count();  // persistent: one CTA per SM walks the tile list
-  k_gemm_tc<BN, GATHER><<<(unsigned)ctas, GATHER ? 512 : 256, Cfg::kSmemBytes, stream()>>>(mA, mB, t, (int)n_tiles_n, (int)n_tiles_m,
+  static long long* trace_buf = nullptr;
+  static const bool trace_on = getenv("PDN_TC_TRACE") != nullptr;
+  TcArgs tt = t;
+  tt.trace = nullptr;
+  if (trace_on) {
+    if (!trace_buf) PDN_CUDA(cudaMalloc(&trace_buf, 16 * sizeof(long long)));
+    PDN_CUDA(cudaMemsetAsync(trace_buf, 0, 16 * sizeof(long long), stream()));
+    tt.trace = trace_buf;
+  }
+  k_gemm_tc<BN, GATHER><<<(unsigned)ctas, GATHER ? 512 : 256, Cfg::kSmemBytes, stream()>>>(mA, mB, tt, (int)n_tiles_n, (int)n_tiles_m,
                                                                                              (long long)total, ga);
   PDN_LAUNCHED(GATHER ? "conv_gemm_tc" : "gemm_tc");
+  if (trace_on) {
+    long long h[16];
+    PDN_CUDA(cudaStreamSynchronize(stream()));
+    PDN_CUDA(cudaMemcpy(h, trace_buf, sizeof(h), cudaMemcpyDeviceToHost));
+    fprintf(stderr, "[tc trace] BN=%d M=%lld N=%lld K=%lld ctas=%lld tiles=%lld splits=%d acc=%d | cycles from entry: setup %lld, tma0 %lld, full0 %lld, "
+                    "mma_done_issue %lld, epi_start %lld, epi_end %lld, all_done %lld, dealloc %lld | chunk0: ld %lld, ld_done %lld, smem %lld, end %lld\n",
+            BN, (long long)t.M, (long long)t.N, (long long)t.K, (long long)ctas, (long long)total, t.splits, t.accumulate, h[1] - h[0], h[2] - h[0],
+            h[3] - h[0], h[4] - h[0], h[5] - h[0], h[6] - h[0], h[7] - h[0], h[8] - h[0], h[9] - h[0], h[10] - h[0], h[11] - h[0], h[12] - h[0]);
+  }
   return 0;
 }
 

@@ -24,6 +24,7 @@ struct TcArgs {
   // greedy-decode epilogue: instead of storing C, keep per (row, N-tile) the maximum of (A·B + bias) and its column
   float*     amax_val;   // [M][n_tiles] (nullptr = normal store epilogue)
   long long* amax_idx;   // [M][n_tiles]
+  long long* trace;      // debug (PDN_TC_TRACE): clock64 stamps of CTA 0's pipeline stages, nullptr = off
 };
 
 int pack_operand_ex(const float* src, int64_t R, int64_t K, int64_t r_stride, int64_t k_stride, int64_t k_inner, int64_t k_outer_stride,
