@@ -441,6 +441,28 @@ __global__ void __launch_bounds__(256) k_rope_kv_append(float* __restrict__ q, f
   if (pos_dev) pos0 = *pos_dev;
   if (pos0 < 0 || pos0 + L > S) return;  // out of the cache: the host-side check could not run for a device-side position
   const int64_t half = D / 2, total = B * L * H * half;
+  if ((D & 3) == 0 && (ld & 3) == 0 && total < 0x7fffffff && B * L * ld < 0x7fffffff && B * S * H * D < 0x7fffffff &&
+      (((uintptr_t)q | (uintptr_t)k | (uintptr_t)v | (uintptr_t)ck | (uintptr_t)cv | (uintptr_t)cosT | (uintptr_t)sinT) & 15) == 0) {
+    // two rotation pairs per thread: 128-bit loads/stores everywhere, 32-bit index arithmetic
+    const uint32_t q4 = (uint32_t)(D >> 2), hq = (uint32_t)H * q4, tot4 = (uint32_t)(B * L) * hq, Lu = (uint32_t)L;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < tot4; i += gridDim.x * blockDim.x) {
+      const uint32_t r = i / hq, rem = i - r * hq, hh = rem / q4, pj = rem - hh * q4;
+      const uint32_t b = r / Lu, l = r - b * Lu;
+      const int64_t pos = pos0 + l;
+      const float2 c = __ldg(reinterpret_cast<const float2*>(cosT + pos * half) + pj), sn = __ldg(reinterpret_cast<const float2*>(sinT + pos * half) + pj);
+      const uint32_t e = r * (uint32_t)ld + hh * (uint32_t)D + 4 * pj;
+      const float4 qq = *reinterpret_cast<const float4*>(q + e), kk = *reinterpret_cast<const float4*>(k + e);
+      *reinterpret_cast<float4*>(q + e) = make_float4(qq.x * c.x - qq.y * sn.x, qq.x * sn.x + qq.y * c.x, qq.z * c.y - qq.w * sn.y, qq.z * sn.y + qq.w * c.y);
+      const float4 kr = make_float4(kk.x * c.x - kk.y * sn.x, kk.x * sn.x + kk.y * c.x, kk.z * c.y - kk.w * sn.y, kk.z * sn.y + kk.w * c.y);
+      *reinterpret_cast<float4*>(k + e) = kr;
+      if (ck) {
+        const int64_t ce = (((int64_t)b * S + pos) * H + hh) * D + 4 * pj;
+        *reinterpret_cast<float4*>(ck + ce) = kr;
+        *reinterpret_cast<float4*>(cv + ce) = *reinterpret_cast<const float4*>(v + e);
+      }
+    }
+    return;
+  }
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int64_t pi = i % half, hh = (i / half) % H, r = i / (half * H);
     const int64_t b = r / L, l = r % L, pos = pos0 + l;

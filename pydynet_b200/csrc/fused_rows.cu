@@ -160,6 +160,48 @@ __global__ void __launch_bounds__(256) k_rmsnorm_planes(const float* __restrict_
   __nv_bfloat16 *hi = planes, *lo = planes + rows * Kp;
   for (int j = lane; j < Kp; j += 32) put_pair(hi, lo, row * Kp + j, j < n ? xr[j] * r * __ldg(w + j) : 0.f);
 }
+// four consecutive values -> 8 bytes of the hi plane + 8 bytes of the lo plane
+__device__ __forceinline__ void put_quad(__nv_bfloat16* hi, __nv_bfloat16* lo, int64_t idx, float4 v) {
+  const __nv_bfloat162 h01 = __floats2bfloat162_rn(v.x, v.y), h23 = __floats2bfloat162_rn(v.z, v.w);
+  const float2 f01 = __bfloat1622float2(h01), f23 = __bfloat1622float2(h23);
+  const __nv_bfloat162 l01 = __floats2bfloat162_rn(v.x - f01.x, v.y - f01.y), l23 = __floats2bfloat162_rn(v.z - f23.x, v.w - f23.y);
+  *reinterpret_cast<uint2*>(hi + idx) = make_uint2(*reinterpret_cast<const uint32_t*>(&h01), *reinterpret_cast<const uint32_t*>(&h23));
+  *reinterpret_cast<uint2*>(lo + idx) = make_uint2(*reinterpret_cast<const uint32_t*>(&l01), *reinterpret_cast<const uint32_t*>(&l23));
+}
+// n % 4 == 0, n <= 128 * NV, 16-byte aligned x / w: the row is read ONCE with 128-bit loads and stays in registers
+template <int NV>
+__global__ void __launch_bounds__(256) k_rmsnorm_planes_v4(const float* __restrict__ x, const float* __restrict__ w, __nv_bfloat16* __restrict__ planes,
+                                                           int64_t rows, int n, int64_t Kp, float eps) {
+  const int lane = threadIdx.x & 31;
+  const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const float4* xr = reinterpret_cast<const float4*>(x + row * n);
+  const int n4 = n >> 2;
+  float4 v[NV];
+  float ss = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int j = lane + i * 32;
+    v[i] = j < n4 ? __ldg(xr + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+    ss += v[i].x * v[i].x + v[i].y * v[i].y + v[i].z * v[i].z + v[i].w * v[i].w;
+  }
+  ss = warp_sum(ss);
+  const float r = 1.f / sqrtf(ss / (float)n + eps);
+  __nv_bfloat16 *hi = planes, *lo = planes + rows * Kp;
+  const int kp4 = (int)(Kp >> 2);
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int j = lane + i * 32;
+    if (j < kp4) {
+      float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (j < n4) {
+        const float4 ww = __ldg(reinterpret_cast<const float4*>(w) + j);
+        o = make_float4(v[i].x * r * ww.x, v[i].y * r * ww.y, v[i].z * r * ww.z, v[i].w * r * ww.w);
+      }
+      put_quad(hi, lo, row * Kp + 4 * j, o);
+    }
+  }
+}
 __global__ void __launch_bounds__(256) k_swiglu_rows_planes(const float* __restrict__ gu, __nv_bfloat16* __restrict__ planes, int64_t rows,
                                                             int64_t F, int64_t Kp);
 
@@ -264,6 +306,22 @@ __global__ void __launch_bounds__(256) k_swiglu_rows_planes(const float* __restr
     put_pair(hi, lo, i, j < F ? silu_f(gu[r * 2 * F + j]) * gu[r * 2 * F + F + j] : 0.f);
   }
 }
+// F % 4 == 0, 16-byte aligned gu, rows * Kp / 4 < 2^31: one thread = four consecutive outputs of one row
+__global__ void __launch_bounds__(256) k_swiglu_rows_planes_v4(const float* __restrict__ gu, __nv_bfloat16* __restrict__ planes, int rows, int F,
+                                                               int Kp) {
+  __nv_bfloat16 *hi = planes, *lo = planes + (int64_t)rows * Kp;
+  const uint32_t kp4 = (uint32_t)Kp >> 2, f4 = (uint32_t)F >> 2, total = (uint32_t)rows * kp4;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const uint32_t r = i / kp4, j = i - r * kp4;
+    float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (j < f4) {
+      const float4* row = reinterpret_cast<const float4*>(gu + (int64_t)r * 2 * F);
+      const float4 a = __ldg(row + j), b = __ldg(row + f4 + j);
+      o = make_float4(silu_f(a.x) * b.x, silu_f(a.y) * b.y, silu_f(a.z) * b.z, silu_f(a.w) * b.w);
+    }
+    put_quad(hi, lo, (int64_t)r * Kp + 4 * j, o);
+  }
+}
 // dgate = g * up * silu'(gate), dup = g * silu(gate); silu'(x) = s + x*s*(1-s), s = sigmoid(x)
 __global__ void __launch_bounds__(256) k_swiglu_bwd(const float* __restrict__ gate, const float* __restrict__ up, const float* __restrict__ g,
                                                     float* __restrict__ dgate, float* __restrict__ dup, int64_t n) {
@@ -362,7 +420,10 @@ int pdn_rmsnorm_planes(const float* x, const float* w, void* planes, int64_t row
   PDN_TRY(ensure_init());
   if (rows == 0 || n == 0) return 0;
   PDN_CHECK(n <= 0x7fffffff && Kp >= n && (Kp & 7) == 0, "rmsnorm_planes: bad K padding");
-  k_rmsnorm_planes<<<rows_grid(rows, 8), 256, 0, stream()>>>(x, w, (__nv_bfloat16*)planes, rows, (int)n, Kp, eps);
+  const bool v4 = (n % 4 == 0) && n <= 1024 && ((((uintptr_t)x) | ((uintptr_t)w) | ((uintptr_t)planes)) & 15) == 0;
+  if (v4 && n <= 384) k_rmsnorm_planes_v4<3><<<rows_grid(rows, 8), 256, 0, stream()>>>(x, w, (__nv_bfloat16*)planes, rows, (int)n, Kp, eps);
+  else if (v4) k_rmsnorm_planes_v4<8><<<rows_grid(rows, 8), 256, 0, stream()>>>(x, w, (__nv_bfloat16*)planes, rows, (int)n, Kp, eps);
+  else k_rmsnorm_planes<<<rows_grid(rows, 8), 256, 0, stream()>>>(x, w, (__nv_bfloat16*)planes, rows, (int)n, Kp, eps);
   PDN_LAUNCHED("rmsnorm_planes");
   return 0;
 }
@@ -371,7 +432,11 @@ int pdn_swiglu_rows_planes(const float* gu, void* planes, int64_t rows, int64_t 
   PDN_TRY(ensure_init());
   if (rows * F == 0) return 0;
   PDN_CHECK(Kp >= F && (Kp & 7) == 0, "swiglu_rows_planes: bad K padding");
-  k_swiglu_rows_planes<<<grid_for(rows * Kp, 256), 256, 0, stream()>>>(gu, (__nv_bfloat16*)planes, rows, F, Kp);
+  if ((F % 4 == 0) && ((((uintptr_t)gu) | ((uintptr_t)planes)) & 15) == 0 && rows * (Kp / 4) < 0x7fffffff && rows < 0x7fffffff) {
+    k_swiglu_rows_planes_v4<<<grid_for(rows * (Kp / 4), 256), 256, 0, stream()>>>(gu, (__nv_bfloat16*)planes, (int)rows, (int)F, (int)Kp);
+  } else {
+    k_swiglu_rows_planes<<<grid_for(rows * Kp, 256), 256, 0, stream()>>>(gu, (__nv_bfloat16*)planes, rows, F, Kp);
+  }
   PDN_LAUNCHED("swiglu_rows_planes");
   return 0;
 }
