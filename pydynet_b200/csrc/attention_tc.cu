@@ -21,6 +21,8 @@
 #include "tc_ptx.cuh"
 #include <cudaTypedefs.h>
 #include <math.h>
+#include <stdlib.h>
+#include <stdio.h>
 
 namespace pdn {
 
@@ -43,6 +45,7 @@ struct AtArgs {
   float* lse_out;      // [BH][Lq] (LSE)
   float* out;          // [B, rows, H, D] fp32 (FWD: O, DQ: dQ, DV: dV, DK: dK)
   int ncol_tiles;
+  long long* trace;  // debug (PDN_TC_TRACE): clock64 stamps of CTA (0,0)
 };
 
 template <int MODE>
@@ -85,11 +88,18 @@ k_attn_tc(const __grid_constant__ CUtensorMap mA1, const __grid_constant__ CUten
   extern __shared__ uint8_t smem_raw[];
   uint8_t*  smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   uint64_t* bars = (uint64_t*)(smem + Cfg::kOffBars);
-  uint64_t *a_full = bars, *b_full = bars + 1, *b_empty = bars + 3, *s_full = bars + 5, *s_empty = bars + 7, *p_full = bars + 9,
-           *p_empty = bars + 11, *acc_full = bars + 13;
-  uint32_t* tmem_slot = (uint32_t*)(bars + 14);
+  // Two operand rings share the stage memory but not the barriers: the score operands of tile j (K, and V for dP) are released by
+  // the score MMAs, the accumulate operand (V / Kt / Qt / dOt) only by the accumulate MMA one softmax later. With one ring the TMA
+  // load of tile j+1 could not start before accumulate(j-1) had finished and every iteration paid a full TMA round trip
+  // (first PDN_TC_TRACE timeline: 3300-cycle period for 1500 cycles of softmax work).
+  uint64_t *a_full = bars, *sc_full = bars + 1, *sc_empty = bars + 3, *s_full = bars + 5, *s_empty = bars + 7, *p_full = bars + 9,
+           *p_empty = bars + 11, *acc_full = bars + 13, *ac_full = bars + 14, *ac_empty = bars + 16;
+  uint32_t* tmem_slot = (uint32_t*)(bars + 18);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const bool tr = a.trace != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && lane == 0;
+#define AT_STAMP(i) do { if (tr) a.trace[i] = clock64(); } while (0)
+  if (warp == 0) AT_STAMP(0);
   const int bh = blockIdx.y;
   const int64_t row0 = (int64_t)blockIdx.x * AT_R;
   const int n = a.ncol_tiles;
@@ -103,8 +113,10 @@ k_attn_tc(const __grid_constant__ CUtensorMap mA1, const __grid_constant__ CUten
   if (warp == 1 && lane == 0) {
     mbar_init(a_full, 1);
     for (int i = 0; i < 2; ++i) {
-      mbar_init(&b_full[i], 1);
-      mbar_init(&b_empty[i], 1);
+      mbar_init(&sc_full[i], 1);
+      mbar_init(&sc_empty[i], 1);
+      mbar_init(&ac_full[i], 1);
+      mbar_init(&ac_empty[i], 1);
       mbar_init(&s_full[i], 1);
       mbar_init(&s_empty[i], 8);  // one arrival per softmax warp
       mbar_init(&p_full[i], 8);
@@ -119,6 +131,7 @@ k_attn_tc(const __grid_constant__ CUtensorMap mA1, const __grid_constant__ CUten
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  if (warp == 0) AT_STAMP(1);
   // TMEM columns: S1[2] at 0/64, S2[2] at 128/192, accumulator at 256
   auto tmS1 = [&](int i) { return tmem_base + (uint32_t)(i * 64); };
   auto tmS2 = [&](int i) { return tmem_base + (uint32_t)(128 + i * 64); };
@@ -134,24 +147,33 @@ k_attn_tc(const __grid_constant__ CUtensorMap mA1, const __grid_constant__ CUten
         tma_load_4d(&mA2, a_full, smem + AT_KA, 0, (int)row0, 0, bh);
         tma_load_4d(&mA2, a_full, smem + AT_KA + AT_KA / 2, 0, (int)row0, 1, bh);
       }
-      for (int j = 0; j < n; ++j) {
+      constexpr int kScoreBytes = AT_KB * (TWO ? 2 : 1);
+      auto load_score = [&](int j) {  // K (and V for dP) rows of column tile j
         const int st = j & 1;
-        mbar_wait(&b_empty[st], (uint32_t)(((j >> 1) & 1) ^ 1));
+        mbar_wait(&sc_empty[st], (uint32_t)(((j >> 1) & 1) ^ 1));
         uint8_t* sb = smem + Cfg::kOffStages + st * Cfg::kStage;
-        mbar_expect_tx(&b_full[st], Cfg::kStage);
+        mbar_expect_tx(&sc_full[st], kScoreBytes);
         const int col0 = j * AT_C;
-        tma_load_4d(&mB1, &b_full[st], sb, 0, col0, 0, bh);
-        tma_load_4d(&mB1, &b_full[st], sb + AT_KB / 2, 0, col0, 1, bh);
-        int off = AT_KB;
+        tma_load_4d(&mB1, &sc_full[st], sb, 0, col0, 0, bh);
+        tma_load_4d(&mB1, &sc_full[st], sb + AT_KB / 2, 0, col0, 1, bh);
         if (TWO) {
-          tma_load_4d(&mB2, &b_full[st], sb + off, 0, col0, 0, bh);
-          tma_load_4d(&mB2, &b_full[st], sb + off + AT_KB / 2, 0, col0, 1, bh);
-          off += AT_KB;
+          tma_load_4d(&mB2, &sc_full[st], sb + AT_KB, 0, col0, 0, bh);
+          tma_load_4d(&mB2, &sc_full[st], sb + AT_KB + AT_KB / 2, 0, col0, 1, bh);
         }
-        if (ACC) {  // [d rows][column items along k]
-          tma_load_4d(&mB3, &b_full[st], sb + off, col0, 0, 0, bh);
-          tma_load_4d(&mB3, &b_full[st], sb + off + AT_KB / 2, col0, 0, 1, bh);
-        }
+      };
+      auto load_acc = [&](int j) {  // [d rows][column items along k]
+        const int st = j & 1;
+        mbar_wait(&ac_empty[st], (uint32_t)(((j >> 1) & 1) ^ 1));
+        uint8_t* sb = smem + Cfg::kOffStages + st * Cfg::kStage + kScoreBytes;
+        mbar_expect_tx(&ac_full[st], AT_KB);
+        const int col0 = j * AT_C;
+        tma_load_4d(&mB3, &ac_full[st], sb, col0, 0, 0, bh);
+        tma_load_4d(&mB3, &ac_full[st], sb + AT_KB / 2, col0, 0, 1, bh);
+      };
+      if (n > 0) load_score(0);
+      for (int j = 0; j < n; ++j) {
+        if (j + 1 < n) load_score(j + 1);
+        if (ACC) load_acc(j);
       }
     }
   } else if (warp == 1) {
@@ -160,22 +182,24 @@ k_attn_tc(const __grid_constant__ CUtensorMap mA1, const __grid_constant__ CUten
       constexpr uint32_t idesc = make_idesc_bf16(AT_R, AT_C);  // M = 128, N = 64 for the score and the accumulate MMAs alike
       mbar_wait(a_full, 0);
       tc_fence_after();
+      AT_STAMP(2);
       const uint32_t sA = smem_u32(smem);
       const uint64_t a1hi = make_smem_desc_sw128(sA), a1lo = make_smem_desc_sw128(sA + AT_KA / 2);
       const uint64_t a2hi = make_smem_desc_sw128(sA + AT_KA), a2lo = make_smem_desc_sw128(sA + AT_KA + AT_KA / 2);
       auto score = [&](int j) {
         const int st = j & 1, sb = j & 1;
-        mbar_wait(&b_full[st], (uint32_t)((j >> 1) & 1));
+        mbar_wait(&sc_full[st], (uint32_t)((j >> 1) & 1));
         mbar_wait(&s_empty[sb], (uint32_t)(((j >> 1) & 1) ^ 1));
         tc_fence_after();
         const uint32_t sB = smem_u32(smem + Cfg::kOffStages + st * Cfg::kStage);
         umma3(tmS1(sb), a1hi, a1lo, make_smem_desc_sw128(sB), make_smem_desc_sw128(sB + AT_KB / 2), idesc, true);
         if (TWO) umma3(tmS2(sb), a2hi, a2lo, make_smem_desc_sw128(sB + AT_KB), make_smem_desc_sw128(sB + AT_KB + AT_KB / 2), idesc, true);
         umma_commit(&s_full[sb]);
-        if (!ACC) umma_commit(&b_empty[st]);
+        umma_commit(&sc_empty[st]);
       };
       auto accumulate = [&](int j) {
         const int st = j & 1, pb = j & 1;
+        mbar_wait(&ac_full[st], (uint32_t)((j >> 1) & 1));
         mbar_wait(&p_full[pb], (uint32_t)((j >> 1) & 1));
         tc_fence_after();
         const uint32_t sP = smem_u32(smem + Cfg::kOffP + pb * AT_KP);
@@ -183,7 +207,7 @@ k_attn_tc(const __grid_constant__ CUtensorMap mA1, const __grid_constant__ CUten
         umma3(tmACC, make_smem_desc_sw128(sP), make_smem_desc_sw128(sP + AT_KP / 2), make_smem_desc_sw128(sB3),
               make_smem_desc_sw128(sB3 + AT_KB / 2), idesc, j == 0);
         umma_commit(&p_empty[pb]);
-        umma_commit(&b_empty[st]);
+        umma_commit(&ac_empty[st]);
       };
       if (n > 0) score(0);
       for (int j = 0; j < n; ++j) {
@@ -210,10 +234,12 @@ k_attn_tc(const __grid_constant__ CUtensorMap mA1, const __grid_constant__ CUten
       const int sb = j & 1;
       mbar_wait(&s_full[sb], (uint32_t)((j >> 1) & 1));
       tc_fence_after();
+      if (warp == 4 && j < 4) AT_STAMP(3 + 4 * j);
       float s[32], dp[TWO ? 32 : 1];
       tmem_ld_32x32(tmS1(sb) + lane_sel, s);
       if (TWO) tmem_ld_32x32(tmS2(sb) + lane_sel, dp);
       tmem_ld_wait();
+      if (warp == 4 && j < 4) AT_STAMP(4 + 4 * j);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&s_empty[sb]);
@@ -222,6 +248,10 @@ k_attn_tc(const __grid_constant__ CUtensorMap mA1, const __grid_constant__ CUten
       // Everything below works in the log2 domain: t = (s*scale + mask) * log2(e), so that exp(x - lse) is ONE ex2.approx of
       // one FFMA result. Column validity only matters in the last tile (uniform branch); masks take the slower path.
       const float c1 = a.scale * 1.4426950408889634f;
+      // without a mask the scale is folded into the exponent FFMA of the P passes (cs = c1); the LSE pass and masked problems
+      // scale here (cs = 1)
+      const bool  prescale = a.mask != nullptr || MODE == AT_LSE;
+      const float cs = prescale ? 1.f : c1;
       if (a.mask) {
 #pragma unroll
         for (int e = 0; e < 32; ++e) {
@@ -233,7 +263,7 @@ k_attn_tc(const __grid_constant__ CUtensorMap mA1, const __grid_constant__ CUten
           }
           s[e] = fmaf(s[e], c1, mk * 1.4426950408889634f);
         }
-      } else {
+      } else if (MODE == AT_LSE) {
 #pragma unroll
         for (int e = 0; e < 32; ++e) s[e] *= c1;
       }
@@ -280,20 +310,21 @@ k_attn_tc(const __grid_constant__ CUtensorMap mA1, const __grid_constant__ CUten
           }
 #pragma unroll
           for (int e = 0; e < 32; ++e) {
-            float p = ex2f(fmaf(cl[e], -1.4426950408889634f, s[e]));
+            float p = ex2f(fmaf(s[e], cs, cl[e] * -1.4426950408889634f));
             if (TWO) p = p * (dp[e] - cd[e]) * a.scale;
             s[e] = p;
           }
         } else {
-          const float lse2 = lse_r * 1.4426950408889634f;
+          const float nlse2 = lse_r * -1.4426950408889634f;
 #pragma unroll
           for (int e = 0; e < 32; ++e) {
-            float p = ex2f(s[e] - lse2);
+            float p = ex2f(fmaf(s[e], cs, nlse2));
             if (TWO) p = p * (dp[e] - delta_r) * a.scale;
             s[e] = p;
           }
         }
         const int pb = j & 1;
+        if (warp == 4 && j < 4) AT_STAMP(5 + 4 * j);
         mbar_wait(&p_empty[pb], (uint32_t)(((j >> 1) & 1) ^ 1));
         uint8_t* ph = smem + Cfg::kOffP + pb * AT_KP;
         uint8_t* pl = ph + AT_KP / 2;
@@ -303,10 +334,10 @@ k_attn_tc(const __grid_constant__ CUtensorMap mA1, const __grid_constant__ CUten
 #pragma unroll
           for (int t = 0; t < 4; ++t) {
             const float v0 = s[c8 * 8 + 2 * t], v1 = s[c8 * 8 + 2 * t + 1];
-            const __nv_bfloat162 hh = __floats2bfloat162_rn(v0, v1);   // one packed convert for two elements
-            const float2         hf = __bfloat1622float2(hh);
-            const __nv_bfloat162 ll = __floats2bfloat162_rn(v0 - hf.x, v1 - hf.y);
-            hw[t] = *reinterpret_cast<const uint32_t*>(&hh);
+            // hi = the upper 16 bits (truncation: integer pipe, no convert), lo = rn(v - hi) with v - hi exact
+            const uint32_t b0 = __float_as_uint(v0), b1 = __float_as_uint(v1);
+            hw[t] = __byte_perm(b0, b1, 0x7632);
+            const __nv_bfloat162 ll = __floats2bfloat162_rn(v0 - __uint_as_float(b0 & 0xffff0000u), v1 - __uint_as_float(b1 & 0xffff0000u));
             lw[t] = *reinterpret_cast<const uint32_t*>(&ll);
           }
           const uint32_t off = sw128_off(r, half * 4 + c8);
@@ -316,8 +347,10 @@ k_attn_tc(const __grid_constant__ CUtensorMap mA1, const __grid_constant__ CUten
         fence_proxy_async_smem();
         __syncwarp();
         if (lane == 0) mbar_arrive(&p_full[pb]);
+        if (warp == 4 && j < 4) AT_STAMP(6 + 4 * j);
       }
     }
+    if (warp == 4) AT_STAMP(19);
     if (MODE == AT_LSE) {
       // combine the two column halves of every row through shared memory (the operand stages are idle by now)
       float* comb = reinterpret_cast<float*>(smem + Cfg::kOffStages);
@@ -332,10 +365,30 @@ k_attn_tc(const __grid_constant__ CUtensorMap mA1, const __grid_constant__ CUten
     } else {
       mbar_wait(acc_full, 0);
       tc_fence_after();
+      if (warp == 4) AT_STAMP(20);
       float o[32];
       tmem_ld_32x32(tmACC + lane_sel, o);
       tmem_ld_wait();
-      if (row_ok) {
+      if ((a.D & 3) == 0 && ((((uintptr_t)a.out) & 15) == 0)) {
+        // a thread owns a row of the accumulator: transpose the warp's 32x32 block through the (now idle) P buffer so that every
+        // store is a 128-bit piece of a row's contiguous D floats (the scalar row-per-thread stores cost 8500 cycles per CTA)
+        float* stg = reinterpret_cast<float*>(smem + Cfg::kOffP) + (warp - 4) * 1024;
+#pragma unroll
+        for (int c = 0; c < 8; ++c)
+          *reinterpret_cast<float4*>(stg + lane * 32 + ((c ^ (lane & 7)) << 2)) = make_float4(o[4 * c], o[4 * c + 1], o[4 * c + 2], o[4 * c + 3]);
+        __syncwarp();
+        const int c = lane & 7, rs = lane >> 3;
+        if (half * 32 + 4 * c < a.D) {
+#pragma unroll
+          for (int it = 0; it < 8; ++it) {
+            const int     rr = it * 4 + rs;
+            const int64_t grow = row0 + q * 32 + rr;
+            if (grow < a.rows)
+              *reinterpret_cast<float4*>(a.out + ((b * a.rows + grow) * a.H + h) * a.D + half * 32 + 4 * c) =
+                  *reinterpret_cast<const float4*>(stg + rr * 32 + ((c ^ (rr & 7)) << 2));
+          }
+        }
+      } else if (row_ok) {
         float* dst = a.out + ((b * a.rows + gr) * a.H + h) * a.D + half * 32;
 #pragma unroll
         for (int d = 0; d < 32; ++d)
@@ -343,9 +396,12 @@ k_attn_tc(const __grid_constant__ CUtensorMap mA1, const __grid_constant__ CUten
       }
     }
   }
+  if (warp == 4) AT_STAMP(21);
   tc_fence_before();
   __syncthreads();
   if (warp == 2) tmem_dealloc(tmem_base, kTmemCols);
+  if (warp == 2) AT_STAMP(22);
+#undef AT_STAMP
 }
 
 // Δ[bh][q] = Σ_d dO·O over [B, Lq, H, D] contiguous tensors; one warp per (b, q, h) row, lanes across d (coalesced)
@@ -389,8 +445,26 @@ static int at_launch(const CUtensorMap& A1, const CUtensorMap& A2, const CUtenso
     attr = true;
   }
   dim3 grd((unsigned)((a.rows + AT_R - 1) / AT_R), (unsigned)BH);
-  k_attn_tc<MODE><<<grd, 384, Cfg::kSmem, stream()>>>(A1, A2, B1, B2, B3, a);
+  static long long* trace_buf = nullptr;
+  static const bool trace_on = getenv("PDN_TC_TRACE") != nullptr;
+  AtArgs aa = a;
+  aa.trace = nullptr;
+  if (trace_on) {
+    if (!trace_buf) PDN_CUDA(cudaMalloc(&trace_buf, 32 * sizeof(long long)));
+    PDN_CUDA(cudaMemsetAsync(trace_buf, 0, 32 * sizeof(long long), stream()));
+    aa.trace = trace_buf;
+  }
+  k_attn_tc<MODE><<<grd, 384, Cfg::kSmem, stream()>>>(A1, A2, B1, B2, B3, aa);
   PDN_LAUNCHED("attn_tc");
+  if (trace_on) {
+    long long h[32];
+    PDN_CUDA(cudaStreamSynchronize(stream()));
+    PDN_CUDA(cudaMemcpy(h, trace_buf, sizeof(h), cudaMemcpyDeviceToHost));
+    fprintf(stderr, "[at trace] mode=%d rows=%lld cols=%lld | setup %lld a_full %lld |", MODE, (long long)a.rows, (long long)a.cols, h[1] - h[0], h[2] - h[0]);
+    for (int j = 0; j < 4; ++j)
+      fprintf(stderr, " it%d: s_full %lld ld %lld math %lld pwr %lld |", j, h[3 + 4 * j] - h[0], h[4 + 4 * j] - h[0], h[5 + 4 * j] - h[0], h[6 + 4 * j] - h[0]);
+    fprintf(stderr, " loop_end %lld acc_full %lld stored %lld dealloc %lld\n", h[19] - h[0], h[20] - h[0], h[21] - h[0], h[22] - h[0]);
+  }
   return 0;
 }
 
