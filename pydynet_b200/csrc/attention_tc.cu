@@ -53,11 +53,11 @@ struct AtCfg {
   static constexpr bool TWO = (MODE == AT_DQ || MODE == AT_DK);
   static constexpr bool ACC = (MODE != AT_LSE);
   static constexpr bool TRANS = (MODE == AT_DV || MODE == AT_DK);
+  static constexpr int  kNst = TWO ? 3 : 4;  // operand stages (P / dS live in tensor memory, so shared memory holds operands only)
   static constexpr int  kStage = AT_KB * (1 + (TWO ? 1 : 0) + (ACC ? 1 : 0));
   static constexpr int  kOffStages = AT_KA * (TWO ? 2 : 1);
-  static constexpr int  kOffP = kOffStages + 2 * kStage;
-  static constexpr int  kOffBars = kOffP + (ACC ? 2 * AT_KP : 0);
-  static constexpr int  kSmem = kOffBars + 256 + 1024;
+  static constexpr int  kOffBars = kOffStages + kNst * kStage;
+  static constexpr int  kSmem = kOffBars + 512 + 1024;
 };
 
 // 16-byte chunk c (8 bf16) of row r in a K-major [rows x 64] bf16 tile with 128-byte swizzle (what TMA writes / UMMA reads)
@@ -79,6 +79,18 @@ __device__ __forceinline__ void umma3(uint32_t d, uint64_t ahi, uint64_t alo, ui
   }
 }
 
+// accumulate MMA with the A operand (P / dS hi and lo planes, 32 columns each) in tensor memory
+__device__ __forceinline__ void umma3_ts(uint32_t d, uint32_t ahi, uint32_t alo, uint64_t bhi, uint64_t blo, uint32_t idesc, bool first_clears) {
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const uint64_t adv = (uint64_t)((k * 16 * 2) >> 4);
+    const uint32_t ac = (uint32_t)(k * 8);  // 16 bf16 = 8 columns
+    umma_bf16_ts(d, alo + ac, bhi + adv, idesc, (first_clears && k == 0) ? 0u : 1u);
+    umma_bf16_ts(d, ahi + ac, blo + adv, idesc, 1u);
+    umma_bf16_ts(d, ahi + ac, bhi + adv, idesc, 1u);
+  }
+}
+
 template <int MODE>
 __global__ void __launch_bounds__(384, 1)
 k_attn_tc(const __grid_constant__ CUtensorMap mA1, const __grid_constant__ CUtensorMap mA2, const __grid_constant__ CUtensorMap mB1,
@@ -92,11 +104,12 @@ k_attn_tc(const __grid_constant__ CUtensorMap mA1, const __grid_constant__ CUten
   // the score MMAs, the accumulate operand (V / Kt / Qt / dOt) only by the accumulate MMA one softmax later. With one ring the TMA
   // load of tile j+1 could not start before accumulate(j-1) had finished and every iteration paid a full TMA round trip
   // (first PDN_TC_TRACE timeline: 3300-cycle period for 1500 cycles of softmax work).
-  uint64_t *a_full = bars, *sc_full = bars + 1, *sc_empty = bars + 3, *s_full = bars + 5, *s_empty = bars + 7, *p_full = bars + 9,
-           *p_empty = bars + 11, *acc_full = bars + 13, *ac_full = bars + 14, *ac_empty = bars + 16;
-  uint32_t* tmem_slot = (uint32_t*)(bars + 18);
+  constexpr int NST = Cfg::kNst;
+  uint64_t *a_full = bars, *acc_full = bars + 1, *s_full = bars + 2, *s_empty = bars + 4, *p_full = bars + 6, *p_empty = bars + 8,
+           *sc_full = bars + 10, *sc_empty = sc_full + NST, *ac_full = sc_empty + NST, *ac_empty = ac_full + NST;
+  uint32_t* tmem_slot = (uint32_t*)(ac_empty + NST);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = warp_id_uniform(), lane = threadIdx.x & 31;
   const bool tr = a.trace != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && lane == 0;
 #define AT_STAMP(i) do { if (tr) a.trace[i] = clock64(); } while (0)
   if (warp == 0) AT_STAMP(0);
@@ -112,11 +125,13 @@ k_attn_tc(const __grid_constant__ CUtensorMap mA1, const __grid_constant__ CUten
   }
   if (warp == 1 && lane == 0) {
     mbar_init(a_full, 1);
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < NST; ++i) {
       mbar_init(&sc_full[i], 1);
       mbar_init(&sc_empty[i], 1);
       mbar_init(&ac_full[i], 1);
       mbar_init(&ac_empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
       mbar_init(&s_full[i], 1);
       mbar_init(&s_empty[i], 8);  // one arrival per softmax warp
       mbar_init(&p_full[i], 8);
@@ -132,14 +147,16 @@ k_attn_tc(const __grid_constant__ CUtensorMap mA1, const __grid_constant__ CUten
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   if (warp == 0) AT_STAMP(1);
-  // TMEM columns: S1[2] at 0/64, S2[2] at 128/192, accumulator at 256
+  // TMEM columns: S1[2] at 0/64, S2[2] at 128/192, accumulator at 256, P / dS operand buffers [2] at 320/384 (hi 32 columns, lo 32)
   auto tmS1 = [&](int i) { return tmem_base + (uint32_t)(i * 64); };
   auto tmS2 = [&](int i) { return tmem_base + (uint32_t)(128 + i * 64); };
+  auto tmP = [&](int i) { return tmem_base + (uint32_t)(320 + i * 64); };
   const uint32_t tmACC = tmem_base + 256u;
 
   if (warp == 0) {
-    // ===== TMA producer =====
-    if (lane == 0) {
+    // ===== TMA producer (whole warp walks the loop, the elected lane issues) =====
+    const bool leader = elect_one();
+    if (leader) {
       mbar_expect_tx(a_full, AT_KA * (TWO ? 2 : 1));
       tma_load_4d(&mA1, a_full, smem, 0, (int)row0, 0, bh);
       tma_load_4d(&mA1, a_full, smem + AT_KA / 2, 0, (int)row0, 1, bh);
@@ -147,10 +164,12 @@ k_attn_tc(const __grid_constant__ CUtensorMap mA1, const __grid_constant__ CUten
         tma_load_4d(&mA2, a_full, smem + AT_KA, 0, (int)row0, 0, bh);
         tma_load_4d(&mA2, a_full, smem + AT_KA + AT_KA / 2, 0, (int)row0, 1, bh);
       }
-      constexpr int kScoreBytes = AT_KB * (TWO ? 2 : 1);
-      auto load_score = [&](int j) {  // K (and V for dP) rows of column tile j
-        const int st = j & 1;
-        mbar_wait(&sc_empty[st], (uint32_t)(((j >> 1) & 1) ^ 1));
+    }
+    constexpr int kScoreBytes = AT_KB * (TWO ? 2 : 1);
+    auto load_score = [&](int j) {  // K (and V for dP) rows of column tile j
+      const int st = j % NST;
+      mbar_wait(&sc_empty[st], (uint32_t)(((j / NST) & 1) ^ 1));
+      if (leader) {
         uint8_t* sb = smem + Cfg::kOffStages + st * Cfg::kStage;
         mbar_expect_tx(&sc_full[st], kScoreBytes);
         const int col0 = j * AT_C;
@@ -160,25 +179,28 @@ k_attn_tc(const __grid_constant__ CUtensorMap mA1, const __grid_constant__ CUten
           tma_load_4d(&mB2, &sc_full[st], sb + AT_KB, 0, col0, 0, bh);
           tma_load_4d(&mB2, &sc_full[st], sb + AT_KB + AT_KB / 2, 0, col0, 1, bh);
         }
-      };
-      auto load_acc = [&](int j) {  // [d rows][column items along k]
-        const int st = j & 1;
-        mbar_wait(&ac_empty[st], (uint32_t)(((j >> 1) & 1) ^ 1));
+      }
+    };
+    auto load_acc = [&](int j) {  // [d rows][column items along k]
+      const int st = j % NST;
+      mbar_wait(&ac_empty[st], (uint32_t)(((j / NST) & 1) ^ 1));
+      if (leader) {
         uint8_t* sb = smem + Cfg::kOffStages + st * Cfg::kStage + kScoreBytes;
         mbar_expect_tx(&ac_full[st], AT_KB);
         const int col0 = j * AT_C;
         tma_load_4d(&mB3, &ac_full[st], sb, col0, 0, 0, bh);
         tma_load_4d(&mB3, &ac_full[st], sb + AT_KB / 2, col0, 0, 1, bh);
-      };
-      if (n > 0) load_score(0);
-      for (int j = 0; j < n; ++j) {
-        if (j + 1 < n) load_score(j + 1);
-        if (ACC) load_acc(j);
       }
+    };
+    if (n > 0) load_score(0);
+    for (int j = 0; j < n; ++j) {
+      if (j + 1 < n) load_score(j + 1);
+      if (ACC) load_acc(j);
     }
   } else if (warp == 1) {
-    // ===== MMA issuer =====
-    if (lane == 0) {
+    // ===== MMA issuer (whole warp walks the loop, the elected lane issues) =====
+    {
+      const bool leader = elect_one();
       constexpr uint32_t idesc = make_idesc_bf16(AT_R, AT_C);  // M = 128, N = 64 for the score and the accumulate MMAs alike
       mbar_wait(a_full, 0);
       tc_fence_after();
@@ -187,34 +209,42 @@ k_attn_tc(const __grid_constant__ CUtensorMap mA1, const __grid_constant__ CUten
       const uint64_t a1hi = make_smem_desc_sw128(sA), a1lo = make_smem_desc_sw128(sA + AT_KA / 2);
       const uint64_t a2hi = make_smem_desc_sw128(sA + AT_KA), a2lo = make_smem_desc_sw128(sA + AT_KA + AT_KA / 2);
       auto score = [&](int j) {
-        const int st = j & 1, sb = j & 1;
-        mbar_wait(&sc_full[st], (uint32_t)((j >> 1) & 1));
+        const int st = j % NST, sb = j & 1;
+        mbar_wait(&sc_full[st], (uint32_t)((j / NST) & 1));
+        if (j == 4) AT_STAMP(25);
         mbar_wait(&s_empty[sb], (uint32_t)(((j >> 1) & 1) ^ 1));
         tc_fence_after();
+        if (j == 4) AT_STAMP(26);
         const uint32_t sB = smem_u32(smem + Cfg::kOffStages + st * Cfg::kStage);
-        umma3(tmS1(sb), a1hi, a1lo, make_smem_desc_sw128(sB), make_smem_desc_sw128(sB + AT_KB / 2), idesc, true);
-        if (TWO) umma3(tmS2(sb), a2hi, a2lo, make_smem_desc_sw128(sB + AT_KB), make_smem_desc_sw128(sB + AT_KB + AT_KB / 2), idesc, true);
-        umma_commit(&s_full[sb]);
-        umma_commit(&sc_empty[st]);
+        if (leader) {
+          umma3(tmS1(sb), a1hi, a1lo, make_smem_desc_sw128(sB), make_smem_desc_sw128(sB + AT_KB / 2), idesc, true);
+          if (TWO) umma3(tmS2(sb), a2hi, a2lo, make_smem_desc_sw128(sB + AT_KB), make_smem_desc_sw128(sB + AT_KB + AT_KB / 2), idesc, true);
+          umma_commit(&s_full[sb]);
+          umma_commit(&sc_empty[st]);
+        }
+        if (j == 4) AT_STAMP(27);
       };
       auto accumulate = [&](int j) {
-        const int st = j & 1, pb = j & 1;
-        mbar_wait(&ac_full[st], (uint32_t)((j >> 1) & 1));
+        const int st = j % NST, pb = j & 1;
+        mbar_wait(&ac_full[st], (uint32_t)((j / NST) & 1));
+        if (j == 2) AT_STAMP(28);
         mbar_wait(&p_full[pb], (uint32_t)((j >> 1) & 1));
         tc_fence_after();
-        const uint32_t sP = smem_u32(smem + Cfg::kOffP + pb * AT_KP);
+        if (j == 2) AT_STAMP(23);
         const uint32_t sB3 = smem_u32(smem + Cfg::kOffStages + st * Cfg::kStage + AT_KB * (TWO ? 2 : 1));
-        umma3(tmACC, make_smem_desc_sw128(sP), make_smem_desc_sw128(sP + AT_KP / 2), make_smem_desc_sw128(sB3),
-              make_smem_desc_sw128(sB3 + AT_KB / 2), idesc, j == 0);
-        umma_commit(&p_empty[pb]);
-        umma_commit(&ac_empty[st]);
+        if (leader) {
+          umma3_ts(tmACC, tmP(pb), tmP(pb) + 32u, make_smem_desc_sw128(sB3), make_smem_desc_sw128(sB3 + AT_KB / 2), idesc, j == 0);
+          umma_commit(&p_empty[pb]);
+          umma_commit(&ac_empty[st]);
+        }
+        if (j == 2) AT_STAMP(24);
       };
       if (n > 0) score(0);
       for (int j = 0; j < n; ++j) {
         if (j + 1 < n) score(j + 1);
         if (ACC) accumulate(j);
       }
-      if (ACC) umma_commit(acc_full);
+      if (ACC && leader) umma_commit(acc_full);
     }
   } else if (warp >= 4) {
     // ===== softmax / epilogue: two threads per row (8 warps): warp w owns TMEM lane quarter w%4 and column half (w-4)/4 =====
@@ -326,25 +356,23 @@ k_attn_tc(const __grid_constant__ CUtensorMap mA1, const __grid_constant__ CUten
         const int pb = j & 1;
         if (warp == 4 && j < 4) AT_STAMP(5 + 4 * j);
         mbar_wait(&p_empty[pb], (uint32_t)(((j >> 1) & 1) ^ 1));
-        uint8_t* ph = smem + Cfg::kOffP + pb * AT_KP;
-        uint8_t* pl = ph + AT_KP / 2;
+        // bf16 hi/lo split on the integer pipe (the XU pipe is saturated by ex2): hi = round-to-nearest of the upper 16 bits
+        // (+0x8000 then mask), lo = the same rounding of the exact remainder v - hi. The packed pairs go straight to tensor memory
+        // (row = lane, two keys per 32-bit column): the accumulate MMA reads its A operand there.
+        uint32_t hw[16], lw[16];
 #pragma unroll
-        for (int c8 = 0; c8 < 4; ++c8) {
-          uint32_t hw[4], lw[4];
-#pragma unroll
-          for (int t = 0; t < 4; ++t) {
-            const float v0 = s[c8 * 8 + 2 * t], v1 = s[c8 * 8 + 2 * t + 1];
-            // hi = the upper 16 bits (truncation: integer pipe, no convert), lo = rn(v - hi) with v - hi exact
-            const uint32_t b0 = __float_as_uint(v0), b1 = __float_as_uint(v1);
-            hw[t] = __byte_perm(b0, b1, 0x7632);
-            const __nv_bfloat162 ll = __floats2bfloat162_rn(v0 - __uint_as_float(b0 & 0xffff0000u), v1 - __uint_as_float(b1 & 0xffff0000u));
-            lw[t] = *reinterpret_cast<const uint32_t*>(&ll);
-          }
-          const uint32_t off = sw128_off(r, half * 4 + c8);
-          *reinterpret_cast<uint4*>(ph + off) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
-          *reinterpret_cast<uint4*>(pl + off) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+        for (int t = 0; t < 16; ++t) {
+          const float v0 = s[2 * t], v1 = s[2 * t + 1];
+          const uint32_t b0 = (__float_as_uint(v0) + 0x8000u) & 0xffff0000u, b1 = (__float_as_uint(v1) + 0x8000u) & 0xffff0000u;
+          hw[t] = __byte_perm(b0, b1, 0x7632);
+          const uint32_t r0 = __float_as_uint(v0 - __uint_as_float(b0)) + 0x8000u, r1 = __float_as_uint(v1 - __uint_as_float(b1)) + 0x8000u;
+          lw[t] = __byte_perm(r0, r1, 0x7632);
         }
-        fence_proxy_async_smem();
+        const uint32_t pdst = tmP(pb) + ((uint32_t)(q * 32) << 16) + (uint32_t)(half * 16);
+        tmem_st_32x16(pdst, hw);
+        tmem_st_32x16(pdst + 32u, lw);
+        tmem_st_wait();
+        tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&p_full[pb]);
         if (warp == 4 && j < 4) AT_STAMP(6 + 4 * j);
@@ -372,7 +400,7 @@ k_attn_tc(const __grid_constant__ CUtensorMap mA1, const __grid_constant__ CUten
       if ((a.D & 3) == 0 && ((((uintptr_t)a.out) & 15) == 0)) {
         // a thread owns a row of the accumulator: transpose the warp's 32x32 block through the (now idle) P buffer so that every
         // store is a 128-bit piece of a row's contiguous D floats (the scalar row-per-thread stores cost 8500 cycles per CTA)
-        float* stg = reinterpret_cast<float*>(smem + Cfg::kOffP) + (warp - 4) * 1024;
+        float* stg = reinterpret_cast<float*>(smem + Cfg::kOffStages) + (warp - 4) * 1024;  // operand stages are idle by now
 #pragma unroll
         for (int c = 0; c < 8; ++c)
           *reinterpret_cast<float4*>(stg + lane * 32 + ((c ^ (lane & 7)) << 2)) = make_float4(o[4 * c], o[4 * c + 1], o[4 * c + 2], o[4 * c + 3]);
@@ -463,7 +491,7 @@ static int at_launch(const CUtensorMap& A1, const CUtensorMap& A2, const CUtenso
     fprintf(stderr, "[at trace] mode=%d rows=%lld cols=%lld | setup %lld a_full %lld |", MODE, (long long)a.rows, (long long)a.cols, h[1] - h[0], h[2] - h[0]);
     for (int j = 0; j < 4; ++j)
       fprintf(stderr, " it%d: s_full %lld ld %lld math %lld pwr %lld |", j, h[3 + 4 * j] - h[0], h[4 + 4 * j] - h[0], h[5 + 4 * j] - h[0], h[6 + 4 * j] - h[0]);
-    fprintf(stderr, " loop_end %lld acc_full %lld stored %lld dealloc %lld\n", h[19] - h[0], h[20] - h[0], h[21] - h[0], h[22] - h[0]);
+    fprintf(stderr, " loop_end %lld acc_full %lld stored %lld dealloc %lld | mma: acfull2 %lld pfull2 %lld acc2_issued %lld scfull4 %lld sempty4 %lld score4_issued %lld\n", h[19] - h[0], h[20] - h[0], h[21] - h[0], h[22] - h[0], h[28] - h[0], h[23] - h[0], h[24] - h[0], h[25] - h[0], h[26] - h[0], h[27] - h[0]);
   }
   return 0;
 }
