@@ -83,8 +83,8 @@ __device__ __forceinline__ void umma3(uint32_t d, uint64_t ahi, uint64_t alo, ui
 __device__ __forceinline__ void umma3_ts(uint32_t d, uint32_t ahi, uint32_t alo, uint64_t bhi, uint64_t blo, uint32_t idesc, bool first_clears) {
 #pragma unroll
   for (int k = 0; k < 4; ++k) {
-    const uint64_t adv = (uint64_t)((k * 16 * 2) >> 4);
-    const uint32_t ac = (uint32_t)(k * 8);  // 16 bf16 = 8 columns
+    const uint64_t adv = (uint64_t)((k * 16 * 128) >> 4);  // MN-major B: 16 k rows of 128 B
+    const uint32_t ac = (uint32_t)(k * 8);                 // 16 bf16 = 8 columns
     umma_bf16_ts(d, alo + ac, bhi + adv, idesc, (first_clears && k == 0) ? 0u : 1u);
     umma_bf16_ts(d, ahi + ac, blo + adv, idesc, 1u);
     umma_bf16_ts(d, ahi + ac, bhi + adv, idesc, 1u);
@@ -181,15 +181,15 @@ k_attn_tc(const __grid_constant__ CUtensorMap mA1, const __grid_constant__ CUten
         }
       }
     };
-    auto load_acc = [&](int j) {  // [d rows][column items along k]
+    auto load_acc = [&](int j) {  // [column items (k of the accumulate MMA)][d]: consumed as an MN-major B operand, no transposed copy
       const int st = j % NST;
       mbar_wait(&ac_empty[st], (uint32_t)(((j / NST) & 1) ^ 1));
       if (leader) {
         uint8_t* sb = smem + Cfg::kOffStages + st * Cfg::kStage + kScoreBytes;
         mbar_expect_tx(&ac_full[st], AT_KB);
         const int col0 = j * AT_C;
-        tma_load_4d(&mB3, &ac_full[st], sb, col0, 0, 0, bh);
-        tma_load_4d(&mB3, &ac_full[st], sb + AT_KB / 2, col0, 0, 1, bh);
+        tma_load_4d(&mB3, &ac_full[st], sb, 0, col0, 0, bh);
+        tma_load_4d(&mB3, &ac_full[st], sb + AT_KB / 2, 0, col0, 1, bh);
       }
     };
     if (n > 0) load_score(0);
@@ -233,7 +233,8 @@ k_attn_tc(const __grid_constant__ CUtensorMap mA1, const __grid_constant__ CUten
         if (j == 2) AT_STAMP(23);
         const uint32_t sB3 = smem_u32(smem + Cfg::kOffStages + st * Cfg::kStage + AT_KB * (TWO ? 2 : 1));
         if (leader) {
-          umma3_ts(tmACC, tmP(pb), tmP(pb) + 32u, make_smem_desc_sw128(sB3), make_smem_desc_sw128(sB3 + AT_KB / 2), idesc, j == 0);
+          umma3_ts(tmACC, tmP(pb), tmP(pb) + 32u, make_smem_desc_sw128_mn(sB3), make_smem_desc_sw128_mn(sB3 + AT_KB / 2),
+                   idesc | IDESC_B_MN_MAJOR, j == 0);
           umma_commit(&p_empty[pb]);
           umma_commit(&ac_empty[st]);
         }
@@ -516,17 +517,17 @@ int pdn_attention_tc_fwd(const float* q, const float* k, const float* v, const f
                          float scale) {
   PDN_TRY(ensure_init());
   PDN_TRY(at_check(B, H, Lq, Lk, D, q_str, k_str, v_str));
-  AtOperand Qp, Kp, Vt;
+  AtOperand Qp, Kp, Vp;
   PDN_TRY(at_pack(&Qp, q, B, H, Lq, D, q_str[2], 1, q_str[0], q_str[1], AT_R));
   PDN_TRY(at_pack(&Kp, k, B, H, Lk, D, k_str[2], 1, k_str[0], k_str[1], AT_C));
-  PDN_TRY(at_pack(&Vt, v, B, H, D, Lk, 1, v_str[2], v_str[0], v_str[1], AT_C));
+  PDN_TRY(at_pack(&Vp, v, B, H, Lk, D, v_str[2], 1, v_str[0], v_str[1], AT_C));  // [keys][d]: MN-major B of O += P V
   AtArgs a;
   a.rows = Lq; a.cols = Lk; a.H = H; a.D = (int)D; a.scale = scale;
   a.mask = mask; a.mask_bs = mask && mask_str ? mask_str[0] : 0; a.mask_qs = mask && mask_str ? mask_str[1] : 0;
   a.lse = lse; a.delta = nullptr; a.lse_out = lse; a.out = out;
   a.ncol_tiles = (int)((Lk + AT_C - 1) / AT_C);
   PDN_TRY((at_launch<AT_LSE>(Qp.map, Qp.map, Kp.map, Kp.map, Kp.map, a, B * H)));
-  PDN_TRY((at_launch<AT_FWD>(Qp.map, Qp.map, Kp.map, Kp.map, Vt.map, a, B * H)));
+  PDN_TRY((at_launch<AT_FWD>(Qp.map, Qp.map, Kp.map, Kp.map, Vp.map, a, B * H)));
   return 0;
 }
 
@@ -545,7 +546,7 @@ int pdn_attention_tc_bwd(const float* q, const float* k, const float* v, const f
   a.mask = mask; a.mask_bs = mask && mask_str ? mask_str[0] : 0; a.mask_qs = mask && mask_str ? mask_str[1] : 0;
   a.lse = lse; a.delta = (const float*)sdelta.p; a.lse_out = nullptr;
   // every tensor is packed ONCE per layout; the row-operand (box 128) and column-operand (box 64) TMA maps share the planes
-  AtOperand Qp, Kp, Vp, dOp, Kt, Qt, dOt;
+  AtOperand Qp, Kp, Vp, dOp;
   CUtensorMap Qp64, Kp128, Vp128, dOp64;
   PDN_TRY(at_pack(&Qp, q, B, H, Lq, D, q_str[2], 1, q_str[0], q_str[1], AT_R));
   PDN_TRY(at_pack(&Kp, k, B, H, Lk, D, k_str[2], 1, k_str[0], k_str[1], AT_C));
@@ -556,21 +557,18 @@ int pdn_attention_tc_bwd(const float* q, const float* k, const float* v, const f
   PDN_TRY(tc_make_map(&Kp128, Kp.op.planes, Lk, D, Kp.op.Kp, Kp.op.nbatch, AT_R));
   PDN_TRY(tc_make_map(&Vp128, Vp.op.planes, Lk, D, Vp.op.Kp, Vp.op.nbatch, AT_R));
   if (dq) {
-    PDN_TRY(at_pack(&Kt, k, B, H, D, Lk, 1, k_str[2], k_str[0], k_str[1], AT_C));
     a.rows = Lq; a.cols = Lk; a.out = dq; a.ncol_tiles = (int)((Lk + AT_C - 1) / AT_C);
-    PDN_TRY((at_launch<AT_DQ>(Qp.map, dOp.map, Kp.map, Vp.map, Kt.map, a, B * H)));
+    PDN_TRY((at_launch<AT_DQ>(Qp.map, dOp.map, Kp.map, Vp.map, Kp.map, a, B * H)));  // dQ += dS K: the K tile again, MN-major
   }
   if (dk || dv) {
     a.rows = Lk; a.cols = Lq; a.ncol_tiles = (int)((Lq + AT_C - 1) / AT_C);
     if (dv) {
-      PDN_TRY(at_pack(&dOt, g_out, B, H, D, Lq, 1, g_str[2], g_str[0], g_str[1], AT_C));
       a.out = dv;
-      PDN_TRY((at_launch<AT_DV>(Kp128, Kp128, Qp64, Qp64, dOt.map, a, B * H)));
+      PDN_TRY((at_launch<AT_DV>(Kp128, Kp128, Qp64, Qp64, dOp64, a, B * H)));  // dV += P^T dO
     }
     if (dk) {
-      PDN_TRY(at_pack(&Qt, q, B, H, D, Lq, 1, q_str[2], q_str[0], q_str[1], AT_C));
       a.out = dk;
-      PDN_TRY((at_launch<AT_DK>(Kp128, Vp128, Qp64, dOp64, Qt.map, a, B * H)));
+      PDN_TRY((at_launch<AT_DK>(Kp128, Vp128, Qp64, dOp64, Qp64, a, B * H)));  // dK += dS^T Q
     }
   }
   return 0;

@@ -134,6 +134,21 @@ __device__ __forceinline__ uint64_t make_smem_desc_sw128(uint32_t saddr) {
   d |= (uint64_t)2 << 61;                  // layout type: SWIZZLE_128B
   return d;
 }
+// MN-major, 128B-swizzled operand: the tile sits in shared memory as [k rows][64 MN elements = 128 B] (what TMA writes for a box of
+// {64 contiguous MN elements, k rows}); 8-row k groups are 1024 B apart (SBO); a second 64-element MN block would be LBO away
+// (unused for N = 64). One UMMA_K = 16 step advances the start address by 16 rows = 2048 B. Needs the b_major (bit 16) / a_major
+// (bit 15) flag of the instruction descriptor.
+__device__ __forceinline__ uint64_t make_smem_desc_sw128_mn(uint32_t saddr, uint32_t lbo_bytes = 16) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+constexpr uint32_t IDESC_B_MN_MAJOR = 1u << 16;
+constexpr uint32_t IDESC_A_MN_MAJOR = 1u << 15;
 // instruction descriptor: c=f32, a=b=bf16, both K-major, M x N
 __host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
