@@ -153,7 +153,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUte
   uint64_t* tempty_bar = tfull_bar + 2;            // [2] accumulator drained by the epilogue
   uint32_t* tmem_slot = (uint32_t*)(tempty_bar + 2);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = warp_id_uniform(), lane = threadIdx.x & 31;
   const bool tr = g.trace != nullptr && blockIdx.x == 0 && lane == 0;
 #define TC_STAMP(i) do { if (tr) g.trace[i] = clock64(); } while (0)
   if (warp == 0) TC_STAMP(0);
@@ -200,19 +200,20 @@ k_gemm_tc(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUte
   };
 
   if (warp == 0) {
-    // ===== TMA producer =====
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      for (uint32_t t = blockIdx.x; t < (uint32_t)total_tiles; t += gridDim.x) {
-        int n_blk, m_blk, split; int64_t i0, i1, i2;
-        decode(t, n_blk, m_blk, split, i0, i1, i2);
-        const int a_batch = (int)(i0 * g.a_pbs[0] + i1 * g.a_pbs[1] + i2 * g.a_pbs[2]);
-        const int b_batch = (int)(i0 * g.b_pbs[0] + i1 * g.b_pbs[1] + i2 * g.b_pbs[2]);
-        const int kb_begin = split * kb_per;
-        const int num_kb = min(all_kb, kb_begin + kb_per) - kb_begin;
-        for (int kb = 0; kb < num_kb; ++kb) {
-          mbar_wait(&empty_bar[stage], phase ^ 1);
+    // ===== TMA producer (the whole warp walks the loop, the elected lane issues: operands stay in uniform registers) =====
+    const bool leader = elect_one();
+    int stage = 0;
+    uint32_t phase = 0;
+    for (uint32_t t = blockIdx.x; t < (uint32_t)total_tiles; t += gridDim.x) {
+      int n_blk, m_blk, split; int64_t i0, i1, i2;
+      decode(t, n_blk, m_blk, split, i0, i1, i2);
+      const int a_batch = (int)(i0 * g.a_pbs[0] + i1 * g.a_pbs[1] + i2 * g.a_pbs[2]);
+      const int b_batch = (int)(i0 * g.b_pbs[0] + i1 * g.b_pbs[1] + i2 * g.b_pbs[2]);
+      const int kb_begin = split * kb_per;
+      const int num_kb = min(all_kb, kb_begin + kb_per) - kb_begin;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        if (leader) {
           uint8_t* st = smem + stage * Cfg::kStageBytes;
           mbar_expect_tx(&full_bar[stage], GATHER ? 2 * (BN * TC_BK * 2) : Cfg::kStageBytes);
           const int k = (kb_begin + kb) * TC_BK;
@@ -222,29 +223,30 @@ k_gemm_tc(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUte
           }
           tma_load_4d(&mapB, &full_bar[stage], st + 2 * TC_BM * TC_BK * 2, k, n_blk * BN, 0, b_batch);
           tma_load_4d(&mapB, &full_bar[stage], st + 2 * TC_BM * TC_BK * 2 + BN * TC_BK * 2, k, n_blk * BN, 1, b_batch);
-          if (kb == 0 && t == blockIdx.x) TC_STAMP(2);
-          if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
         }
+        if (kb == 0 && t == blockIdx.x) TC_STAMP(2);
+        if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
       }
     }
   } else if (warp == 1) {
-    // ===== MMA issuer (single elected lane) =====
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_bf16(TC_BM, BN);
-      int stage = 0, acc = 0;
-      uint32_t phase = 0, acc_phase = 0;
-      for (uint32_t t = blockIdx.x; t < (uint32_t)total_tiles; t += gridDim.x) {
-        int n_blk, m_blk, split; int64_t i0, i1, i2;
-        decode(t, n_blk, m_blk, split, i0, i1, i2);
-        const int kb_begin = split * kb_per;
-        const int num_kb = min(all_kb, kb_begin + kb_per) - kb_begin;
-        mbar_wait(&tempty_bar[acc], acc_phase ^ 1);  // the epilogue has drained this accumulator (passes on first use)
+    // ===== MMA issuer (the whole warp walks the loop, the elected lane issues) =====
+    const bool leader = elect_one();
+    constexpr uint32_t idesc = make_idesc_bf16(TC_BM, BN);
+    int stage = 0, acc = 0;
+    uint32_t phase = 0, acc_phase = 0;
+    for (uint32_t t = blockIdx.x; t < (uint32_t)total_tiles; t += gridDim.x) {
+      int n_blk, m_blk, split; int64_t i0, i1, i2;
+      decode(t, n_blk, m_blk, split, i0, i1, i2);
+      const int kb_begin = split * kb_per;
+      const int num_kb = min(all_kb, kb_begin + kb_per) - kb_begin;
+      mbar_wait(&tempty_bar[acc], acc_phase ^ 1);  // the epilogue has drained this accumulator (passes on first use)
+      tc_fence_after();
+      const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BN);
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(&full_bar[stage], phase);
         tc_fence_after();
-        const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BN);
-        for (int kb = 0; kb < num_kb; ++kb) {
-          mbar_wait(&full_bar[stage], phase);
-          tc_fence_after();
-          if (kb == 0 && t == blockIdx.x) TC_STAMP(3);
+        if (kb == 0 && t == blockIdx.x) TC_STAMP(3);
+        if (leader) {
           const uint32_t sa = smem_u32(smem + stage * Cfg::kStageBytes);
           const uint64_t d_ahi = make_smem_desc_sw128(sa);
           const uint64_t d_alo = make_smem_desc_sw128(sa + TC_BM * TC_BK * 2);
@@ -259,12 +261,12 @@ k_gemm_tc(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUte
             umma_bf16(tmem_d, d_ahi + adv, d_bhi + adv, idesc, 1u);
           }
           umma_commit(&empty_bar[stage]);  // frees this smem stage once the MMAs above have read it
-          if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
         }
-        umma_commit(&tfull_bar[acc]);  // accumulator complete
-        if (t == blockIdx.x) TC_STAMP(4);
-        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
       }
+      if (leader) umma_commit(&tfull_bar[acc]);  // accumulator complete
+      if (t == blockIdx.x) TC_STAMP(4);
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
   } else if (warp >= 4 && warp < 8) {
     // ===== epilogue: TMEM -> registers -> (+bias) -> {swizzled smem transpose -> 128-bit coalesced stores | NCHW | argmax} =====
