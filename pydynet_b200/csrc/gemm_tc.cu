@@ -218,11 +218,28 @@ k_gemm_tc(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUte
           mbar_expect_tx(&full_bar[stage], GATHER ? 2 * (BN * TC_BK * 2) : Cfg::kStageBytes);
           const int k = (kb_begin + kb) * TC_BK;
           if (!GATHER) {
-            tma_load_4d(&mapA, &full_bar[stage], st, k, m_blk * TC_BM, 0, a_batch);
-            tma_load_4d(&mapA, &full_bar[stage], st + TC_BM * TC_BK * 2, k, m_blk * TC_BM, 1, a_batch);
+            if (!g.a_mn) {
+              tma_load_4d(&mapA, &full_bar[stage], st, k, m_blk * TC_BM, 0, a_batch);
+              tma_load_4d(&mapA, &full_bar[stage], st + TC_BM * TC_BK * 2, k, m_blk * TC_BM, 1, a_batch);
+            } else {  // MN-major: [64 k rows][64 operand rows = 128 B] blocks, 8 KB each
+#pragma unroll
+              for (int pl = 0; pl < 2; ++pl)
+#pragma unroll
+                for (int i = 0; i < TC_BM / 64; ++i)
+                  tma_load_4d(&mapA, &full_bar[stage], st + pl * (TC_BM * TC_BK * 2) + i * 8192, m_blk * TC_BM + 64 * i, k, pl, a_batch);
+            }
           }
-          tma_load_4d(&mapB, &full_bar[stage], st + 2 * TC_BM * TC_BK * 2, k, n_blk * BN, 0, b_batch);
-          tma_load_4d(&mapB, &full_bar[stage], st + 2 * TC_BM * TC_BK * 2 + BN * TC_BK * 2, k, n_blk * BN, 1, b_batch);
+          uint8_t* sb = st + 2 * TC_BM * TC_BK * 2;
+          if (!g.b_mn) {
+            tma_load_4d(&mapB, &full_bar[stage], sb, k, n_blk * BN, 0, b_batch);
+            tma_load_4d(&mapB, &full_bar[stage], sb + BN * TC_BK * 2, k, n_blk * BN, 1, b_batch);
+          } else {
+#pragma unroll
+            for (int pl = 0; pl < 2; ++pl)
+#pragma unroll
+              for (int i = 0; i < BN / 64; ++i)
+                tma_load_4d(&mapB, &full_bar[stage], sb + pl * (BN * TC_BK * 2) + i * 8192, n_blk * BN + 64 * i, k, pl, b_batch);
+          }
         }
         if (kb == 0 && t == blockIdx.x) TC_STAMP(2);
         if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
@@ -231,7 +248,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUte
   } else if (warp == 1) {
     // ===== MMA issuer (the whole warp walks the loop, the elected lane issues) =====
     const bool leader = elect_one();
-    constexpr uint32_t idesc = make_idesc_bf16(TC_BM, BN);
+    const uint32_t idesc = make_idesc_bf16(TC_BM, BN) | (g.a_mn ? IDESC_A_MN_MAJOR : 0u) | (g.b_mn ? IDESC_B_MN_MAJOR : 0u);
     int stage = 0, acc = 0;
     uint32_t phase = 0, acc_phase = 0;
     for (uint32_t t = blockIdx.x; t < (uint32_t)total_tiles; t += gridDim.x) {
@@ -247,18 +264,20 @@ k_gemm_tc(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUte
         tc_fence_after();
         if (kb == 0 && t == blockIdx.x) TC_STAMP(3);
         if (leader) {
-          const uint32_t sa = smem_u32(smem + stage * Cfg::kStageBytes);
-          const uint64_t d_ahi = make_smem_desc_sw128(sa);
-          const uint64_t d_alo = make_smem_desc_sw128(sa + TC_BM * TC_BK * 2);
-          const uint64_t d_bhi = make_smem_desc_sw128(sa + 2 * TC_BM * TC_BK * 2);
-          const uint64_t d_blo = make_smem_desc_sw128(sa + 2 * TC_BM * TC_BK * 2 + BN * TC_BK * 2);
+          const uint32_t sa = smem_u32(smem + stage * Cfg::kStageBytes), sb = sa + 2 * TC_BM * TC_BK * 2;
+          const uint64_t d_ahi = g.a_mn ? make_smem_desc_sw128_mn(sa, 8192) : make_smem_desc_sw128(sa);
+          const uint64_t d_alo = g.a_mn ? make_smem_desc_sw128_mn(sa + TC_BM * TC_BK * 2, 8192) : make_smem_desc_sw128(sa + TC_BM * TC_BK * 2);
+          const uint64_t d_bhi = g.b_mn ? make_smem_desc_sw128_mn(sb, 8192) : make_smem_desc_sw128(sb);
+          const uint64_t d_blo = g.b_mn ? make_smem_desc_sw128_mn(sb + BN * TC_BK * 2, 8192) : make_smem_desc_sw128(sb + BN * TC_BK * 2);
+          // one UMMA_K = 16 step: 32 B inside the swizzle span (K-major) or 16 rows of 128 B (MN-major), in 16-byte units
+          const uint64_t a_step = g.a_mn ? 128 : 2, b_step = g.b_mn ? 128 : 2;
 #pragma unroll
           for (int k = 0; k < TC_BK / 16; ++k) {
-            const uint64_t adv = (uint64_t)((k * 16 * 2) >> 4);  // 32 B per UMMA_K step inside the swizzle span
+            const uint64_t aa = a_step * k, bb = b_step * k;
             // small cross terms first, then the leading term
-            umma_bf16(tmem_d, d_alo + adv, d_bhi + adv, idesc, (kb | k) ? 1u : 0u);
-            umma_bf16(tmem_d, d_ahi + adv, d_blo + adv, idesc, 1u);
-            umma_bf16(tmem_d, d_ahi + adv, d_bhi + adv, idesc, 1u);
+            umma_bf16(tmem_d, d_alo + aa, d_bhi + bb, idesc, (kb | k) ? 1u : 0u);
+            umma_bf16(tmem_d, d_ahi + aa, d_blo + bb, idesc, 1u);
+            umma_bf16(tmem_d, d_ahi + aa, d_bhi + bb, idesc, 1u);
           }
           umma_commit(&empty_bar[stage]);  // frees this smem stage once the MMAs above have read it
         }
@@ -586,6 +605,18 @@ int pack_operand_ex(const float* src, int64_t R, int64_t K, int64_t r_stride, in
   return 0;
 }
 
+int pack_operand_auto(const float* src, int64_t rows, int64_t kc, int64_t r_stride, int64_t k_stride, const int64_t* nb, const int64_t* bs,
+                      Scratch* buf, PackedOperand* out) {
+  if (k_stride != 1 && r_stride == 1 && rows > 1 && kc > 1) {
+    PDN_TRY(pack_operand_ex(src, kc, rows, k_stride, 1, 0, 0, nb, bs, buf, out));
+    out->mn = 1;
+    return 0;
+  }
+  PDN_TRY(pack_operand_ex(src, rows, kc, r_stride, k_stride, 0, 0, nb, bs, buf, out));
+  out->mn = 0;
+  return 0;
+}
+
 template <int BN, int GATHER>
 static int launch_tc(const CUtensorMap& mA, const CUtensorMap& mB, const TcArgs& t, const GatherArgs& ga) {
   using Cfg = TcCfg<BN>;
@@ -674,8 +705,10 @@ int gemm_tc_packed(const PackedOperand& A, const PackedOperand& B, TcArgs t, int
   }
   if (n_tiles_out) *n_tiles_out = (int)((t.N + BN - 1) / BN);
   CUtensorMap mA, mB;
-  PDN_TRY(make_map(&mA, A.planes, A.R, A.K, A.Kp, A.nbatch, TC_BM));
-  PDN_TRY(make_map(&mB, B.planes, B.R, B.K, B.Kp, B.nbatch, BN));
+  t.a_mn = A.mn; t.b_mn = B.mn;
+  // MN-major operands are fetched as [64 contraction rows][64 operand rows] boxes of their own row-major planes
+  PDN_TRY(make_map(&mA, A.planes, A.R, A.K, A.Kp, A.nbatch, A.mn ? TC_BK : TC_BM));
+  PDN_TRY(make_map(&mB, B.planes, B.R, B.K, B.Kp, B.nbatch, B.mn ? TC_BK : BN));
   GatherArgs none{};
   return launch_bn<0>(BN, mA, mB, t, none);
 }
@@ -710,9 +743,11 @@ int gemm_tc_conv(const float* src, const ConvGeom& geom, int mode, int64_t Mtot,
 int gemm_tc_launch(const GemmArgs& g) {
   Scratch       bufA, bufB;
   PackedOperand A, B;
-  // A: rows = M, k along a_cs.  B: rows = N (we need Bᵀ K-major), k along b_rs.
-  PDN_TRY(pack_operand_ex((const float*)g.A, g.M, g.K, g.a_rs, g.a_cs, 0, 0, g.nb, g.a_bs, &bufA, &A));
-  PDN_TRY(pack_operand_ex((const float*)g.B, g.N, g.K, g.b_cs, g.b_rs, 0, 0, g.nb, g.b_bs, &bufB, &B));
+  // Every operand is packed in its OWN memory orientation (no transposing pack): contraction axis unit-stride -> K-major planes
+  // [rows][K]; operand rows unit-stride (W [K][N] as B of x @ W, x [M][K] as A of x^T @ g) -> MN-major planes [K][rows].
+  // A: rows = M, k along a_cs.  B: rows = N, k along b_rs.
+  PDN_TRY(pack_operand_auto((const float*)g.A, g.M, g.K, g.a_rs, g.a_cs, g.nb, g.a_bs, &bufA, &A));
+  PDN_TRY(pack_operand_auto((const float*)g.B, g.N, g.K, g.b_cs, g.b_rs, g.nb, g.b_bs, &bufB, &B));
   TcArgs t;
   t.C = (float*)g.C;
   t.bias = (const float*)g.bias;

@@ -6,10 +6,14 @@
 namespace pdn {
 
 // K-major bf16 planes [nbatch][2 (hi, lo)][R][Kp]; pbs = packed-batch index stride per GEMM batch dim (0 = broadcast)
+// mn = 0: K-major, planes [nbatch][2][R = operand rows][Kp], K = contraction length.
+// mn = 1: MN-major, planes [nbatch][2][R = contraction length][Kp], K = operand rows (M or N) — the operand's own row-major layout
+//         when its rows are the unit-stride axis (W [K][N] as the B of x @ W, x [M][K] as the A of x^T @ g): no transposed copy.
 struct PackedOperand {
   void*   planes;
   int64_t R, K, Kp, nbatch;
   int64_t pbs[3];
+  int     mn = 0;
 };
 
 struct TcArgs {
@@ -24,11 +28,15 @@ struct TcArgs {
   // greedy-decode epilogue: instead of storing C, keep per (row, N-tile) the maximum of (A·B + bias) and its column
   float*     amax_val;   // [M][n_tiles] (nullptr = normal store epilogue)
   long long* amax_idx;   // [M][n_tiles]
-  long long* trace;      // debug (PDN_TC_TRACE): clock64 stamps of CTA 0's pipeline stages, nullptr = off
+  int a_mn = 0, b_mn = 0;  // operand orientation in shared memory (filled by gemm_tc_packed from PackedOperand::mn)
+  long long* trace = nullptr;  // debug (PDN_TC_TRACE): clock64 stamps of CTA 0's pipeline stages, nullptr = off
 };
 
 int pack_operand_ex(const float* src, int64_t R, int64_t K, int64_t r_stride, int64_t k_stride, int64_t k_inner, int64_t k_outer_stride,
                     const int64_t* nb, const int64_t* bs, Scratch* buf, PackedOperand* out);
+// packs `src` (logical [rows][kc] with the given element strides) in its own orientation: K-major, or MN-major when rows are unit-stride
+int pack_operand_auto(const float* src, int64_t rows, int64_t kc, int64_t r_stride, int64_t k_stride, const int64_t* nb, const int64_t* bs,
+                      Scratch* buf, PackedOperand* out);
 // 4-D TMA map over operand planes [batch][2][R][Kp] (bf16), box = 64 (k) x box_rows x 1 x 1, 128-byte swizzle
 int tc_make_map(CUtensorMap* map, const void* base, int64_t R, int64_t K, int64_t Kp, int64_t nbatch, int box_rows);
 struct ConvGeom;
