@@ -150,6 +150,17 @@ int pdn_index_scatter(void* dst, int dtype, const void* values, int K, const voi
 int pdn_gemm(int dtype, const void* A, const void* B, void* C, int64_t M, int64_t N, int64_t K, int64_t a_rs,
              int64_t a_cs, int64_t b_rs, int64_t b_cs, int64_t ldc, const int64_t* nb, const int64_t* a_bs,
              const int64_t* b_bs, const int64_t* c_bs, const void* bias, int accumulate, int prec);
+/* Same product with operand-plane caching for the tcgen05 path. Training multiplies the same buffers several times per step (x in
+ * the Q/K/V projections and again in dW = x^T @ g, tensor.py:672-676; g in both gradient products; W in forward and dX), and every
+ * use reads the same bf16 hi/lo planes because operands are packed in their own orientation. a_version / b_version are the
+ * caller's write counters of the buffers holding A / B (pydynet_b200: DeviceBuffer.version): >= 0 lets the library keep the planes
+ * until the counter changes or the memory is freed (pdn_free); -1 = transient operand (pdn_gemm). Capacity: PDN_PLANE_CACHE_MB
+ * (default 16384), PDN_PLANE_CACHE=0 disables. */
+int pdn_gemm_cached(int dtype, const void* A, const void* B, void* C, int64_t M, int64_t N, int64_t K, int64_t a_rs,
+                    int64_t a_cs, int64_t b_rs, int64_t b_cs, int64_t ldc, const int64_t* nb, const int64_t* a_bs,
+                    const int64_t* b_bs, const int64_t* c_bs, const void* bias, int accumulate, int prec, int64_t a_version,
+                    int64_t b_version);
+int pdn_plane_cache_stats(uint64_t* hits, uint64_t* misses, uint64_t* bytes, uint64_t* entries);
 /* Inference: pack a constant fp32 weight matrix B (K x N, element strides b_rs/b_cs) once into the tcgen05 operand format
  * and reuse it: C[M,N] (+)= A[M,K] @ B (+ bias). The handle owns device memory until pdn_gemm_prepack_free. The caller
  * must re-pack when the weight values change (pydynet_b200 tracks a per-buffer version for that). */

@@ -714,9 +714,11 @@ def gemm_into(out: ndarray | None, a: ndarray, b: ndarray, bias: ndarray | None 
         assert bias.shape == (N, ) and bias.is_contiguous
         if bias.dtype != dt:
             bias = bias.astype(dt)
-    L.call("pdn_gemm", _code(dt), ab.ptr, bb.ptr, out.ptr, M, N, K, ab.estrides[-2], ab.estrides[-1], bb.estrides[-2],
+    out.buf.version += 1
+    # the operands' write counters let the library keep their tensor-core operand planes across the products of one training step
+    L.call("pdn_gemm_cached", _code(dt), ab.ptr, bb.ptr, out.ptr, M, N, K, ab.estrides[-2], ab.estrides[-1], bb.estrides[-2],
            bb.estrides[-1], out.estrides[-2], _arr(bs), _arr(sa), _arr(sb), _arr(sc), bias.ptr if bias is not None else None,
-           1 if accumulate else 0, prec)
+           1 if accumulate else 0, prec, ab.buf.version, bb.buf.version)
     return out
 
 

@@ -70,6 +70,8 @@ _PROTOS = {
     "pdn_index_gather": [vp, i32, vp, i32, C.POINTER(vp), pi64, pi64, i64, i32, pi64, pi64, i32, pi64, pi64],
     "pdn_index_scatter": [vp, i32, vp, i32, C.POINTER(vp), pi64, pi64, i64, i32, pi64, pi64, i32, pi64, pi64, i32],
     "pdn_gemm": [i32, vp, vp, vp, i64, i64, i64, i64, i64, i64, i64, i64, pi64, pi64, pi64, pi64, vp, i32, i32],
+    "pdn_gemm_cached": [i32, vp, vp, vp, i64, i64, i64, i64, i64, i64, i64, i64, pi64, pi64, pi64, pi64, vp, i32, i32, i64, i64],
+    "pdn_plane_cache_stats": [C.POINTER(u64), C.POINTER(u64), C.POINTER(u64), C.POINTER(u64)],
     "pdn_gemm_last_path": [],
     "pdn_gemm_prepack": [vp, i64, i64, i64, i64, C.POINTER(vp)],
     "pdn_gemm_prepacked": [vp, vp, vp, i64, i64, i64, i64, vp, i32],

@@ -56,6 +56,10 @@ int          ensure_init();
 // scratch allocations served by the caching allocator (runtime.cu)
 int  dev_alloc(void** p, size_t bytes);
 void dev_free(void* p);
+size_t dev_block_size(void* p);  // size of the live allocation starting at p (0 if unknown)
+// operand-plane cache of the tcgen05 GEMM (gemm_tc.cu): entries derived from memory inside [p, p + n) are dropped when it is freed
+void plane_cache_drop_range(const void* p, size_t n);
+bool is_capturing();
 
 struct Scratch {  // RAII scratch buffer
   void* p = nullptr;

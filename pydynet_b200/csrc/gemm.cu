@@ -166,6 +166,17 @@ int pdn_gemm_last_path(void) { return g_last_path; }
 int pdn_gemm(int dtype, const void* A, const void* B, void* C, int64_t M, int64_t N, int64_t K, int64_t a_rs, int64_t a_cs,
              int64_t b_rs, int64_t b_cs, int64_t ldc, const int64_t* nb, const int64_t* a_bs, const int64_t* b_bs,
              const int64_t* c_bs, const void* bias, int accumulate, int prec) {
+  return pdn_gemm_cached(dtype, A, B, C, M, N, K, a_rs, a_cs, b_rs, b_cs, ldc, nb, a_bs, b_bs, c_bs, bias, accumulate, prec, -1, -1);
+}
+
+int pdn_plane_cache_stats(uint64_t* hits, uint64_t* misses, uint64_t* bytes, uint64_t* entries) {
+  plane_cache_stats(hits, misses, bytes, entries);
+  return 0;
+}
+
+int pdn_gemm_cached(int dtype, const void* A, const void* B, void* C, int64_t M, int64_t N, int64_t K, int64_t a_rs, int64_t a_cs,
+                    int64_t b_rs, int64_t b_cs, int64_t ldc, const int64_t* nb, const int64_t* a_bs, const int64_t* b_bs,
+                    const int64_t* c_bs, const void* bias, int accumulate, int prec, int64_t a_version, int64_t b_version) {
   PDN_TRY(ensure_init());
   GemmArgs g;
   g.A = A; g.B = B; g.C = C; g.bias = bias;
@@ -194,7 +205,7 @@ int pdn_gemm(int dtype, const void* A, const void* B, void* C, int64_t M, int64_
   if (prec == 0 && env_mode == 1) prec = 1;
   if (dtype == PDN_F32 && prec != 1 && gemm_tc_eligible(g)) {
     g_last_path = 1;
-    return gemm_tc_launch(g);
+    return gemm_tc_launch(g, a_version, b_version);
   }
   PDN_CHECK(prec != 2, "pdn_gemm: tcgen05 path forced but shape/strides are not eligible");
   if (dtype == PDN_F32 && M <= 16 && b_cs == 1 && K >= 32 && nbatch <= 65535) {

@@ -10,5 +10,7 @@ struct GemmArgs {
   int accumulate;
 };
 bool gemm_tc_eligible(const GemmArgs& g);
-int  gemm_tc_launch(const GemmArgs& g);
+// a_version / b_version: the caller's write counters of the operand buffers (>= 0: operand planes may be cached), -1 = transient
+int  gemm_tc_launch(const GemmArgs& g, long long a_version = -1, long long b_version = -1);
+void plane_cache_stats(uint64_t* hits, uint64_t* misses, uint64_t* bytes, uint64_t* entries);
 }  // namespace pdn

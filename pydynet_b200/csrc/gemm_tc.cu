@@ -19,6 +19,8 @@
 #include <cuda.h>
 #include <cudaTypedefs.h>
 #include <stdlib.h>
+#include <mutex>
+#include <vector>
 
 namespace pdn {
 
@@ -577,8 +579,9 @@ bool gemm_tc_eligible(const GemmArgs& g) {
   return true;
 }
 
-int pack_operand_ex(const float* src, int64_t R, int64_t K, int64_t r_stride, int64_t k_stride, int64_t k_inner, int64_t k_outer_stride,
-                    const int64_t* nb, const int64_t* bs, Scratch* buf, PackedOperand* out) {
+// planes of `src` written to `dst` (or to a fresh allocation of `buf` when dst == nullptr)
+static int pack_operand_to(const float* src, int64_t R, int64_t K, int64_t r_stride, int64_t k_stride, int64_t k_inner, int64_t k_outer_stride,
+                           const int64_t* nb, const int64_t* bs, Scratch* buf, void* dst, PackedOperand* out) {
   int64_t Kp = (K + 7) & ~(int64_t)7;
   int64_t pb = 1;
   PackArgs p;
@@ -590,9 +593,12 @@ int pack_operand_ex(const float* src, int64_t R, int64_t K, int64_t r_stride, in
     p.bs[d] = bs[d];
   }
   PDN_CHECK(pb <= 65535, "gemm_tc: too many operand batches");
-  PDN_TRY(buf->alloc((size_t)pb * 2 * R * Kp * sizeof(__nv_bfloat16)));
+  if (!dst) {
+    PDN_TRY(buf->alloc((size_t)pb * 2 * R * Kp * sizeof(__nv_bfloat16)));
+    dst = buf->p;
+  }
   p.src = src;
-  p.dst = (__nv_bfloat16*)buf->p;
+  p.dst = (__nv_bfloat16*)dst;
   p.R = R; p.K = K; p.Kp = Kp;
   p.r_stride = r_stride; p.k_stride = k_stride;
   p.k_inner = k_inner > 0 ? k_inner : (K > 0 ? K : 1);
@@ -601,7 +607,134 @@ int pack_operand_ex(const float* src, int64_t R, int64_t K, int64_t r_stride, in
   PDN_CHECK(grd.y <= 65535, "gemm_tc: operand has too many rows for the pack grid");
   k_pack_split<<<grd, 256, 0, stream()>>>(p);
   PDN_LAUNCHED("pack_split");
-  out->planes = buf->p; out->R = R; out->K = K; out->Kp = Kp; out->nbatch = pb;
+  out->planes = dst; out->R = R; out->K = K; out->Kp = Kp; out->nbatch = pb;
+  return 0;
+}
+
+int pack_operand_ex(const float* src, int64_t R, int64_t K, int64_t r_stride, int64_t k_stride, int64_t k_inner, int64_t k_outer_stride,
+                    const int64_t* nb, const int64_t* bs, Scratch* buf, PackedOperand* out) {
+  return pack_operand_to(src, R, K, r_stride, k_stride, k_inner, k_outer_stride, nb, bs, buf, nullptr, out);
+}
+
+// ------------------------------------------------------------------ operand-plane cache --------
+// Training re-uses GEMM operands: x feeds the Q/K/V projections and, in backward, dW = x^T g; g feeds dX = g W^T and dW; W feeds the
+// forward and dX. With every operand packed in its own orientation (MN-major support above) all these uses read the SAME planes,
+// so they are packed once and kept until the source buffer is written (the caller passes its write-version counter) or freed
+// (allocator hook). First ncu launch list of the encoder step: k_pack_split = 33 % of GPU time, 48 launches per step.
+struct PlaneEntry {
+  const float* src; int64_t R, K, rs, ks; int64_t nb[3], bs[3];
+  long long version; PackedOperand op; size_t bytes; uint64_t stamp;
+};
+static std::vector<PlaneEntry> g_planes;
+static std::mutex              g_planes_mu;
+static uint64_t                g_planes_clock = 0;
+static size_t                  g_planes_bytes = 0;
+static uint64_t                g_planes_hits = 0, g_planes_misses = 0;
+
+static size_t plane_cache_cap() {
+  static size_t cap = 0;
+  if (!cap) {
+    const char* e = getenv("PDN_PLANE_CACHE_MB");
+    cap = (e ? (size_t)atoll(e) : (size_t)16384) << 20;
+  }
+  return cap;
+}
+
+void plane_cache_drop_range(const void* p, size_t n) {
+  if (n == 0) n = 1;
+  std::vector<void*> victims;
+  {
+    std::lock_guard<std::mutex> lk(g_planes_mu);
+    if (g_planes.empty()) return;
+    const char *lo = (const char*)p, *hi = lo + n;
+    for (size_t i = 0; i < g_planes.size();) {
+      const char* sp = (const char*)g_planes[i].src;
+      if (sp >= lo && sp < hi) {
+        victims.push_back(g_planes[i].op.planes);
+        g_planes_bytes -= g_planes[i].bytes;
+        g_planes[i] = g_planes.back();
+        g_planes.pop_back();
+      } else {
+        ++i;
+      }
+    }
+  }
+  for (void* v : victims) dev_free(v);
+}
+
+// operand planes of `src` in its own orientation, from the cache when `version` >= 0 (the caller's write counter of the buffer)
+static int planes_cached(const float* src, int64_t rows, int64_t kc, int64_t r_stride, int64_t k_stride, const int64_t* nb, const int64_t* bs,
+                         long long version, Scratch* buf, PackedOperand* out) {
+  const bool mn = (k_stride != 1 && r_stride == 1 && rows > 1 && kc > 1);
+  const int64_t R = mn ? kc : rows, K = mn ? rows : kc, rs = mn ? k_stride : r_stride, ks = mn ? 1 : k_stride;
+  static const bool off = getenv("PDN_PLANE_CACHE") != nullptr && atoi(getenv("PDN_PLANE_CACHE")) == 0;
+  if (version < 0 || off || is_capturing()) {
+    PDN_TRY(pack_operand_to(src, R, K, rs, ks, 0, 0, nb, bs, buf, nullptr, out));
+    out->mn = mn ? 1 : 0;
+    return 0;
+  }
+  void* reuse = nullptr;
+  std::vector<void*> evict;
+  {
+    std::lock_guard<std::mutex> lk(g_planes_mu);
+    for (auto& e : g_planes) {
+      if (e.src != src || e.R != R || e.K != K || e.rs != rs || e.ks != ks) continue;
+      bool same = true;
+      for (int d = 0; d < 3; ++d) same = same && e.nb[d] == nb[d] && e.bs[d] == bs[d];
+      if (!same) continue;
+      e.stamp = ++g_planes_clock;
+      if (e.version == version) {
+        *out = e.op;
+        out->mn = mn ? 1 : 0;  // the same planes serve a K-major use (rows x k) and an MN-major use (k x rows) of the buffer
+        ++g_planes_hits;
+        return 0;
+      }
+      e.version = version;  // the buffer was written since: refresh the planes in place
+      reuse = e.op.planes;
+      break;
+    }
+  }
+  ++g_planes_misses;
+  if (reuse) {
+    PDN_TRY(pack_operand_to(src, R, K, rs, ks, 0, 0, nb, bs, nullptr, reuse, out));
+    out->mn = mn ? 1 : 0;
+    return 0;
+  }
+  void* mem = nullptr;
+  int64_t pb = 1;
+  for (int d = 0; d < 3; ++d)
+    if (bs[d] != 0 && nb[d] > 1) pb *= nb[d];
+  const size_t bytes = (size_t)pb * 2 * R * ((K + 7) & ~(int64_t)7) * sizeof(__nv_bfloat16);
+  if (dev_alloc(&mem, bytes) != 0) {  // no room to keep it: transient planes
+    PDN_TRY(pack_operand_to(src, R, K, rs, ks, 0, 0, nb, bs, buf, nullptr, out));
+    out->mn = mn ? 1 : 0;
+    return 0;
+  }
+  int r = pack_operand_to(src, R, K, rs, ks, 0, 0, nb, bs, nullptr, mem, out);
+  if (r) { dev_free(mem); return r; }
+  out->mn = mn ? 1 : 0;
+  {
+    std::lock_guard<std::mutex> lk(g_planes_mu);
+    PlaneEntry e;
+    e.src = src; e.R = R; e.K = K; e.rs = rs; e.ks = ks;
+    for (int d = 0; d < 3; ++d) { e.nb[d] = nb[d]; e.bs[d] = bs[d]; }
+    e.version = version; e.op = *out; e.bytes = bytes; e.stamp = ++g_planes_clock;
+    g_planes.push_back(e);
+    g_planes_bytes += bytes;
+    while ((g_planes_bytes > plane_cache_cap() || g_planes.size() > 256) && g_planes.size() > 1) {  // evict least recently used (never the new one)
+      size_t lru = 0;
+      for (size_t i = 1; i + 1 < g_planes.size(); ++i)
+        if (g_planes[i].stamp < g_planes[lru].stamp) lru = i;
+      if (lru + 1 == g_planes.size()) break;
+      evict.push_back(g_planes[lru].op.planes);
+      g_planes_bytes -= g_planes[lru].bytes;
+      g_planes[lru] = g_planes.back();
+      g_planes.pop_back();
+    }
+  }
+  // NOTE: planes evicted here may still be read by GEMMs already queued on the stream; the allocator is stream-ordered (single
+  // compute stream), so handing the block to later work is safe.
+  for (void* v : evict) dev_free(v);
   return 0;
 }
 
@@ -740,14 +873,14 @@ int gemm_tc_conv(const float* src, const ConvGeom& geom, int mode, int64_t Mtot,
   return mode == 1 ? launch_bn<1>(BN, mB, mB, t, ga) : launch_bn<2>(BN, mB, mB, t, ga);
 }
 
-int gemm_tc_launch(const GemmArgs& g) {
+int gemm_tc_launch(const GemmArgs& g, long long a_version, long long b_version) {
   Scratch       bufA, bufB;
   PackedOperand A, B;
   // Every operand is packed in its OWN memory orientation (no transposing pack): contraction axis unit-stride -> K-major planes
   // [rows][K]; operand rows unit-stride (W [K][N] as B of x @ W, x [M][K] as A of x^T @ g) -> MN-major planes [K][rows].
   // A: rows = M, k along a_cs.  B: rows = N, k along b_rs.
-  PDN_TRY(pack_operand_auto((const float*)g.A, g.M, g.K, g.a_rs, g.a_cs, g.nb, g.a_bs, &bufA, &A));
-  PDN_TRY(pack_operand_auto((const float*)g.B, g.N, g.K, g.b_cs, g.b_rs, g.nb, g.b_bs, &bufB, &B));
+  PDN_TRY(planes_cached((const float*)g.A, g.M, g.K, g.a_rs, g.a_cs, g.nb, g.a_bs, a_version, &bufA, &A));
+  PDN_TRY(planes_cached((const float*)g.B, g.N, g.K, g.b_cs, g.b_rs, g.nb, g.b_bs, b_version, &bufB, &B));
   TcArgs t;
   t.C = (float*)g.C;
   t.bias = (const float*)g.bias;
@@ -760,6 +893,11 @@ int gemm_tc_launch(const GemmArgs& g) {
   t.amax_val = nullptr; t.amax_idx = nullptr;
   // split-K only for single-batch products (batched ones already fill the grid or have strided C)
   return gemm_tc_packed(A, B, t, nbatch > 1 ? 1 : 0);
+}
+
+void plane_cache_stats(uint64_t* hits, uint64_t* misses, uint64_t* bytes, uint64_t* entries) {
+  std::lock_guard<std::mutex> lk(g_planes_mu);
+  *hits = g_planes_hits; *misses = g_planes_misses; *bytes = g_planes_bytes; *entries = g_planes.size();
 }
 
 }  // namespace pdn

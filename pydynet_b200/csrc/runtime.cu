@@ -171,10 +171,22 @@ static void free_in(DevState& d, std::unordered_map<void*, DevState::Block>::ite
   d.live.erase(it);
 }
 
+size_t dev_block_size(void* p) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  for (auto& d : g_dev) {
+    auto it = d.live.find(p);
+    if (it != d.live.end()) return it->second.size;
+  }
+  return 0;
+}
+
+bool is_capturing() { return g_capturing; }
+
 void dev_free(void* p) {
   if (!p) return;
   DevState* s = cur();
   if (!s) return;
+  plane_cache_drop_range(p, dev_block_size(p));  // cached GEMM operand planes derived from this block die with it
   std::lock_guard<std::mutex> lk(g_mu);
   auto it = s->live.find(p);
   if (it != s->live.end()) {
