@@ -251,6 +251,7 @@ def micro(args, conv=True):
     def att():
         for t in (q, k, v):
             t.zero_grad()
+            t.data.buf.version += 1  # fresh q, k, v every step as far as the operand-plane cache can tell
         _fused.attention(q, k, v, None, 1.0 / D**.5).sum().backward()
 
     sec, nl = timed(att, max(2, args.steps // 2), warmup=2)

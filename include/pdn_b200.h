@@ -253,16 +253,19 @@ int pdn_attention_bwd(const float* q, const float* k, const float* v, const floa
                       int64_t Lq, int64_t Lk, int64_t D, const int64_t* q_str, const int64_t* k_str,
                       const int64_t* v_str, const int64_t* mask_str, float scale);
 
-/* Tensor-core form of the same operator (D <= 64): scores live in TMEM only, P / dS go to the accumulate MMA through
- * swizzled shared memory, fp32 parity via the BF16x3 split; same arguments and layouts as pdn_attention_fwd / _bwd
- * (csrc/attention_tc.cu). Chosen by the Python layer for training-sized problems. */
+/* Tensor-core form of the same operator (D <= 64): scores live in TMEM only, P / dS are written back to TMEM as bf16 hi/lo
+ * planes and read by the accumulate MMA from there (TS-mode tcgen05.mma), V / K / Q / dO tiles are consumed as MN-major B
+ * operands (no transposed copies), fp32 parity via the BF16x3 split; same arguments and layouts as pdn_attention_fwd / _bwd
+ * (csrc/attention_tc.cu). Chosen by the Python layer for training-sized problems. versions (nullable) = write counters of the
+ * buffers holding q, k, v: >= 0 keeps their operand planes in the plane cache so that backward re-uses the forward's packs. */
 int pdn_attention_tc_fwd(const float* q, const float* k, const float* v, const float* mask, float* out, float* lse,
                          int64_t B, int64_t H, int64_t Lq, int64_t Lk, int64_t D, const int64_t* q_str,
-                         const int64_t* k_str, const int64_t* v_str, const int64_t* mask_str, float scale);
+                         const int64_t* k_str, const int64_t* v_str, const int64_t* mask_str, float scale,
+                         const int64_t* versions);
 int pdn_attention_tc_bwd(const float* q, const float* k, const float* v, const float* mask, const float* out,
                          const float* lse, const float* g_out, float* dq, float* dk, float* dv, int64_t B, int64_t H,
                          int64_t Lq, int64_t Lk, int64_t D, const int64_t* q_str, const int64_t* k_str,
-                         const int64_t* v_str, const int64_t* mask_str, float scale);
+                         const int64_t* v_str, const int64_t* mask_str, float scale, const int64_t* versions);
 
 /* ---------------------------------------------------------------- recurrent ----------------- */
 /* GRU sequence (rnn.py:529-544 cell, :702-708 loop). xp1 [T,B,2H] = x@Wx1+b1 and xp2 [T,B,H] = x@Wx2+b2 are

@@ -89,8 +89,8 @@ _PROTOS = {
     "pdn_pool2d_fwd": [vp, vp, i64, i64, i64, i64, i32, i32, i32, i32],
     "pdn_pool2d_bwd": [vp, vp, vp, vp, i64, i64, i64, i64, i32, i32, i32, i32],
     "pdn_attention_fwd": [vp, vp, vp, vp, vp, vp, i64, i64, i64, i64, i64, pi64, pi64, pi64, pi64, f32, vp, i64],
-    "pdn_attention_tc_fwd": [vp, vp, vp, vp, vp, vp, i64, i64, i64, i64, i64, pi64, pi64, pi64, pi64, f32],
-    "pdn_attention_tc_bwd": [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i64, i64, i64, i64, i64, pi64, pi64, pi64, pi64, f32],
+    "pdn_attention_tc_fwd": [vp, vp, vp, vp, vp, vp, i64, i64, i64, i64, i64, pi64, pi64, pi64, pi64, f32, pi64],
+    "pdn_attention_tc_bwd": [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i64, i64, i64, i64, i64, pi64, pi64, pi64, pi64, f32, pi64],
     "pdn_attention_bwd": [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i64, i64, i64, i64, i64, pi64, pi64, pi64, pi64, f32],
     "pdn_gru_seq_fwd": [vp, vp, vp, vp, vp, vp, vp, vp, i64, i64, i64],
     "pdn_gru_seq_bwd": [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i64, i64, i64],

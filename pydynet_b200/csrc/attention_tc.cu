@@ -456,9 +456,10 @@ struct AtOperand {
 
 // rows x K fp32 view of a [B, L, H, D]-style tensor given (batch, head, row) strides -> planes [B*H][2][R][Kp] + TMA map
 static int at_pack(AtOperand* o, const float* src, int64_t B, int64_t H, int64_t R, int64_t K, int64_t r_stride, int64_t k_stride, int64_t bs,
-                   int64_t hs, int box_rows) {
+                   int64_t hs, int box_rows, long long version = -1) {
   const int64_t nb[3] = {1, B, H}, st[3] = {0, bs, hs};
-  PDN_TRY(pack_operand_ex(src, R, K, r_stride, k_stride, 0, 0, nb, st, &o->buf, &o->op));
+  // version >= 0: the planes come from / stay in the operand-plane cache (backward re-uses the forward's Q, K, V planes)
+  PDN_TRY(planes_cached(src, R, K, r_stride, k_stride, nb, st, version, &o->buf, &o->op));
   // a degenerate batch dimension (B*H == 1) or broadcast strides would collapse the packed batch count; attention always
   // has distinct (b, h) slices, so the packed batch index is b*H + h whenever the strides are non-zero
   return tc_make_map(&o->map, o->op.planes, R, K, o->op.Kp, o->op.nbatch, box_rows);
@@ -514,13 +515,14 @@ extern "C" {
 
 int pdn_attention_tc_fwd(const float* q, const float* k, const float* v, const float* mask, float* out, float* lse, int64_t B, int64_t H, int64_t Lq,
                          int64_t Lk, int64_t D, const int64_t* q_str, const int64_t* k_str, const int64_t* v_str, const int64_t* mask_str,
-                         float scale) {
+                         float scale, const int64_t* versions) {
+  const long long qv = versions ? versions[0] : -1, kv = versions ? versions[1] : -1, vv = versions ? versions[2] : -1;
   PDN_TRY(ensure_init());
   PDN_TRY(at_check(B, H, Lq, Lk, D, q_str, k_str, v_str));
   AtOperand Qp, Kp, Vp;
-  PDN_TRY(at_pack(&Qp, q, B, H, Lq, D, q_str[2], 1, q_str[0], q_str[1], AT_R));
-  PDN_TRY(at_pack(&Kp, k, B, H, Lk, D, k_str[2], 1, k_str[0], k_str[1], AT_C));
-  PDN_TRY(at_pack(&Vp, v, B, H, Lk, D, v_str[2], 1, v_str[0], v_str[1], AT_C));  // [keys][d]: MN-major B of O += P V
+  PDN_TRY(at_pack(&Qp, q, B, H, Lq, D, q_str[2], 1, q_str[0], q_str[1], AT_R, qv));
+  PDN_TRY(at_pack(&Kp, k, B, H, Lk, D, k_str[2], 1, k_str[0], k_str[1], AT_C, kv));
+  PDN_TRY(at_pack(&Vp, v, B, H, Lk, D, v_str[2], 1, v_str[0], v_str[1], AT_C, vv));  // [keys][d]: MN-major B of O += P V
   AtArgs a;
   a.rows = Lq; a.cols = Lk; a.H = H; a.D = (int)D; a.scale = scale;
   a.mask = mask; a.mask_bs = mask && mask_str ? mask_str[0] : 0; a.mask_qs = mask && mask_str ? mask_str[1] : 0;
@@ -533,7 +535,8 @@ int pdn_attention_tc_fwd(const float* q, const float* k, const float* v, const f
 
 int pdn_attention_tc_bwd(const float* q, const float* k, const float* v, const float* mask, const float* out, const float* lse, const float* g_out,
                          float* dq, float* dk, float* dv, int64_t B, int64_t H, int64_t Lq, int64_t Lk, int64_t D, const int64_t* q_str,
-                         const int64_t* k_str, const int64_t* v_str, const int64_t* mask_str, float scale) {
+                         const int64_t* k_str, const int64_t* v_str, const int64_t* mask_str, float scale, const int64_t* versions) {
+  const long long qv = versions ? versions[0] : -1, kv = versions ? versions[1] : -1, vv = versions ? versions[2] : -1;
   PDN_TRY(ensure_init());
   PDN_TRY(at_check(B, H, Lq, Lk, D, q_str, k_str, v_str));
   Scratch sdelta;
@@ -548,10 +551,10 @@ int pdn_attention_tc_bwd(const float* q, const float* k, const float* v, const f
   // every tensor is packed ONCE per layout; the row-operand (box 128) and column-operand (box 64) TMA maps share the planes
   AtOperand Qp, Kp, Vp, dOp;
   CUtensorMap Qp64, Kp128, Vp128, dOp64;
-  PDN_TRY(at_pack(&Qp, q, B, H, Lq, D, q_str[2], 1, q_str[0], q_str[1], AT_R));
-  PDN_TRY(at_pack(&Kp, k, B, H, Lk, D, k_str[2], 1, k_str[0], k_str[1], AT_C));
+  PDN_TRY(at_pack(&Qp, q, B, H, Lq, D, q_str[2], 1, q_str[0], q_str[1], AT_R, qv));
+  PDN_TRY(at_pack(&Kp, k, B, H, Lk, D, k_str[2], 1, k_str[0], k_str[1], AT_C, kv));
   PDN_TRY(at_pack(&dOp, g_out, B, H, Lq, D, g_str[2], 1, g_str[0], g_str[1], AT_R));
-  PDN_TRY(at_pack(&Vp, v, B, H, Lk, D, v_str[2], 1, v_str[0], v_str[1], AT_C));
+  PDN_TRY(at_pack(&Vp, v, B, H, Lk, D, v_str[2], 1, v_str[0], v_str[1], AT_C, vv));
   PDN_TRY(tc_make_map(&Qp64, Qp.op.planes, Lq, D, Qp.op.Kp, Qp.op.nbatch, AT_C));
   PDN_TRY(tc_make_map(&dOp64, dOp.op.planes, Lq, D, dOp.op.Kp, dOp.op.nbatch, AT_C));
   PDN_TRY(tc_make_map(&Kp128, Kp.op.planes, Lk, D, Kp.op.Kp, Kp.op.nbatch, AT_R));

@@ -37,6 +37,9 @@ int pack_operand_ex(const float* src, int64_t R, int64_t K, int64_t r_stride, in
 // packs `src` (logical [rows][kc] with the given element strides) in its own orientation: K-major, or MN-major when rows are unit-stride
 int pack_operand_auto(const float* src, int64_t rows, int64_t kc, int64_t r_stride, int64_t k_stride, const int64_t* nb, const int64_t* bs,
                       Scratch* buf, PackedOperand* out);
+// operand planes of `src` in its own orientation, served from the operand-plane cache when version >= 0 (see gemm_tc.cu)
+int planes_cached(const float* src, int64_t rows, int64_t kc, int64_t r_stride, int64_t k_stride, const int64_t* nb, const int64_t* bs,
+                  long long version, Scratch* buf, PackedOperand* out);
 // 4-D TMA map over operand planes [batch][2][R][Kp] (bf16), box = 64 (k) x box_rows x 1 x 1, 128-byte swizzle
 int tc_make_map(CUtensorMap* map, const void* base, int64_t R, int64_t K, int64_t Kp, int64_t nbatch, int box_rows);
 struct ConvGeom;

@@ -280,9 +280,10 @@ def attention(xq, xk, xv, mask, scale):
         assert impl, "attention: shape not supported by the fused kernels (check attention_fits first)"
         out, lse = _empty((B, Lq, H, D)), _empty((B, H, Lq))
         keep, mptr, mstr = _mask_args(mask, B, H, Lq, Lk)
+        vers = _i64((q.buf.version, k.buf.version, v.buf.version)) if is_grad_enable() else None  # backward re-uses the packs
         if impl == "tc":
             _call("pdn_attention_tc_fwd", q.ptr, k.ptr, v.ptr, mptr, out.ptr, lse.ptr, B, H, Lq, Lk, D, _bhl_strides(q), _bhl_strides(k),
-                  _bhl_strides(v), mstr, scale)
+                  _bhl_strides(v), mstr, scale, vers)
         else:
             _call("pdn_attention_fwd", q.ptr, k.ptr, v.ptr, mptr, out.ptr, lse.ptr, B, H, Lq, Lk, D, _bhl_strides(q), _bhl_strides(k),
                   _bhl_strides(v), mstr, scale, None, 0)
@@ -292,9 +293,10 @@ def attention(xq, xk, xv, mask, scale):
         dq = _empty((B, Lq, H, D)) if xq.requires_grad else None
         dk = _empty((B, Lk, H, D)) if xk.requires_grad else None
         dv = _empty((B, Lk, H, D)) if xv.requires_grad else None
+        extra = (_i64((q.buf.version, k.buf.version, v.buf.version)), ) if impl == "tc" else ()
         _call("pdn_attention_tc_bwd" if impl == "tc" else "pdn_attention_bwd", q.ptr, k.ptr, v.ptr, mptr, out.ptr, lse.ptr, g.ptr,
               dq.ptr if dq is not None else None, dk.ptr if dk is not None else None, dv.ptr if dv is not None else None, B, H, Lq, Lk, D,
-              _bhl_strides(q), _bhl_strides(k), _bhl_strides(v), mstr, scale)
+              _bhl_strides(q), _bhl_strides(k), _bhl_strides(v), mstr, scale, *extra)
         _ = keep
         return dq, dk, dv
 
