@@ -217,15 +217,19 @@ int pdn_bnorm_bwd_dx(const float* x, const float* mean, const float* var, const 
 
 /* ---------------------------------------------------------------- conv / pool --------------- */
 /* F.conv2d (functional.py:254-281): pad → im2col → GEMM → NCHW, fused; x [N,C,H,W], w [O,C,k,k],
- * bias nullable [O] (Conv2d.forward conv.py:99-103), y [N,O,oh,ow] all C-contiguous fp32. */
+ * bias nullable [O] (Conv2d.forward conv.py:99-103), y [N,O,oh,ow] all C-contiguous fp32.
+ * Stride-1 convolutions with >= 16 contraction channels run as TMA-tiled implicit GEMMs (csrc/conv_tma.cu: shifted 5-D TMA boxes of
+ * the activation's bf16 hi/lo NCHW planes, zero padding by out-of-bounds fill); others through the gather producer of
+ * csrc/gemm_tc.cu. *_version: write counters of the activation buffers (>= 0: their operand planes stay in the plane cache so
+ * backward-weight re-uses the forward's pack of x and backward-data's pack of g), -1 = transient. */
 int pdn_conv2d_fwd(const float* x, const float* w, const float* bias, float* y, int64_t N, int64_t C, int64_t H,
-                   int64_t W, int64_t O, int k, int stride, int pad);
+                   int64_t W, int64_t O, int k, int stride, int pad, int64_t x_version);
 /* dx = col2im(g_col @ Wmat) — replaces xp.add.at (functional.py:224-232) */
 int pdn_conv2d_bwd_data(const float* g, const float* w, float* dx, int64_t N, int64_t C, int64_t H, int64_t W,
-                        int64_t O, int k, int stride, int pad);
+                        int64_t O, int k, int stride, int pad, int64_t g_version);
 /* dw = colᵀ @ g ; dbias = sum over N,oh,ow (nullable) */
 int pdn_conv2d_bwd_weight(const float* x, const float* g, float* dw, float* dbias, int64_t N, int64_t C, int64_t H,
-                          int64_t W, int64_t O, int k, int stride, int pad);
+                          int64_t W, int64_t O, int k, int stride, int pad, int64_t x_version, int64_t g_version);
 /* F.max_pool2d / avg_pool2d (functional.py:284-339); mode 0 = max, 1 = avg. Padding is zero padding that
  * takes part in max/mean like the reference's xp.pad. bwd for max: EVERY element equal to the window max
  * receives the window's gradient (tensor.py:741-747). */

@@ -83,9 +83,9 @@ _PROTOS = {
     "pdn_bnorm_stats": [vp, vp, vp, i64, i64, i64],
     "pdn_bnorm_apply": [vp, vp, vp, vp, vp, vp, i64, i64, i64, f32],
     "pdn_bnorm_bwd": [vp, vp, vp, vp, vp, vp, vp, vp, i64, i64, i64, f32],
-    "pdn_conv2d_fwd": [vp, vp, vp, vp, i64, i64, i64, i64, i64, i32, i32, i32],
-    "pdn_conv2d_bwd_data": [vp, vp, vp, i64, i64, i64, i64, i64, i32, i32, i32],
-    "pdn_conv2d_bwd_weight": [vp, vp, vp, vp, i64, i64, i64, i64, i64, i32, i32, i32],
+    "pdn_conv2d_fwd": [vp, vp, vp, vp, i64, i64, i64, i64, i64, i32, i32, i32, i64],
+    "pdn_conv2d_bwd_data": [vp, vp, vp, i64, i64, i64, i64, i64, i32, i32, i32, i64],
+    "pdn_conv2d_bwd_weight": [vp, vp, vp, vp, i64, i64, i64, i64, i64, i32, i32, i32, i64, i64],
     "pdn_pool2d_fwd": [vp, vp, i64, i64, i64, i64, i32, i32, i32, i32],
     "pdn_pool2d_bwd": [vp, vp, vp, vp, i64, i64, i64, i64, i32, i32, i32, i32],
     "pdn_attention_fwd": [vp, vp, vp, vp, vp, vp, i64, i64, i64, i64, i64, pi64, pi64, pi64, pi64, f32, vp, i64],

@@ -164,7 +164,7 @@ using namespace pdn;
 extern "C" {
 
 int pdn_conv2d_fwd(const float* x, const float* w, const float* bias, float* y, int64_t N, int64_t C, int64_t H, int64_t W, int64_t O, int k,
-                   int stride, int pad) {
+                   int stride, int pad, int64_t x_version) {
   PDN_TRY(ensure_init());
   ConvGeom g;
   PDN_TRY(make_geom(g, N, C, H, W, O, k, stride, pad));
@@ -173,6 +173,12 @@ int pdn_conv2d_fwd(const float* x, const float* w, const float* bias, float* y, 
   Scratch       bufA, bufB;
   PackedOperand A, B;
   const int64_t one[3] = {1, 1, 1}, zero[3] = {0, 0, 0};
+  if (conv_tma_ok(C, stride, N, C, H, W)) {
+    // weights per tap as K-major planes [tap][O][C]: w[o, c, ky, kx] -> rows o (stride C k k), contraction c (stride k k), batch tap
+    const int64_t kk = (int64_t)k * k, tnb[3] = {1, 1, kk}, tbs[3] = {0, 0, 1};
+    PDN_TRY(pack_operand_ex(w, O, C, C * kk, kk, 0, 0, tnb, tbs, &bufB, &B));
+    return conv_tma_forward(x, N, C, H, W, B, bias, y, O, g.oh, g.ow, k, pad, +1, x_version);
+  }
   PDN_TRY(pack_operand_ex(w, O, K, K, 1, 0, 0, one, zero, &bufB, &B));
   TcArgs t;
   tc_defaults(t);
@@ -185,7 +191,7 @@ int pdn_conv2d_fwd(const float* x, const float* w, const float* bias, float* y, 
 }
 
 int pdn_conv2d_bwd_data(const float* gy, const float* w, float* dx, int64_t N, int64_t C, int64_t H, int64_t W, int64_t O, int k, int stride,
-                        int pad) {
+                        int pad, int64_t gy_version) {
   PDN_TRY(ensure_init());
   ConvGeom g;
   PDN_TRY(make_geom(g, N, C, H, W, O, k, stride, pad));
@@ -193,6 +199,12 @@ int pdn_conv2d_bwd_data(const float* gy, const float* w, float* dx, int64_t N, i
   if (M == 0 || C == 0) return 0;
   Scratch       bufA, bufB;
   PackedOperand A, B;
+  if (conv_tma_ok(O, stride, N, O, g.oh, g.ow)) {
+    // dx[n, c, y, x] = Σ_{tap, o} gy[n, o, y - ky + pad, x - kx + pad] · w[o, c, ky, kx]: planes [tap][C rows][O contraction]
+    const int64_t kk = (int64_t)k * k, tnb[3] = {1, 1, kk}, tbs[3] = {0, 0, 1};
+    PDN_TRY(pack_operand_ex(w, C, O, kk, C * kk, 0, 0, tnb, tbs, &bufB, &B));
+    return conv_tma_forward(gy, N, O, g.oh, g.ow, B, nullptr, dx, C, H, W, k, pad, -1, gy_version);
+  }
   // B rows = input channel c; k index (o, ky, kx) -> W[o, c, ky, kx]
   const int64_t one[3] = {1, 1, 1}, zero[3] = {0, 0, 0};
   PDN_TRY(pack_operand_ex(w, C, K, (int64_t)k * k, 1, (int64_t)k * k, C * (int64_t)k * k, one, zero, &bufB, &B));
@@ -207,7 +219,7 @@ int pdn_conv2d_bwd_data(const float* gy, const float* w, float* dx, int64_t N, i
 }
 
 int pdn_conv2d_bwd_weight(const float* x, const float* gy, float* dw, float* dbias, int64_t N, int64_t C, int64_t H, int64_t W, int64_t O, int k,
-                          int stride, int pad) {
+                          int stride, int pad, int64_t x_version, int64_t gy_version) {
   PDN_TRY(ensure_init());
   ConvGeom g;
   PDN_TRY(make_geom(g, N, C, H, W, O, k, stride, pad));
@@ -225,6 +237,8 @@ int pdn_conv2d_bwd_weight(const float* x, const float* gy, float* dw, float* dbi
     PDN_CUDA(cudaMemsetAsync(dw, 0, (size_t)O * K * sizeof(float), stream()));
     return 0;
   }
+  if (conv_tma_ok(16, stride, N, C, H, W) && C >= 8 && O >= 8 && N * O * g.oh < 0x7fffffff)
+    return conv_tma_bwd_weight(x, gy, dw, N, C, H, W, O, g.oh, g.ow, k, pad, x_version, gy_version);
   Scratch       bufA, bufB;
   PackedOperand A, B;
   // A rows = o, contraction index m = (n, pix): g[n, o, pix]

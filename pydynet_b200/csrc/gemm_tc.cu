@@ -664,8 +664,8 @@ void plane_cache_drop_range(const void* p, size_t n) {
 
 // operand planes of `src` in its own orientation, from the cache when `version` >= 0 (the caller's write counter of the buffer)
 int planes_cached(const float* src, int64_t rows, int64_t kc, int64_t r_stride, int64_t k_stride, const int64_t* nb, const int64_t* bs,
-                         long long version, Scratch* buf, PackedOperand* out) {
-  const bool mn = (k_stride != 1 && r_stride == 1 && rows > 1 && kc > 1);
+                  long long version, Scratch* buf, PackedOperand* out, bool force_kmajor) {
+  const bool mn = !force_kmajor && (k_stride != 1 && r_stride == 1 && rows > 1 && kc > 1);
   const int64_t R = mn ? kc : rows, K = mn ? rows : kc, rs = mn ? k_stride : r_stride, ks = mn ? 1 : k_stride;
   static const bool off = getenv("PDN_PLANE_CACHE") != nullptr && atoi(getenv("PDN_PLANE_CACHE")) == 0;
   if (version < 0 || off || is_capturing()) {

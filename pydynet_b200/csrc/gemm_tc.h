@@ -39,10 +39,16 @@ int pack_operand_auto(const float* src, int64_t rows, int64_t kc, int64_t r_stri
                       Scratch* buf, PackedOperand* out);
 // operand planes of `src` in its own orientation, served from the operand-plane cache when version >= 0 (see gemm_tc.cu)
 int planes_cached(const float* src, int64_t rows, int64_t kc, int64_t r_stride, int64_t k_stride, const int64_t* nb, const int64_t* bs,
-                  long long version, Scratch* buf, PackedOperand* out);
+                  long long version, Scratch* buf, PackedOperand* out, bool force_kmajor = false);
 // 4-D TMA map over operand planes [batch][2][R][Kp] (bf16), box = 64 (k) x box_rows x 1 x 1, 128-byte swizzle
 int tc_make_map(CUtensorMap* map, const void* base, int64_t R, int64_t K, int64_t Kp, int64_t nbatch, int box_rows);
 struct ConvGeom;
+// TMA-tiled stride-1 convolution (conv_tma.cu)
+bool conv_tma_ok(int64_t contr_channels, int stride, int64_t N, int64_t Cc, int64_t Hh, int64_t Ww);
+int conv_tma_forward(const float* act, int64_t N, int64_t Cc, int64_t Hh, int64_t Ww, const PackedOperand& wt, const float* bias, float* out,
+                     int64_t n_out, int64_t oh, int64_t ow, int k, int pad, int sign, long long act_version);
+int conv_tma_bwd_weight(const float* x, const float* gy, float* dw, int64_t N, int64_t C, int64_t H, int64_t W, int64_t O, int64_t oh, int64_t ow,
+                        int k, int pad, long long x_version, long long gy_version);
 int gemm_tc_conv(const float* src, const ConvGeom& geom, int mode, int64_t Mtot, int Ktot, const PackedOperand& B, TcArgs t);
 int gemm_tc_packed(const PackedOperand& A, const PackedOperand& B, TcArgs t, int splits, int* n_tiles_out = nullptr);
 

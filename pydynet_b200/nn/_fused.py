@@ -469,20 +469,21 @@ def conv2d(x, kernel, padding, stride, bias=None):
         oh, ow = (H + 2 * padding - k) // stride + 1, (W + 2 * padding - k) // stride + 1
         y = _empty((N, O, oh, ow))
         bd = _c(bias.data).reshape(-1) if bias is not None else None
-        _call("pdn_conv2d_fwd", xd.ptr, wd.ptr, bd.ptr if bd is not None else None, y.ptr, N, Cin, H, W, O, k, stride, padding)
+        xver = xd.buf.version if is_grad_enable() else -1  # backward-weight re-uses the forward's operand planes of x
+        _call("pdn_conv2d_fwd", xd.ptr, wd.ptr, bd.ptr if bd is not None else None, y.ptr, N, Cin, H, W, O, k, stride, padding, xver)
 
     def backward(g):
         g = _c(g)
         dx = dw = db = None
         if x.requires_grad:
             dx = _empty(xd.shape)
-            _call("pdn_conv2d_bwd_data", g.ptr, wd.ptr, dx.ptr, N, Cin, H, W, O, k, stride, padding)
+            _call("pdn_conv2d_bwd_data", g.ptr, wd.ptr, dx.ptr, N, Cin, H, W, O, k, stride, padding, g.buf.version)
         need_b = bias is not None and bias.requires_grad
         if kernel.requires_grad or need_b:
             dw = _empty(wd.shape) if kernel.requires_grad else None
             db = _empty(bias.shape) if need_b else None
             _call("pdn_conv2d_bwd_weight", xd.ptr, g.ptr, dw.ptr if dw is not None else None, db.ptr if db is not None else None, N, Cin, H,
-                  W, O, k, stride, padding)
+                  W, O, k, stride, padding, xd.buf.version, g.buf.version)
         return (dx, dw, db) if bias is not None else (dx, dw)
 
     ins = (x, kernel) + ((bias, ) if bias is not None else ())
