@@ -70,6 +70,32 @@ __global__ void __launch_bounds__(256) k_gather(const T* src, T* out, IdxDesc d)
   }
 }
 
+// Row form of both kernels (F.embedding, functional.py:14-20, and its gradient): one index array over the leading axis of a
+// matrix whose rows are contiguous 16-byte multiples — a warp copies whole rows with 128-bit accesses, no per-element index math.
+// (The generic kernels above spent ~15 64-bit divisions per 4-byte element: 1.2 TB/s on the encoder's embedding lookup.)
+__global__ void __launch_bounds__(256) k_gather_rows16(const uint4* __restrict__ src, uint4* __restrict__ out, const long long* __restrict__ idx,
+                                                       int64_t J, int64_t dim, int64_t src_row16, int row16) {
+  const int64_t total = J * row16;
+  for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t j = t / row16;
+    const int     i = (int)(t - j * row16);
+    long long v = __ldg(idx + j);
+    if (v < 0) v += dim;
+    if (v >= 0 && v < dim) out[t] = __ldg(src + v * src_row16 + i);
+  }
+}
+__global__ void __launch_bounds__(256) k_scatter_rows16(uint4* __restrict__ dst, const uint4* __restrict__ values, const long long* __restrict__ idx,
+                                                        const long long* __restrict__ winner, int64_t J, int64_t dim, int64_t dst_row16, int row16) {
+  const int64_t total = J * row16;
+  for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t j = t / row16;
+    const int     i = (int)(t - j * row16);
+    long long v = __ldg(idx + j);
+    if (v < 0) v += dim;
+    if (v >= 0 && v < dim && __ldg(winner + v) == j) dst[v * dst_row16 + i] = __ldg(values + t);  // last occurrence wins
+  }
+}
+
 __global__ void __launch_bounds__(256) k_winner(long long* winner, IdxDesc d) {
   for (int64_t j = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; j < d.J; j += (int64_t)gridDim.x * blockDim.x) {
     int64_t slot = idx_slot(d, j);
@@ -134,6 +160,17 @@ int pdn_index_gather(const void* src, int dtype, void* out, int K, const void* c
   PDN_TRY(fill_desc(&d, K, idx, idx_dim, idx_stride, J, n_outer, outer_shape, outer_stride, n_inner, inner_shape, inner_stride));
   int64_t total = d.outer_n * d.J * d.inner_n;
   if (total == 0) return 0;
+  {
+    const int64_t row_bytes = d.inner_n * dtype_size(dtype);
+    if (K == 1 && n_outer == 0 && n_inner == 1 && d.ist[0] == 1 && row_bytes % 16 == 0 && row_bytes / 16 < 0x7fffffff &&
+        (d.stride[0] * dtype_size(dtype)) % 16 == 0 && ((((uintptr_t)src) | ((uintptr_t)out)) & 15) == 0) {
+      const int row16 = (int)(row_bytes / 16);
+      k_gather_rows16<<<grid_for(d.J * row16, 256, 2), 256, 0, stream()>>>((const uint4*)src, (uint4*)out, d.idx[0], d.J, d.dim[0],
+                                                                            d.stride[0] * dtype_size(dtype) / 16, row16);
+      PDN_LAUNCHED("index_gather_rows");
+      return 0;
+    }
+  }
   int g = grid_for(total, 256, 2);
   switch (dtype_size(dtype)) {
     case 1: k_gather<unsigned char><<<g, 256, 0, stream()>>>((const unsigned char*)src, (unsigned char*)out, d); break;
@@ -172,6 +209,17 @@ int pdn_index_scatter(void* dst, int dtype, const void* values, int K, const voi
   PDN_CUDA(cudaMemsetAsync(win.p, 0xff, sizeof(long long) * (size_t)slots, stream()));  // -1
   k_winner<<<grid_for(J, 256, 1), 256, 0, stream()>>>((long long*)win.p, d);
   PDN_LAUNCHED("index_winner");
+  {
+    const int64_t row_bytes = d.inner_n * dtype_size(dtype);
+    if (K == 1 && n_outer == 0 && n_inner == 1 && d.ist[0] == 1 && row_bytes % 16 == 0 && row_bytes / 16 < 0x7fffffff &&
+        (d.stride[0] * dtype_size(dtype)) % 16 == 0 && ((((uintptr_t)dst) | ((uintptr_t)values)) & 15) == 0) {
+      const int row16 = (int)(row_bytes / 16);
+      k_scatter_rows16<<<grid_for(d.J * row16, 256, 2), 256, 0, stream()>>>((uint4*)dst, (const uint4*)values, d.idx[0], (const long long*)win.p, d.J,
+                                                                             d.dim[0], d.stride[0] * dtype_size(dtype) / 16, row16);
+      PDN_LAUNCHED("index_scatter_rows");
+      return 0;
+    }
+  }
   switch (dtype_size(dtype)) {
     case 1: k_scatter<unsigned char, false><<<g, 256, 0, stream()>>>((unsigned char*)dst, (const unsigned char*)values, (const long long*)win.p, d); break;
     case 2: k_scatter<unsigned short, false><<<g, 256, 0, stream()>>>((unsigned short*)dst, (const unsigned short*)values, (const long long*)win.p, d); break;

@@ -208,3 +208,42 @@ def test_matmul_paths_and_views(xp):
     v = _rand(rng, (384, ), np.float32)
     np.testing.assert_allclose((da @ xp.array(v)).get(), a @ v, rtol=1e-4, atol=1e-4)
     np.testing.assert_allclose((xp.array(v) @ db).get(), v @ b, rtol=1e-4, atol=1e-4)
+
+
+def test_operand_plane_cache_tracks_writes(xp):
+    """pdn_gemm_cached keeps the tensor-core operand planes of a buffer until its write counter changes or it is freed: every
+    way the Python layer writes device memory in place must invalidate them (stale planes would silently reuse old values)."""
+    import ctypes as C
+    from pydynet_b200.backend import lib
+    rng = np.random.default_rng(11)
+    a, b = _rand(rng, (256, 192), np.float32), _rand(rng, (192, 320), np.float32)
+    da, db = xp.array(a), xp.array(b)
+
+    def check(tag):
+        got = (da @ db).get()
+        assert _relerr(got, da.get().astype(np.float64) @ db.get().astype(np.float64)) < 2e-5, tag
+
+    def stats():
+        v = [C.c_uint64() for _ in range(4)]
+        lib.call("pdn_plane_cache_stats", *[C.byref(x) for x in v])
+        return [x.value for x in v]
+
+    check("first")
+    h0 = stats()[0]
+    check("second (cache hit)")
+    assert stats()[0] >= h0 + 2  # both operands served from the cache
+    da[3:7, :] = 5.0  # __setitem__
+    check("after setitem")
+    db += 1.5  # in-place arithmetic
+    check("after iadd")
+    da[...] = xp.array(_rand(rng, (256, 192), np.float32))  # copy-into
+    check("after copy")
+    # transposed re-use of the same planes (MN-major) and a view of the same buffer
+    gt = (da.swapaxes(0, 1) @ xp.array(_rand(rng, (256, 64), np.float32))).get()
+    assert gt.shape == (192, 64)
+    # freed and re-allocated memory must not inherit planes: allocate/free in a loop with fresh values
+    for i in range(4):
+        t = xp.array(_rand(rng, (256, 192), np.float32))
+        ref = t.get().astype(np.float64) @ db.get().astype(np.float64)
+        assert _relerr((t @ db).get(), ref) < 2e-5, f"realloc {i}"
+        del t
