@@ -24,8 +24,9 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 CFG = dict(V=32000, D=288, H=6, FF=768, S=1024, L=6)
-# dram__bytes_read.sum + dram__bytes_write.sum of ONE k_attention_rows launch from `ncu --set full`, keyed by (batch, keys)
-ATT_NCU_TRAFFIC = {}
+# dram__bytes_read.sum + dram__bytes_write.sum of ONE k_attention_rows launch from `ncu --set full`, keyed by (batch, keys):
+# profiles/r1g_ncu_extract.txt (605.26 MB read + 17.01 MB written at batch 1024, 256 keys; algorithmic 606.3 MB)
+ATT_NCU_TRAFFIC = {(1024, 256): 622.27e6}
 PROMPT_LEN, TOTAL_LEN = 4, int(os.environ.get("PDN_BENCH_TOTAL_LEN", 256))  # the env override exists for short ncu captures only
 
 
@@ -265,14 +266,14 @@ def run_ours(args):
         "wall_ms_per_step": wall / args.steps * 1e3,
         "roofline": {"kernel": "k_attention_rows<16,4,4,8> (KV-cache decode attention, one launch per layer: q [B,1,6,48] over cache[:, :Lk] of "
                                "[B,1024,6,48] fp32, output as GEMM operand planes) - the top kernel of the decode step at this batch "
-                               "(profiles/r1e_launches_b1024.csv)",
+                               "(profiles/r1g_launches_b1024.csv)",
                      "bound": "hbm", "achieved": att_bytes / max(a_avg_s, 1e-12) / 1e9, "peak": hbm, "unit": "GB/s",
                      "frac": att_bytes / max(a_avg_s, 1e-12) / 1e9 / hbm, "traffic": ATT_NCU_TRAFFIC.get((B, TOTAL_LEN)), "peak_source": which,
                      "launch_us": a_avg_s * 1e6, "launches_timed": a_n,
                      "note": "achieved = algorithmic bytes (K and V rows of the batch once at Lk = total length, + q in + planes out) / CUDA-event "
-                             "time of the launch, bracketed by event-record nodes inside the replayed CUDA graph (last decode step of every "
-                             "timed pass, all 6 layers); traffic = ncu dram bytes of one launch at the same shape (profiles/), null if that "
-                             "shape was not captured",
+                             "time of the launch, bracketed by event-record nodes inside the replayed CUDA graph (layer 0 of the last decode step "
+                             "of every timed pass); traffic = ncu dram bytes of one launch at the same shape (profiles/r1g_ncu_extract.txt), "
+                             "null if that shape was not captured",
                      "gemm_view": {"kernel": "k_gemm_tc<256> with argmax epilogue (lm_head [B,288]x[288,32000] on cached bf16 hi/lo weight planes, "
                                              "tcgen05 BF16x3) - the longest launch of the GEMM family", "bound": "tensor",
                                    "achieved": alg_flops / max(k_avg_s, 1e-12) / 1e12, "peak": tf, "unit": "TFLOP/s",

@@ -191,8 +191,8 @@ def decode(args):
     from pydynet_b200.nn import _fused
     from pydynet_b200.backend.array import ndarray
     rng = np.random.default_rng(2)
-    B, H, D, S, Lk = (64 if args.small else 1024), 6, 48, 1024, 130
-    for Bv in ([B] if args.small else [B, 128]):
+    B, H, D, S = (64 if args.small else 1024), 6, 48, 1024
+    for Bv, Lk in ([(B, 130)] if args.small else [(B, 130), (B, 256), (128, 130)]):
         q = T(rng.standard_normal((Bv, 1, H, D)).astype(f32))
         # several cache pairs so that consecutive launches do not find their K/V rows in the 126 MB L2
         n_caches = 1 if args.small else max(2, int(400e6 / (2 * Bv * Lk * H * D * 4)) + 1)

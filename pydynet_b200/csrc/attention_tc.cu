@@ -447,6 +447,29 @@ __global__ void __launch_bounds__(256) k_attn_delta(const float* __restrict__ g,
     if (lane == 0) delta[(b * H + h) * Lq + q] = s;
   }
 }
+// D % 4 == 0, 16-byte aligned: G = D/4 rounded up to a power of two lanes per row with one 128-bit load each, 32/G rows per warp
+template <int G>
+__global__ void __launch_bounds__(256) k_attn_delta_v4(const float4* __restrict__ g, const float4* __restrict__ o, float* __restrict__ delta,
+                                                       int64_t B, int64_t Lq, int64_t H, int d4) {
+  const int lane = threadIdx.x & 31, gl = lane & (G - 1), gr = lane / G;
+  constexpr int RPW = 32 / G;
+  const int64_t total = B * Lq * H;
+  const int64_t wid = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), nw = (int64_t)gridDim.x * (blockDim.x >> 5);
+  for (int64_t i0 = wid * RPW; i0 < total; i0 += nw * RPW) {
+    const int64_t i = i0 + gr;
+    float s = 0.f;
+    if (i < total && gl < d4) {
+      const float4 a = __ldg(g + i * d4 + gl), c = __ldg(o + i * d4 + gl);
+      s = a.x * c.x + a.y * c.y + a.z * c.z + a.w * c.w;
+    }
+#pragma unroll
+    for (int off = G / 2; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+    if (i < total && gl == 0) {
+      const int64_t h = i % H, q = (i / H) % Lq, b = i / (H * Lq);
+      delta[(b * H + h) * Lq + q] = s;
+    }
+  }
+}
 
 struct AtOperand {
   Scratch       buf;
@@ -541,7 +564,15 @@ int pdn_attention_tc_bwd(const float* q, const float* k, const float* v, const f
   PDN_TRY(at_check(B, H, Lq, Lk, D, q_str, k_str, v_str));
   Scratch sdelta;
   PDN_TRY(sdelta.alloc((size_t)B * H * Lq * sizeof(float)));
-  k_attn_delta<<<grid_for(B * Lq * H, 8), 256, 0, stream()>>>(g_out, out, (float*)sdelta.p, B, Lq, H, (int)D);
+  if ((D & 3) == 0 && ((((uintptr_t)g_out) | ((uintptr_t)out)) & 15) == 0) {
+    const int d4 = (int)(D / 4);
+    const int grd = grid_for(B * Lq * H, 8 * 4);
+    if (d4 <= 4) k_attn_delta_v4<4><<<grd, 256, 0, stream()>>>((const float4*)g_out, (const float4*)out, (float*)sdelta.p, B, Lq, H, d4);
+    else if (d4 <= 8) k_attn_delta_v4<8><<<grd, 256, 0, stream()>>>((const float4*)g_out, (const float4*)out, (float*)sdelta.p, B, Lq, H, d4);
+    else k_attn_delta_v4<16><<<grd, 256, 0, stream()>>>((const float4*)g_out, (const float4*)out, (float*)sdelta.p, B, Lq, H, d4);
+  } else {
+    k_attn_delta<<<grid_for(B * Lq * H, 8), 256, 0, stream()>>>(g_out, out, (float*)sdelta.p, B, Lq, H, (int)D);
+  }
   PDN_LAUNCHED("attn_delta");
   const int64_t g_str[3] = {Lq * H * D, D, H * D};  // g_out is [B, Lq, H, D] contiguous
   AtArgs a;
