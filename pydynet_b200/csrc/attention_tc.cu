@@ -91,6 +91,18 @@ __device__ __forceinline__ void umma3_ts(uint32_t d, uint32_t ahi, uint32_t alo,
   }
 }
 
+// score MMA with the A operand (row operand hi / lo planes) in tensor memory and a K-major B tile in shared memory
+__device__ __forceinline__ void umma3_ts_k(uint32_t d, uint32_t ahi, uint32_t alo, uint64_t bhi, uint64_t blo, uint32_t idesc, bool first_clears) {
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const uint64_t adv = (uint64_t)((k * 16 * 2) >> 4);
+    const uint32_t ac = (uint32_t)(k * 8);
+    umma_bf16_ts(d, alo + ac, bhi + adv, idesc, (first_clears && k == 0) ? 0u : 1u);
+    umma_bf16_ts(d, ahi + ac, blo + adv, idesc, 1u);
+    umma_bf16_ts(d, ahi + ac, bhi + adv, idesc, 1u);
+  }
+}
+
 template <int MODE>
 __global__ void __launch_bounds__(384, 1)
 k_attn_tc(const __grid_constant__ CUtensorMap mA1, const __grid_constant__ CUtensorMap mA2, const __grid_constant__ CUtensorMap mB1,
@@ -107,7 +119,8 @@ k_attn_tc(const __grid_constant__ CUtensorMap mA1, const __grid_constant__ CUten
   constexpr int NST = Cfg::kNst;
   uint64_t *a_full = bars, *acc_full = bars + 1, *s_full = bars + 2, *s_empty = bars + 4, *p_full = bars + 6, *p_empty = bars + 8,
            *sc_full = bars + 10, *sc_empty = sc_full + NST, *ac_full = sc_empty + NST, *ac_empty = ac_full + NST;
-  uint32_t* tmem_slot = (uint32_t*)(ac_empty + NST);
+  uint64_t* a_tmem = ac_empty + NST;  // the resident row operand (Q / K rows) has been copied from shared memory to tensor memory
+  uint32_t* tmem_slot = (uint32_t*)(a_tmem + 1);
 
   const int warp = warp_id_uniform(), lane = threadIdx.x & 31;
   const bool tr = a.trace != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && lane == 0;
@@ -125,6 +138,7 @@ k_attn_tc(const __grid_constant__ CUtensorMap mA1, const __grid_constant__ CUten
   }
   if (warp == 1 && lane == 0) {
     mbar_init(a_full, 1);
+    mbar_init(a_tmem, 8);
     for (int i = 0; i < NST; ++i) {
       mbar_init(&sc_full[i], 1);
       mbar_init(&sc_empty[i], 1);
@@ -140,7 +154,7 @@ k_attn_tc(const __grid_constant__ CUtensorMap mA1, const __grid_constant__ CUten
     mbar_init(acc_full, 1);
     fence_barrier_init();
   }
-  constexpr uint32_t kTmemCols = ACC ? 512u : 128u;  // LSE needs only the two score buffers (lets several CTAs share an SM)
+  constexpr uint32_t kTmemCols = ACC ? 512u : 256u;  // LSE: two score buffers + the row operand
   if (warp == 2) tmem_alloc(tmem_slot, kTmemCols);
   tc_fence_before();
   __syncthreads();
@@ -152,6 +166,10 @@ k_attn_tc(const __grid_constant__ CUtensorMap mA1, const __grid_constant__ CUten
   auto tmS2 = [&](int i) { return tmem_base + (uint32_t)(128 + i * 64); };
   auto tmP = [&](int i) { return tmem_base + (uint32_t)(320 + i * 64); };
   const uint32_t tmACC = tmem_base + 256u;
+  // the first row operand (Q rows, or K rows in the key-row passes) as bf16 hi / lo A planes of the score MMA: 32 + 32 columns.
+  // A from tensor memory costs no shared-memory bandwidth (SS-mode re-reads the 128 x 16 A slice for every MMA: 6 KB per 32-cycle
+  // MMA against 128 B/clk) — measured 65 vs 37 cycles per 128x64x16 MMA.
+  const uint32_t tmA1 = tmem_base + (ACC ? 448u : 128u);
 
   if (warp == 0) {
     // ===== TMA producer (whole warp walks the loop, the elected lane issues) =====
@@ -203,10 +221,10 @@ k_attn_tc(const __grid_constant__ CUtensorMap mA1, const __grid_constant__ CUten
       const bool leader = elect_one();
       constexpr uint32_t idesc = make_idesc_bf16(AT_R, AT_C);  // M = 128, N = 64 for the score and the accumulate MMAs alike
       mbar_wait(a_full, 0);
+      mbar_wait(a_tmem, 0);
       tc_fence_after();
       AT_STAMP(2);
       const uint32_t sA = smem_u32(smem);
-      const uint64_t a1hi = make_smem_desc_sw128(sA), a1lo = make_smem_desc_sw128(sA + AT_KA / 2);
       const uint64_t a2hi = make_smem_desc_sw128(sA + AT_KA), a2lo = make_smem_desc_sw128(sA + AT_KA + AT_KA / 2);
       auto score = [&](int j) {
         const int st = j % NST, sb = j & 1;
@@ -217,7 +235,7 @@ k_attn_tc(const __grid_constant__ CUtensorMap mA1, const __grid_constant__ CUten
         if (j == 4) AT_STAMP(26);
         const uint32_t sB = smem_u32(smem + Cfg::kOffStages + st * Cfg::kStage);
         if (leader) {
-          umma3(tmS1(sb), a1hi, a1lo, make_smem_desc_sw128(sB), make_smem_desc_sw128(sB + AT_KB / 2), idesc, true);
+          umma3_ts_k(tmS1(sb), tmA1, tmA1 + 32u, make_smem_desc_sw128(sB), make_smem_desc_sw128(sB + AT_KB / 2), idesc, true);
           if (TWO) umma3(tmS2(sb), a2hi, a2lo, make_smem_desc_sw128(sB + AT_KB), make_smem_desc_sw128(sB + AT_KB + AT_KB / 2), idesc, true);
           umma_commit(&s_full[sb]);
           umma_commit(&sc_empty[st]);
@@ -259,6 +277,25 @@ k_attn_tc(const __grid_constant__ CUtensorMap mA1, const __grid_constant__ CUten
     if (!TRANS && MODE != AT_LSE && row_ok) {
       lse_r = a.lse[(int64_t)bh * Lq + gr];
       if (TWO) delta_r = a.delta[(int64_t)bh * Lq + gr];
+    }
+    {
+      // copy this thread's row of the first row operand from (swizzled) shared memory into tensor memory: the warps of column half
+      // 0 take the hi plane, those of half 1 the lo plane (32 columns = 64 bf16 each)
+      mbar_wait(a_full, 0);
+      const uint8_t* arow = smem + half * (AT_KA / 2);
+      uint32_t w[32];
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        const uint4 v = *reinterpret_cast<const uint4*>(arow + sw128_off(r, c));
+        w[4 * c] = v.x; w[4 * c + 1] = v.y; w[4 * c + 2] = v.z; w[4 * c + 3] = v.w;
+      }
+      const uint32_t adst = tmA1 + ((uint32_t)(q * 32) << 16) + (uint32_t)(half * 32);
+      tmem_st_32x16(adst, w);
+      tmem_st_32x16(adst + 16u, w + 16);
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(a_tmem);
     }
     float m_run = -INFINITY, l_run = 0.f;
     for (int j = 0; j < n; ++j) {

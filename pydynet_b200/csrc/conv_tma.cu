@@ -25,7 +25,7 @@
 
 namespace pdn {
 
-enum { CT_F = 0, CT_W = 1 };
+enum { CT_F = 0, CT_W = 1, CT_W3 = 2 };  // W3: backward-weight with the 3 taps of one kernel row per tile sharing the dY tile
 
 struct CtArgs {
   float*       out;    // F: NCHW [n_img][n_out][oh][ow];  W: tmp [taps][M = O][N = C] row-major (atomic accumulation, pre-zeroed)
@@ -41,14 +41,16 @@ struct CtArgs {
   unsigned total_tiles;
 };
 
-template <int BN>
+template <int BN, int MODE>
 struct CtCfg {
-  static constexpr int kABytes = 2 * 128 * 128;          // hi + lo, 128 rows (or 2 x 64-channel blocks) of 128 B
+  static constexpr int kTaps = MODE == CT_W3 ? 3 : 1;     // B tiles (and accumulators) per k-block
+  static constexpr int kAcc = MODE == CT_W3 ? 1 : 2;      // accumulator sets (W3: one tile per CTA, no ping-pong needed)
+  static constexpr int kABytes = 2 * 128 * 128;           // hi + lo, 128 rows (or 2 x 64-channel blocks) of 128 B
   static constexpr int kBBytes = 2 * BN * 128;
-  static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kStages = (BN == 64) ? 4 : ((BN == 128) ? 3 : 2);
+  static constexpr int kStageBytes = kABytes + kTaps * kBBytes;
+  static constexpr int kStages = MODE == CT_W3 ? 2 : ((BN == 64) ? 4 : ((BN == 128) ? 3 : 2));
   static constexpr int kSmem = kStages * kStageBytes + 1024 + 256;
-  static constexpr int kTmemCols = 2 * BN;
+  static constexpr int kTmemCols = kTaps * kAcc * BN <= 128 ? 128 : (kTaps * kAcc * BN <= 256 ? 256 : 512);
 };
 
 __device__ __forceinline__ void tma_load_5d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1, int c2, int c3, int c4) {
@@ -62,7 +64,9 @@ __device__ __forceinline__ void tma_load_5d(const CUtensorMap* map, uint64_t* ba
 template <int BN, int MODE>
 __global__ void __launch_bounds__(256, 1)
 k_conv_tma(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, CtArgs g) {
-  using Cfg = CtCfg<BN>;
+  using Cfg = CtCfg<BN, MODE>;
+  constexpr bool kW = MODE != CT_F;  // backward-weight family: MN-major operands, contraction over pixel patches
+  constexpr int  T = Cfg::kTaps, NACC = Cfg::kAcc;
   extern __shared__ uint8_t smem_raw[];
   uint8_t*  smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   uint64_t* full_bar = (uint64_t*)(smem + Cfg::kStages * Cfg::kStageBytes);
@@ -76,7 +80,7 @@ k_conv_tma(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUt
   if (warp == 0 && lane == 0) { tma_prefetch_desc(&mapA); tma_prefetch_desc(&mapB); }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < Cfg::kStages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-    for (int a = 0; a < 2; ++a) { mbar_init(&tfull_bar[a], 1); mbar_init(&tempty_bar[a], 4); }
+    for (int a = 0; a < 2; ++a) { mbar_init(&tfull_bar[a], 1); mbar_init(&tempty_bar[a], 4); }  // W3 uses set 0 only
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc(tmem_slot, Cfg::kTmemCols);
@@ -104,7 +108,7 @@ k_conv_tma(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUt
     return r;
   };
   auto kb_count = [&](const Tile& tl) {
-    if (MODE == CT_F) return taps * g.cblks;
+    if (MODE == CT_F) return taps * g.cblks;  // (W / W3: pixel patches of this split)
     const int total = g.n_img * g.TY * g.TX, b0 = tl.b * g.per_split;
     const int e = b0 + g.per_split < total ? b0 + g.per_split : total;
     return e > b0 ? e - b0 : 0;
@@ -136,16 +140,19 @@ k_conv_tma(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUt
           } else {
             const int p = tl.b * g.per_split + kb;
             const int q1 = p / g.TX, px = p - q1 * g.TX, img = q1 / g.TY, py = q1 - img * g.TY;
-            const int ky = tl.c / g.k, kx = tl.c - ky * g.k;
+            // W: tl.c = tap.  W3: tl.c = kernel row ky, the T = 3 taps kx = 0..2 share this k-block's dY tile
+            const int ky = MODE == CT_W3 ? tl.c : tl.c / g.k, kx0 = MODE == CT_W3 ? 0 : tl.c - ky * g.k;
 #pragma unroll
             for (int pl = 0; pl < 2; ++pl) {
 #pragma unroll
               for (int i = 0; i < 2; ++i)  // dY patch [64 px][64 o] x 2 channel blocks
                 tma_load_5d(&mapA, &full_bar[stage], sa + pl * 16384 + i * 8192, tl.a * 128 + 64 * i, px * 16, py * 4, pl, img);
 #pragma unroll
-              for (int i = 0; i < BN / 64; ++i)  // shifted x patch [64 px][64 c] x BN/64 channel blocks
-                tma_load_5d(&mapB, &full_bar[stage], sb + pl * (BN * 128) + i * 8192, tl.n_blk * BN + 64 * i, px * 16 + kx - g.pad,
-                            py * 4 + ky - g.pad, pl, img);
+              for (int tp = 0; tp < T; ++tp)
+#pragma unroll
+                for (int i = 0; i < BN / 64; ++i)  // shifted x patch [64 px][64 c] x BN/64 channel blocks
+                  tma_load_5d(&mapB, &full_bar[stage], sb + tp * Cfg::kBBytes + pl * (BN * 128) + i * 8192, tl.n_blk * BN + 64 * i,
+                              px * 16 + kx0 + tp - g.pad, py * 4 + ky - g.pad, pl, img);
             }
           }
         }
@@ -155,7 +162,7 @@ k_conv_tma(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUt
   } else if (warp == 1) {
     // ===== MMA issuer =====
     const bool leader = elect_one();
-    const uint32_t idesc = make_idesc_bf16(128, BN) | (MODE == CT_W ? (IDESC_A_MN_MAJOR | IDESC_B_MN_MAJOR) : 0u);
+    const uint32_t idesc = make_idesc_bf16(128, BN) | (kW ? (IDESC_A_MN_MAJOR | IDESC_B_MN_MAJOR) : 0u);
     int stage = 0, acc = 0;
     uint32_t phase = 0, acc_phase = 0;
     for (uint32_t t = blockIdx.x; t < g.total_tiles; t += gridDim.x) {
@@ -164,34 +171,39 @@ k_conv_tma(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUt
       if (nkb == 0) continue;  // (mode W) an empty split: neither this warp nor the epilogue touches an accumulator
       mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
       tc_fence_after();
-      const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BN);
+      const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BN * T);
       for (int kb = 0; kb < nkb; ++kb) {
         mbar_wait(&full_bar[stage], phase);
         tc_fence_after();
         if (leader) {
           const uint32_t sa = smem_u32(smem + stage * Cfg::kStageBytes), sb = sa + Cfg::kABytes;
-          const uint64_t d_ahi = MODE == CT_W ? make_smem_desc_sw128_mn(sa, 8192) : make_smem_desc_sw128(sa);
-          const uint64_t d_alo = MODE == CT_W ? make_smem_desc_sw128_mn(sa + 16384, 8192) : make_smem_desc_sw128(sa + 16384);
-          const uint64_t d_bhi = MODE == CT_W ? make_smem_desc_sw128_mn(sb, 8192) : make_smem_desc_sw128(sb);
-          const uint64_t d_blo = MODE == CT_W ? make_smem_desc_sw128_mn(sb + BN * 128, 8192) : make_smem_desc_sw128(sb + BN * 128);
+          const uint64_t d_ahi = kW ? make_smem_desc_sw128_mn(sa, 8192) : make_smem_desc_sw128(sa);
+          const uint64_t d_alo = kW ? make_smem_desc_sw128_mn(sa + 16384, 8192) : make_smem_desc_sw128(sa + 16384);
           int nks = 4;
           if (MODE == CT_F) {  // channel tail: k-steps made only of zero-filled channels are skipped
             const int tap = kb / g.cblks, cb = kb - tap * g.cblks, left = g.n_contr - cb * 64;
             nks = left >= 64 ? 4 : (left + 15) >> 4;
           }
-          const uint64_t step = MODE == CT_W ? 128 : 2;  // one UMMA_K = 16: 16 pixel rows of 128 B (MN-major) or 32 B of channels
-          for (int k = 0; k < nks; ++k) {
-            const uint64_t o = step * (uint64_t)k;
-            umma_bf16(tmem_d, d_alo + o, d_bhi + o, idesc, (kb | k) ? 1u : 0u);
-            umma_bf16(tmem_d, d_ahi + o, d_blo + o, idesc, 1u);
-            umma_bf16(tmem_d, d_ahi + o, d_bhi + o, idesc, 1u);
+          const uint64_t step = kW ? 128 : 2;  // one UMMA_K = 16: 16 pixel rows of 128 B (MN-major) or 32 B of channels
+#pragma unroll
+          for (int tp = 0; tp < T; ++tp) {
+            const uint32_t sbt = sb + tp * Cfg::kBBytes;
+            const uint64_t d_bhi = kW ? make_smem_desc_sw128_mn(sbt, 8192) : make_smem_desc_sw128(sbt);
+            const uint64_t d_blo = kW ? make_smem_desc_sw128_mn(sbt + BN * 128, 8192) : make_smem_desc_sw128(sbt + BN * 128);
+            const uint32_t dt = tmem_d + (uint32_t)(tp * BN);
+            for (int k = 0; k < nks; ++k) {
+              const uint64_t o = step * (uint64_t)k;
+              umma_bf16(dt, d_alo + o, d_bhi + o, idesc, (kb | k) ? 1u : 0u);
+              umma_bf16(dt, d_ahi + o, d_blo + o, idesc, 1u);
+              umma_bf16(dt, d_ahi + o, d_bhi + o, idesc, 1u);
+            }
           }
           umma_commit(&empty_bar[stage]);
         }
         if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
       }
       if (leader) umma_commit(&tfull_bar[acc]);
-      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      if (++acc == NACC) { acc = 0; acc_phase ^= 1; }
     }
   } else if (warp >= 4) {
     // ===== epilogue =====
@@ -202,9 +214,9 @@ k_conv_tma(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUt
     for (uint32_t t = blockIdx.x; t < g.total_tiles; t += gridDim.x) {
       const Tile tl = decode(t);
       const int  nkb = kb_count(tl);
-      const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BN) + ((uint32_t)(q * 32) << 16);
+      const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BN * T) + ((uint32_t)(q * 32) << 16);
       const int m = q * 32 + lane;  // accumulator row of this thread
-      float*    p0 = nullptr;       // F: address of (image, channel 0, y, x); W: address of row (tap, o), column 0
+      float*    p0 = nullptr;       // F: address of (image, channel 0, y, x); W: address of row (first tap of the tile, o), column 0
       int64_t   cstride = 1;
       if (MODE == CT_F) {
         const int y = tl.b * 8 + (m >> 4), x = tl.a * 16 + (m & 15);
@@ -212,51 +224,55 @@ k_conv_tma(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUt
         if (y < g.oh && x < g.ow) p0 = g.out + (int64_t)tl.c * g.n_out * cstride + (int64_t)y * g.ow + x;
       } else {
         const int o = tl.a * 128 + m;
-        if (o < g.m_rows) p0 = g.out + ((int64_t)tl.c * g.m_rows + o) * g.n_out;
+        if (o < g.m_rows) p0 = g.out + ((int64_t)tl.c * T * g.m_rows + o) * g.n_out;
       }
       if (nkb == 0) continue;  // W: an empty split contributes nothing (the MMA warp skips it as well)
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
 #pragma unroll 1
-      for (int c0 = 0; c0 < BN; c0 += 32) {
-        const int col0 = tl.n_blk * BN + c0;
-        if (col0 >= g.n_out) break;
-        const int ncol = (g.n_out - col0) < 32 ? (g.n_out - col0) : 32;
-        float v[32];
-        tmem_ld_32x32(tmem_d + (uint32_t)c0, v);
-        tmem_ld_wait();
-        if (c0 + 32 >= BN || col0 + 32 >= g.n_out) {
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&tempty_bar[acc]);
-        }
-        if (MODE == CT_F) {
-          if (g.bias) {
-            if (ncol == 32 && bias_vec) {
+      for (int tp = 0; tp < T; ++tp) {
+#pragma unroll 1
+        for (int c0 = 0; c0 < BN; c0 += 32) {
+          const int col0 = tl.n_blk * BN + c0;
+          if (col0 >= g.n_out) break;
+          const int ncol = (g.n_out - col0) < 32 ? (g.n_out - col0) : 32;
+          float v[32];
+          tmem_ld_32x32(tmem_d + (uint32_t)(tp * BN + c0), v);
+          tmem_ld_wait();
+          if (tp == T - 1 && (c0 + 32 >= BN || col0 + 32 >= g.n_out)) {
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+          }
+          if (MODE == CT_F) {
+            if (g.bias) {
+              if (ncol == 32 && bias_vec) {
 #pragma unroll
-              for (int c = 0; c < 8; ++c) {
-                const float4 b4 = __ldg(reinterpret_cast<const float4*>(g.bias + col0) + c);
-                v[4 * c] += b4.x; v[4 * c + 1] += b4.y; v[4 * c + 2] += b4.z; v[4 * c + 3] += b4.w;
+                for (int c = 0; c < 8; ++c) {
+                  const float4 b4 = __ldg(reinterpret_cast<const float4*>(g.bias + col0) + c);
+                  v[4 * c] += b4.x; v[4 * c + 1] += b4.y; v[4 * c + 2] += b4.z; v[4 * c + 3] += b4.w;
+                }
+              } else {
+#pragma unroll
+                for (int j = 0; j < 32; ++j)
+                  if (j < ncol) v[j] += __ldg(g.bias + col0 + j);
               }
-            } else {
+            }
+            if (p0) {  // for a fixed channel the 32 lanes write two runs of 16 consecutive pixels
+              float* p = p0 + (int64_t)col0 * cstride;
 #pragma unroll
               for (int j = 0; j < 32; ++j)
-                if (j < ncol) v[j] += __ldg(g.bias + col0 + j);
+                if (j < ncol) p[(int64_t)j * cstride] = v[j];
             }
-          }
-          if (p0) {  // for a fixed channel the 32 lanes write two runs of 16 consecutive pixels
-            float* p = p0 + (int64_t)col0 * cstride;
+          } else if (p0) {
+            float* p = p0 + (int64_t)tp * g.m_rows * g.n_out + col0;  // tmp[tap][o][c]
 #pragma unroll
             for (int j = 0; j < 32; ++j)
-              if (j < ncol) p[(int64_t)j * cstride] = v[j];
+              if (j < ncol) atomicAdd(p + j, v[j]);
           }
-        } else if (p0) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j)
-            if (j < ncol) atomicAdd(p0 + col0 + j, v[j]);
         }
       }
-      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      if (++acc == NACC) { acc = 0; acc_phase ^= 1; }
     }
   }
   tc_fence_before();
@@ -313,7 +329,7 @@ static int nhwc_planes(const float* act, int64_t N, int64_t Cc, int64_t Hh, int6
 
 template <int BN, int MODE>
 static int launch_ct(const CUtensorMap& mA, const CUtensorMap& mB, const CtArgs& g) {
-  using Cfg = CtCfg<BN>;
+  using Cfg = CtCfg<BN, MODE>;
   static bool attr = false;
   if (!attr) {
     PDN_CUDA(cudaFuncSetAttribute(k_conv_tma<BN, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmem));
@@ -374,12 +390,16 @@ int conv_tma_bwd_weight(const float* x, const float* gy, float* dw, int64_t N, i
   g.oh = (int)oh; g.ow = (int)ow;
   g.TY = (int)((oh + 3) / 4); g.TX = (int)((ow + 15) / 16);
   g.k = k; g.pad = pad; g.sign = 1; g.cblks = 0;
-  const int BN = C <= 64 ? 64 : 128;
+  // k = 3: the three taps of a kernel row share one dY tile per k-block (three accumulators, BN = 64): 80 KB of TMA traffic per
+  // pixel patch instead of 3 x 48 KB — the one-tap form is bound by L2->SM operand delivery
+  static const bool w3_off = getenv("PDN_CONV_W1") != nullptr;
+  const bool w3 = k == 3 && !w3_off;
+  const int BN = (w3 || C <= 64) ? 64 : 128;
   g.n_tiles_n = (int)((C + BN - 1) / BN);
   g.m_tiles = (int)((O + 127) / 128);
   const int64_t patches = N * g.TY * g.TX;
   PDN_CHECK(patches < 0x7fffffff, "conv_tma: too many patches");
-  const int64_t base_tiles = (int64_t)taps * g.m_tiles * g.n_tiles_n;
+  const int64_t base_tiles = (int64_t)(w3 ? k : taps) * g.m_tiles * g.n_tiles_n;
   int64_t splits = (sm_count() + base_tiles - 1) / base_tiles;
   if (splits > patches) splits = patches;
   if (splits < 1) splits = 1;
@@ -390,7 +410,8 @@ int conv_tma_bwd_weight(const float* x, const float* gy, float* dw, int64_t N, i
   CUtensorMap mA, mB;
   PDN_TRY(make_map_nhwc(&mA, G.planes, N, O, oh, ow, G.Kp, 4));
   PDN_TRY(make_map_nhwc(&mB, X.planes, N, C, H, W, X.Kp, 4));
-  if (BN == 64) PDN_TRY((launch_ct<64, CT_W>(mA, mB, g)));
+  if (w3) PDN_TRY((launch_ct<64, CT_W3>(mA, mB, g)));
+  else if (BN == 64) PDN_TRY((launch_ct<64, CT_W>(mA, mB, g)));
   else PDN_TRY((launch_ct<128, CT_W>(mA, mB, g)));
   k_conv_dw_permute<<<grid_for((int64_t)O * C * taps, 256), 256, 0, stream()>>>((const float*)tmp.p, dw, (int)O, (int)C, taps);
   PDN_LAUNCHED("conv_dw_permute");
