@@ -196,6 +196,21 @@ __global__ void __launch_bounds__(256) k_binary_rowvec_f32(int op, const float4*
   }
 }
 
+// dense rows + one broadcast value per row: a[r, c] op b[r] (padding masks, per-row scales: F.embedding's pad mask functional.py:17-19)
+__global__ void __launch_bounds__(256) k_binary_colvec_f32(int op, const float4* __restrict__ a, const float* __restrict__ b,
+                                                          float4* __restrict__ out, int64_t n4, int cols4, int64_t b_stride, int b_left) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+    const float  s = __ldg(b + (i / cols4) * b_stride);
+    float4 x = a[i], y = make_float4(s, s, s, s), r;
+    if (b_left) { float4 t = x; x = y; y = t; }
+    r.x = binary_arith<float>(op, x.x, y.x);
+    r.y = binary_arith<float>(op, x.y, y.y);
+    r.z = binary_arith<float>(op, x.z, y.z);
+    r.w = binary_arith<float>(op, x.w, y.w);
+    out[i] = r;
+  }
+}
+
 template <typename T, typename TO, bool CMP>
 __global__ void __launch_bounds__(256) k_binary_scalar(int op, const T* a, double scalar, int reverse, TO* out, StridedDesc d) {
   using A = typename Acc<T>::type;
@@ -395,6 +410,17 @@ int pdn_ew_binary(int op, int dtype, const void* a, const void* b, void* out, in
         k_binary_rowvec_f32<<<grid_for(d.n / 4, 256, 2), 256, 0, stream()>>>(op, (const float4*)full, (const float4*)vec, (float4*)out,
                                                                             d.n / 4, (int)(d.shape[1] / 4), a_full ? 0 : 1);
         PDN_LAUNCHED("binary_rowvec_f32");
+        return 0;
+      }
+      // [rows, cols] op [rows, 1]
+      bool a_col = d.s[0][1] == 0, b_col = d.s[1][1] == 0;
+      if ((a_full && b_col) || (a_col && b_full)) {
+        const void* full = a_full ? a : b;
+        const void* vec = a_full ? b : a;
+        const int64_t vs = a_full ? d.s[1][0] : d.s[0][0];
+        k_binary_colvec_f32<<<grid_for(d.n / 4, 256, 2), 256, 0, stream()>>>(op, (const float4*)full, (const float*)vec, (float4*)out, d.n / 4,
+                                                                            (int)(d.shape[1] / 4), vs, a_full ? 0 : 1);
+        PDN_LAUNCHED("binary_colvec_f32");
         return 0;
       }
     }

@@ -102,6 +102,68 @@ __global__ void __launch_bounds__(256) k_pack_split(PackArgs p) {
   }
 }
 
+// Transposing form for sources whose ROWS are the unit-stride axis (channels-last conv planes from NCHW activations): 64 (rows) x 64
+// (k) tile, 128-bit loads along the rows, 16 bf16 (two 128-bit stores) per thread and plane along k. The generic kernel above moves
+// 4 bytes per thread access in this orientation (2.3 TB/s).
+__global__ void __launch_bounds__(256) k_pack_split_t(PackArgs p) {
+  __shared__ float tile[64][65];  // [k][r]
+  int64_t z = blockIdx.z, off = 0;
+  {
+    int64_t rem = z;
+    for (int d = 2; d >= 0; --d) {
+      int64_t n = (p.bs[d] != 0 && p.nb[d] > 1) ? p.nb[d] : 1;
+      off += (rem % n) * p.bs[d];
+      rem /= n;
+    }
+  }
+  const float* src = p.src + off;
+  __nv_bfloat16* hi = p.dst + (size_t)z * 2 * p.R * p.Kp;
+  __nv_bfloat16* lo = hi + (size_t)p.R * p.Kp;
+  const int64_t r0 = (int64_t)blockIdx.y * 64, k0 = (int64_t)blockIdx.x * 64;
+  {
+    const int r4 = threadIdx.x & 15, kk = threadIdx.x >> 4;
+    const int64_t r = r0 + 4 * r4;
+#pragma unroll
+    for (int ps = 0; ps < 4; ++ps) {
+      const int     kl = kk + 16 * ps;
+      const int64_t k = k0 + kl;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (k < p.K) {
+        const float* q = src + k * p.k_stride + r;
+        if (r + 3 < p.R) v = __ldg(reinterpret_cast<const float4*>(q));
+        else {
+          if (r < p.R) v.x = __ldg(q);
+          if (r + 1 < p.R) v.y = __ldg(q + 1);
+          if (r + 2 < p.R) v.z = __ldg(q + 2);
+        }
+      }
+      float* t = &tile[kl][4 * r4];
+      t[0] = v.x; t[1] = v.y; t[2] = v.z; t[3] = v.w;
+    }
+  }
+  __syncthreads();
+  const int rl = threadIdx.x >> 2, kq = threadIdx.x & 3;
+  const int64_t r = r0 + rl;
+  if (r >= p.R) return;
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    const int64_t k = k0 + kq * 16 + 8 * h;
+    if (k >= p.Kp) break;  // Kp is a multiple of 8
+    uint32_t hw[4], lw[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const float x0 = tile[kq * 16 + 8 * h + 2 * u][rl], x1 = tile[kq * 16 + 8 * h + 2 * u + 1][rl];
+      const __nv_bfloat162 hh = __floats2bfloat162_rn(x0, x1);
+      const float2         hf = __bfloat1622float2(hh);
+      const __nv_bfloat162 ll = __floats2bfloat162_rn(x0 - hf.x, x1 - hf.y);
+      hw[u] = *reinterpret_cast<const uint32_t*>(&hh);
+      lw[u] = *reinterpret_cast<const uint32_t*>(&ll);
+    }
+    *reinterpret_cast<uint4*>(hi + r * p.Kp + k) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+    *reinterpret_cast<uint4*>(lo + r * p.Kp + k) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+  }
+}
+
 // ------------------------------------------------------------------ the MMA kernel -------------
 constexpr int TC_BM = 128;
 constexpr int TC_BK = 64;  // 64 bf16 = 128 B = one swizzle span
@@ -603,10 +665,19 @@ static int pack_operand_to(const float* src, int64_t R, int64_t K, int64_t r_str
   p.r_stride = r_stride; p.k_stride = k_stride;
   p.k_inner = k_inner > 0 ? k_inner : (K > 0 ? K : 1);
   p.k_outer_stride = k_outer_stride;
-  dim3 grd((unsigned)((Kp + 63) / 64), (unsigned)((R + 31) / 32), (unsigned)pb);
-  PDN_CHECK(grd.y <= 65535, "gemm_tc: operand has too many rows for the pack grid");
-  k_pack_split<<<grd, 256, 0, stream()>>>(p);
-  PDN_LAUNCHED("pack_split");
+  bool bs_al = true;
+  for (int d = 0; d < 3; ++d) bs_al = bs_al && (bs[d] & 3) == 0;
+  if (r_stride == 1 && k_stride != 1 && p.k_inner >= K && (k_stride & 3) == 0 && bs_al && ((((uintptr_t)src) & 15) == 0) && R >= 16 &&
+      (R + 63) / 64 <= 65535) {
+    dim3 grd((unsigned)((Kp + 63) / 64), (unsigned)((R + 63) / 64), (unsigned)pb);
+    k_pack_split_t<<<grd, 256, 0, stream()>>>(p);
+    PDN_LAUNCHED("pack_split_t");
+  } else {
+    dim3 grd((unsigned)((Kp + 63) / 64), (unsigned)((R + 31) / 32), (unsigned)pb);
+    PDN_CHECK(grd.y <= 65535, "gemm_tc: operand has too many rows for the pack grid");
+    k_pack_split<<<grd, 256, 0, stream()>>>(p);
+    PDN_LAUNCHED("pack_split");
+  }
   out->planes = dst; out->R = R; out->K = K; out->Kp = Kp; out->nbatch = pb;
   return 0;
 }
