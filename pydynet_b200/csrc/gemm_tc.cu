@@ -696,8 +696,9 @@ struct PlaneEntry {
   const float* src; int64_t R, K, rs, ks; int64_t nb[3], bs[3];
   long long version; PackedOperand op; size_t bytes; uint64_t stamp;
 };
-static std::vector<PlaneEntry> g_planes;
-static std::mutex              g_planes_mu;
+// heap objects that are never destroyed: device arrays may still be freed (-> plane_cache_drop_range) while the process shuts down
+static std::vector<PlaneEntry>& g_planes = *new std::vector<PlaneEntry>();
+static std::mutex&              g_planes_mu = *new std::mutex();
 static uint64_t                g_planes_clock = 0;
 static size_t                  g_planes_bytes = 0;
 static uint64_t                g_planes_hits = 0, g_planes_misses = 0;
