@@ -86,7 +86,7 @@ uint64_t pdn_kernel_launch_count(void);
 void pdn_reset_launch_count(void);
 int pdn_event_create(void** ev);
 int pdn_event_destroy(void* ev);
-int pdn_event_record(void* ev);
+int pdn_event_record(void* ev); /* while a graph is being recorded: an event-record NODE (cudaEventRecordExternal), re-stamped by every replay */
 int pdn_event_elapsed_ms(void* start, void* stop, float* ms); /* synchronises on stop */
 
 /* CUDA-graph capture of a launch sequence on the library stream (decode loop replay) */

@@ -2,20 +2,31 @@
 //
 // The reference materialises the [B,H,Lq,Lk] score tensor and ≥5 same-sized temporaries (llm/llama/model.py:112-121,
 // examples/pydynet/transformer.py:93-104: 1.07 GB each at BASELINE config 4). Here one kernel template serves five passes
-// that all have the same shape — "score MMA(s) into TMEM → element-wise in registers → one bf16 hi/lo operand tile into
-// swizzled shared memory → accumulate MMA into TMEM":
+// that all have the same shape — "score MMA(s) into TMEM → element-wise in registers → bf16 hi/lo operand back INTO TMEM →
+// accumulate MMA into TMEM":
 //     LSE  rows = queries   S = Q·Kᵀ                      row-wise log-sum-exp (online), nothing accumulated
 //     FWD  rows = queries   S = Q·Kᵀ                      P = exp(S − lse)              O  += P · V
 //     DQ   rows = queries   S = Q·Kᵀ, dP = dO·Vᵀ          dS = P∘(dP − Δ)·scale         dQ += dS · K
 //     DV   rows = keys      Sᵀ = K·Qᵀ                     Pᵀ = exp(Sᵀ − lse)            dV += Pᵀ · dO
 //     DK   rows = keys      Sᵀ = K·Qᵀ, dPᵀ = V·dOᵀ        dSᵀ = Pᵀ∘(dPᵀ − Δ)·scale      dK += dSᵀ · Q
 // Because lse is known before P is formed (LSE pass first), no accumulator is ever rescaled; the price is recomputing S.
-// Every MMA operand is K-major: the transposed operands (Vᵀ, Kᵀ, Qᵀ, dOᵀ as [d][seq]) come from the strided pack kernel,
-// and P / dS are written by the softmax warps directly in the 128-byte-swizzled layout tcgen05 expects. fp32 parity comes
-// from the same BF16x3 split as the GEMM (hi·hi + hi·lo + lo·hi), applied to P/dS as well.
 //
-// CTA = one 128-row tile of one (batch, head); warp 0 TMA producer (2-stage ring over 64-column tiles), warp 1 MMA issuer,
-// warp 2 TMEM allocator, warps 4-7 = 128 softmax threads (one row each: row max / sum need no shuffles at all).
+// Operand placement (what the PDN_TC_TRACE timelines led to):
+//   * the resident row operand (Q rows; K rows in the key-row passes) is copied once from its TMA-filled shared-memory tile into
+//     TMEM and read there by the score MMAs (TS-mode tcgen05.mma): an SS-mode 128x64x16 MMA re-reads 4 KB of A from shared memory
+//     every 32 cycles, more than the 128 B/clk the SM has;
+//   * P / dS are split into bf16 hi/lo on the integer pipe (the XU pipe is saturated by ex2) and written with tcgen05.st into two
+//     TMEM operand buffers; the accumulate MMA reads them as its A operand (TS-mode), no shared-memory round trip;
+//   * the accumulate MMA's B operand (V, K, Q or dO tile, [64 items][d]) is consumed MN-major exactly as TMA loads it from the
+//     tensors' row-major planes: no transposed copies of V / K / Q / dO exist;
+//   * score operands and accumulate operands have separate full/empty barrier rings over 3-4 stages, so the TMA producer runs
+//     ahead of the softmax instead of waiting for the accumulate MMA of the previous tile.
+// fp32 parity comes from the same BF16x3 split as the GEMM (hi·hi + hi·lo + lo·hi), applied to P/dS as well.
+//
+// CTA = one 128-row tile of one (batch, head); warp 0 TMA producer, warp 1 MMA issuer (both walk their loops on all lanes and
+// predicate the issuing instructions with elect.sync: uniform-register operands), warp 2 TMEM allocator, warps 4-11 = 256 softmax
+// threads (two per row: a 32-column half each, row max / sum combined through shared memory only in the LSE pass).
+// TMEM columns: S1[2] 0/64, S2[2] 128/192, accumulator 256, P/dS buffers 320/384 (hi 32 + lo 32 each), row operand 448 (hi 32 + lo 32).
 #include "common.cuh"
 #include "gemm_tc.h"
 #include "tc_ptx.cuh"

@@ -5,12 +5,15 @@
 // of each operand: x = hi + lo, C = Ahi·Bhi + Ahi·Blo + Alo·Bhi accumulated in fp32 TMEM (3 BF16 MMAs per
 // product, ~16 effective mantissa bits, 4.5e-6 measured normwise error in emulation).
 //
-// Two kernels:
-//   k_pack_split   fp32 operand with arbitrary (row, col, batch) element strides -> K-major bf16 planes
-//                  [batch][hi|lo][rows][Kp]; this absorbs every transposed / strided / broadcast view the
-//                  reference feeds to `@` (tensor.py:657-676) so the MMA kernel sees one canonical layout.
-//   k_gemm_tc      one CTA per 128xBN output tile; warp 0 = TMA producer, warp 1 = MMA issuer (one elected
-//                  lane), warp 2 = TMEM allocator, warps 4-7 = epilogue (tcgen05.ld -> +bias/+C -> st.global).
+// Pieces:
+//   k_pack_split(_t)  fp32 operand with arbitrary (row, col, batch) element strides -> bf16 planes [batch][hi|lo][rows][Cp] in the
+//                     operand's OWN orientation (strided / broadcast batch views of `@`, tensor.py:657-676, are absorbed here)
+//   planes_cached     operand-plane cache: one pack per source buffer and write-version, shared by every product that reads it
+//   k_gemm_tc         persistent CTAs walking 128xBN output tiles; warp 0 = TMA producer, warp 1 = MMA issuer (elected lane,
+//                     warp-uniform operands), warp 2 = TMEM allocator, warps 4-7 = epilogue over two TMEM accumulators. Each operand
+//                     is read K-major (contraction axis contiguous) or MN-major (rows contiguous: W [K][N] in x @ W, x [M][K] in
+//                     x^T @ g) — a descriptor flag, never a transposed copy. GATHER = 1/2: implicit-GEMM producer warps for the
+//                     convolutions conv_tma.cu does not take (stride > 1, < 16 channels).
 #include "common.cuh"
 #include "gemm_args.h"
 #include "gemm_tc.h"
