@@ -78,3 +78,41 @@ def test_reference_example_models_run_unchanged(aliased):
     X = pdn.Tensor(g["X"])
     out = net(X, ns["construct_mask"](X))
     np.testing.assert_allclose(out.numpy(), g["out0"], rtol=1e-4, atol=1e-5)
+
+
+def test_reference_llama_demo_modules_run_unchanged(aliased):
+    """llm/llama/{io,tokenizer,model,finetune}.py imported AS THEY ARE (package `llm.llama` from /root/reference) with `pydynet`
+    aliased to pydynet_b200: checkpoint loading, tokenizer, generation and the fine-tune helpers reproduce the fixtures the
+    unmodified reference produced on its own NumPy backend (tests/golden/llama_app)."""
+    pdn = aliased
+    app = os.path.join(GOLD, "llama_app")
+    sys.path.insert(0, REF)
+    try:
+        io_mod = importlib.import_module("llm.llama.io")
+        tok_mod = importlib.import_module("llm.llama.tokenizer")
+        model_mod = importlib.import_module("llm.llama.model")
+        ft_mod = importlib.import_module("llm.llama.finetune")
+        g = np.load(os.path.join(app, "llama_app.npz"))
+        V, D, H, FF, S, B, L = (int(v) for v in g["cfg"])
+        np.random.seed(7)
+        net = io_mod.load_model(model_mod.Llama(V, D, H, FF, S, B, L, dtype=np.float32), os.path.join(app, "checkpoint.model.npz"))
+        for name, p in net._parameters.items():
+            np.testing.assert_array_equal(p.numpy(), g["p." + name], err_msg=name)  # incl. the seeded, never-loaded lm_head.bias
+        tok = tok_mod.Tokenizer(os.path.join(app, "tokenizer.model.np"))
+        prompt = np.array([tok.encode("There was a boy")])
+        np.testing.assert_array_equal(prompt, g["gen.prompt"])
+        net.eval()
+        with pdn.no_grad():
+            toks = np.concatenate([t.numpy() for t in net.generate(prompt, 40)], axis=1)
+        np.testing.assert_array_equal(toks, g["gen.tokens"])
+        pdn.autograd.set_grad_enabled(True)
+        net.train()
+        assert tuple(net.set_trainable_parameters(("lm_head", ))) == tuple(int(v) for v in g["ft.counts"])
+        opt = pdn.optim.Adam(net.parameters(), lr=1e-3)
+        x, y = ft_mod.build_causal_training_pair(tok, "the boy was there", S)
+        losses = [net.finetune_step(x, y, opt) for _ in range(3)]
+        np.testing.assert_allclose(losses, g["ft.losses"], rtol=1e-4)
+    finally:
+        sys.path.remove(REF)
+        for k in [k for k in sys.modules if k == "llm" or k.startswith("llm.")]:
+            sys.modules.pop(k, None)
