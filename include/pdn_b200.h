@@ -77,6 +77,13 @@ int pdn_memcpy_h2d(void* dst, const void* host_src, size_t bytes);
 int pdn_memcpy_d2h(void* host_dst, const void* src, size_t bytes);
 int pdn_memcpy_d2d(void* dst, const void* src, size_t bytes);
 int pdn_memcpy_h2d_async(void* dst, const void* pinned_src, size_t bytes);
+/* Input pipeline (pydynet/data.py:73-123 DataLoader, examples/pydynet/mnist.py:161-162: every batch is a synchronous
+ * Tensor(numpy) upload in the reference): the batch is copied from PINNED memory on a dedicated copy stream while the compute stream
+ * works on the previous one; `done` is an event from pdn_event_create. pdn_stream_wait_event(done) orders the compute stream after
+ * the copy; pdn_event_synchronize(done) tells the host the pinned staging buffer may be overwritten. */
+int pdn_prefetch_h2d(void* dst, const void* pinned_src, size_t bytes, void* done);
+int pdn_stream_wait_event(void* ev);
+int pdn_event_synchronize(void* ev);
 int pdn_memcpy_d2h_async(void* pinned_dst, const void* src, size_t bytes);
 int pdn_memset(void* dst, int byte, size_t bytes);
 int pdn_sync(void);

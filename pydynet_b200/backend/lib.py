@@ -42,6 +42,9 @@ _PROTOS = {
     "pdn_malloc": [C.POINTER(vp), C.c_size_t],
     "pdn_free": [vp],
     "pdn_malloc_host": [C.POINTER(vp), C.c_size_t],
+    "pdn_prefetch_h2d": [vp, vp, C.c_size_t, vp],
+    "pdn_stream_wait_event": [vp],
+    "pdn_event_synchronize": [vp],
     "pdn_free_host": [vp],
     "pdn_mem_stats": [C.POINTER(u64), C.POINTER(u64), C.POINTER(u64)],
     "pdn_empty_cache": [],

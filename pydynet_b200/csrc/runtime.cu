@@ -41,6 +41,8 @@ int after_launch(const char* name) {
 struct DevState {
   bool         inited = false;
   cudaStream_t compute = nullptr;
+  cudaStream_t copy = nullptr;     // H2D prefetch engine of the input pipeline (pdn_prefetch_h2d)
+  cudaEvent_t  copy_fence = nullptr;
   cudaStream_t comm = nullptr;
   int          sms = 0;
   // caching allocator: free blocks by size; live blocks by pointer
@@ -83,6 +85,8 @@ int ensure_init() {
   s->sms = prop.multiProcessorCount;
   PDN_CUDA(cudaStreamCreateWithFlags(&s->compute, cudaStreamNonBlocking));
   PDN_CUDA(cudaStreamCreateWithFlags(&s->comm, cudaStreamNonBlocking));
+  PDN_CUDA(cudaStreamCreateWithFlags(&s->copy, cudaStreamNonBlocking));
+  PDN_CUDA(cudaEventCreateWithFlags(&s->copy_fence, cudaEventDisableTiming));
   s->inited = true;
   return 0;
 }
@@ -317,6 +321,30 @@ int pdn_memcpy_d2d(void* dst, const void* src, size_t bytes) {
 int pdn_memcpy_h2d_async(void* dst, const void* src, size_t bytes) {
   PDN_TRY(ensure_init());
   if (bytes) PDN_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, stream()));
+  return 0;
+}
+// Input pipeline: copy a batch from PINNED host memory into `dst` on a dedicated copy stream, overlapping the compute stream's
+// kernels. `dst` comes from the stream-ordered allocator (a block may have been handed back by compute work that is still queued),
+// so the copy first waits for everything queued on the compute stream so far; `done` (an event from pdn_event_create) is recorded
+// after the copy: the consumer calls pdn_stream_wait_event(done) before its first kernel that reads dst, and
+// pdn_event_synchronize(done) before the pinned staging buffer is overwritten.
+int pdn_prefetch_h2d(void* dst, const void* pinned_src, size_t bytes, void* done) {
+  PDN_TRY(ensure_init());
+  DevState* s = cur();
+  PDN_CHECK(done != nullptr, "prefetch_h2d: null event");
+  PDN_CUDA(cudaEventRecord(s->copy_fence, s->compute));
+  PDN_CUDA(cudaStreamWaitEvent(s->copy, s->copy_fence, 0));
+  if (bytes) PDN_CUDA(cudaMemcpyAsync(dst, pinned_src, bytes, cudaMemcpyHostToDevice, s->copy));
+  PDN_CUDA(cudaEventRecord((cudaEvent_t)done, s->copy));
+  return 0;
+}
+int pdn_stream_wait_event(void* ev) {
+  PDN_TRY(ensure_init());
+  PDN_CUDA(cudaStreamWaitEvent(stream(), (cudaEvent_t)ev, 0));
+  return 0;
+}
+int pdn_event_synchronize(void* ev) {
+  PDN_CUDA(cudaEventSynchronize((cudaEvent_t)ev));
   return 0;
 }
 int pdn_memcpy_d2h_async(void* dst, const void* src, size_t bytes) {
