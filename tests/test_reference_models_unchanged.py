@@ -116,3 +116,25 @@ def test_reference_llama_demo_modules_run_unchanged(aliased):
         sys.path.remove(REF)
         for k in [k for k in sys.modules if k == "llm" or k.startswith("llm.")]:
             sys.modules.pop(k, None)
+
+
+def test_reference_autograd_examples_run_unchanged(aliased):
+    """examples/pydynet/autograd1d.py / autograd2d.py: scalar-Tensor gradient descent written against the reference API
+    (`x.zero_grad()`, `y.backward()`, in-place `x.data -= lr * x.grad`, `x.item()`) must follow the hand-derived trajectory."""
+    pdn = aliased
+    ns = _exec(os.path.join(REF, "examples/pydynet/autograd1d.py"), 8, 33, {"pdn": pdn, "np": np, "device": "cpu"})
+    auto, manual = ns["auto_grad"](1., 1.5, 20), ns["manual_grad"](1., 1.5, 20)
+    np.testing.assert_allclose(auto, manual, rtol=1e-6, atol=1e-9)
+    # 2-D quadratic: 1-D @ 2-D @ 1-D products, `.numpy()` of a leaf inside the loop
+    ns = _exec(os.path.join(REF, "examples/pydynet/autograd2d.py"), 4, 50, {"pdn": pdn, "np": np, "device": "cpu"})
+    x0 = np.array([0.3, -1.2])
+    a = ns["auto_grad"](x0.copy(), 0.2, 15)
+    An, bn = np.array([[3, 1.], [1, 2.]]), np.array([-1., 1.])
+    xs, x = [], x0.copy()
+    for _ in range(15):
+        xs.append(x.copy())
+        x = x - 0.2 * (An @ x + bn)
+    xs = np.array(xs)
+    np.testing.assert_allclose(a[0], xs[:, 0], rtol=1e-6, atol=1e-9)
+    np.testing.assert_allclose(a[1], xs[:, 1], rtol=1e-6, atol=1e-9)
+    np.testing.assert_allclose(a[2], [x @ An @ x / 2 + bn @ x for x in xs], rtol=1e-6, atol=1e-9)
