@@ -18,6 +18,17 @@ def is_available() -> bool:
     return _L.device_count() > 0
 
 
+def __getattr__(name):
+    # reference cuda.py:5-13 exposes a module-level flag (True when CuPy imported); here: a GPU that libpdn_b200.so can serve
+    if name == "cuda_available":
+        return is_available()
+    raise AttributeError(f"module {__name__!r} has no attribute {name!r}")
+
+
+def __dir__():
+    return sorted(list(globals()) + ["cuda_available"])
+
+
 def device_count() -> int:
     return _L.device_count()
 

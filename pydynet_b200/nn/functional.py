@@ -9,6 +9,7 @@ import numpy as np
 
 from ..core import tensor, function
 from ..core.tensor import Tensor, _result
+from ..core.function import unsqueeze  # noqa: F401  (the reference's functional.py re-exports it, functional.py:4)
 from ..autograd import no_grad
 from . import _fused
 

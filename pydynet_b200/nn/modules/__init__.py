@@ -3,6 +3,7 @@ from .layers import (Sigmoid, Tanh, ReLU, LeakyReLU, Softmax, Conv1d, Conv2d, Ma
 from .norm import BatchNorm1d, BatchNorm2d, LayerNorm, RMSNorm
 from .module import Module, Sequential, ModuleList
 from .rnn import RNN, LSTM, GRU, RNNCell, LSTMCell, GRUCell
+from . import activation, conv, dropout, linear, loss, pool  # the reference's submodule import paths
 
 __all__ = [
     "Sigmoid", "Tanh", "ReLU", "LeakyReLU", "Softmax", "BatchNorm1d", "BatchNorm2d", "LayerNorm", "RMSNorm", "Conv1d", "Conv2d",
