@@ -138,3 +138,42 @@ def test_reference_autograd_examples_run_unchanged(aliased):
     np.testing.assert_allclose(a[0], xs[:, 0], rtol=1e-6, atol=1e-9)
     np.testing.assert_allclose(a[1], xs[:, 1], rtol=1e-6, atol=1e-9)
     np.testing.assert_allclose(a[2], [x @ An @ x / 2 + bn @ x for x in xs], rtol=1e-6, atol=1e-9)
+
+
+def test_reference_clip_model_runs_unchanged(aliased):
+    """llm/clip/model.py (ViT image encoder with a 6-D reshape/transpose patch projection, causal text encoder, fancy-indexed
+    end-of-text pooling, cosine logits) imported AS IT IS on this package: logits, loss and the text-encoder gradients of a small
+    synthetic configuration equal what the unmodified reference produced (tests/golden/clip.npz) — SURVEY.md §8(f) row f4."""
+    pdn = aliased
+    g = np.load(os.path.join(GOLD, "clip.npz"))
+    cfg = {str(k): int(v) for k, v in zip(g["cfg_keys"], g["cfg_vals"])}
+    sys.path.insert(0, REF)
+    try:
+        CLIP = importlib.import_module("llm.clip.model").CLIP
+        np.random.seed(3)
+        net = CLIP(**cfg)
+        for name, p in net._parameters.items():
+            p.data[...] = g["p." + name]
+        net.eval()
+        with pdn.no_grad():
+            logits = net(pdn.Tensor(g["img"]), g["idx"]).numpy()
+        pdn.autograd.set_grad_enabled(True)
+        np.testing.assert_allclose(logits, g["logits"], rtol=1e-4, atol=1e-6)
+        net.train()
+        assert tuple(net.set_trainable_parameters(("text_encoder", ))) == tuple(int(v) for v in g["counts"])
+        out = net(pdn.Tensor(g["img"]), g["idx"])
+        loss = pdn.nn.CrossEntropyLoss()(out.reshape(1, 4), pdn.Tensor(g["targets"], dtype=np.int64))
+        np.testing.assert_allclose(loss.item(), float(g["loss"]), rtol=1e-5)
+        loss.backward()
+        n = 0
+        for name, p in net._parameters.items():
+            if p.requires_grad and "g." + name in g.files:
+                ref = g["g." + name]
+                np.testing.assert_allclose(np.asarray(p.grad), ref, rtol=1e-4, atol=1e-6 + 1e-4 * np.abs(ref).max(), err_msg=name)
+                n += 1
+        assert n == len([k for k in g.files if k.startswith("g.")])
+    finally:
+        sys.path.remove(REF)
+        for k in [k for k in sys.modules if k == "llm" or k.startswith("llm.")]:
+            sys.modules.pop(k, None)
+        pdn.autograd.set_grad_enabled(True)
