@@ -384,12 +384,34 @@ def _result(data, device: Device, inputs, backward, name) -> Tensor:
     return out
 
 
+_SCALARS = {}  # (device, dtype, value bits) -> constant Tensor already resident on that cuda device
+
+
+def _wrap_scalar(value, like):
+    """``Tensor(value, dtype=like.dtype, device=like.device)`` (reference tensor.py:488-493). On a cuda device a Python / NumPy
+    SCALAR is uploaded once and the constant Tensor is reused: the reference's idioms wrap one on every call
+    (``relu = maximum(0., x)``, ``x * 2``, ``1 - z``), and every fresh wrap costs an allocation plus a SYNCHRONOUS 4-byte
+    host-to-device copy — a stream drain per ReLU in a launch-bound training step."""
+    if like.device.is_cuda and isinstance(value, (int, float, np.floating, np.integer)) and not isinstance(value, bool):
+        from ..cuda import is_capturing
+        if not is_capturing():  # memory allocated while a CUDA graph is recorded belongs to that graph
+            v = np.asarray(value, dtype=like.dtype)
+            key = (like.device, v.dtype.str, v.tobytes())
+            t = _SCALARS.get(key)
+            if t is None:
+                if len(_SCALARS) >= 512:
+                    _SCALARS.clear()
+                t = _SCALARS[key] = Tensor(value, dtype=like.dtype, device=like.device)
+            return t
+    return Tensor(value, dtype=like.dtype, device=like.device)
+
+
 def _binary_prepare(x, y):
     """Scalar/array operands take the dtype and device of the Tensor operand (reference tensor.py:488-494)."""
     if not isinstance(x, Tensor) and isinstance(y, Tensor):
-        x = Tensor(x, dtype=y.dtype, device=y.device)
+        x = _wrap_scalar(x, y)
     elif isinstance(x, Tensor) and not isinstance(y, Tensor):
-        y = Tensor(y, dtype=x.dtype, device=x.device)
+        y = _wrap_scalar(y, x)
     elif not (isinstance(x, Tensor) and isinstance(y, Tensor)):
         x, y = Tensor(x), Tensor(y)
     assert x.device == y.device
