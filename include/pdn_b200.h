@@ -334,6 +334,21 @@ int pdn_swiglu_rows(const float* gu, float* out, int64_t rows, int64_t F);
 int pdn_swiglu_rows_planes(const float* gu, void* planes, int64_t rows, int64_t F, int64_t Kp);
 int pdn_swiglu_bwd(const float* gate, const float* up, const float* g, float* dgate, float* dup, int64_t n);
 
+/* Whole decode step for small batches (rows < 32) as ONE cooperative persistent kernel (csrc/decode_mega.cu): replaces the
+ * ~490 eager array expressions per token of the reference's own B = 1 loop — llm/llama/model.py:254-256 (forward), 192-207
+ * (_forward_hidden), 142-150 (block), 95-121 (attention with KV cache), 23-44 (RoPE), 56-58 (SwiGLU), norm.py:245-248, and the
+ * greedy argmax of model.py:268. Weights are passed as TRANSPOSED copies ([out][in] row-major, made by the caller):
+ * layer_ptrs[l*8 + {0..7}] = {[Wq|Wk|Wv]ᵀ [3*dim][dim], Woᵀ [dim][dim], gate/up rows interleaved [2*FF][dim], W_downᵀ [dim][FF],
+ * input_norm weight, post_attn_norm weight, cache_k, cache_v ([Bmax][S][H][hd] fp32, contiguous)}; layer_eps[l*2 + {0,1}] the two
+ * RMSNorm eps. The handle owns its scratch (residual rows, attention partials, grid barrier) until pdn_decoder_destroy. */
+int pdn_decoder_create(void** handle, int n_layers, int B, int dim, int H, int FF, int V, int S, const void* const* layer_ptrs,
+                       const float* layer_eps, const float* emb, const float* cosT, const float* sinT, const float* norm_w, float eps_f,
+                       const float* wlm_t, const float* lm_bias);
+/* One token for each of the B sequences: ids[b * ids_stride] at position pos -> KV cache updated at [b, pos], logits [B][V]
+ * and ids_out[b] = argmax (first occurrence). logits == ids_out == NULL: cache update only (prompt positions before the last). */
+int pdn_decoder_step(void* handle, const int64_t* ids, int64_t ids_stride, int64_t pos, float* logits, int64_t* ids_out);
+int pdn_decoder_destroy(void* handle);
+
 /* ---------------------------------------------------------------- data-parallel comm -------- */
 /* Not in the reference (single process); defined by BASELINE north_star: NCCL all-reduce of the flat
  * parameter-gradient bucket over NVLink. */

@@ -372,6 +372,40 @@ class LlamaOracle:
         return np.concatenate(out, axis=1)
 
 
+    def generate_with_margins(self, prompt, max_total_len):
+        """generate() that also returns, per step and sequence, the relative top-1/top-2 logit margin
+        (l1 - l2) / max|logit| — the quantity the parity rule of SURVEY.md §8(c) is stated on."""
+        _, L = prompt.shape
+        out, mar, nxt = [], [], None
+        for i, cur in enumerate(range(L, max_total_len)):
+            logits = (self.step(prompt, 0) if i == 0 else self.step(nxt, cur))[:, -1, :]
+            nxt = logits.argmax(-1, keepdims=True)
+            top2 = np.partition(logits, -2, axis=-1)[:, -2:]
+            mar.append((top2[:, 1] - top2[:, 0]) / np.maximum(np.abs(logits).max(axis=-1), 1e-30))
+            out.append(nxt)
+        return np.concatenate(out, axis=1), np.stack(mar, axis=1)
+
+
+def check_greedy_tokens(got, ref_tokens, ref_margins, tol=1e-4):
+    """The token parity rule: every sequence must equal the oracle's greedy ids EXACTLY up to (excluding) the first
+    step at which the oracle's own top-1/top-2 margin is below ``tol`` (an fp32 near-tie: a different but equally accurate summation
+    order may legitimately pick the other token, after which the contexts differ). Returns (n_exact_sequences, n_diverged_at_near_tie);
+    raises AssertionError on any mismatch at a step whose margin is above ``tol``."""
+    got, ref_tokens = np.asarray(got), np.asarray(ref_tokens)
+    assert got.shape == ref_tokens.shape, (got.shape, ref_tokens.shape)
+    exact = near = 0
+    for b in range(got.shape[0]):
+        bad = np.nonzero(got[b] != ref_tokens[b])[0]
+        if bad.size == 0:
+            exact += 1
+            continue
+        t = int(bad[0])
+        assert ref_margins[b, t] < tol, (f"sequence {b} differs from the oracle at step {t} (got {got[b, t]}, oracle {ref_tokens[b, t]}) "
+                                         f"although the oracle's top-1/top-2 margin there is {ref_margins[b, t]:.3e} >= {tol:g}")
+        near += 1
+    return exact, near
+
+
 def synthetic_llama_params(V, D, H, FF, n_layers, seed=0, std=0.05, dtype=np.float32):
     """Random-init weights of the BASELINE config-3 architecture (no checkpoints are reachable offline): every matrix
     N(0, std), norm weights 1, lm_head bias N(0, std) — SURVEY.md §8(d) C3."""

@@ -24,6 +24,9 @@ _DT = {
 }
 _FLOATS = (np.dtype(np.float16), np.dtype(np.float32), np.dtype(np.float64))
 _I64A = C.c_int64 * 8
+# bumped by every USER-LEVEL in-place write to a device buffer (setitem, fill, += ...): inference plans (nn/_plans.py) compare it
+# against the value they saw last and re-check their weight signatures only when it moved
+WRITE_EPOCH = [0]
 
 
 def _code(dt) -> int:
@@ -215,6 +218,7 @@ class ndarray:
 
     def fill(self, value):
         self.buf.version += 1
+        WRITE_EPOCH[0] += 1
         L.call("pdn_fill", self.ptr, _code(self.dtype), len(self.shape), _arr(self.shape), _arr(self.estrides), float(value))
 
     # ------------------------------------------------------------------ views -------------------
@@ -279,6 +283,7 @@ class ndarray:
         return _gather(view, adv)
 
     def __setitem__(self, key, value):
+        WRITE_EPOCH[0] += 1
         view, adv = _apply_basic(self, key)
         if adv is None:
             _assign(view, value)
@@ -319,6 +324,7 @@ class ndarray:
         if r.shape != self.shape:
             raise ValueError("in-place matmul changes the shape")
         r._copy_into(self)
+        WRITE_EPOCH[0] += 1
         return self
 
     # ------------------------------------------------------------------ reductions --------------
@@ -545,6 +551,7 @@ def _binary(op, a, b, out: ndarray | None = None, true_div: bool = False) -> nda
             dt = np.dtype(np.int64) if op in (L.ADD, L.SUB, L.MUL) else dt
         if out is not None:
             out.buf.version += 1
+            WRITE_EPOCH[0] += 1
             dt_c = out.dtype  # in-place ops compute in the destination dtype
             x = arr if arr.dtype == dt_c else arr.astype(dt_c)
             L.call("pdn_ew_binary_scalar", op, _code(dt_c), x.ptr, float(sc), rev, out.ptr, len(out.shape), _arr(out.shape),
@@ -567,6 +574,7 @@ def _binary(op, a, b, out: ndarray | None = None, true_div: bool = False) -> nda
         return r.astype(np.bool_)
     if out is not None:
         out.buf.version += 1
+        WRITE_EPOCH[0] += 1
         dt = out.dtype  # in-place ops compute in the destination dtype (same-kind casting)
         shape = out.shape
         if np.broadcast_shapes(a.shape, b.shape) != shape:

@@ -113,6 +113,9 @@ _PROTOS = {
     "pdn_gemm_prepacked_planes_argmax": [vp, i64, i64, vp, vp, vp],
     "pdn_swiglu": [vp, vp, vp, i64],
     "pdn_swiglu_bwd": [vp, vp, vp, vp, vp, i64],
+    "pdn_decoder_create": [C.POINTER(vp), i32, i32, i32, i32, i32, i32, i32, C.POINTER(vp), C.POINTER(f32), vp, vp, vp, vp, f32, vp, vp],
+    "pdn_decoder_step": [vp, vp, i64, i64, vp, vp],
+    "pdn_decoder_destroy": [vp],
     "pdn_nccl_unique_id": [C.c_char_p],
     "pdn_nccl_init": [i32, i32, C.c_char_p],
     "pdn_nccl_world": [C.POINTER(i32), C.POINTER(i32)],

@@ -57,6 +57,7 @@ class _Node:
 
 class Tensor:
     """Differentiable array (reference tensor.py:30-413)."""
+    _pdn_hint = None  # set on logits produced by an inference plan (nn/_plans.py): memoised argmax over the vocabulary
 
     def __init__(self, data, dtype=None, copy=True, device=None, requires_grad: bool = False) -> None:
         if isinstance(data, Tensor):
@@ -663,6 +664,11 @@ def _arg(name, x, axis, keepdims) -> Tensor:
 
 
 def argmax(x, axis=None, keepdims=False) -> Tensor:
+    if isinstance(x, Tensor) and x._pdn_hint is not None:
+        from ..nn import _plans
+        memo = _plans.hint_argmax(x, axis, keepdims)
+        if memo is not None:
+            return memo
     return _arg("argmax", x, axis, keepdims)
 
 
@@ -706,6 +712,11 @@ def _get_slice(x, key) -> Tensor:
     """x[key]; backward is zeros + *assignment* so duplicate indices are last-write-wins, not accumulated
     (reference tensor.py:934-940)."""
     x = _wrap(x)
+    if x._pdn_hint is not None:  # logits of an inference plan: ``logits[:, -1, :]`` is a ready-made view carrying the argmax memo
+        from ..nn import _plans
+        out = _plans.hint_getitem(x, key)
+        if out is not None:
+            return out
     if isinstance(key, tuple):
         key = tuple(k.data if isinstance(k, Tensor) else k for k in key)
     elif isinstance(key, Tensor):

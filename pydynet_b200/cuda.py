@@ -33,14 +33,21 @@ def device_count() -> int:
     return _L.device_count()
 
 
+_current = [None]  # device id this process last selected through this module (every switch goes through set_device)
+
+
 def current_device() -> int:
-    d = C.c_int(0)
-    _L.call("pdn_get_device", C.byref(d))
-    return int(d.value)
+    cur = _current[0]
+    if cur is None:
+        d = C.c_int(0)
+        _L.call("pdn_get_device", C.byref(d))
+        cur = _current[0] = int(d.value)
+    return cur
 
 
 def set_device(device: int) -> None:
     _L.call("pdn_set_device", int(device))
+    _current[0] = int(device)
 
 
 def synchronize() -> None:
@@ -134,8 +141,9 @@ def _ensure_init(dev_id: int):
         except Exception:
             pass
         _L.call("pdn_init", dev_id)
+        _current[0] = None  # pdn_init selects dev_id: re-query
         if cur is not None and cur != dev_id and cur in _inited:
-            _L.call("pdn_set_device", cur)
+            set_device(cur)
         _inited.add(dev_id)
 
 

@@ -329,44 +329,6 @@ def rmsnorm_planes(x, weight, eps):
     return pl
 
 
-def swiglu_rows_planes(gu, F_):
-    with gu.device:
-        g = _c(gu.data)
-        pl = Planes(g.shape[:-1], F_, gu.device)
-        _call("pdn_swiglu_rows_planes", g.ptr, pl.ptr, pl.M, F_, pl.Kp)
-    return pl
-
-
-def _cat_packed(owner, key, weights):
-    """Pre-packed operand planes of [W0 | W1 | ...] (column-wise concatenation), cached on ``owner`` until any of the
-    weight buffers is written again."""
-    sig = tuple((w.data.ptr, w.data.buf.version, w.data.shape) for w in weights)
-    ent = getattr(owner, key, None)
-    if ent is None or ent[0] != sig:
-        bk = _bk()
-        cat = bk.concatenate([w.data for w in weights], axis=1)
-        ent = (sig, _PackedWeight(cat), cat.shape[1])
-        setattr(owner, key, ent)
-    return ent[1], ent[2]
-
-
-def linear_cat(owner, key, x, weights):
-    """x @ [W0 | W1 | ...] as ONE GEMM (inference): the Q/K/V projections, or gate|up of the SwiGLU block, share their
-    input, so their weight planes are concatenated once and a single launch produces all outputs side by side."""
-    bk = _bk()
-    with x.device:
-        pw, N = _cat_packed(owner, key, weights)
-        if isinstance(x, Planes):
-            out = _empty((x.M, N))
-            _call("pdn_gemm_prepacked_planes", x.ptr, x.M, x.Kp, pw.handle, out.ptr, N, None, 0)
-            return _result(out.reshape(x.lead + (N, )), x.device, (), None, "linear_cat")
-        xd = x.data
-        x2 = bk.ext._flat2d(xd) if xd.ndim != 2 else xd
-        out = _empty((x2.shape[0], N))
-        _call("pdn_gemm_prepacked", x2.ptr, pw.handle, out.ptr, x2.shape[0], x2.estrides[0], x2.estrides[1], N, None, 0)
-    return _result(out.reshape(xd.shape[:-1] + (N, )), x.device, (), None, "linear_cat")
-
-
 def linear_residual_(a, weight, res):
     """res += a @ W, accumulated in the GEMM epilogue INTO res's buffer (inference only: the residual stream is not
     needed in its old state). Returns res."""
@@ -385,76 +347,12 @@ def linear_residual_(a, weight, res):
     return res
 
 
-def lm_head_argmax(pl, weight, bias):
-    """argmax over the vocabulary of (h @ W + b) for greedy decoding, fused into the GEMM epilogue: the [B, V] logits are
-    never written to HBM (reference llm/llama/model.py:254-256, 268). Returns int64 ids [B, 1]."""
-    from ..backend.array import ndarray
-    with pl.device:
-        out = ndarray.empty((pl.M, 1), np.int64)
-        bd = _c(bias.data) if bias is not None else None
-        _call("pdn_gemm_prepacked_planes_argmax", pl.ptr, pl.M, pl.Kp, _packed(weight).handle, bd.ptr if bd is not None else None, out.ptr)
-    return _result(out, pl.device, (), None, "lm_head_argmax")
-
-
-def swiglu_rows(gu, F_):
-    """silu(gu[..., :F]) * gu[..., F:] on the fused gate|up projection output."""
-    with gu.device:
-        g = _c(gu.data)
-        rows = g.size // (2 * F_)
-        out = _empty(g.shape[:-1] + (F_, ))
-        _call("pdn_swiglu_rows", g.ptr, out.ptr, rows, F_)
-    return _result(out, gu.device, (), None, "swiglu_rows")
-
-
 class DevicePos:
     """Sequence position of a decode step held in DEVICE memory (an int64 [1] tensor) so that a CUDA-graph recording of
     the step stays valid while the position advances."""
 
     def __init__(self, tensor):
         self.tensor = tensor
-
-
-@fused_op
-def llama_cached_attention(att, xq, xk, xv, start_pos, mask, scale, ld=0, as_planes=False):
-    """Inference step of the Llama attention block (reference llm/llama/model.py:101-121): interleaved-pair RoPE on q and k,
-    append k/v to the per-layer KV cache at [start_pos, start_pos+L), attention of the new queries over cache[:start_pos+L].
-    Two kernels (rope_kv_append, attention_fwd) instead of ~40 eager nodes. Inference only (no tape). ``start_pos`` is a
-    host int, or a DevicePos while one decode step is being recorded into a CUDA graph. q/k/v are [B, L, H, D] arrays with
-    unit-stride D and a common row stride ``ld`` (0: contiguous H*D; 3*H*D: column blocks of a fused QKV projection)."""
-    assert not _needs(xq, xk, xv), "llama_cached_attention is the eval-mode path"
-    model_cos, model_sin = att._rope_tables
-    with xq.device:
-        if ld:
-            q, k, v = xq.data, xk.data, xv.data  # strided views of one fresh QKV buffer: rotated in place
-        else:
-            q, k, v = _c(xq.data), _c(xk.data), _c(xv.data)  # projection outputs are fresh buffers: rotated in place
-        B, L, H, D = q.shape
-        ck, cv = att.cache_k.data, att.cache_v.data
-        S = ck.shape[1]
-        if as_planes:  # the O-projection consumes the result as operand planes: skip the fp32 output and its pack
-            pl = Planes((B, L), H * D, xq.device)
-            out, optr, pptr, pkp = None, None, pl.ptr, pl.Kp
-        else:
-            out = _empty((B, L, H, D))
-            optr, pptr, pkp = out.ptr, None, 0
-        cstr = _i64((ck.estrides[0], ck.estrides[2], ck.estrides[1]))
-        if isinstance(start_pos, DevicePos):
-            assert mask is None
-            pos_ptr = start_pos.tensor.data.ptr
-            _call("pdn_rope_kv_append_dev", q.ptr, k.ptr, v.ptr, model_cos.ptr, model_sin.ptr, ck.ptr, cv.ptr, B, L, H, D, S, pos_ptr, ld)
-            _call("pdn_attention_fwd_dev", q.ptr, ck.ptr, cv.ptr, optr, B, H, L, D, _bhl_strides(q), cstr, cstr, scale, pos_ptr, L, pptr, pkp)
-        else:
-            _call("pdn_rope_kv_append", q.ptr, k.ptr, v.ptr, model_cos.ptr, model_sin.ptr, ck.ptr, cv.ptr, B, L, H, D, S, int(start_pos), ld)
-            Lk = int(start_pos) + L
-            keep, mptr, mstr = _mask_args(mask, B, H, L, Lk)
-            _call("pdn_attention_fwd", q.ptr, ck.ptr, cv.ptr, mptr, optr, None, B, H, L, Lk, D, _bhl_strides(q), cstr, cstr, mstr, scale, pptr,
-                  pkp)
-            _ = keep
-        ck.buf.version += 1
-        cv.buf.version += 1
-    if as_planes:
-        return pl
-    return _result(out.reshape(B, L, H * D), xq.device, (), None, "llama_cached_attention")
 
 
 # ---------------------------------------------------------------------------------- conv / pool --------------

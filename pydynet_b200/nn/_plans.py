@@ -1,0 +1,612 @@
+"""Inference plans: fused execution of a whole eval-mode forward BEHIND the unchanged ``nn.Module`` surface.
+
+The reference runs a model as a chain of ~490 eager array expressions per decoded token (SURVEY.md §3.4,
+llm/llama/model.py:95-121, 142-150, 192-207, 254-256).  A model file written against the reference — its own
+``llm/llama/model.py``, exec'd unchanged with ``import pydynet_b200 as pydynet`` — calls ``model(input_ids, start_pos)``;
+``Module.__call__`` (nn/modules/module.py) asks this module for a plan before it falls through to ``forward``:
+
+* ``DecoderPlan.match`` recognises the Llama-style decoder STRUCTURALLY (token embedding, RoPE tables, blocks of
+  {RMSNorm, bias-free Q/K/V/O, KV-cache parameters, RMSNorm, gate/up/down SwiGLU}, final RMSNorm, lm_head) — attribute
+  names and parameter shapes, nothing about the class identity;
+* the FIRST call of each kind (prefill, decode) is verified against the model's own eager ``forward`` on the same
+  inputs (normwise 1e-3); a mismatch retires the plan for good and the model keeps running eagerly, so a class that
+  merely looks like the reference's but computes something else is never mis-served;
+* afterwards a call costs: rows >= 32 (batched decode / prefill) — 9 launches per block on the tcgen05 GEMM path
+  (RMSNorm -> operand planes, fused QKV GEMM, RoPE + cache append, cached attention -> planes, O-proj accumulating onto
+  the residual, RMSNorm -> planes, fused gate|up GEMM, SwiGLU -> planes, down-proj accumulating onto the residual), the
+  decode step recorded once per batch size as a CUDA graph with position and token ids in device memory and replayed per
+  token; rows < 32 (the reference's own B = 1 loop) — ONE cooperative persistent kernel per token
+  (csrc/decode_mega.cu).
+
+Results are those of the eager chain (fp32; tested token-exact against the oracle).  A plan only ever serves
+``not model._train and not grad-mode`` calls on a cuda device; everything else falls through.  Validity is tracked by two
+epochs: module structure / parameter rebinding (``note_structure_change``) and user-level in-place writes to device
+buffers (``backend.array.WRITE_EPOCH``); a change triggers a re-check of every weight pointer and write counter and
+drops recorded graphs and packed weights that no longer match.
+
+``logits[:, -1, :].argmax(-1, True)`` (reference model.py:268) on a plan's logits returns the argmax the lm_head GEMM
+epilogue / the decode kernel already produced (``Tensor._pdn_hint``): same values, no second pass over [B, 32000].
+"""
+import math
+import os
+import sys
+import warnings
+
+import numpy as np
+
+from ..autograd import is_grad_enable
+from ..backend.array import WRITE_EPOCH
+from ..core.tensor import Tensor, _result
+from . import _fused
+from ._fused import Planes, DevicePos, _call, _empty, _i64, _bhl_strides, _PackedWeight, _c
+from ..backend.array import ndarray
+
+ENABLED = os.environ.get("PDN_PLANS", "1") != "0"
+VERIFY = os.environ.get("PDN_PLAN_VERIFY", "1") != "0"
+STRUCT_EPOCH = [0]
+F32 = np.dtype(np.float32)
+I64 = np.dtype(np.int64)
+MEGA_MAX_ROWS = 8  # batch rows one decode_mega launch serves (register accumulators per warp)
+
+
+def note_structure_change():
+    """A Module gained / lost a Parameter or sub-Module, a Parameter was re-bound or moved: every plan re-validates."""
+    STRUCT_EPOCH[0] += 1
+
+
+def _write_epoch():
+    return WRITE_EPOCH[0]
+
+
+def attach(module):
+    """Called once per Module instance from ``Module.__call__``; returns a plan or False."""
+    plan = False
+    if ENABLED:
+        try:
+            plan = DecoderPlan.match(module) or False
+        except Exception:  # a structural probe must never break a forward
+            plan = False
+    object.__setattr__(module, "_pdn_plan", plan)
+    return plan
+
+
+class _Hint:
+    """Memoised ``argmax over the vocabulary`` of a plan's logits, valid while the producing step is the latest one."""
+    __slots__ = ("state", "step_no", "slot", "sliced")
+
+    def __init__(self, state, step_no, slot, sliced=False):
+        self.state, self.step_no, self.slot, self.sliced = state, step_no, slot, sliced
+
+
+_ALL = slice(None)
+
+
+def hint_getitem(x, key):
+    """``logits[:, -1, :]`` on a plan's [B, 1, V] logits (reference model.py:268): the [B, V] view, built directly (no generic
+    index parsing) and still carrying the argmax memo. Any other key: None (the generic path serves it, memo dropped)."""
+    h = x._pdn_hint
+    if (not h.sliced and type(key) is tuple and len(key) == 3 and key[0] == _ALL and key[2] == _ALL
+            and isinstance(key[1], (int, np.integer)) and key[1] in (-1, 0)):
+        d = x.data
+        out = _result(d._view((d.shape[0], d.shape[2]), (d.estrides[0], d.estrides[2])), x.device, (), None, "_get_slice")
+        out._pdn_hint = _Hint(h.state, h.step_no, h.slot, True)
+        return out
+    return None
+
+
+def hint_argmax(x, axis, keepdims):
+    """Returns the memoised ids Tensor for ``x.argmax(-1, True)`` or None when the hint does not apply (any more)."""
+    h = x._pdn_hint
+    if not h.sliced or not keepdims or axis not in (-1, 1) or x.ndim != 2:
+        return None
+    return h.state.take_ids(h)
+
+
+# ------------------------------------------------------------------------------------------- decode state -----
+class _DecodeState:
+    """Per (plan, batch size) buffers of the recorded decode step: ping-pong ids / logits buffers, the device position,
+    the two CUDA graphs."""
+
+    def __init__(self, plan, B):
+        self.plan, self.B = plan, B
+        dev = plan.device
+        with dev:
+            self.ids = [ndarray.empty((B, 1), I64) for _ in range(2)]
+            self.pos = DevicePos(Tensor(np.zeros(1, dtype=np.int64), device=dev))
+        self.logits = [None, None]
+        self.graphs = [None, None]
+        self.base_ref = [0, 0]
+        self.slot = 0  # slot the NEXT step writes
+        self.step_no = 0
+        self.dev_pos = None  # value currently held by the device-side position (None: unknown)
+        self.last_out = None  # (ids Tensor handed to the caller, version of its buffer, slot whose device copy equals it)
+        self.steps_run = 0
+        self.recaptures = 0
+        self.copy_mode = False
+
+    def destroy(self):
+        for g in self.graphs:
+            if g is not None:
+                with self.plan.device:
+                    g.destroy()
+        self.graphs = [None, None]
+
+    def take_ids(self, hint):
+        if hint.step_no != self.step_no:
+            return None  # a later step has overwritten the slot: the caller's argmax runs on the logits it holds
+        with self.plan.device:
+            out = ndarray.empty((self.B, 1), I64)
+            _call("pdn_memcpy_d2d", out.ptr, self.ids[hint.slot].ptr, self.B * 8)
+        t = _result(out, self.plan.device, (), None, "argmax")
+        self.last_out = (t, out.buf.version, hint.slot)
+        return t
+
+
+# ------------------------------------------------------------------------------------------- the plan ---------
+def _is_linear(m, bias):
+    w = getattr(m, "weight", None)
+    if not isinstance(w, Tensor) or w.ndim != 2:
+        return False
+    b = getattr(m, "bias", None)
+    return (b is None) if bias is False else True
+
+
+def _is_rmsnorm(m, dim):
+    w = getattr(m, "weight", None)
+    return isinstance(w, Tensor) and w.shape == (dim, ) and hasattr(m, "eps") and type(m).__name__ == "RMSNorm"
+
+
+class DecoderPlan:
+
+    @classmethod
+    def match(cls, m):
+        from .modules.module import Module, ModuleList
+        from .modules.layers import Embedding, Linear
+        emb, layers = getattr(m, "tok_embedding", None), getattr(m, "layers", None)
+        if not isinstance(emb, Embedding) or emb.padding_idx is not None or not isinstance(layers, ModuleList) or len(layers) == 0:
+            return None
+        cos, sin = getattr(m, "freqs_cos", None), getattr(m, "freqs_sin", None)
+        head, norm = getattr(m, "lm_head", None), getattr(m, "norm", None)
+        if not (isinstance(cos, Tensor) and isinstance(sin, Tensor) and isinstance(head, Linear)):
+            return None
+        V, D = emb.weight.shape
+        if not _is_rmsnorm(norm, D) or head.weight.shape != (D, V) or cos.ndim != 2 or cos.shape != sin.shape:
+            return None
+        blocks = []
+        for blk in layers:
+            att, ffn = getattr(blk, "attention", None), getattr(blk, "ffn", None)
+            n1, n2 = getattr(blk, "input_norm", None), getattr(blk, "post_attn_norm", None)
+            if not (isinstance(att, Module) and isinstance(ffn, Module) and _is_rmsnorm(n1, D) and _is_rmsnorm(n2, D)):
+                return None
+            for nm in "QKVO":
+                lin = getattr(att, nm, None)
+                if not isinstance(lin, Linear) or lin.bias is not None or lin.weight.shape != (D, D):
+                    return None
+            ck, cv = getattr(att, "cache_k", None), getattr(att, "cache_v", None)
+            H, hd = getattr(att, "n_heads", None), getattr(att, "head_dim", None)
+            if not (isinstance(ck, Tensor) and isinstance(cv, Tensor) and isinstance(H, int) and isinstance(hd, int)):
+                return None
+            if H * hd != D or ck.ndim != 4 or ck.shape != cv.shape or ck.shape[2:] != (H, hd) or cos.shape[1] * 2 != hd:
+                return None
+            up, gate, down = (getattr(ffn, nm, None) for nm in ("up", "gate", "down"))
+            if not all(isinstance(x, Linear) and x.bias is None for x in (up, gate, down)):
+                return None
+            FF = up.weight.shape[1]
+            if up.weight.shape != (D, FF) or gate.weight.shape != (D, FF) or down.weight.shape != (FF, D):
+                return None
+            blocks.append((blk, att, ffn, n1, n2))
+        if hd > 128 or hd % 4 != 0 or D % 8 != 0:
+            return None
+        return cls(m, blocks)
+
+    def __init__(self, model, blocks):
+        self.model, self.blocks = model, blocks
+        self.dead = False
+        self.verified = set()
+        self.device = None
+        self._epoch = None
+        self._sig = None
+        self._cat = {}  # fused [W0 | W1 | ...] operand planes per (layer, kind)
+        self._dec = {}  # batch size -> _DecodeState
+        self._mega = None
+        self._masks = {}
+
+    # ---------------------------------------------------------------- validity -----------------
+    def _weights(self):
+        m = self.model
+        ws = [m.tok_embedding.weight, m.freqs_cos, m.freqs_sin, m.norm.weight, m.lm_head.weight]
+        if m.lm_head.bias is not None:
+            ws.append(m.lm_head.bias)
+        caches = []
+        for blk, att, ffn, n1, n2 in self.blocks:
+            ws += [att.Q.weight, att.K.weight, att.V.weight, att.O.weight, ffn.gate.weight, ffn.up.weight, ffn.down.weight, n1.weight,
+                   n2.weight]
+            caches += [att.cache_k, att.cache_v]
+        return ws, caches
+
+    def _revalidate(self) -> bool:
+        """Re-derives the weight signature; drops recorded graphs / packed operands when a weight buffer moved or was
+        written. False: the model cannot be served right now (not on one cuda device in fp32)."""
+        ws, caches = self._weights()
+        dev = ws[0].device
+        if not dev.is_cuda:
+            return False
+        for t in ws + caches:
+            if t.device != dev or t.data.dtype != F32 or not t.data.is_contiguous:
+                return False
+        sig = tuple((t.data.ptr, t.data.buf.version, t.data.shape) for t in ws) + tuple((t.data.ptr, t.data.shape) for t in caches)
+        if sig != self._sig:
+            self._drop_recorded()
+            self._sig, self.device = sig, dev
+        return True
+
+    def _drop_recorded(self):
+        for st in self._dec.values():
+            st.destroy()
+        self._dec.clear()
+        self._cat.clear()
+        self._mega = None
+
+    # ---------------------------------------------------------------- entry --------------------
+    def __call__(self, args):
+        m = self.model
+        if self.dead or not ENABLED or m._train or is_grad_enable() or len(args) != 2:
+            return NotImplemented
+        ids, pos = args
+        if isinstance(pos, (bool, float)) or not isinstance(pos, (int, np.integer)):
+            return NotImplemented
+        epoch = (STRUCT_EPOCH[0], _write_epoch())
+        if epoch != self._epoch:
+            if not self._revalidate():
+                return NotImplemented
+        if isinstance(ids, Tensor):
+            if ids.device != self.device or ids.ndim != 2 or ids.data.dtype != I64:
+                return NotImplemented
+        elif isinstance(ids, np.ndarray) and ids.ndim == 2 and np.issubdtype(ids.dtype, np.integer):
+            pass
+        else:
+            return NotImplemented
+        B, L = ids.shape
+        pos = int(pos)
+        ck = self.blocks[0][1].cache_k
+        if B > ck.shape[0] or pos < 0 or pos + L > ck.shape[1] or L == 0:
+            return NotImplemented  # the eager path raises the reference's own error for these
+        kind = "decode" if L == 1 else "prefill"
+        path = "mega" if (B * L < 32 and B <= MEGA_MAX_ROWS and self._mega_ok()) else ("tc" if B * L >= 32 else None)
+        if path is None:
+            return NotImplemented
+        with self.device:
+            if VERIFY and (kind, path) not in self.verified:
+                out = self._verified_first_call(kind, path, ids, pos, B, L)
+            else:
+                out = self._run(kind, path, ids, pos, B, L)
+        self._epoch = (STRUCT_EPOCH[0], _write_epoch())  # absorbs this call's own internal writes
+        return out
+
+    def _verified_first_call(self, kind, path, ids, pos, B, L):
+        m = self.model
+        want = m.forward(ids, pos)
+        got = self._run(kind, path, ids, pos, B, L)
+        a, b = want.numpy().astype(np.float64), got.numpy().astype(np.float64)
+        err = np.linalg.norm(a - b) / max(np.linalg.norm(a), 1e-30) if a.shape == b.shape else float("inf")
+        if not (err < 1e-3):
+            self.dead = True
+            self._drop_recorded()
+            warnings.warn(f"pydynet_b200: inference plan for {type(m).__name__} disagrees with its eager forward "
+                          f"({kind}/{path}: normwise {err:.2e}); the model keeps running eagerly")
+            return want
+        self.verified.add((kind, path))
+        return got
+
+    def _run(self, kind, path, ids, pos, B, L):
+        if path == "mega":
+            return self._run_mega(ids, pos, B, L)
+        if kind == "prefill":
+            return self._prefill_tc(ids, pos, B, L)
+        return self._decode_tc(ids, pos, B)
+
+    # ---------------------------------------------------------------- rows >= 32: tcgen05 GEMM path ------------
+    def _ids_tensor(self, ids):
+        return ids if isinstance(ids, Tensor) else Tensor(ids, dtype=np.int64, device=self.device)
+
+    def _packed_cat(self, key, weights):
+        sig = tuple((w.data.ptr, w.data.buf.version) for w in weights)
+        ent = self._cat.get(key)
+        if ent is None or ent[0] != sig:
+            from .. import backend as bk
+            cat = bk.concatenate([w.data for w in weights], axis=1)
+            ent = self._cat[key] = (sig, _PackedWeight(cat), cat.shape[1])
+        return ent[1], ent[2]
+
+    def _gemm_cat(self, key, pl, weights):
+        pw, N = self._packed_cat(key, weights)
+        out = _empty((pl.M, N))
+        _call("pdn_gemm_prepacked_planes", pl.ptr, pl.M, pl.Kp, pw.handle, out.ptr, N, None, 0)
+        return out
+
+    def _block(self, i, x, start_pos, mask, B, L):
+        """One transformer block in place on the residual stream ``x`` [B, L, dim] (reference model.py:142-150, 95-121)."""
+        blk, att, ffn, n1, n2 = self.blocks[i]
+        m = self.model
+        H, D = att.n_heads, att.head_dim
+        dim = H * D
+        qkv = self._gemm_cat((i, "qkv"), _fused.rmsnorm_planes(x, n1.weight, n1.eps), (att.Q.weight, att.K.weight, att.V.weight))
+        q3 = qkv.reshape(B, L, 3, H, D)
+        q, k, v = q3[:, :, 0], q3[:, :, 1], q3[:, :, 2]
+        ck, cv = att.cache_k.data, att.cache_v.data
+        S = ck.shape[1]
+        cos, sin = m.freqs_cos.data, m.freqs_sin.data
+        pl = Planes((B, L), dim, self.device)
+        cstr = _i64((ck.estrides[0], ck.estrides[2], ck.estrides[1]))
+        scale = 1.0 / math.sqrt(D)
+        ld = 3 * dim
+        if isinstance(start_pos, DevicePos):
+            pp = start_pos.tensor.data.ptr
+            _call("pdn_rope_kv_append_dev", q.ptr, k.ptr, v.ptr, cos.ptr, sin.ptr, ck.ptr, cv.ptr, B, L, H, D, S, pp, ld)
+            _call("pdn_attention_fwd_dev", q.ptr, ck.ptr, cv.ptr, None, B, H, L, D, _bhl_strides(q), cstr, cstr, scale, pp, L, pl.ptr, pl.Kp)
+        else:
+            _call("pdn_rope_kv_append", q.ptr, k.ptr, v.ptr, cos.ptr, sin.ptr, ck.ptr, cv.ptr, B, L, H, D, S, start_pos, ld)
+            Lk = start_pos + L
+            keep, mptr, mstr = _fused._mask_args(mask, B, H, L, Lk)
+            _call("pdn_attention_fwd", q.ptr, ck.ptr, cv.ptr, mptr, None, None, B, H, L, Lk, D, _bhl_strides(q), cstr, cstr, mstr, scale,
+                  pl.ptr, pl.Kp)
+            del keep
+        ck.buf.version += 1
+        cv.buf.version += 1
+        z = _fused.linear_residual_(pl, att.O.weight, x)
+        gu = self._gemm_cat((i, "gu"), _fused.rmsnorm_planes(z, n2.weight, n2.eps), (ffn.gate.weight, ffn.up.weight))
+        FF = ffn.up.weight.shape[1]
+        hp = Planes((B, L), FF, self.device)
+        _call("pdn_swiglu_rows_planes", gu.ptr, hp.ptr, hp.M, FF, hp.Kp)
+        return _fused.linear_residual_(hp, ffn.down.weight, z)
+
+    def _mask(self, L, start_pos):
+        """Causal mask over [cached positions | new positions], built on the host like the reference (model.py:199-203)."""
+        key = (L, start_pos)
+        mk = self._masks.get(key)
+        if mk is None:
+            if len(self._masks) > 16:
+                self._masks.clear()
+            host = np.concatenate([np.zeros((L, start_pos)), np.triu(np.full((L, L), float("-inf")), k=1)], axis=1)
+            mk = self._masks[key] = Tensor(host, device=self.device, dtype=np.float32)
+        return mk
+
+    def _hidden_tc(self, ids_t, start_pos, B, L):
+        from . import functional as F
+        m = self.model
+        h = F.embedding(ids_t, m.tok_embedding.weight, None)  # fresh [B, L, dim] buffer: becomes the residual stream
+        mask = self._mask(L, start_pos) if L > 1 else None
+        for i in range(len(self.blocks)):
+            h = self._block(i, h, start_pos, mask, B, L)
+        return h
+
+    def _head_planes(self, h, B, L):
+        m = self.model
+        last = h if L == 1 else h[:, -1, :]
+        return _fused.rmsnorm_planes(last, m.norm.weight, m.norm.eps)
+
+    def _prefill_tc(self, ids, start_pos, B, L):
+        m = self.model
+        h = self._hidden_tc(self._ids_tensor(ids), start_pos, B, L)
+        pl = self._head_planes(h, B, L)
+        V = m.lm_head.weight.shape[1]
+        out = _empty((B, V))
+        bias = m.lm_head.bias
+        _call("pdn_gemm_prepacked_planes", pl.ptr, pl.M, pl.Kp, _fused._packed(m.lm_head.weight).handle, out.ptr, V,
+              _c(bias.data).ptr if bias is not None else None, 0)
+        return _result(out.reshape(B, 1, V), self.device, (), None, "plan_logits")
+
+    def _decode_step_into(self, st, slot_in, slot_out, pos):
+        """Launch sequence of one decode step: ids[slot_in] -> logits[slot_out], ids[slot_out] = argmax; ``pos`` is a host
+        int (eager launches) or the state's DevicePos (graph recording; the recorded step also advances it)."""
+        m, B = self.model, st.B
+        ids_t = _result(st.ids[slot_in], self.device, (), None, "ids")
+        h = self._hidden_tc(ids_t, pos, B, 1)
+        pl = self._head_planes(h, B, 1)
+        V = m.lm_head.weight.shape[1]
+        bias = m.lm_head.bias
+        bptr = _c(bias.data).ptr if bias is not None else None
+        handle = _fused._packed(m.lm_head.weight).handle
+        if st.logits[slot_out] is None:
+            st.logits[slot_out] = _empty((B, V))
+        _call("pdn_gemm_prepacked_planes", pl.ptr, pl.M, pl.Kp, handle, st.logits[slot_out].ptr, V, bptr, 0)
+        _call("pdn_gemm_prepacked_planes_argmax", pl.ptr, pl.M, pl.Kp, handle, bptr, st.ids[slot_out].ptr)
+        if isinstance(pos, DevicePos):
+            pos.tensor += 1
+
+    def _decode_tc(self, ids, start_pos, B):
+        from .. import cuda
+        st = self._dec.get(B)
+        if st is None:
+            st = self._dec[B] = _DecodeState(self, B)
+        slot_out, slot_in = st.slot, st.slot ^ 1
+        # token ids of this step: already in ids[slot_in] when the caller passes back the argmax Tensor of the previous step
+        lo = st.last_out
+        if not (lo is not None and ids is lo[0] and lo[2] == slot_in and ids.data.buf.version == lo[1]):
+            if isinstance(ids, Tensor):
+                _call("pdn_memcpy_d2d", st.ids[slot_in].ptr, _c(ids.data).ptr, B * 8)
+            else:
+                host = np.ascontiguousarray(ids, dtype=np.int64)
+                _call("pdn_memcpy_h2d", st.ids[slot_in].ptr, host.ctypes.data, host.nbytes)
+        st.last_out = None
+        use_graph = os.environ.get("PDN_DECODE_GRAPH", "1") != "0" and st.steps_run >= 1 and not cuda.is_capturing()
+        lg = st.logits[slot_out]
+        if lg is not None and not st.copy_mode and sys.getrefcount(lg.buf) > st.base_ref[slot_out]:
+            # a caller still holds a view of the logits this step would overwrite: this slot gets a fresh buffer (and, because a
+            # recorded graph writes fixed addresses, a fresh recording); callers that keep every step's logits end up in copy mode
+            st.recaptures += 1
+            if st.recaptures > 4:
+                st.copy_mode = True
+            else:
+                if st.graphs[slot_out] is not None:
+                    st.graphs[slot_out].destroy()
+                    st.graphs[slot_out] = None
+                st.logits[slot_out] = None
+        if not use_graph:
+            self._decode_step_into(st, slot_in, slot_out, start_pos)
+        else:
+            if st.dev_pos != start_pos:
+                st.pos.tensor.data.fill(start_pos)
+            g = st.graphs[slot_out]
+            if g is None:
+                g = cuda.Graph()
+                g.begin()
+                try:
+                    self._decode_step_into(st, slot_in, slot_out, st.pos)
+                finally:
+                    g.end()
+                st.graphs[slot_out] = g
+            g.launch()
+            st.dev_pos = start_pos + 1  # the recorded step advances it
+            for blk, att, ffn, n1, n2 in self.blocks:
+                att.cache_k.data.buf.version += 1
+                att.cache_v.data.buf.version += 1
+        V = self.model.lm_head.weight.shape[1]
+        lg = st.logits[slot_out]
+        if not st.copy_mode:
+            st.base_ref[slot_out] = sys.getrefcount(lg.buf)  # no caller view of this buffer exists at this point
+        st.steps_run += 1
+        st.step_no += 1
+        st.slot = slot_in
+        data = lg.copy() if st.copy_mode else lg
+        out = _result(data.reshape(B, 1, V), self.device, (), None, "plan_logits")
+        out._pdn_hint = _Hint(st, st.step_no, slot_out)
+        return out
+
+    # ---------------------------------------------------------------- rows < 32: persistent decode kernel ------
+    def _mega_ok(self):
+        if os.environ.get("PDN_DECODE_MEGA", "1") == "0":
+            return False
+        att, ffn = self.blocks[0][1], self.blocks[0][2]
+        D, FF = att.n_heads * att.head_dim, ffn.up.weight.shape[1]
+        return (att.head_dim in (32, 48, 64) and D % 4 == 0 and FF % 4 == 0 and D <= 1024 and FF <= 1024
+                and all(b[2].up.weight.shape[1] == FF for b in self.blocks))
+
+    def _mega_weights(self):
+        """Transposed ([out][in]) copies the persistent kernel streams row by row; rebuilt when a weight buffer changes
+        (``_drop_recorded``)."""
+        if self._mega is None:
+            from .. import backend as bk
+            m = self.model
+            T = lambda w: w.data.swapaxes(0, 1).copy()
+            layers = []
+            for blk, att, ffn, n1, n2 in self.blocks:
+                wqkv = bk.concatenate([T(att.Q.weight), T(att.K.weight), T(att.V.weight)], axis=0)
+                FF, D = ffn.up.weight.shape[1], ffn.up.weight.shape[0]
+                wgu = ndarray.empty((FF, 2, D), F32)
+                wgu[:, 0, :] = T(ffn.gate.weight)
+                wgu[:, 1, :] = T(ffn.up.weight)
+                layers.append((wqkv, T(att.O.weight), wgu, T(ffn.down.weight), n1, n2, att))
+            self._mega = {"layers": layers, "wlm": T(m.lm_head.weight), "states": {}}
+        return self._mega
+
+    def _run_mega(self, ids, pos, B, L):
+        mg = self._mega_weights()
+        st = mg["states"].get(B)
+        if st is None:
+            st = mg["states"][B] = _MegaState(self, mg, B)
+        return st.run(ids, pos, L)
+
+
+class _MegaState:
+    """Handle + output buffers of the persistent decode kernel for one batch size (csrc/decode_mega.cu)."""
+
+    def __init__(self, plan, mg, B):
+        import ctypes as C
+        self.plan, self.B = plan, B
+        m = plan.model
+        att, ffn = plan.blocks[0][1], plan.blocks[0][2]
+        self.H, self.D, self.FF = att.n_heads, att.n_heads * att.head_dim, ffn.up.weight.shape[1]
+        self.V, self.S = m.lm_head.weight.shape[1], att.cache_k.shape[1]
+        n = len(mg["layers"])
+        ptrs = (C.c_void_p * (8 * n))()
+        eps = (C.c_float * (2 * n))()
+        for i, (wqkv, wo, wgu, wd, n1, n2, a) in enumerate(mg["layers"]):
+            for j, arr in enumerate((wqkv, wo, wgu, wd, n1.weight.data, n2.weight.data, a.cache_k.data, a.cache_v.data)):
+                ptrs[8 * i + j] = arr.ptr
+            eps[2 * i], eps[2 * i + 1] = n1.eps, n2.eps
+        bias = m.lm_head.bias
+        self.handle = C.c_void_p()
+        _call("pdn_decoder_create", C.byref(self.handle), n, B, self.D, self.H, self.FF, self.V, self.S, ptrs, eps,
+              m.tok_embedding.weight.data.ptr, m.freqs_cos.data.ptr, m.freqs_sin.data.ptr, m.norm.weight.data.ptr, m.norm.eps,
+              mg["wlm"].ptr, bias.data.ptr if bias is not None else None)
+        self._keep = mg  # the transposed weights live as long as the handle
+        self.logits = [None, None]
+        self.base_ref = [0, 0]
+        self.slot = 0
+        self.hist = None  # [S + 1, B] int64: the id produced at position p lives in row p (distinct storage per step)
+        self.hist_ref = 0
+        self.gen = 0
+        self.last_row = -1
+        self.last_out = None  # (ids Tensor handed out, version, row)
+        self.staging = ndarray.empty((B, 1), I64)
+        self.caches = [(a.cache_k.data.buf, a.cache_v.data.buf) for (_, _, _, _, _, _, a) in mg["layers"]]
+
+    def __del__(self):
+        try:
+            from ..backend import lib
+            if lib._lib is not None and self.handle:
+                lib._lib.pdn_decoder_destroy(self.handle)
+        except Exception:
+            pass
+
+    def _new_hist(self):
+        self.hist = ndarray.empty((self.S + 1, self.B), I64)
+        self.hist_ref = sys.getrefcount(self.hist.buf)
+        self.gen += 1
+
+    def take_ids(self, hint):
+        if hint.step_no != self.gen:
+            return None
+        row = hint.slot
+        view = self.hist._view((self.B, 1), (1, 1), row * self.B)
+        t = _result(view, self.plan.device, (), None, "argmax")
+        self.last_out = (t, self.hist.buf.version, row)
+        return t
+
+    def run(self, ids, pos, L):
+        B, V = self.B, self.V
+        # where this step's token ids live on the device: the history row when the caller passes back our own argmax Tensor,
+        # the caller's own int64 buffer otherwise (no copy), a staging buffer for host ids
+        lo = self.last_out
+        if lo is not None and ids is lo[0] and L == 1 and self.hist.buf.version == lo[1]:
+            ids_ptr, stride = self.hist.ptr + lo[2] * B * 8, 1
+        elif isinstance(ids, Tensor):
+            d = ids.data
+            if d.estrides[1] != 1 and L > 1:
+                d = d.copy()
+            ids_ptr, stride = d.ptr, d.estrides[0] if B > 1 else L
+            keep = d
+        else:
+            host = np.ascontiguousarray(ids, dtype=np.int64)
+            if L > 1:
+                keep = ndarray.from_host(host)
+                ids_ptr, stride = keep.ptr, L
+            else:
+                _call("pdn_memcpy_h2d", self.staging.ptr, host.ctypes.data, host.nbytes)
+                ids_ptr, stride = self.staging.ptr, 1
+        row = pos + L - 1
+        if self.hist is None or row <= self.last_row:
+            # a new generation (positions restart): id Tensors of the previous one that the caller still holds keep their rows
+            if self.hist is None or sys.getrefcount(self.hist.buf) > self.hist_ref:
+                self._new_hist()
+            else:
+                self.gen += 1
+        self.last_row = row
+        slot = self.slot
+        lg = self.logits[slot]
+        if lg is None or sys.getrefcount(lg.buf) > self.base_ref[slot]:
+            lg = self.logits[slot] = ndarray.empty((B, V), F32)
+        self.base_ref[slot] = sys.getrefcount(lg.buf)
+        h = self.handle
+        for l in range(L - 1):  # prompt positions before the last one: KV cache only
+            _call("pdn_decoder_step", h, ids_ptr + 8 * l, stride, pos + l, None, None)
+        _call("pdn_decoder_step", h, ids_ptr + 8 * (L - 1), stride, row, lg.ptr, self.hist.ptr + row * B * 8)
+        for ck, cv in self.caches:
+            ck.version += 1
+            cv.version += 1
+        self.slot = slot ^ 1
+        self.last_out = None
+        out = _result(lg.reshape(B, 1, V), self.plan.device, (), None, "plan_logits")
+        out._pdn_hint = _Hint(self, self.gen, row)
+        return out

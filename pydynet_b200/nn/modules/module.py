@@ -7,6 +7,7 @@ from ..parameter import Parameter
 from ...autograd import set_grad_enabled
 from ...core import Tensor
 from ...cuda import Device, current_device
+from .. import _plans
 
 
 class Module:
@@ -17,15 +18,26 @@ class Module:
         self._parameters = OrderedDict()
 
     def __call__(self, *x):
+        # eval-mode calls on a cuda device may be served by a fused inference plan (nn/_plans.py) whose results are those of
+        # forward(); anything a plan does not cover falls through to the eager forward like the reference (module.py:16-17)
+        plan = self.__dict__.get("_pdn_plan")
+        if plan is None:
+            plan = _plans.attach(self)
+        if plan is not False:
+            out = plan(x)
+            if out is not NotImplemented:
+                return out
         return self.forward(*x)
 
     def __setattr__(self, name: str, value) -> None:
         object.__setattr__(self, name, value)
         if isinstance(value, Parameter):
             self._parameters[name] = value
+            _plans.note_structure_change()
         elif isinstance(value, Module):
             for key, p in value._parameters.items():
                 self._parameters[name + "." + key] = p
+            _plans.note_structure_change()
 
     def _children(self):
         return [(k, v) for k, v in self.__dict__.items() if isinstance(v, Module)]

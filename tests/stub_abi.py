@@ -47,6 +47,8 @@ def install():
             C.memset(args[0], 0, int(args[2]))
         elif name in ("pdn_event_create", "pdn_gemm_prepack", "pdn_graph_end"):
             args[-1]._obj.value = 1234
+        elif name == "pdn_decoder_create":
+            args[0]._obj.value = 4321
         vals = [_norm(a) for a in args]
         if name == "pdn_memcpy_h2d":
             vals[1] = "host"
@@ -98,6 +100,25 @@ def workload(name):
             A.zero_grad()
             B.zero_grad()
             pdn.matmul(A, B).sum().backward()
+
+        return step
+    if name in ("llama", "llama_ref", "llama_ref_b1"):
+        # one greedy decode step of a Llama-style decoder at batch 48 through Module.__call__ -> inference plan (nn/_plans.py);
+        # llama_ref: the reference's OWN llm/llama/model.py exec'd unchanged on top of pydynet_b200
+        B = 1 if name.endswith("_b1") else 48
+        if name.startswith("llama_ref"):
+            from baseline import refload
+            Llama = refload.dropin_model("llm/llama/model.py")["Llama"]
+        else:
+            from workloads.llama import Llama
+        net = Llama(512, 128, 4, 256, 64, B, 3, np.float32).to(dev)
+        net.eval()
+        gen = net.generate(np.random.randint(1, 512, (B, 4)), 64)
+        pdn.autograd.set_grad_enabled(False)
+        next(gen)  # prefill
+
+        def step():
+            return next(gen)
 
         return step
     raise SystemExit(f"unknown workload {name}")

@@ -1,7 +1,14 @@
-"""GPU parity of the batched Llama inference fast path (fused QKV / gate|up GEMMs on cached weight planes, residual adds
-in the GEMM epilogue, CUDA-graph replay of the decode step) against the CPU oracle (oracle/pdn_oracle.py, itself pinned to
-the reference by tests/test_oracle.py): greedy token ids exact wherever the oracle's top-1/top-2 logit margin is above the
-fp32 noise floor, prefill logits within 1e-4 normwise. Also: fast path == generic path == no-graph path."""
+"""GPU parity of Llama inference THROUGH THE UNCHANGED MODULE SURFACE: the reference's own llm/llama/model.py (exec'd with
+``pydynet`` aliased to ``pydynet_b200``; from /root/reference or the staged copy under baseline/_ref) and the repo's stand-in
+definition are served by the inference plan (nn/_plans.py: fused blocks on the tcgen05 GEMM path, CUDA-graph replay of the decode
+step, the persistent decode kernel for rows < 32) and compared with the CPU oracle (oracle/pdn_oracle.py, pinned to the reference
+by tests/test_oracle.py):
+
+* prefill logits within 1e-4 normwise;
+* greedy token ids under the margin rule of SURVEY.md §8(c): EXACT up to the first step where the oracle's own top-1/top-2
+  logit margin is below 1e-4 (oracle.check_greedy_tokens) — no quota of matching sequences;
+* plan == eager (plans disabled) under the same rule, graph replay == eager launches of the same step bit for bit.
+"""
 import os
 
 import numpy as np
@@ -10,9 +17,16 @@ import pytest
 pytestmark = pytest.mark.gpu
 
 
-def _build(B, cfg, params):
-    import pydynet_b200 as pdn
+def _model_classes():
+    from baseline import refload
     from workloads.llama import Llama
+    out = [("standin", Llama)]
+    if refload.available():
+        out.append(("reference_file", refload.dropin_model("llm/llama/model.py")["Llama"]))
+    return out
+
+
+def _build(Llama, B, cfg, params):
     V, D, H, FF, S, L = cfg
     net = Llama(V, D, H, FF, S, B, L, np.float32).to("cuda:0")
     for name, p in net._parameters.items():
@@ -23,49 +37,96 @@ def _build(B, cfg, params):
     return net
 
 
-def _generate(net, prompt, total):
+def _generate(net, prompt, total, host_prompt=False):
     import pydynet_b200 as pdn
     for layer in net.layers:
         with layer.attention.cache_k.device:
             layer.attention.cache_k.data[...] = 0
             layer.attention.cache_v.data[...] = 0
     with pdn.no_grad():
-        return np.concatenate([t.numpy() for t in net.generate(pdn.Tensor(prompt, device="cuda:0"), total)], axis=1)
+        ids = prompt if host_prompt else pdn.Tensor(prompt, device="cuda:0")
+        return np.concatenate([t.numpy() for t in net.generate(ids, total)], axis=1)
 
 
-def test_batched_fast_path_matches_oracle_and_generic_path():
+def test_reference_file_is_available_on_this_box():
+    """The drop-in claim is about the reference's own file: the staged copy must have travelled with the snapshot."""
+    from baseline import refload
+    assert refload.available(), "neither /root/reference nor baseline/_ref is present (run __graft_entry__.build() before gpurun)"
+
+
+@pytest.mark.parametrize("B,total", [(48, 40), (1, 40), (3, 24)])
+@pytest.mark.parametrize("which", ["standin", "reference_file"])
+def test_plan_matches_oracle_and_eager(which, B, total):
     import pydynet_b200 as pdn
+    from pydynet_b200.nn import _plans
     from oracle import pdn_oracle as O
-    cfg = (V, D, H, FF, S, L) = (512, 96, 4, 256, 64, 3)
-    B, total = 48, 40
+    classes = dict(_model_classes())
+    if which not in classes:
+        pytest.skip("reference tree not present on this box")
+    # rows < 32 run the persistent decode kernel, which is instantiated for head sizes 32 / 48 / 64 (the reference's is 48)
+    cfg = (V, D, H, FF, S, L) = (512, 96, 4, 256, 64, 3) if B >= 32 else (512, 96, 2, 256, 64, 3)
     params = O.synthetic_llama_params(V, D, H, FF, L, seed=3, std=0.08)
     rng = np.random.default_rng(5)
     prompt = rng.integers(1, V, (B, 4))
-    ref = O.LlamaOracle(params, H, S, B, L)
-    ref_logits = ref.step(prompt, 0)
-    ref = O.LlamaOracle(params, H, S, B, L)
-    ref_toks = ref.generate(prompt, total)
+    ref_logits = O.LlamaOracle(params, H, S, B, L).step(prompt, 0)
+    ref_toks, margins = O.LlamaOracle(params, H, S, B, L).generate_with_margins(prompt, total)
     try:
-        net = _build(B, cfg, params)
+        net = _build(classes[which], B, cfg, params)
         with pdn.no_grad():
             logits = net(pdn.Tensor(prompt, device="cuda:0"), 0).numpy()
         err = np.linalg.norm(logits - ref_logits) / np.linalg.norm(ref_logits)
         assert err < 1e-4, err
         toks = _generate(net, prompt, total)
-        os.environ["PDN_LLAMA_FAST"] = "0"
-        toks_generic = _generate(net, prompt, total)
-        os.environ["PDN_LLAMA_FAST"] = "1"
+        toks_host = _generate(net, prompt, total, host_prompt=True)  # the reference's infer.py passes a NumPy prompt
+        plan = net.__dict__.get("_pdn_plan")
+        assert plan and not plan.dead and plan.verified, "the inference plan did not serve this model"
         os.environ["PDN_DECODE_GRAPH"] = "0"
         toks_nograph = _generate(net, prompt, total)
+        os.environ.pop("PDN_DECODE_GRAPH")
+        _plans.ENABLED = False
+        toks_eager = _generate(net, prompt, total)
     finally:
-        os.environ.pop("PDN_LLAMA_FAST", None)
+        _plans.ENABLED = True
         os.environ.pop("PDN_DECODE_GRAPH", None)
         pdn.autograd.set_grad_enabled(True)
-    np.testing.assert_array_equal(toks, toks_nograph)  # graph replay == eager launches, bit for bit
-    # a sequence may legitimately diverge after a near-tie argmax (different but equally accurate summation order);
-    # require exact equality of every sequence up to its first near-tie in the oracle, and of >= 90 % of all sequences overall
-    same = (toks == ref_toks).all(axis=1)
-    assert same.mean() >= 0.9, f"only {same.mean():.2%} of the sequences match the oracle exactly"
-    same_g = (toks_generic == ref_toks).all(axis=1)
-    assert same_g.mean() >= 0.9
-    assert (toks[:, 0] == ref_toks[:, 0]).all()
+    np.testing.assert_array_equal(toks, toks_nograph)  # graph replay == eager launches of the same kernels, bit for bit
+    np.testing.assert_array_equal(toks, toks_host)
+    O.check_greedy_tokens(toks, ref_toks, margins)
+    O.check_greedy_tokens(toks_eager, ref_toks, margins)
+
+
+def test_plan_survives_weight_update_and_held_logits():
+    """In-place weight writes re-pack / re-record; logits tensors kept by the caller are never overwritten by later steps."""
+    import pydynet_b200 as pdn
+    from oracle import pdn_oracle as O
+    from workloads.llama import Llama
+    cfg = (V, D, H, FF, S, L) = (256, 64, 4, 128, 48, 2)
+    B = 40
+    params = O.synthetic_llama_params(V, D, H, FF, L, seed=11, std=0.08)
+    prompt = np.random.default_rng(2).integers(1, V, (B, 4))
+    try:
+        net = _build(Llama, B, cfg, params)
+        _generate(net, prompt, 16)
+        # (1) keep every step's logits: each must still equal what it was when produced
+        kept, snaps = [], []
+        with pdn.no_grad():
+            ids = pdn.Tensor(prompt, device="cuda:0")
+            lg = net(ids, 0)
+            for pos in range(4, 14):
+                nxt = lg[:, -1, :].argmax(-1, True)
+                lg = net(nxt, pos + 1)
+                kept.append(lg)
+                snaps.append(lg.numpy())
+        for t, s in zip(kept, snaps):
+            np.testing.assert_array_equal(t.numpy(), s)
+        # (2) new weights in place: the plan must serve the NEW model
+        params2 = O.synthetic_llama_params(V, D, H, FF, L, seed=12, std=0.08)
+        for name, p in net._parameters.items():
+            if name in params2:
+                with p.device:
+                    p.data[...] = params2[name]
+        toks = _generate(net, prompt, 20)
+        ref_toks, margins = O.LlamaOracle(params2, H, S, B, L).generate_with_margins(prompt, 20)
+        O.check_greedy_tokens(toks, ref_toks, margins)
+    finally:
+        pdn.autograd.set_grad_enabled(True)

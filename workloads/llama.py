@@ -3,8 +3,10 @@ RoPE, per-layer KV cache, SwiGLU feed-forward, greedy ``generate``.
 
 Results follow the reference exactly — including ``generate``'s position bookkeeping: decode step i feeds the token of
 position L+i-1 with start_pos = L+i (model.py:258-267), so one zero KV slot sits between prompt and generated tokens; and
-``lm_head`` having a bias (model.py:190).  On a cuda device the per-token work runs as fused kernels (RoPE + cache append,
-attention over the strided cache view, SwiGLU, RMSNorm, skinny GEMMs) instead of ~490 eager nodes per token.
+``lm_head`` having a bias (model.py:190).  This file is a plain model definition with the reference's structure and parameter
+names: on a cuda device in eval mode ``Module.__call__`` serves it — exactly like the reference's own unchanged model.py —
+through the inference plan of pydynet_b200/nn/_plans.py (fused blocks, CUDA-graph / persistent-kernel decode); nothing
+model-specific lives here.  It is the stand-in for the reference's file where that is not available.
 """
 import math
 import os
@@ -70,12 +72,6 @@ class FeedForward(nn.Module):
             return self.down(_fused.swiglu(self.gate(x), self.up(x)))
         return self.down(F.silu(self.gate(x)) * self.up(x))
 
-    def hidden_fast(self, x):
-        """Inference: gate|up as one GEMM on concatenated weight planes, then SwiGLU; the down projection is applied by the
-        block together with the residual add."""
-        gu = _fused.linear_cat(self, "_pdn_gate_up", x, (self.gate.weight, self.up.weight))
-        return _fused.swiglu_rows_planes(gu, self.up_dim)
-
 
 class Attention(nn.Module):
 
@@ -96,10 +92,6 @@ class Attention(nn.Module):
         H, D = self.n_heads, self.head_dim
         xq, xk, xv = (proj(x).reshape(B, L, H, D) for proj in (self.Q, self.K, self.V))
         scale = 1.0 / math.sqrt(D)
-        if not self._train and not pdn.autograd.is_grad_enable() and _fused.usable(xq, xk, xv, op="llama_cached_attention"):
-            self._rope_tables = self._rope_src()
-            out = _fused.llama_cached_attention(self, xq, xk, xv, start_pos, mask, scale)
-            return self.O(out)
         xq, xk = apply_rotary_emb(xq, xk, freqs_cos, freqs_sin)
         if not self._train:
             self.cache_k[:B, start_pos:start_pos + L] = xk
@@ -126,35 +118,9 @@ class TransformerBlock(nn.Module):
         self.input_norm = nn.RMSNorm(dim, dtype=dtype)
         self.post_attn_norm = nn.RMSNorm(dim, dtype=dtype)
 
-    def _fast_ok(self, x, rows) -> bool:
-        """Inference fast path applies: eval mode, no tape, fp32 cuda tensors, at least 32 token rows (below that the
-        skinny FFMA GEMM of the generic path is the better kernel)."""
-        return (os.environ.get("PDN_LLAMA_FAST", "1") != "0" and not self._train and not pdn.autograd.is_grad_enable()
-                and rows >= 32 and _fused.usable(x, self.attention.Q.weight, op="llama_cached_attention"))
-
     def forward(self, x, start_pos, mask, freqs_cos, freqs_sin):
-        if self._fast_ok(x, x.shape[0] * x.shape[1]):
-            return self._forward_inference(x, start_pos, mask)
         z = x + self.attention(self.input_norm(x), start_pos, mask, freqs_cos, freqs_sin)
         return z + self.ffn(self.post_attn_norm(z))
-
-    def _forward_inference(self, x, start_pos, mask):
-        """Same block (reference llm/llama/model.py:142-150) with 9 launches instead of 22: RMSNorm emitting GEMM operand
-        planes, fused QKV GEMM, RoPE + cache append, cached attention emitting operand planes, O-projection accumulating
-        onto the residual stream in its epilogue, RMSNorm -> planes, fused gate|up GEMM, SwiGLU -> planes, down-projection
-        accumulating onto the residual stream. ``x``'s buffer becomes the block output."""
-        att = self.attention
-        B, L, dim = x.shape
-        H, D = att.n_heads, att.head_dim
-        norm_in, norm_post = self.input_norm, self.post_attn_norm
-        qkv = _fused.linear_cat(att, "_pdn_qkv", _fused.rmsnorm_planes(x, norm_in.weight, norm_in.eps), (att.Q.weight, att.K.weight, att.V.weight))
-        with x.device:
-            q3 = qkv.data.reshape(B, L, 3, H, D)
-        att._rope_tables = att._rope_src()
-        parts = [pdn.Tensor(q3[:, :, j], dtype=np.float32, copy=None, device=x.device) for j in range(3)]
-        o = _fused.llama_cached_attention(att, parts[0], parts[1], parts[2], start_pos, mask, 1.0 / math.sqrt(D), ld=3 * dim, as_planes=True)
-        z = _fused.linear_residual_(o, att.O.weight, x)
-        return _fused.linear_residual_(self.ffn.hidden_fast(_fused.rmsnorm_planes(z, norm_post.weight, norm_post.eps)), self.ffn.down.weight, z)
 
 
 class Llama(nn.Module):
@@ -170,25 +136,20 @@ class Llama(nn.Module):
         self.freqs_sin = nn.Parameter(sin, False)
         self.layers = nn.ModuleList(
             [TransformerBlock(embed_dim, n_heads, ffn_dim, max_seq_len, max_batch_size, dtype) for _ in range(n_layers)])
-        for layer in self.layers:  # the fused inference path reads the full RoPE tables by position
-            layer.attention._rope_src = lambda: (self.freqs_cos.data, self.freqs_sin.data)
         self.norm = nn.RMSNorm(embed_dim, dtype=dtype)
         self.lm_head = nn.Linear(embed_dim, vocab_size, dtype=dtype)
 
-    def _forward_hidden(self, input_ids, start_pos, final_norm=True):
+    def _forward_hidden(self, input_ids, start_pos):
         L = input_ids.shape[-1]
         h = self.tok_embedding(input_ids)
-        if isinstance(start_pos, _fused.DevicePos):  # graph-recorded decode step: the fused kernels index the RoPE tables
-            cos = sin = None
-        else:
-            cos, sin = self.freqs_cos[start_pos:start_pos + L], self.freqs_sin[start_pos:start_pos + L]
+        cos, sin = self.freqs_cos[start_pos:start_pos + L], self.freqs_sin[start_pos:start_pos + L]
         mask = None
         if L > 1:  # causal mask over [cached positions | new positions], built on the host like the reference
             mask = np.concatenate([np.zeros((L, start_pos)), np.triu(np.full((L, L), float("-inf")), k=1)], axis=1)
             mask = pdn.Tensor(mask, device=h.device, dtype=h.dtype)
         for layer in self.layers:
             h = layer(h, start_pos, mask, cos, sin)
-        return self.norm(h) if final_norm else h
+        return self.norm(h)
 
     def forward_logits(self, input_ids, start_pos: int = 0):
         return self.lm_head(self._forward_hidden(input_ids, start_pos))
@@ -216,59 +177,13 @@ class Llama(nn.Module):
         h = self._forward_hidden(input_ids, start_pos)
         return self.lm_head(h if h.shape[1] == 1 else h[:, [-1], :])  # logits of the last position, [B, 1, V]
 
-    def _next_ids(self, input_ids, start_pos):
-        """Greedy next token ids [B, 1] = argmax of the last position's logits (reference model.py:266-268). Inference fast
-        path: final RMSNorm emitted as GEMM operand planes and the vocabulary argmax taken in the lm_head GEMM epilogue, so
-        the [B, 32000] logits never reach HBM."""
-        B = input_ids.shape[0]
-        if self.layers[0]._fast_ok(self.norm.weight, input_ids.size) and os.environ.get("PDN_LM_HEAD_ARGMAX", "1") != "0":
-            h = self._forward_hidden(input_ids, start_pos, final_norm=False)
-            last = h if h.shape[1] == 1 else h[:, -1, :]
-            pl = _fused.rmsnorm_planes(last, self.norm.weight, self.norm.eps)
-            return _fused.lm_head_argmax(pl, self.lm_head.weight, self.lm_head.bias)
-        return self(input_ids, start_pos)[:, -1, :].argmax(-1, True)
-
-    def _graph_decode_ok(self, ids) -> bool:
-        return (os.environ.get("PDN_DECODE_GRAPH", "1") != "0" and ids.device.is_cuda and not self._train
-                and not pdn.autograd.is_grad_enable() and self.freqs_cos.dtype == np.float32
-                and _fused.usable(self.freqs_cos, op="llama_cached_attention"))
-
     def generate(self, input_ids, max_new_tokens: int):
-        """Greedy decoding; yields one (B, 1) id tensor per step until the total length reaches max_new_tokens
-        (reference llm/llama/model.py:258-269, including its position bookkeeping: decode step i feeds the token produced
-        at step i-1 with start_pos = L + i).
-
-        On a cuda device the decode step is recorded ONCE as a CUDA graph (position and current ids live in device
-        memory) and replayed for every further token: one graph launch per token instead of ~130 kernel launches driven
-        from Python."""
+        """Greedy decoding; yields one (B, 1) id tensor per step until the total length reaches max_new_tokens (reference
+        llm/llama/model.py:258-269, including its position bookkeeping: decode step i feeds the token produced at step i-1 with
+        start_pos = L + i)."""
         _, L = input_ids.shape
-        next_id, graph, ids_buf, pos = None, None, None, None
-        try:
-            for i, curr_pos in enumerate(range(L, max_new_tokens)):
-                if i == 0:  # prefill
-                    next_id = self._next_ids(input_ids, 0)
-                elif i == 1 or not self._graph_decode_ok(next_id):  # eager decode step (also warms caches for the capture)
-                    next_id = self._next_ids(next_id, curr_pos)
-                else:
-                    assert curr_pos + 1 <= self.max_seq_len, "generation runs past the KV cache"
-                    if graph is None:
-                        with next_id.device:
-                            ids_buf = pdn.Tensor(next_id.data, dtype=np.int64, device=next_id.device, copy=True)
-                            pos = _fused.DevicePos(pdn.Tensor(np.array([curr_pos], dtype=np.int64), device=next_id.device))
-                            graph = pdn.cuda.Graph()
-                            graph.begin()
-                            try:
-                                nid = self._next_ids(ids_buf, pos)
-                                ids_buf[...] = nid  # feeds the next replay
-                                pos.tensor += 1
-                            finally:
-                                graph.end()
-                            del nid
-                    with next_id.device:
-                        graph.launch()
-                        next_id = pdn.Tensor(ids_buf.data, dtype=np.int64, device=ids_buf.device, copy=True)
-                yield next_id
-        finally:
-            if graph is not None:
-                with ids_buf.device:
-                    graph.destroy()
+        next_id = None
+        for i, curr_pos in enumerate(range(L, max_new_tokens)):
+            logits = self(input_ids, 0) if i == 0 else self(next_id, curr_pos)
+            next_id = logits[:, -1, :].argmax(-1, True)
+            yield next_id
