@@ -55,6 +55,9 @@ class _Node:
         self.name = name
 
 
+_LEAF_READY_HOOK = [None]  # callable(leaf | None) installed by distributed.DataParallel(overlap=True); None = sweep finished
+
+
 class Tensor:
     """Differentiable array (reference tensor.py:30-413)."""
     _pdn_hint = None  # set on logits produced by an inference plan (nn/_plans.py): memoised argmax over the vocabulary
@@ -99,7 +102,12 @@ class Tensor:
 
     @grad.setter
     def grad(self, value):
-        self._grad = value
+        if self._pinned_grad and self._grad is not None and value is not None and value is not self._grad:
+            # the storage is a view into a flat bucket (fused Adam / data-parallel all-reduce read THAT memory): write through
+            with self.device:
+                self._grad[...] = value
+        else:
+            self._grad = value
         self._grad_stale = False
 
     @property
@@ -297,10 +305,22 @@ class Tensor:
                         seen.add(id(i))
                         stack.append(i)
             order.sort(key=lambda t: -t._node.seq)
+            # data-parallel overlap (distributed.DataParallel): a leaf whose gradient lives in the flat bucket is reported the moment
+            # its LAST consumer in this sweep has run, so that the all-reduce of a finished bucket range can start on the side
+            # stream while the rest of the backward pass is still computing
+            hook, uses = _LEAF_READY_HOOK[0], None
+            if hook is not None:
+                uses = {}
+                for t in order:
+                    for i in t._node.inputs:
+                        if i._pinned_grad and i._node is None and i.requires_grad:
+                            uses[id(i)] = uses.get(id(i), 0) + 1
             pending = {id(self): [seed, True]}
             for t in order:
                 slot = pending.pop(id(t), None)
                 node = t._node
+                if uses:
+                    leaves = [i for i in node.inputs if id(i) in uses]
                 if slot is not None:
                     gout = slot[0]
                     if retain_graph:
@@ -322,9 +342,16 @@ class Tensor:
                         else:
                             s[0] = s[0] + g
                             s[1] = True
+                if uses:
+                    for i in leaves:
+                        uses[id(i)] -= 1
+                        if uses[id(i)] == 0:
+                            hook(i)
                 if not retain_graph:
                     t._node = None
                     t._freed = True
+            if hook is not None:
+                hook(None)  # sweep finished
 
     # kept for API compatibility with user code that wires edges by hand
     def _build_edge(self, node: "Tensor"):

@@ -18,10 +18,15 @@ struct NcclApi {
   ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
   ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
   ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+  ncclResult_t (*CommSplit)(ncclComm_t, int, int, ncclComm_t*, void*) = nullptr;  // optional (NCCL >= 2.18)
+  ncclResult_t (*CommCount)(const ncclComm_t, int*) = nullptr;
+  ncclResult_t (*CommUserRank)(const ncclComm_t, int*) = nullptr;
   const char* (*GetErrorString)(ncclResult_t) = nullptr;
 };
 static NcclApi     g_nccl;
-static ncclComm_t  g_comm = nullptr;
+static ncclComm_t  g_comm = nullptr;         // compute stream: small inline reductions (batch statistics of coupled norms)
+static ncclComm_t  g_comm_bucket = nullptr;  // side stream: gradient-bucket all-reduces (its own communicator, so the two streams
+                                             // never serialise on one NCCL work queue while backward is still running)
 static int         g_world = 1, g_rank = 0;
 static cudaEvent_t g_ev_compute = nullptr, g_ev_comm = nullptr;
 
@@ -46,6 +51,9 @@ static int load_nccl() {
   PDN_SYM(CommDestroy, "ncclCommDestroy")
   PDN_SYM(GetErrorString, "ncclGetErrorString")
 #undef PDN_SYM
+  *(void**)(&g_nccl.CommSplit) = dlsym(g_nccl.handle, "ncclCommSplit");
+  *(void**)(&g_nccl.CommCount) = dlsym(g_nccl.handle, "ncclCommCount");
+  *(void**)(&g_nccl.CommUserRank) = dlsym(g_nccl.handle, "ncclCommUserRank");
   return 0;
 }
 
@@ -81,6 +89,11 @@ int pdn_nccl_init(int rank, int world, const char* id128) {
   ncclUniqueId id;
   memcpy(&id, id128, 128);
   PDN_NCCL(g_nccl.CommInitRank(&g_comm, world, id, rank));
+  g_comm_bucket = g_comm;
+  if (g_nccl.CommSplit && world > 1 && !getenv("PDN_NCCL_ONE_COMM")) {
+    ncclComm_t dup = nullptr;
+    if (g_nccl.CommSplit(g_comm, 0, rank, &dup, nullptr) == ncclSuccess && dup) g_comm_bucket = dup;
+  }
   g_world = world;
   g_rank = rank;
   PDN_CUDA(cudaEventCreateWithFlags(&g_ev_compute, cudaEventDisableTiming));
@@ -91,6 +104,10 @@ int pdn_nccl_init(int rank, int world, const char* id128) {
 int pdn_nccl_world(int* rank, int* world) {
   *rank = g_rank;
   *world = g_comm ? g_world : 1;
+  if (g_comm && g_nccl.CommCount && g_nccl.CommUserRank) {  // what the live communicator itself reports
+    PDN_NCCL(g_nccl.CommCount(g_comm_bucket, world));
+    PDN_NCCL(g_nccl.CommUserRank(g_comm_bucket, rank));
+  }
   return 0;
 }
 
@@ -100,7 +117,7 @@ int pdn_allreduce_sum_f32(float* buf, int64_t n) {
   // comm stream starts after everything queued on the compute stream so far (the backward pass that filled the bucket)
   PDN_CUDA(cudaEventRecord(g_ev_compute, stream()));
   PDN_CUDA(cudaStreamWaitEvent(comm_stream(), g_ev_compute, 0));
-  PDN_NCCL(g_nccl.AllReduce(buf, buf, (size_t)n, ncclFloat32, ncclSum, g_comm, comm_stream()));
+  PDN_NCCL(g_nccl.AllReduce(buf, buf, (size_t)n, ncclFloat32, ncclSum, g_comm_bucket, comm_stream()));
   PDN_CUDA(cudaEventRecord(g_ev_comm, comm_stream()));
   return 0;
 }
@@ -122,8 +139,9 @@ int pdn_nccl_destroy(void) {
   if (g_comm) {
     cudaStreamSynchronize(comm_stream());
     cudaStreamSynchronize(stream());
+    if (g_comm_bucket && g_comm_bucket != g_comm) g_nccl.CommDestroy(g_comm_bucket);
     g_nccl.CommDestroy(g_comm);
-    g_comm = nullptr;
+    g_comm = g_comm_bucket = nullptr;
     g_world = 1;
     g_rank = 0;
   }

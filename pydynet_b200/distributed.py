@@ -45,7 +45,9 @@ def sync_stats_enabled() -> bool:
 
 
 def _exchange_id(rank, world, make_id) -> bytes:
-    """Rank 0 creates the 128-byte NCCL id; everybody else receives it (torch.distributed if it is up, else a file)."""
+    """Rank 0 creates the 128-byte NCCL id; everybody else receives it: through torch.distributed when a process group is up,
+    else over a one-shot TCP rendezvous on MASTER_ADDR:(MASTER_PORT + 23) (``PDN_ID_PORT`` overrides the port). Nothing is left
+    behind on disk, so a second job on the same host and port can never pick up a previous job's id."""
     try:
         import torch.distributed as dist
         if dist.is_available() and dist.is_initialized():
@@ -54,21 +56,38 @@ def _exchange_id(rank, world, make_id) -> bytes:
             return box[0]
     except ImportError:
         pass
-    tag = f"{os.environ.get('MASTER_PORT', '0')}_{os.environ.get('TORCHELASTIC_RUN_ID', os.environ.get('PDN_JOB_ID', 'job'))}"
-    path = os.path.join(os.environ.get("PDN_STORE_DIR", "/tmp"), f"pdn_nccl_id_{tag}")
+    import socket
+    addr = os.environ.get("MASTER_ADDR", "127.0.0.1")
+    port = int(os.environ.get("PDN_ID_PORT", int(os.environ.get("MASTER_PORT", "29500")) + 23))
     if rank == 0:
         data = make_id()
-        with open(path + ".tmp", "wb") as f:
-            f.write(data)
-        os.replace(path + ".tmp", path)
+        with socket.socket(socket.AF_INET, socket.SOCK_STREAM) as srv:
+            srv.setsockopt(socket.SOL_SOCKET, socket.SO_REUSEADDR, 1)
+            srv.bind((addr, port))
+            srv.listen(world)
+            srv.settimeout(120)
+            for _ in range(world - 1):
+                conn, _peer = srv.accept()
+                with conn:
+                    conn.sendall(data)
         return data
     deadline = time.time() + 120
-    while not os.path.exists(path):
+    while True:
+        try:
+            with socket.create_connection((addr, port), timeout=5) as c:
+                data = b""
+                while len(data) < 128:
+                    chunk = c.recv(128 - len(data))
+                    if not chunk:
+                        break
+                    data += chunk
+            if len(data) == 128:
+                return data
+        except OSError:
+            pass
         if time.time() > deadline:
-            raise RuntimeError(f"timed out waiting for the NCCL id at {path}")
-        time.sleep(0.01)
-    with open(path, "rb") as f:
-        return f.read()
+            raise RuntimeError(f"timed out waiting for the NCCL id from rank 0 at {addr}:{port}")
+        time.sleep(0.05)
 
 
 def init_process_group(backend: str = "nccl", rank: int | None = None, world_size: int | None = None) -> None:
@@ -154,27 +173,151 @@ class DataParallel:
 
         ddp = DataParallel(net, Adam(net.parameters()))
         loss = loss_fn(net(shard(X)), shard(y)); ddp.zero_grad(); loss.backward(); ddp.step()
-    """
 
-    def __init__(self, module, optimizer):
+    With the flat Adam state (cuda, fp32) the gradient bucket is cut into ``buckets`` contiguous ranges of the flat gradient buffer
+    and, with ``overlap=True``, the backward sweep reports every parameter whose gradient is final (core/tensor.py,
+    ``_LEAF_READY_HOOK``): as soon as all parameters of a range are final its ``ncclAllReduce`` is queued on the side stream
+    (ordered after the compute stream by an event) while the rest of the backward pass keeps computing; ``step()`` queues the
+    ranges that are left (parameters without a gradient this step) and makes the compute stream wait for the side stream before
+    the fused Adam kernel. One backward per step (gradient accumulation across several backward calls needs ``overlap=False``).
+    Construction makes the replicas identical: parameters, Adam moments and registered buffers of rank 0 reach every rank."""
+
+    def __init__(self, module, optimizer, buckets: int = 4, overlap: bool = True, broadcast: bool = True):
         self.module, self.optimizer = module, optimizer
         self.world = _S["world"]
         self._flat = getattr(optimizer, "_flat", None)
+        self.overlap = bool(overlap and self._flat is not None and self.world > 1 and _S["backend"] == "nccl")
+        self._ranges, self._owner, self._left, self._launched, self._armed = [], {}, [], [], False
+        self.launch_log = []  # (bucket index, number of tape sweeps finished when it was queued): evidence of the overlap
+        self._sweeps = 0
         if self._flat is not None:
             optimizer.grad_scale = 1.0 / self.world  # folded into the fused Adam kernel
+            self._make_buckets(max(1, int(buckets)))
+        if broadcast and self.world > 1:
+            self._broadcast_state()
+        self._arm()
+
+    # -------------------------------------------------------------------------------------------------- set-up
+    def _make_buckets(self, n):
+        fl = self._flat
+        sizes = [int(o2 - o1) for o1, o2 in zip(fl.offs, fl.offs[1:] + [fl.total])]
+        target, ranges, start, acc, members = fl.total / n, [], 0, 0, []
+        for i, (o, sz) in enumerate(zip(fl.offs, sizes)):
+            members.append(i)
+            acc += sz
+            if acc >= target and len(ranges) < n - 1:
+                ranges.append((start, o + sz - start, members))
+                start, acc, members = o + sz, 0, []
+        if members:
+            ranges.append((start, fl.total - start, members))
+        self._ranges = ranges
+        self._owner = {id(fl.params[i]): b for b, (_, _, mem) in enumerate(ranges) for i in mem}
+
+    def _broadcast_state(self):
+        """Rank 0's parameters / Adam moments / running statistics everywhere: the other ranks zero theirs and a sum all-reduce
+        delivers rank 0's values exactly (x + 0 == x)."""
+        arrays = []
+        if self._flat is not None:
+            arrays += [self._flat.flat_p, self._flat.flat_m, self._flat.flat_v]
+        else:
+            arrays += [p.data for p in self.optimizer.params]
+        for m in self._modules(self.module):
+            for nm in ("running_mean", "running_var"):
+                t = getattr(m, nm, None)
+                if isinstance(t, Tensor):
+                    arrays.append(t.data)
+        for a in arrays:
+            dev = self._flat.device if self._flat is not None else None
+            if isinstance(a, np.ndarray):
+                if _S["rank"] != 0:
+                    a[...] = 0
+                all_reduce_sum_(a)
+            elif a.dtype == np.float32 and a.is_contiguous:
+                with (dev or self.optimizer.params[0].device):
+                    if _S["rank"] != 0:
+                        a.fill(0.0)
+                    all_reduce_sum_(a)
+
+    @staticmethod
+    def _modules(root):
+        out, stack = [], [root]
+        while stack:
+            m = stack.pop()
+            out.append(m)
+            for v in m.__dict__.values():
+                if hasattr(v, "_parameters") and hasattr(v, "forward"):
+                    stack.append(v)
+                elif isinstance(v, (list, tuple)):
+                    stack.extend(x for x in v if hasattr(x, "_parameters") and hasattr(x, "forward"))
+        return out
 
     def __call__(self, *a):
         return self.module(*a)
 
+    # -------------------------------------------------------------------------------------------------- per step
     def zero_grad(self):
         self.optimizer.zero_grad()
+
+    def _arm(self):
+        """The NEXT backward sweep reports finished parameters (armed at construction and after every ``step()``, so the usual loop
+        ``opt.zero_grad(); loss.backward(); ddp.step()`` overlaps without further calls)."""
+        if self.overlap:
+            self._flat.repin()
+            self._left = [len(mem) for (_, _, mem) in self._ranges]
+            self._launched = [False] * len(self._ranges)
+            self._sweeps = 0
+            self._armed = True
+            from .core import tensor as _t
+            _t._LEAF_READY_HOOK[0] = self._leaf_ready
+
+    def _leaf_ready(self, leaf):
+        if leaf is None:  # a backward sweep finished
+            self._sweeps += 1
+            from .core import tensor as _t
+            _t._LEAF_READY_HOOK[0] = None  # one sweep per step feeds the early launches
+            return
+        b = self._owner.get(id(leaf))
+        if b is None or not self._armed:
+            return
+        self._left[b] -= 1
+        if self._left[b] == 0:
+            self._launch(b)
+
+    def _launch(self, b):
+        from .backend import lib
+        fl = self._flat
+        off, n, mem = self._ranges[b]
+        with fl.device:
+            for i in mem:  # a parameter of this range that received no gradient holds stale values: its gradient is zero
+                p = fl.params[i]
+                if p._grad_stale:
+                    p._grad.fill(0.0)
+                    p._grad_stale = False
+            fl.flat_g.buf.version += 1
+            lib.call("pdn_allreduce_sum_f32", fl.flat_g.ptr + 4 * off, n)  # side stream, after what the compute stream queued so far
+        self._launched[b] = True
+        if len(self.launch_log) < 64:
+            self.launch_log.append((b, self._sweeps))
 
     def sync_gradients(self):
         if self.world == 1:
             return
         if self._flat is not None:
             from .backend import lib
+            if self.overlap and self._armed:
+                if self._sweeps > 1:
+                    raise RuntimeError("DataParallel(overlap=True) supports one backward per step; use overlap=False to accumulate")
+                for b in range(len(self._ranges)):
+                    if not self._launched[b]:
+                        self._launch(b)
+                self._armed = False
+                from .core import tensor as _t
+                _t._LEAF_READY_HOOK[0] = None
+                with self._flat.device:
+                    lib.call("pdn_allreduce_wait")
+                return
             with self._flat.device:
+                self._flat.repin()
                 self._flat._settle_grads()
                 self._flat.flat_g.buf.version += 1
                 lib.call("pdn_allreduce_sum_f32", self._flat.flat_g.ptr, self._flat.total)  # comm stream, after backward
@@ -196,3 +339,4 @@ class DataParallel:
     def step(self):
         self.sync_gradients()
         self.optimizer.step()
+        self._arm()

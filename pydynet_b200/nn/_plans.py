@@ -63,7 +63,7 @@ def attach(module):
     plan = False
     if ENABLED:
         try:
-            plan = DecoderPlan.match(module) or False
+            plan = DecoderPlan.match(module) or AttentionPlan.match(module) or False
         except Exception:  # a structural probe must never break a forward
             plan = False
     object.__setattr__(module, "_pdn_plan", plan)
@@ -78,6 +78,64 @@ class _Hint:
         self.state, self.step_no, self.slot, self.sliced = state, step_no, slot, sliced
 
 
+class _LogitsCore:
+    """The lm_head input of one batched decode step (final-RMSNorm rows as GEMM operand planes) + where its argmax went.
+    The step itself ran the lm_head GEMM with the argmax epilogue only — greedy decoding (reference model.py:268) needs
+    nothing else and the [B, 32000] logits never reach HBM.  Anything that reads the logits' values materialises them here
+    with the same GEMM (+bias) from the kept planes; a recorded step that is about to overwrite the planes of a core that is
+    still alive materialises it first (``_DecodeState.release_slot``), so a caller can never observe later data."""
+    __slots__ = ("plan", "planes", "buf", "__weakref__")
+
+    def __init__(self, plan, planes):
+        self.plan, self.planes, self.buf = plan, planes, None
+
+    def materialise(self):
+        if self.buf is None:
+            plan, pl = self.plan, self.planes
+            m = plan.model
+            V = m.lm_head.weight.shape[1]
+            bias = m.lm_head.bias
+            with plan.device:
+                out = _empty((pl.M, V))
+                _call("pdn_gemm_prepacked_planes", pl.ptr, pl.M, pl.Kp, _fused._packed(m.lm_head.weight).handle, out.ptr, V,
+                      _c(bias.data).ptr if bias is not None else None, 0)
+            self.buf, self.planes = out, None
+        return self.buf
+
+
+class _LazyLogits(Tensor):
+    """``Tensor`` whose array ([B, 1, V], or the [B, V] slice of it) is produced on first access of ``.data``."""
+
+    @classmethod
+    def make(cls, core, shape, device, hint):
+        out = Tensor.__new__(cls)
+        out.device = device
+        out._core, out._shape, out._data = core, shape, None
+        out._grad = None
+        out._pinned_grad = out._grad_stale = False
+        out._node = None
+        out.requires_grad = False
+        out._pdn_hint = hint
+        return out
+
+    @property
+    def data(self):
+        d = self._data
+        if d is None:
+            d = self._data = self._core.materialise().reshape(self._shape)
+        return d
+
+    @data.setter
+    def data(self, value):
+        self._data = value
+        self._pdn_hint = None  # re-bound storage: the memo no longer describes this tensor
+
+    shape = property(lambda self: self._shape if self._data is None else self._data.shape)
+    ndim = property(lambda self: len(self.shape))
+    dtype = property(lambda self: F32 if self._data is None else self._data.dtype)
+    size = property(lambda self: int(np.prod(self.shape)))
+
+
 _ALL = slice(None)
 
 
@@ -87,9 +145,12 @@ def hint_getitem(x, key):
     h = x._pdn_hint
     if (not h.sliced and type(key) is tuple and len(key) == 3 and key[0] == _ALL and key[2] == _ALL
             and isinstance(key[1], (int, np.integer)) and key[1] in (-1, 0)):
+        hint = _Hint(h.state, h.step_no, h.slot, True)
+        if type(x) is _LazyLogits and x._data is None:
+            return _LazyLogits.make(x._core, (x._shape[0], x._shape[2]), x.device, hint)
         d = x.data
         out = _result(d._view((d.shape[0], d.shape[2]), (d.estrides[0], d.estrides[2])), x.device, (), None, "_get_slice")
-        out._pdn_hint = _Hint(h.state, h.step_no, h.slot, True)
+        out._pdn_hint = hint
         return out
     return None
 
@@ -104,8 +165,8 @@ def hint_argmax(x, axis, keepdims):
 
 # ------------------------------------------------------------------------------------------- decode state -----
 class _DecodeState:
-    """Per (plan, batch size) buffers of the recorded decode step: ping-pong ids / logits buffers, the device position,
-    the two CUDA graphs."""
+    """Per (plan, batch size) buffers of the recorded decode step: ping-pong ids buffers and lm_head operand planes, the
+    device position, the two CUDA graphs (one per slot)."""
 
     def __init__(self, plan, B):
         self.plan, self.B = plan, B
@@ -113,23 +174,33 @@ class _DecodeState:
         with dev:
             self.ids = [ndarray.empty((B, 1), I64) for _ in range(2)]
             self.pos = DevicePos(Tensor(np.zeros(1, dtype=np.int64), device=dev))
-        self.logits = [None, None]
+        self.planes = [None, None]  # lm_head operand planes written by the recorded step of each slot
+        self.live = [None, None]  # weakref to the _LogitsCore that still points at planes[slot]
         self.graphs = [None, None]
-        self.base_ref = [0, 0]
         self.slot = 0  # slot the NEXT step writes
         self.step_no = 0
         self.dev_pos = None  # value currently held by the device-side position (None: unknown)
         self.last_out = None  # (ids Tensor handed to the caller, version of its buffer, slot whose device copy equals it)
         self.steps_run = 0
-        self.recaptures = 0
-        self.copy_mode = False
 
     def destroy(self):
+        for slot in (0, 1):
+            self.release_slot(slot)
         for g in self.graphs:
             if g is not None:
                 with self.plan.device:
                     g.destroy()
         self.graphs = [None, None]
+
+    def release_slot(self, slot):
+        """The planes of ``slot`` are about to be overwritten (or freed): a logits tensor that still refers to them gets its
+        values now."""
+        ref = self.live[slot]
+        if ref is not None:
+            core = ref()
+            if core is not None and core.buf is None and core.planes is not None:
+                core.materialise()
+            self.live[slot] = None
 
     def take_ids(self, hint):
         if hint.step_no != self.step_no:
@@ -397,24 +468,22 @@ class DecoderPlan:
         return _result(out.reshape(B, 1, V), self.device, (), None, "plan_logits")
 
     def _decode_step_into(self, st, slot_in, slot_out, pos):
-        """Launch sequence of one decode step: ids[slot_in] -> logits[slot_out], ids[slot_out] = argmax; ``pos`` is a host
-        int (eager launches) or the state's DevicePos (graph recording; the recorded step also advances it)."""
+        """Launch sequence of one decode step: ids[slot_in] -> lm_head operand planes, ids[slot_out] = argmax of the logits
+        (GEMM epilogue); ``pos`` is a host int (eager launches) or the state's DevicePos (graph recording; the recorded step
+        also advances it). Returns the planes."""
         m, B = self.model, st.B
         ids_t = _result(st.ids[slot_in], self.device, (), None, "ids")
         h = self._hidden_tc(ids_t, pos, B, 1)
         pl = self._head_planes(h, B, 1)
-        V = m.lm_head.weight.shape[1]
         bias = m.lm_head.bias
         bptr = _c(bias.data).ptr if bias is not None else None
-        handle = _fused._packed(m.lm_head.weight).handle
-        if st.logits[slot_out] is None:
-            st.logits[slot_out] = _empty((B, V))
-        _call("pdn_gemm_prepacked_planes", pl.ptr, pl.M, pl.Kp, handle, st.logits[slot_out].ptr, V, bptr, 0)
-        _call("pdn_gemm_prepacked_planes_argmax", pl.ptr, pl.M, pl.Kp, handle, bptr, st.ids[slot_out].ptr)
+        _call("pdn_gemm_prepacked_planes_argmax", pl.ptr, pl.M, pl.Kp, _fused._packed(m.lm_head.weight).handle, bptr, st.ids[slot_out].ptr)
         if isinstance(pos, DevicePos):
             pos.tensor += 1
+        return pl
 
     def _decode_tc(self, ids, start_pos, B):
+        import weakref
         from .. import cuda
         st = self._dec.get(B)
         if st is None:
@@ -430,21 +499,11 @@ class DecoderPlan:
                 _call("pdn_memcpy_h2d", st.ids[slot_in].ptr, host.ctypes.data, host.nbytes)
         st.last_out = None
         use_graph = os.environ.get("PDN_DECODE_GRAPH", "1") != "0" and st.steps_run >= 1 and not cuda.is_capturing()
-        lg = st.logits[slot_out]
-        if lg is not None and not st.copy_mode and sys.getrefcount(lg.buf) > st.base_ref[slot_out]:
-            # a caller still holds a view of the logits this step would overwrite: this slot gets a fresh buffer (and, because a
-            # recorded graph writes fixed addresses, a fresh recording); callers that keep every step's logits end up in copy mode
-            st.recaptures += 1
-            if st.recaptures > 4:
-                st.copy_mode = True
-            else:
-                if st.graphs[slot_out] is not None:
-                    st.graphs[slot_out].destroy()
-                    st.graphs[slot_out] = None
-                st.logits[slot_out] = None
         if not use_graph:
-            self._decode_step_into(st, slot_in, slot_out, start_pos)
+            pl = self._decode_step_into(st, slot_in, slot_out, start_pos)  # fresh planes: the core simply keeps them
+            core = _LogitsCore(self, pl)
         else:
+            st.release_slot(slot_out)
             if st.dev_pos != start_pos:
                 st.pos.tensor.data.fill(start_pos)
             g = st.graphs[slot_out]
@@ -452,7 +511,7 @@ class DecoderPlan:
                 g = cuda.Graph()
                 g.begin()
                 try:
-                    self._decode_step_into(st, slot_in, slot_out, st.pos)
+                    st.planes[slot_out] = self._decode_step_into(st, slot_in, slot_out, st.pos)
                 finally:
                     g.end()
                 st.graphs[slot_out] = g
@@ -461,17 +520,13 @@ class DecoderPlan:
             for blk, att, ffn, n1, n2 in self.blocks:
                 att.cache_k.data.buf.version += 1
                 att.cache_v.data.buf.version += 1
+            core = _LogitsCore(self, st.planes[slot_out])
+            st.live[slot_out] = weakref.ref(core)
         V = self.model.lm_head.weight.shape[1]
-        lg = st.logits[slot_out]
-        if not st.copy_mode:
-            st.base_ref[slot_out] = sys.getrefcount(lg.buf)  # no caller view of this buffer exists at this point
         st.steps_run += 1
         st.step_no += 1
         st.slot = slot_in
-        data = lg.copy() if st.copy_mode else lg
-        out = _result(data.reshape(B, 1, V), self.device, (), None, "plan_logits")
-        out._pdn_hint = _Hint(st, st.step_no, slot_out)
-        return out
+        return _LazyLogits.make(core, (B, 1, V), self.device, _Hint(st, st.step_no, slot_out))
 
     # ---------------------------------------------------------------- rows < 32: persistent decode kernel ------
     def _mega_ok(self):
@@ -610,3 +665,71 @@ class _MegaState:
         out = _result(lg.reshape(B, 1, V), self.plan.device, (), None, "plan_logits")
         out._pdn_hint = _Hint(self, self.gen, row)
         return out
+
+
+# ------------------------------------------------------------------------------------------- attention module ---
+class AttentionPlan:
+    """A multi-head self-attention MODULE written as an operator chain — the reference's examples/pydynet/transformer.py:53-104:
+    bias-free ``Q/K/V/O`` projections of ``values``, head split by reshape / transpose, ``q kT / sqrt(hd)`` (+ additive mask whose
+    entries equal to 1 are first turned into -inf IN PLACE) -> softmax -> ``@ v`` -> merge heads -> ``O`` — is served by ONE fused
+    attention operator (forward and backward, csrc/attention_tc.cu / attention.cu) between the unchanged projections; the
+    [B, H, L, L] score tensor and its five temporaries never exist. Works in training and inference; the first call is checked
+    against the module's own ``forward`` (normwise 1e-3), a mismatch retires the plan."""
+
+    @classmethod
+    def match(cls, m):
+        import inspect
+        from .modules.layers import Linear
+        E, H, hd = getattr(m, "embed_size", None), getattr(m, "heads", None), getattr(m, "head_dim", None)
+        if not (isinstance(E, int) and isinstance(H, int) and isinstance(hd, int) and H * hd == E):
+            return None
+        for nm in "QKVO":
+            lin = getattr(m, nm, None)
+            if not isinstance(lin, Linear) or lin.bias is not None or lin.weight.shape != (E, E):
+                return None
+        try:
+            names = tuple(inspect.signature(m.forward).parameters)
+        except (TypeError, ValueError):
+            return None
+        if names != ("values", "keys", "query", "mask"):
+            return None
+        return cls(m)
+
+    def __init__(self, module):
+        self.m, self.dead, self.verified = module, False, False
+
+    def __call__(self, args):
+        if self.dead or not ENABLED or len(args) != 4:
+            return NotImplemented
+        values, keys, query, mask = args
+        m = self.m
+        if not (isinstance(values, Tensor) and isinstance(keys, Tensor) and isinstance(query, Tensor) and values.ndim == 3
+                and values.shape == keys.shape == query.shape and values.shape[2] == m.embed_size):
+            return NotImplemented
+        if mask is not None and not isinstance(mask, Tensor):
+            return NotImplemented
+        if not _fused.usable(values, m.Q.weight, m.K.weight, m.V.weight, m.O.weight, op="attention"):
+            return NotImplemented
+        N, L = values.shape[0], values.shape[1]
+        H, D = m.heads, m.head_dim
+        if _fused._attention_impl(N, H, L, L, D) == "":
+            return NotImplemented
+        if VERIFY and not self.verified:
+            from ..autograd import no_grad
+            with no_grad():
+                want = m.forward(values, keys, query, mask).numpy().astype(np.float64)
+                got = self._run(values, mask, N, L, H, D).numpy().astype(np.float64)
+            err = np.linalg.norm(want - got) / max(np.linalg.norm(want), 1e-30) if want.shape == got.shape else float("inf")
+            if not (err < 1e-3):
+                self.dead = True
+                warnings.warn(f"pydynet_b200: fused attention plan for {type(m).__name__} disagrees with its forward ({err:.2e}); eager path kept")
+                return NotImplemented
+            self.verified = True
+        return self._run(values, mask, N, L, H, D)
+
+    def _run(self, values, mask, N, L, H, D):
+        m = self.m
+        xq, xk, xv = (proj(values).reshape(N, L, H, D) for proj in (m.Q, m.K, m.V))
+        if mask is not None:
+            mask[mask.eq(1)] = np.float32("-inf")  # the reference mutates the caller's mask (transformer.py:97)
+        return m.O(_fused.attention(xq, xk, xv, mask, 1.0 / D**.5))

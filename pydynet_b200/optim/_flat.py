@@ -20,7 +20,7 @@ class FlatAdamState:
         for p in params:
             offs.append(total)
             total += _align(p.size)
-        self.total = total
+        self.total, self.offs = total, offs
         with dev:
             self.device = dev
             self.flat_p = ndarray.empty((total, ), np.float32)
@@ -31,12 +31,10 @@ class FlatAdamState:
                 buf.fill(0.0)
             self.m_views, self.v_views = [], []
             for p, o in zip(params, offs):
-                def view(buf):
-                    return buf._view((p.size, ), (1, ), o).reshape(p.shape)
-                pv = view(self.flat_p)
+                pv = self._view(self.flat_p, p, o)
                 pv[...] = p.data
                 p.data = pv
-                gv = view(self.flat_g)
+                gv = self._view(self.flat_g, p, o)
                 if p._grad is not None and not p._grad_stale:
                     gv[...] = p._grad
                     p._grad = gv
@@ -46,8 +44,37 @@ class FlatAdamState:
                     p._grad_stale = True
                 p._pinned_grad = True
                 p._grad_dtype = np.dtype(np.float32)
-                self.m_views.append(view(self.flat_m))
-                self.v_views.append(view(self.flat_v))
+                self.m_views.append(self._view(self.flat_m, p, o))
+                self.v_views.append(self._view(self.flat_v, p, o))
+
+    @staticmethod
+    def _view(buf, p, o):
+        return buf._view((p.size, ), (1, ), o).reshape(p.shape)
+
+    def repin(self):
+        """User code may re-bind a parameter's storage after the optimizer was built (``p.data = w``, ``p.grad = g`` on an un-pinned
+        tensor, ``Module.to`` to the same device): the fused kernel and the data-parallel bucket only see the flat buffers, so a
+        stray array is copied back into its segment and the parameter re-pinned. A parameter that left the device is an error."""
+        for p, o in zip(self.params, self.offs):
+            d = p.data
+            if getattr(d, "buf", None) is not self.flat_p.buf:
+                if p.device != self.device:
+                    raise RuntimeError("a parameter was moved to another device after its optimizer was created; build a new optimizer")
+                pv = self._view(self.flat_p, p, o)
+                pv[...] = d
+                p.data = pv
+                self.flat_p.buf.version += 1
+            g = p._grad
+            if g is None or getattr(g, "buf", None) is not self.flat_g.buf:
+                gv = self._view(self.flat_g, p, o)
+                if g is not None and not p._grad_stale:
+                    gv[...] = g
+                    p._grad_stale = False
+                else:
+                    p._grad_stale = True
+                p._grad = gv
+                p._pinned_grad = True
+                p._grad_dtype = np.dtype(np.float32)
 
     def _settle_grads(self):
         """A parameter that received no gradient since zero_grad() holds stale values: its grad is zero."""
@@ -58,6 +85,7 @@ class FlatAdamState:
 
     def step(self, lr, b1, b2, eps, wd, t, grad_scale):
         with self.device:
+            self.repin()
             self._settle_grads()
             self.flat_p.buf.version += 1
             L.call("pdn_adam_step", self.flat_p.ptr, self.flat_g.ptr, self.flat_m.ptr, self.flat_v.ptr, self.total, lr, b1, b2, eps,

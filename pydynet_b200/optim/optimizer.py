@@ -85,8 +85,10 @@ class Adam(Optimizer):
         self.t = 1
         self.grad_scale = 1.0  # set by the data-parallel wrapper to 1/world_size
         self._flat = None
+        # flat buffers need one private segment per parameter: parameters that alias one buffer (Parameter(copy=False) tying) keep the
+        # reference's per-tensor update, which writes the shared array once per alias
         if self.params and all(p.device.is_cuda and p.dtype == np.float32 and p.requires_grad for p in self.params) \
-                and len({p.device for p in self.params}) == 1:
+                and len({p.device for p in self.params}) == 1 and len({p.data.ptr for p in self.params}) == len(self.params):
             from ._flat import FlatAdamState
             self._flat = FlatAdamState(self.params)
             self.m, self.v = self._flat.m_views, self._flat.v_views

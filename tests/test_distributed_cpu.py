@@ -87,3 +87,83 @@ def test_shard_and_world_defaults():
     a = np.arange(12).reshape(4, 3)
     np.testing.assert_array_equal(dist.shard(a), a)
     assert not dist.sync_stats_enabled()
+
+
+def test_backward_reports_each_pinned_leaf_after_its_last_consumer():
+    """The overlap hook of the tape (core/tensor.py, _LEAF_READY_HOOK): every leaf whose gradient lives in a flat bucket is reported
+    exactly once, only after the LAST node that consumes it has run (its gradient is final), newest consumers first, and the end of
+    the sweep is signalled — the contract DataParallel(overlap=True) launches its bucket all-reduces on."""
+    import pydynet_b200 as pdn
+    from pydynet_b200.core import tensor as T
+    rng = np.random.default_rng(0)
+    mk = lambda *s: pdn.Tensor(rng.standard_normal(s), dtype=np.float64, requires_grad=True)
+    w1, w2, w3, x = mk(4, 4), mk(4, 4), mk(4, 4), mk(2, 4)
+    for p in (w1, w2, w3):  # what FlatAdamState does: gradient storage pinned to a preallocated view
+        p._grad = np.zeros(p.shape)
+        p._pinned_grad = True
+        p._grad_stale = True
+    events, snap = [], {}
+
+    def hook(leaf):
+        events.append(None if leaf is None else id(leaf))
+        if leaf is not None:
+            snap[id(leaf)] = np.array(leaf._grad)
+
+    h1 = x @ w1
+    h2 = (h1 @ w2) * 2.0 + h1 @ w1  # w1 is consumed twice: by the first and by a late node
+    loss = ((h2 @ w3) ** 2).sum()
+    T._LEAF_READY_HOOK[0] = hook
+    try:
+        loss.backward()
+    finally:
+        T._LEAF_READY_HOOK[0] = None
+    assert events == [id(w3), id(w2), id(w1), None]  # w1 only after its EARLIEST consumer (last in the reverse sweep)
+    for p in (w1, w2, w3):
+        np.testing.assert_array_equal(snap[id(p)], p.grad)  # the gradient was final when it was reported
+    assert not x._pinned_grad and id(x) not in snap
+
+
+def test_bucket_ranges_cover_the_flat_buffer_in_order():
+    from pydynet_b200.distributed import DataParallel
+
+    class P:
+        def __init__(self, n): self.size = n
+
+    class Flat:
+        params = [P(n) for n in (1000, 64, 5000, 64, 3000, 10, 2000)]
+        offs, total = [], 0
+        for p in params:
+            offs.append(total)
+            total += (p.size + 63) // 64 * 64
+
+    dp = DataParallel.__new__(DataParallel)
+    dp._flat = Flat
+    dp._make_buckets(3)
+    assert 1 < len(dp._ranges) <= 3
+    pos, members = 0, []
+    for off, n, mem in dp._ranges:
+        assert off == pos and n > 0
+        pos += n
+        members += mem
+    assert pos == Flat.total and members == list(range(len(Flat.params)))
+    assert set(dp._owner.values()) == set(range(len(dp._ranges)))
+
+
+def test_nccl_id_rendezvous_over_tcp_leaves_nothing_behind(tmp_path, monkeypatch):
+    """Without torch.distributed the 128-byte id travels over a one-shot TCP socket (no predictable /tmp file that a second job or
+    another user could read or plant)."""
+    import threading
+    from pydynet_b200 import distributed as dist
+    port = 31000 + (os.getpid() % 2000)
+    monkeypatch.setenv("MASTER_ADDR", "127.0.0.1")
+    monkeypatch.setenv("PDN_ID_PORT", str(port))
+    payload = bytes(range(128))
+    got = {}
+    th = [threading.Thread(target=lambda r=r: got.__setitem__(r, dist._exchange_id(r, 3, lambda: payload))) for r in range(3)]
+    for t in th[1:]:
+        t.start()
+    th[0].start()
+    for t in th:
+        t.join(timeout=60)
+    assert got == {0: payload, 1: payload, 2: payload}
+    assert not [f for f in os.listdir("/tmp") if f.startswith("pdn_nccl_id_")]

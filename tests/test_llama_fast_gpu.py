@@ -119,6 +119,21 @@ def test_plan_survives_weight_update_and_held_logits():
                 snaps.append(lg.numpy())
         for t, s in zip(kept, snaps):
             np.testing.assert_array_equal(t.numpy(), s)
+        # (1b) logits whose values were never asked for while they were current (the batched decode step only produced their
+        # argmax): reading them LATER must still give that step's values, not those of a step recorded over the same buffers
+        _generate(net, prompt, 8)
+        with pdn.no_grad():
+            lg = net(pdn.Tensor(prompt, device="cuda:0"), 0)
+            late = []
+            for pos in range(4, 14):
+                nxt = lg[:, -1, :].argmax(-1, True)
+                lg = net(nxt, pos + 1)
+                late.append(lg)
+            sliced = late[-1][:, -1, :]
+            assert sliced.shape == (B, V) and late[0].shape == (B, 1, V) and late[0].dtype == np.float32
+        for t, s in zip(late, snaps):
+            np.testing.assert_array_equal(t.numpy(), s)
+        np.testing.assert_array_equal(sliced.numpy(), snaps[-1][:, 0, :])
         # (2) new weights in place: the plan must serve the NEW model
         params2 = O.synthetic_llama_params(V, D, H, FF, L, seed=12, std=0.08)
         for name, p in net._parameters.items():
