@@ -337,10 +337,12 @@ int pdn_swiglu_bwd(const float* gate, const float* up, const float* g, float* dg
 /* Whole decode step for small batches (rows < 32) as ONE cooperative persistent kernel (csrc/decode_mega.cu): replaces the
  * ~490 eager array expressions per token of the reference's own B = 1 loop — llm/llama/model.py:254-256 (forward), 192-207
  * (_forward_hidden), 142-150 (block), 95-121 (attention with KV cache), 23-44 (RoPE), 56-58 (SwiGLU), norm.py:245-248, and the
- * greedy argmax of model.py:268. Weights are passed as TRANSPOSED copies ([out][in] row-major, made by the caller):
- * layer_ptrs[l*8 + {0..7}] = {[Wq|Wk|Wv]ᵀ [3*dim][dim], Woᵀ [dim][dim], gate/up rows interleaved [2*FF][dim], W_downᵀ [dim][FF],
- * input_norm weight, post_attn_norm weight, cache_k, cache_v ([Bmax][S][H][hd] fp32, contiguous)}; layer_eps[l*2 + {0,1}] the two
- * RMSNorm eps. The handle owns its scratch (residual rows, attention partials, grid barrier) until pdn_decoder_destroy. */
+ * greedy argmax of model.py:268. Weights are passed as re-laid-out copies (made by the caller, rebuilt when a weight changes):
+ * layer_ptrs[l*8 + {0..7}] = {[Wq|Wk|Wv]ᵀ [3*dim][dim], Wo by head [H][dim][hd] (element [h][n][d] = Wo[h*hd + d][n]), gate/up
+ * rows interleaved [2*FF][dim], W_downᵀ [dim][FF], input_norm weight, post_attn_norm weight, cache_k, cache_v ([Bmax][S][H][hd]
+ * fp32, contiguous)}; layer_eps[l*2 + {0,1}] the two RMSNorm eps; wlm_t = lm_headᵀ [V][dim]. B <= 8, head size 32 / 48 / 64,
+ * dim and FF multiples of 4 and <= 1024, S <= 2048; an unsupported model is an error (PDN_ERR_INVALID), never a silent fallback.
+ * The handle owns its scratch (residual rows, attention partials, grid barrier) until pdn_decoder_destroy. */
 int pdn_decoder_create(void** handle, int n_layers, int B, int dim, int H, int FF, int V, int S, const void* const* layer_ptrs,
                        const float* layer_eps, const float* emb, const float* cosT, const float* sinT, const float* norm_w, float eps_f,
                        const float* wlm_t, const float* lm_bias);

@@ -280,6 +280,7 @@ class DecoderPlan:
         self._cat = {}  # fused [W0 | W1 | ...] operand planes per (layer, kind)
         self._dec = {}  # batch size -> _DecodeState
         self._mega = None
+        self._mega_failed = False  # the decode kernel refused this model (too wide for one task per warp on this GPU)
         self._masks = {}
 
     # ---------------------------------------------------------------- validity -----------------
@@ -534,8 +535,8 @@ class DecoderPlan:
             return False
         att, ffn = self.blocks[0][1], self.blocks[0][2]
         D, FF = att.n_heads * att.head_dim, ffn.up.weight.shape[1]
-        return (att.head_dim in (32, 48, 64) and D % 4 == 0 and FF % 4 == 0 and D <= 1024 and FF <= 1024
-                and all(b[2].up.weight.shape[1] == FF for b in self.blocks))
+        return (not self._mega_failed and att.head_dim in (32, 48, 64) and D % 4 == 0 and FF % 4 == 0 and D <= 1024 and FF <= 1024
+                and att.cache_k.shape[1] <= 2048 and all(b[2].up.weight.shape[1] == FF for b in self.blocks))
 
     def _mega_weights(self):
         """Transposed ([out][in]) copies the persistent kernel streams row by row; rebuilt when a weight buffer changes
@@ -551,7 +552,9 @@ class DecoderPlan:
                 wgu = ndarray.empty((FF, 2, D), F32)
                 wgu[:, 0, :] = T(ffn.gate.weight)
                 wgu[:, 1, :] = T(ffn.up.weight)
-                layers.append((wqkv, T(att.O.weight), wgu, T(ffn.down.weight), n1, n2, att))
+                H, hd = att.n_heads, att.head_dim
+                wo_h = att.O.weight.data.reshape(H, hd, D).swapaxes(1, 2).copy()  # [H][out][hd]: the head slice of Woᵀ is contiguous
+                layers.append((wqkv, wo_h, wgu, T(ffn.down.weight), n1, n2, att))
             self._mega = {"layers": layers, "wlm": T(m.lm_head.weight), "states": {}}
         return self._mega
 
@@ -559,7 +562,11 @@ class DecoderPlan:
         mg = self._mega_weights()
         st = mg["states"].get(B)
         if st is None:
-            st = mg["states"][B] = _MegaState(self, mg, B)
+            try:
+                st = mg["states"][B] = _MegaState(self, mg, B)
+            except RuntimeError:
+                self._mega_failed = True
+                return self.model.forward(ids, pos)
         return st.run(ids, pos, L)
 
 

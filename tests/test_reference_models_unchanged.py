@@ -183,6 +183,16 @@ def test_reference_clip_model_runs_unchanged(aliased, dev):
             with p.device:
                 p.data[...] = g["p." + name]
         net.eval()
+        if dev != "cpu":
+            # the reference's file builds its causal mask as a CPU tensor (llm/clip/model.py:9-14, 152) and adds it to the scores of
+            # whatever device the model lives on: on cuda the reference's own operator protocol raises its device-mismatch
+            # AssertionError (tensor.py:494). Same file, same error here - the image tower, which has no such constant, runs.
+            with pdn.no_grad():
+                feat = net.image_encoder(pdn.Tensor(g["img"], device=dev), net.class_embed, net.v_pos_emb)
+                assert feat.device.is_cuda and np.isfinite(feat.numpy()).all()
+                with pytest.raises(AssertionError):
+                    net(pdn.Tensor(g["img"], device=dev), g["idx"])
+            return
         with pdn.no_grad():
             logits = net(pdn.Tensor(g["img"], device=dev), g["idx"]).numpy()
         pdn.autograd.set_grad_enabled(True)
