@@ -23,7 +23,7 @@ import tempfile
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 SRC = "/root/reference"
 DST = os.path.join(ROOT, "baseline", "_ref")
-SCRIPT_DIRS = ("llm/llama", "llm/clip", "examples/pydynet")  # python files only (no weights / images)
+SCRIPT_DIRS = ("llm/llama", "llm/clip", "examples/pydynet", "tests")  # python files only (no weights / images)
 
 
 def reference_root():

@@ -24,6 +24,7 @@ from pydynet_b200.optim import Adam  # noqa: E402
 
 DEV = "cuda:0"
 f32 = np.float32
+ARGS = None
 PEAK_BF16 = 1362.4e12
 PEAK_HBM = 6552.6e9
 try:
@@ -68,6 +69,62 @@ def T(a, rg=False):
     return pdn.Tensor(a, dtype=a.dtype, device=DEV, requires_grad=rg)
 
 
+# ------------------------------------------------------------------------------------------------- the reference beside every number
+# The UNMODIFIED reference package (NumPy path) from /root/reference or the staged copy baseline/_ref, timed on this box's host
+# cores on a bounded sample of the same workload; None when neither tree is present (--no-cpu skips it).
+_REF = {}
+
+
+def ref_ns():
+    if "ns" not in _REF:
+        _REF["ns"] = None
+        try:
+            from baseline import refload
+            if refload.available():
+                ns = dict(refload.ref_extra())
+                ns["refload"] = refload
+                try:
+                    import threadpoolctl
+                    threadpoolctl.threadpool_limits(limits=os.cpu_count())
+                    ns["cores"] = max([i.get("num_threads", 1) for i in threadpoolctl.threadpool_info()] or [os.cpu_count()])
+                except Exception:
+                    ns["cores"] = os.cpu_count()
+                _REF["ns"] = ns
+        except Exception as e:  # noqa: BLE001
+            print(f"note: reference not usable ({e})", file=sys.stderr)
+    return _REF["ns"]
+
+
+def cpu_ref(build, reps, sample, scale=1.0, warm=1):
+    """build(ns) -> step callable on the reference; returns the cpu_baseline object (ms_per_step scaled by ``scale`` to the
+    full workload, the scaling stated in ``sample``)."""
+    ns = ref_ns() if ARGS.cpu else None
+    if ns is None:
+        return None
+    try:
+        step = build(ns)
+        for _ in range(warm):
+            step()
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            step()
+        dt = (time.perf_counter() - t0) / reps
+        ns["pdn"].autograd.set_grad_enabled(True) if hasattr(ns["pdn"], "autograd") else None
+        return {"ms_per_step": dt * scale * 1e3, "kind": "reference", "cores": int(ns["cores"]),
+                "sample": f"{sample}; {reps} rep(s) of {dt * 1e3:.1f} ms after {warm} warm-up" + (f", x{scale:g} to the full workload" if scale != 1.0 else "")}
+    except Exception as e:  # noqa: BLE001
+        return {"error": repr(e)[:200]}
+
+
+def with_ref(extra, sec, base):
+    if base and "ms_per_step" in base:
+        extra["cpu_baseline"] = base
+        extra["speedup_vs_cpu_reference"] = base["ms_per_step"] / (sec * 1e3)
+    elif base:
+        extra["cpu_baseline"] = base
+    return extra
+
+
 def c1(args):
     rng = np.random.default_rng(0)
     for n in ([512] if args.small else [512, 1024, 2048, 4096, 8192]):
@@ -82,15 +139,23 @@ def c1(args):
             pdn.matmul(x, w).sum().backward()
 
         sec, nl = timed(step, args.steps if n < 8192 else max(2, args.steps // 2))
-        cpu = None
-        if n == 512:
-            t0 = time.perf_counter()
-            for _ in range(5):
-                ones = np.ones((n, n), f32)
-                _ = A @ B; _ = ones @ B.T; _ = A.T @ ones
-            cpu = (time.perf_counter() - t0) / 5
+        base = None
+        if n <= 1024:
+            def build(ns, A=A, B=B):
+                rx, rw = ns["pdn"].Tensor(A, dtype=f32, requires_grad=True), ns["pdn"].Tensor(B, dtype=f32, requires_grad=True)
+
+                def rstep():
+                    rx.zero_grad(); rw.zero_grad()
+                    ns["pdn"].matmul(rx, rw).sum().backward()
+                return rstep
+            base = cpu_ref(build, 5, f"the full workload: matmul(x, w).sum().backward() at {n}^3 through the reference's Tensor/autograd")
         emit(f"C1 matmul fwd+bwd {n}^3 fp32 (matmul(x,w).sum().backward())", sec, flops=6.0 * n**3, nbytes=9 * 4.0 * n * n, launches=nl,
-             cpu_numpy_3_sgemms_ms=cpu * 1e3 if cpu else None)
+             **with_ref({}, sec, base))
+        if n <= 1024:  # the same step recorded once into a CUDA graph (pdn.cuda.graphed_step): the per-op Python cost disappears
+            gs = pdn.cuda.graphed_step(step)
+            sec_g, nl_g = timed(gs, max(args.steps, 50), warmup=5)
+            emit(f"C1 matmul fwd+bwd {n}^3 fp32, step recorded with pdn.cuda.graphed_step (CUDA-graph replay)", sec_g, flops=6.0 * n**3,
+                 nbytes=9 * 4.0 * n * n, launches=nl_g, **with_ref({}, sec_g, base))
     for n in ([] if args.small else [4096, 8192]):
         a, b = pdn.backend.array(rng.standard_normal((n, n)).astype(f32)), pdn.backend.array(rng.standard_normal((n, n)).astype(f32))
         out = pdn.backend.empty((n, n), f32)
@@ -156,7 +221,26 @@ def c2(args):
     X, y = T(np.random.rand(B, 1, 28, 28).astype(f32)), T(np.random.randint(0, 10, B))
     net.train()
     sec, nl = timed(lambda: train_step(net, opt, X, y), args.steps)
-    emit("C2 LeNet b256 train step (CE, backward, Adam)", sec, flops=4_743_290_880, nbytes=170e6, launches=nl, images_per_s=B / sec)
+
+    def build(ns):
+        ConvNet_r = ns["refload"].ref_model("examples/pydynet/mnist.py", lines=(81, 98), extra=ns["refload"].ref_extra())["ConvNet"]
+        np.random.seed(42)
+        rnet = ConvNet_r()
+        ropt = ns["refload"]._REF_PKG["mods"]["pydynet.optim"].Adam(rnet.parameters(), lr=1e-4)
+        rX, ry = ns["pdn"].Tensor(X.numpy(), dtype=f32), ns["pdn"].Tensor(y.numpy())
+        rnet.train()
+
+        def rstep():
+            loss = ns["F"].cross_entropy_loss(rnet(rX), ry)
+            ropt.zero_grad(); loss.backward(); ropt.step()
+        return rstep
+    base = cpu_ref(build, 2, "the full workload: reference ConvNet (examples/pydynet/mnist.py:82-98) batch 256, CE + backward + Adam")
+    emit("C2 LeNet b256 train step (CE, backward, Adam)", sec, flops=4_743_290_880, nbytes=170e6, launches=nl, images_per_s=B / sec,
+         **with_ref({}, sec, base))
+    gs = pdn.cuda.graphed_step(lambda a, b: train_step(net, opt, a, b), optimizers=[opt])
+    sec_g, nl_g = timed(lambda: gs(X, y), max(args.steps, 30), warmup=5)
+    emit("C2 LeNet b256 train step, recorded with pdn.cuda.graphed_step (CUDA-graph replay)", sec_g, flops=4_743_290_880, nbytes=170e6,
+         launches=nl_g, images_per_s=B / sec_g, **with_ref({}, sec_g, base))
 
 
 def c4(args):
@@ -171,7 +255,24 @@ def c4(args):
     net.train()
     sec, nl = timed(lambda: train_step(net, opt, X, y, None), max(2, args.steps // 2), warmup=2)
     fl = 3 * (2.0 * B * S * 512 * 512 * 4 + 4.0 * B * 8 * S * S * 64 + 2.0 * B * S * 512 * 1536 * 2)
-    emit(f"C4 Transformer encoder d512 h8 S{S} B{B} train step", sec, flops=fl, launches=nl, tokens_per_s=B * S / sec)
+    Bc = 8 if args.small else 16
+
+    def build(ns):
+        Tr = ns["refload"].ref_model("examples/pydynet/transformer.py", lines=(52, 192), extra=ns["refload"].ref_extra())["Transformer"]
+        np.random.seed(0)
+        rnet = Tr(512, 1, 8, 3, 0.05, V, S)
+        rnet.word_embedding.reset_parameters()
+        ropt = ns["refload"]._REF_PKG["mods"]["pydynet.optim"].Adam(rnet.parameters(), lr=5e-4)
+        rX, ry = ns["pdn"].Tensor(X.numpy()[:Bc]), ns["pdn"].Tensor(y.numpy()[:Bc], dtype=f32)
+        rnet.train()
+
+        def rstep():
+            loss = ns["pdn"].log(1 + ns["pdn"].exp(-ry * ns["pdn"].squeeze(rnet(rX, None)))).mean()
+            ropt.zero_grad(); loss.backward(); ropt.step()
+        return rstep
+    base = cpu_ref(build, 1, f"reference Transformer (examples/pydynet/transformer.py:53-192) at batch {Bc} of {B} (batch {B} needs 22 GB of host RAM "
+                             "for its score temporaries); time scaled linearly in the batch", scale=B / Bc, warm=1)
+    emit(f"C4 Transformer encoder d512 h8 S{S} B{B} train step", sec, flops=fl, launches=nl, tokens_per_s=B * S / sec, **with_ref({}, sec, base))
 
 
 def c5(args):
@@ -182,7 +283,24 @@ def c5(args):
     opt = Adam(net.parameters(), lr=0.01)
     X, Y = T(np.random.randn(B, Tn, 512).astype(f32)), T(np.random.randn(B, 1).astype(f32))
     sec, nl = timed(lambda: train_step(net, opt, X, Y), max(2, args.steps // 3), warmup=2)
-    emit(f"C5 GRU in512 h512 T{Tn} B{B} train step", sec, flops=2_013_265_920.0 * Tn * B / 256, launches=nl, us_per_time_step=sec / Tn * 1e6)
+    Tc = 32 if args.small else 64
+
+    def build(ns):
+        np.random.seed(0)
+        rg = ns["nn"].GRU(512, 512, 1, batch_first=True, dtype=f32)
+        rh = ns["nn"].Linear(512, 1, dtype=f32)
+        ropt = ns["refload"]._REF_PKG["mods"]["pydynet.optim"].Adam(list(rg.parameters()) + list(rh.parameters()), lr=0.01)
+        rX, rY = ns["pdn"].Tensor(X.numpy()[:, :Tc], dtype=f32), ns["pdn"].Tensor(Y.numpy(), dtype=f32)
+
+        def rstep():
+            _, h = rg(rX, None)
+            loss = ns["F"].mse_loss(rh(h[:, 0, :]), rY)
+            ropt.zero_grad(); loss.backward(); ropt.step()
+        return rstep
+    base = cpu_ref(build, 1, f"reference nn.GRU at T = {Tc} of {Tn} time steps, batch {B} (the reference's step time grows faster than linearly in T: "
+                             "92 s at T = 1024 on 8 cores, SURVEY.md 6); time scaled LINEARLY in T, which favours the CPU", scale=Tn / Tc, warm=0)
+    emit(f"C5 GRU in512 h512 T{Tn} B{B} train step", sec, flops=2_013_265_920.0 * Tn * B / 256, launches=nl, us_per_time_step=sec / Tn * 1e6,
+         **with_ref({}, sec, base))
 
 
 def decode(args):
@@ -242,7 +360,18 @@ def micro(args, conv=True):
             conv(x).sum().backward()
 
         sec, nl = timed(step, args.steps)
-        emit(f"micro Conv2d {Ci}->{O} {HW}x{HW} k3p1 b{N} fwd+bwd", sec, flops=3 * 2.0 * N * HW * HW * Ci * 9 * O, launches=nl)
+        Nc = min(N, 16)
+
+        def build(ns, Ci=Ci, O=O, HW=HW, Nc=Nc, xh=x.numpy()):
+            rconv = ns["nn"].Conv2d(Ci, O, 3, 1, 1, dtype=f32)
+            rx = ns["pdn"].Tensor(xh[:Nc], dtype=f32, requires_grad=True)
+
+            def rstep():
+                rx.zero_grad(); rconv.weight.zero_grad(); rconv.bias.zero_grad()
+                rconv(rx).sum().backward()
+            return rstep
+        base = cpu_ref(build, 1, f"reference nn.Conv2d (im2col + add.at) at batch {Nc} of {N}; time scaled linearly in the batch", scale=N / Nc)
+        emit(f"micro Conv2d {Ci}->{O} {HW}x{HW} k3p1 b{N} fwd+bwd", sec, flops=3 * 2.0 * N * HW * HW * Ci * 9 * O, launches=nl, **with_ref({}, sec, base))
     B, H, S, D = (8, 8, 128, 64) if args.small else (128, 8, 512, 64)
     q, k, v = (T(rng.standard_normal((B, S, H, D)).astype(f32), True) for _ in range(3))
 
@@ -255,7 +384,22 @@ def micro(args, conv=True):
         _fused.attention(q, k, v, None, 1.0 / D**.5).sum().backward()
 
     sec, nl = timed(att, max(2, args.steps // 2), warmup=2)
-    emit(f"micro attention core B{B} H{H} S{S} hd{D} fwd+bwd (fused tcgen05 flash kernels, BF16x3)", sec, flops=3 * 4.0 * B * H * S * S * D, launches=nl)
+    Bc = min(B, 8)
+
+    def build(ns, qh=q.numpy(), kh=k.numpy(), vh=v.numpy()):
+        rq, rk, rv = (ns["pdn"].Tensor(a[:Bc], dtype=f32, requires_grad=True) for a in (qh, kh, vh))
+
+        def rstep():
+            for t in (rq, rk, rv):
+                t.zero_grad()
+            sc = rq.transpose(0, 2, 1, 3) @ rk.transpose(0, 2, 3, 1) / D**.5  # the operator chain of transformer.py:93-104
+            out = ns["F"].softmax(sc, axis=-1) @ rv.transpose(0, 2, 1, 3)
+            out.transpose(0, 2, 1, 3).reshape(Bc, S, -1).sum().backward()
+        return rstep
+    base = cpu_ref(build, 1, f"the reference's attention operator chain (q kT / sqrt(d) -> softmax -> @ v, transformer.py:93-104) at batch {Bc} of {B}; "
+                             "time scaled linearly in the batch", scale=B / Bc)
+    emit(f"micro attention core B{B} H{H} S{S} hd{D} fwd+bwd (fused tcgen05 flash kernels, BF16x3)", sec, flops=3 * 4.0 * B * H * S * S * D, launches=nl,
+         **with_ref({}, sec, base))
 
 
 if __name__ == "__main__":
@@ -263,7 +407,9 @@ if __name__ == "__main__":
     ap.add_argument("--only", default="c1,c2,c4,c5,micro")
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--small", action="store_true")
+    ap.add_argument("--no-cpu", dest="cpu", action="store_false", help="skip the reference-on-host-cores run beside every config")
     args = ap.parse_args()
+    ARGS = args
     for name in args.only.split(","):
         try:
             {"c1": c1, "c2": c2, "c4": c4, "c5": c5, "micro": micro, "micro_att": micro_att, "gemm": gemm, "rows": rows, "decode": decode}[name](args)

@@ -88,6 +88,12 @@ int pdn_memcpy_d2h_async(void* pinned_dst, const void* src, size_t bytes);
 int pdn_memset(void* dst, int byte, size_t bytes);
 int pdn_sync(void);
 
+/* NVTX ranges around the phases of a step (forward / backward / optimizer / all-reduce; pydynet_b200.cuda.nvtx_range, active with
+ * PDN_NVTX=1, which also marks every kernel launch with its entry-point name) for `ncu --nvtx --nvtx-include` and nsys timelines.
+ * Nothing in the reference corresponds to this (it has no tracing). */
+int pdn_nvtx_push(const char* name);
+int pdn_nvtx_pop(void);
+
 /* launch accounting (bench.py "gpu_launches") and device-side timing on the library stream */
 uint64_t pdn_kernel_launch_count(void);
 void pdn_reset_launch_count(void);
@@ -98,6 +104,7 @@ int pdn_event_elapsed_ms(void* start, void* stop, float* ms); /* synchronises on
 
 /* CUDA-graph capture of a launch sequence on the library stream (decode loop replay) */
 int pdn_graph_begin(void);
+int pdn_graph_status(int* status); /* 0 none, 1 recording, 2 recording invalidated (an operation that cannot be recorded was issued) */
 int pdn_graph_end(void** graph_exec);
 int pdn_graph_launch(void* graph_exec);
 int pdn_graph_destroy(void* graph_exec);
@@ -310,6 +317,11 @@ int pdn_adam_step(float* p, const float* grad, float* m, float* v, int64_t n, fl
 /* multi-tensor form: arrays of n_tensors device pointers/sizes (host arrays), one launch. */
 int pdn_adam_multi(int n_tensors, float* const* p, const float* const* grad, float* const* m, float* const* v,
                    const int64_t* sizes, float lr, float b1, float b2, float eps, float wd, int t, float grad_scale);
+/* The same update with its host arithmetic moved to the device, for steps recorded into a CUDA graph (pydynet_b200.cuda.graphed_step):
+ * t_dev (int, starts at 1) and lr_dev (float) live in device memory; a one-thread kernel writes step_dev = lr * sqrt(1 - b2^t) /
+ * (1 - b1^t) and advances t before the update kernel reads it, so every replay performs the next optimizer step. */
+int pdn_adam_step_dev(float* p, const float* grad, float* m, float* v, int64_t n, float b1, float b2, float eps, float wd, float grad_scale,
+                      int* t_dev, const float* lr_dev, float* step_dev);
 
 /* ---------------------------------------------------------------- Llama decode fast path ---- */
 /* interleaved-pair RoPE (llm/llama/model.py:23-44) applied in place to q and k rows [rows, H, D] using

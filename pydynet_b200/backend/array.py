@@ -11,6 +11,7 @@ H2D/D2H staging; all element math runs in libpdn_b200.so kernels.
 from __future__ import annotations
 
 import ctypes as C
+import os
 import math
 import numbers
 
@@ -27,6 +28,7 @@ _I64A = C.c_int64 * 8
 # bumped by every USER-LEVEL in-place write to a device buffer (setitem, fill, += ...): inference plans (nn/_plans.py) compare it
 # against the value they saw last and re-check their weight signatures only when it moved
 WRITE_EPOCH = [0]
+IMPLICIT_NUMPY = os.environ.get("PDN_IMPLICIT_NUMPY") == "1"
 
 
 def _code(dt) -> int:
@@ -190,6 +192,11 @@ class ndarray:
         return str(self.get())
 
     def __array__(self, dtype=None, copy=None):
+        # like CuPy, a device array does not silently turn into a host array (a hidden synchronising copy); PDN_IMPLICIT_NUMPY=1 opts
+        # in — tests/test_variant_b_gpu.py uses it: the reference's own test-suite hands raw ``.grad`` arrays to np.testing
+        if IMPLICIT_NUMPY:
+            out = self.get()
+            return out if dtype is None else out.astype(dtype)
         raise TypeError("implicit conversion of a device array to NumPy is not allowed; call .get()")
 
     # ------------------------------------------------------------------ copies / casts ----------
@@ -332,6 +339,15 @@ class ndarray:
     def mean(self, axis=None, keepdims=False, dtype=None): return _reduce(L.R_MEAN, self, axis, keepdims)
     def max(self, axis=None, keepdims=False): return _reduce(L.R_MAX, self, axis, keepdims)
     def min(self, axis=None, keepdims=False): return _reduce(L.R_MIN, self, axis, keepdims)
+    def cumsum(self, axis=None):
+        """Index arithmetic only (reference core/function.py:39,75,111: section boundaries of split): computed on the host."""
+        return ndarray.from_host(np.cumsum(self.get(), axis=axis))
+
+    def __index__(self):
+        if self.size != 1 or not np.issubdtype(self.dtype, np.integer):
+            raise TypeError("only integer scalar device arrays can be converted to an index")
+        return int(self.get().reshape(()))
+
     def argmax(self, axis=None, keepdims=False): return _reduce(L.R_ARGMAX, self, axis, keepdims)
     def argmin(self, axis=None, keepdims=False): return _reduce(L.R_ARGMIN, self, axis, keepdims)
 

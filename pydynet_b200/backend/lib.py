@@ -102,6 +102,10 @@ _PROTOS = {
     "pdn_ce_loss_fwd": [vp, vp, vp, vp, i64, i64, i32],
     "pdn_ce_loss_bwd": [vp, vp, vp, vp, vp, i64, i64, i32],
     "pdn_adam_step": [vp, vp, vp, vp, i64, f32, f32, f32, f32, f32, i32, f32],
+    "pdn_graph_status": [C.POINTER(i32)],
+    "pdn_nvtx_push": [C.c_char_p],
+    "pdn_nvtx_pop": [],
+    "pdn_adam_step_dev": [vp, vp, vp, vp, i64, f32, f32, f32, f32, f32, vp, vp, vp],
     "pdn_adam_multi": [i32, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), pi64, f32, f32, f32, f32, f32, i32, f32],
     "pdn_rope_kv_append": [vp, vp, vp, vp, vp, vp, vp, i64, i64, i64, i64, i64, i64, i64],
     "pdn_rope_kv_append_dev": [vp, vp, vp, vp, vp, vp, vp, i64, i64, i64, i64, i64, vp, i64],

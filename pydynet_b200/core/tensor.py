@@ -290,6 +290,14 @@ class Tensor:
             raise ValueError("Auto-grad is failed because current node is not in graph.")
         if self.size > 1:
             raise ValueError("backward should be called only on a scalar.")
+        from .. import cuda as _cuda
+        if _cuda.NVTX and self.device.is_cuda:
+            with _cuda.nvtx_range("backward"):
+                _cuda.NVTX = False  # one range per sweep, not one per nested call
+                try:
+                    return self.backward(retain_graph)
+                finally:
+                    _cuda.NVTX = True
         with self.device:
             seed = self.xp.ones(self.shape, dtype=self.dtype)
             if self._node is None:  # a leaf: d self / d self
@@ -422,14 +430,18 @@ def _wrap_scalar(value, like):
     host-to-device copy — a stream drain per ReLU in a launch-bound training step."""
     if like.device.is_cuda and isinstance(value, (int, float, np.floating, np.integer)) and not isinstance(value, bool):
         from ..cuda import is_capturing
-        if not is_capturing():  # memory allocated while a CUDA graph is recorded belongs to that graph
-            v = np.asarray(value, dtype=like.dtype)
-            key = (like.device, v.dtype.str, v.tobytes())
-            t = _SCALARS.get(key)
-            if t is None:
-                if len(_SCALARS) >= 512:
-                    _SCALARS.clear()
-                t = _SCALARS[key] = Tensor(value, dtype=like.dtype, device=like.device)
+        v = np.asarray(value, dtype=like.dtype)
+        key = (like.device, v.dtype.str, v.tobytes())
+        t = _SCALARS.get(key)
+        if t is not None:
+            return t  # (also while a CUDA graph is being recorded: the constant was allocated outside the recording and is never freed)
+        if is_capturing():
+            # a constant first seen INSIDE a recording: a host-to-device copy cannot be recorded, a fill kernel can; its memory belongs to
+            # the graph, so it is not cached
+            with like.device:
+                return _result(like.device.xp.full((), v.item(), dtype=v.dtype), like.device, (), None, "const")
+        if len(_SCALARS) < 4096:  # never evicted: recorded graphs may reference the cached buffers
+            t = _SCALARS[key] = Tensor(value, dtype=like.dtype, device=like.device)
             return t
     return Tensor(value, dtype=like.dtype, device=like.device)
 

@@ -336,7 +336,8 @@ __global__ void __launch_bounds__(256) k_swiglu_bwd(const float* __restrict__ ga
 // ---------------------------------------------------------------- Adam ------------------------------------------
 __global__ void __launch_bounds__(256) k_adam(float4* p, const float4* grad, float4* m, float4* v,
                                               int64_t n4, float step_size, float b1, float b2, float eps, float wd, float gscale,
-                                              float* ps, const float* gs, float* ms, float* vs, int64_t n) {
+                                              float* ps, const float* gs, float* ms, float* vs, int64_t n, const float* step_dev) {
+  if (step_dev) step_size = __ldg(step_dev);  // recorded steps (CUDA graph): the bias-corrected step size lives in device memory
   auto upd = [&](float& pp, float g, float& mm, float& vv) {
     g = g * gscale + wd * pp;
     mm = b1 * mm + (1.f - b1) * g;
@@ -350,6 +351,15 @@ __global__ void __launch_bounds__(256) k_adam(float4* p, const float4* grad, flo
   }
   if (blockIdx.x == 0)
     for (int64_t i = n4 * 4 + threadIdx.x; i < n; i += blockDim.x) upd(ps[i], gs[i], ms[i], vs[i]);
+}
+
+// state = {t (as float bits of an int), lr}: writes lr * sqrt(1 - b2^t) / (1 - b1^t) and advances t — the host arithmetic of
+// pdn_adam_step (reference optimizer.py:185-196), done on the device so that a recorded step can be replayed
+__global__ void k_adam_prepare(int* t, const float* lr, float* step_size, float b1, float b2) {
+  const int    tt = *t;
+  const double a_t = sqrt(1.0 - pow((double)b2, (double)tt)) / (1.0 - pow((double)b1, (double)tt));
+  *step_size = (float)((double)*lr * a_t);
+  *t = tt + 1;
 }
 
 static inline int rows_grid(int64_t rows, int warps_per_block) { return (int)((rows + warps_per_block - 1) / warps_per_block); }
@@ -510,7 +520,21 @@ int pdn_adam_step(float* p, const float* grad, float* m, float* v, int64_t n, fl
   bool    al = (((uintptr_t)p | (uintptr_t)grad | (uintptr_t)m | (uintptr_t)v) & 15) == 0;
   int64_t n4 = al ? n / 4 : 0;
   k_adam<<<grid_for(n4 > 0 ? n4 : 1, 256), 256, 0, stream()>>>((float4*)p, (const float4*)grad, (float4*)m, (float4*)v, n4, step_size, b1, b2, eps,
-                                                                wd, grad_scale, p, grad, m, v, n);
+                                                                wd, grad_scale, p, grad, m, v, n, nullptr);
+  PDN_LAUNCHED("adam");
+  return 0;
+}
+
+int pdn_adam_step_dev(float* p, const float* grad, float* m, float* v, int64_t n, float b1, float b2, float eps, float wd, float grad_scale,
+                      int* t_dev, const float* lr_dev, float* step_dev) {
+  PDN_TRY(ensure_init());
+  if (n == 0) return 0;
+  k_adam_prepare<<<1, 1, 0, stream()>>>(t_dev, lr_dev, step_dev, b1, b2);
+  PDN_LAUNCHED("adam_prepare");
+  bool    al = (((uintptr_t)p | (uintptr_t)grad | (uintptr_t)m | (uintptr_t)v) & 15) == 0;
+  int64_t n4 = al ? n / 4 : 0;
+  k_adam<<<grid_for(n4 > 0 ? n4 : 1, 256), 256, 0, stream()>>>((float4*)p, (const float4*)grad, (float4*)m, (float4*)v, n4, 0.f, b1, b2, eps, wd,
+                                                                grad_scale, p, grad, m, v, n, step_dev);
   PDN_LAUNCHED("adam");
   return 0;
 }

@@ -2,6 +2,7 @@
 // Replaces what the reference gets from CuPy's runtime + memory pool (reference pydynet/cuda.py:16-32,
 // tensor.py:80,90): nothing here is ported, the reference has no native runtime.
 #include "common.cuh"
+#include <nvtx3/nvToolsExt.h>  // header-only: resolves the profiler's injection library at run time, no link dependency
 
 #include <stdarg.h>
 #include <map>
@@ -26,8 +27,11 @@ int cuda_fail(cudaError_t e, const char* what, const char* file, int line) {
   return e == cudaErrorMemoryAllocation ? PDN_ERR_OOM : PDN_ERR_CUDA;
 }
 
+static bool g_nvtx = getenv("PDN_NVTX") != nullptr;  // PDN_NVTX=1: every kernel launch is marked by its entry-point name
+
 int after_launch(const char* name) {
   ++g_launches;
+  if (g_nvtx) nvtxMarkA(name);
   cudaError_t e = cudaPeekAtLastError();
   if (e != cudaSuccess) {
     cudaGetLastError();
@@ -401,6 +405,14 @@ int pdn_graph_begin(void) {
   g_capture_launch0 = g_launches;
   return 0;
 }
+/* debugging aid: 0 = no capture, 1 = capture active, 2 = capture invalidated by an operation that cannot be recorded */
+int pdn_graph_status(int* status) {
+  cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
+  cudaError_t e = cudaStreamIsCapturing(stream(), &st);
+  if (e != cudaSuccess) cudaGetLastError();
+  *status = (e != cudaSuccess || st == cudaStreamCaptureStatusInvalidated) ? 2 : (st == cudaStreamCaptureStatusActive ? 1 : 0);
+  return 0;
+}
 int pdn_graph_end(void** graph_exec) {
   PDN_CHECK(g_capturing, "no graph capture active");
   int gid;
@@ -496,3 +508,13 @@ int make_desc(int ndim, const int64_t* shape, int nops, const int64_t* const* st
   return 0;
 }
 }  // namespace pdn
+
+// ---- NVTX ranges (profiling aid): phases of a step as named ranges for ncu --nvtx / nsys -------------------------
+extern "C" int pdn_nvtx_push(const char* name) {
+  nvtxRangePushA(name ? name : "pdn");
+  return 0;
+}
+extern "C" int pdn_nvtx_pop(void) {
+  nvtxRangePop();
+  return 0;
+}

@@ -302,6 +302,11 @@ class DataParallel:
     def sync_gradients(self):
         if self.world == 1:
             return
+        from .cuda import nvtx_range
+        with nvtx_range("grad_allreduce"):
+            self._sync_gradients()
+
+    def _sync_gradients(self):
         if self._flat is not None:
             from .backend import lib
             if self.overlap and self._armed:

@@ -84,9 +84,39 @@ class FlatAdamState:
                 p._grad_stale = False
 
     def step(self, lr, b1, b2, eps, wd, t, grad_scale):
+        from .. import cuda
         with self.device:
             self.repin()
             self._settle_grads()
             self.flat_p.buf.version += 1
+            if cuda.is_capturing():
+                # a step being RECORDED (cuda.graphed_step): the step counter and the learning rate live in device memory and the
+                # bias correction is computed there, so every replay of the recording is the NEXT optimizer step
+                st = self.device_state(t, lr)
+                L.call("pdn_adam_step_dev", self.flat_p.ptr, self.flat_g.ptr, self.flat_m.ptr, self.flat_v.ptr, self.total, b1, b2, eps, wd,
+                       grad_scale, st["t"].ptr, st["lr"].ptr, st["step"].ptr)
+                return
             L.call("pdn_adam_step", self.flat_p.ptr, self.flat_g.ptr, self.flat_m.ptr, self.flat_v.ptr, self.total, lr, b1, b2, eps,
                    wd, t, grad_scale)
+
+    _dev_state = None
+
+    def device_state(self, t=None, lr=None):
+        """{t: int32[1], lr: float32[1], step: float32[1]} on the device (created outside a recording by cuda.graphed_step)."""
+        if self._dev_state is None:
+            if t is None:
+                return None
+            from .. import cuda
+            assert not cuda.is_capturing(), "the device-side optimizer state must exist before the step is recorded"
+            with self.device:
+                self._dev_state = {"t": ndarray.from_host(np.array([t], np.int32)), "lr": ndarray.from_host(np.array([lr], np.float32)),
+                                   "step": ndarray.from_host(np.zeros(1, np.float32)), "lr_host": float(lr)}
+        return self._dev_state
+
+    def sync_device_state(self, t, lr):
+        """Host -> device before a recording or when the host values were changed behind its back (lr schedulers)."""
+        st = self.device_state(t, lr)
+        with self.device:
+            st["t"][...] = np.array([t], np.int32)
+            st["lr"][...] = np.array([lr], np.float32)
+            st["lr_host"] = float(lr)

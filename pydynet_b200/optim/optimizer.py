@@ -98,7 +98,9 @@ class Adam(Optimizer):
 
     def step(self):
         if self._flat is not None:
-            self._flat.step(self.lr, self.beta1, self.beta2, self.eps, self.weight_decay, self.t, self.grad_scale)
+            from ..cuda import nvtx_range
+            with nvtx_range("optimizer.step"):
+                self._flat.step(self.lr, self.beta1, self.beta2, self.eps, self.weight_decay, self.t, self.grad_scale)
             self.t += 1
             return
         a_t = sqrt(1 - self.beta2**self.t) / (1 - self.beta1**self.t)

@@ -82,6 +82,18 @@ def workload(name):
         X, y = pdn.Tensor(np.random.rand(64, 1, 28, 28).astype(np.float32), device=dev), pdn.Tensor(np.random.randint(0, 10, 64), device=dev)
         net.train()
         return lambda: train_step(net, opt, X, y)
+    if name == "lenet_graphed":
+        # the same step recorded into a CUDA graph by pydynet_b200.cuda.graphed_step (2 eager warm-up calls, 1 recording, replays)
+        from workloads.lenet import ConvNet, train_step
+        np.random.seed(42)
+        net = ConvNet().to(dev)
+        opt = Adam(net.parameters(), lr=1e-4)
+        X, y = pdn.Tensor(np.random.rand(64, 1, 28, 28).astype(np.float32), device=dev), pdn.Tensor(np.random.randint(0, 10, 64), device=dev)
+        net.train()
+        gs = pdn.cuda.graphed_step(lambda a, b: train_step(net, opt, a, b), optimizers=[opt])
+        step = lambda: gs(X, y)
+        step.optimizer = opt
+        return step
     if name == "encoder":
         from workloads.encoder import Transformer, train_step
         np.random.seed(0)
@@ -127,6 +139,8 @@ def workload(name):
 def measure(name, warm=2, steps=3):
     install()
     step = workload(name)
+    if name.endswith("_graphed"):
+        warm = 4  # 2 eager calls + the recording + its first replay
     for _ in range(warm):
         step()
     per_step = []
@@ -134,7 +148,10 @@ def measure(name, warm=2, steps=3):
         trace.clear()
         step()
         per_step.append(collections.Counter(ev[0] for ev in trace))
-    return [dict(c) for c in per_step]
+    out = [dict(c) for c in per_step]
+    if hasattr(step, "optimizer"):
+        out.append({"adam_t": step.optimizer.t})
+    return out
 
 
 if __name__ == "__main__":

@@ -28,3 +28,17 @@ def test_steady_state_step_has_no_synchronising_copies(name, budget):
         assert launches <= budget, (launches, s)
     if name == "matmul":  # x @ w forward + two gradient products: three GEMMs through the plane-caching entry point
         assert steps[0].get("pdn_gemm_cached", 0) == 3 and steps[0].get("pdn_gemm", 0) == 0
+
+
+def test_graphed_step_replays_one_graph_launch_per_step():
+    """pydynet_b200.cuda.graphed_step: after 2 eager calls and the recording, a training step is the two input copies + ONE graph
+    launch — no kernel launch, allocation or synchronising copy issued from Python — and the optimizer's host step counter keeps
+    counting (it starts at 1; 4 warm + 3 measured steps have run)."""
+    *steps, extra = _measure("lenet_graphed")
+    assert steps[0] == steps[1] == steps[2]
+    s = steps[0]
+    assert s.get("pdn_graph_launch") == 1, s
+    assert not any(s.get(k, 0) for k in SYNCING), s
+    others = {k: v for k, v in s.items() if k not in ("pdn_graph_launch", "pdn_get_device", "pdn_set_device")}
+    assert sum(others.values()) <= 4, others  # copies of X and y into the recorded input buffers
+    assert extra["adam_t"] == 1 + 7
