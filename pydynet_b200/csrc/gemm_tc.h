@@ -51,5 +51,9 @@ int conv_tma_bwd_weight(const float* x, const float* gy, float* dw, int64_t N, i
                         int k, int pad, long long x_version, long long gy_version);
 int gemm_tc_conv(const float* src, const ConvGeom& geom, int mode, int64_t Mtot, int Ktot, const PackedOperand& B, TcArgs t);
 int gemm_tc_packed(const PackedOperand& A, const PackedOperand& B, TcArgs t, int splits, int* n_tiles_out = nullptr);
+// persistent whole-sequence GRU recurrence (rnn_persist.cu)
+bool gru_persist_ok(int64_t T, int64_t B, int64_t H);
+int  gru_persist_forward(const float* xp1, const float* xp2, const float* h0, const PackedOperand& W1p, const PackedOperand& W2p, const PackedOperand& hP0,
+                         const PackedOperand& hP1, const PackedOperand& rhP, float* hs, float* zr, float* nn, int64_t T, int64_t B, int64_t H);
 
 }  // namespace pdn

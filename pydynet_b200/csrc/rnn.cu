@@ -167,8 +167,6 @@ int pdn_gru_seq_fwd(const float* xp1, const float* xp2, const float* h0, const f
   PDN_TRY(ensure_init());
   if (T == 0 || B == 0 || H == 0) return 0;
   const int64_t BH = B * H;
-  PDN_CUDA(cudaMemcpyAsync(zr, xp1, (size_t)T * BH * 2 * sizeof(float), cudaMemcpyDeviceToDevice, stream()));
-  PDN_CUDA(cudaMemcpyAsync(nn, xp2, (size_t)T * BH * sizeof(float), cudaMemcpyDeviceToDevice, stream()));
   Scratch       sW1, sW2, sH, sRH;
   PackedOperand W1, W2, Hp, RHp;
   // B operands: rows = output column n, k = hidden index: Wh[k, n]
@@ -179,6 +177,14 @@ int pdn_gru_seq_fwd(const float* xp1, const float* xp2, const float* h0, const f
   const int grd = grid_for(BH, 256);
   k_rows_to_planes<<<grd, 256, 0, stream()>>>(h0, H, (__nv_bfloat16*)Hp.planes, B, H, Hp.Kp);
   PDN_LAUNCHED("rows_to_planes");
+  if (gru_persist_ok(T, B, H)) {  // the whole recurrence as ONE persistent cooperative launch (rnn_persist.cu)
+    Scratch       sH1;
+    PackedOperand Hp1;
+    PDN_TRY(alloc_planes(&sH1, &Hp1, B, H));
+    return gru_persist_forward(xp1, xp2, h0, W1, W2, Hp, Hp1, RHp, hs, zr, nn, T, B, H);
+  }
+  PDN_CUDA(cudaMemcpyAsync(zr, xp1, (size_t)T * BH * 2 * sizeof(float), cudaMemcpyDeviceToDevice, stream()));
+  PDN_CUDA(cudaMemcpyAsync(nn, xp2, (size_t)T * BH * sizeof(float), cudaMemcpyDeviceToDevice, stream()));
   TcArgs t;
   for (int64_t s = 0; s < T; ++s) {
     const float* hprev = s == 0 ? h0 : hs + (s - 1) * BH;

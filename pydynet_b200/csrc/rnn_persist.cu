@@ -1,0 +1,371 @@
+// rnn_persist.cu — the GRU recurrence of a WHOLE sequence as one persistent cooperative kernel (forward and BPTT).
+//
+// Reference: a Python loop of cells, per time step zr = sigmoid(x Wx1 + h Wh1 + b1), n = tanh(x Wx2 + (r o h) Wh2 + b2),
+// h' = (1 - z) o h + z o n (pydynet/nn/modules/rnn.py:529-544, 702-708): 18 eager nodes and 4 small sgemms per step. The input
+// projections of all T steps are hoisted into one large GEMM by the caller (rnn.cu); what is left is inherently sequential: two
+// DEPENDENT [B, H] x [H, *] products per step. With one launch per product (rnn.cu's loop: 8 launches per step forward + backward)
+// a step costs 71 us on B200, almost all of it launch / pipeline fill / drain of kernels that each run a few microseconds.
+//
+// Here one launch runs all T steps:
+//   * every CTA owns 64 columns of a recurrent weight matrix for the whole sequence: its bf16 hi/lo planes (BF16x3 operand split,
+//     fp32 accuracy) are loaded ONCE by TMA and stay in shared memory (128 KB at H = 512) as the B operand of tcgen05.mma;
+//   * the batch is tiled by 128 rows (MMA M); per step a CTA streams the 128 x H activation planes (h, then r o h) through a
+//     3-stage TMA ring as the A operand, accumulates in TMEM, and its 4 epilogue warps (one thread per batch row) apply the gate
+//     math straight from tensor memory: phase A CTAs (Wh1 columns) write z / r and the r o h planes, phase B CTAs (Wh2 columns)
+//     write n, h_t and the h planes of the next step;
+//   * batch tiles never synchronise with each other (the recurrence is independent per row); inside a batch tile the two phases
+//     hand over through three monotonic counters in global memory (release: threadfence + atomicAdd by one thread after the CTA's
+//     stores; acquire: ld.acquire poll + fence.proxy.async before the TMA loads) — no grid-wide barrier, no kernel boundary.
+// Gate functions are the reference's piecewise forms (tensor.py:1000-1015), identical to rnn.cu's.
+#include "common.cuh"
+#include "gemm_tc.h"
+#include "tc_ptx.cuh"
+
+#include <cuda_bf16.h>
+
+namespace pdn {
+
+constexpr int GP_BM = 128;    // MMA M (tcgen05 M = 64 costs the same cycles and has a different accumulator layout)
+constexpr int GP_BMV = 64;    // batch rows per tile that are real: only they are loaded (TMA box of 64 rows) and written back; the MMA
+                              // also multiplies whatever lies in the other half of the shared-memory tile into accumulator rows
+                              // nobody reads. Half the activation stream per CTA and twice the CTAs per sequence (measured: the
+                              // 256 KB stream of a full tile was 3 us of an 11 us phase)
+constexpr int GP_BN = 64;     // weight columns per CTA (MMA N)
+constexpr int GP_BK = 64;     // k-block: 64 bf16 = one 128-byte swizzle span
+constexpr int GP_STAGES = 3;  // activation ring
+constexpr int GP_MAXKB = 8;   // resident weight tile: up to 8 k-blocks (H <= 512)
+constexpr int GP_ASTAGE = 2 * GP_BM * GP_BK * 2;  // hi + lo tiles of the activations: 32 KB of shared memory (16 KB of it loaded)
+constexpr int GP_ALOAD = 2 * GP_BMV * GP_BK * 2;
+constexpr int GP_WBLOCK = GP_BN * GP_BK * 2;      // one plane of one weight k-block: 8 KB
+
+struct GruPersistArgs {
+  const float *xp1, *xp2, *h0;
+  float *      hs, *zr, *nn;
+  __nv_bfloat16 *hP0, *hP1, *rhP;  // operand planes [2][B][Kp]
+  int           T, B, H, Kp, nbt, ct1, ct2;
+  unsigned int* cnt;  // [nbt][4]: 0 r columns done, 1 z columns done, 2 h done (monotonic over the sequence)
+  unsigned long long* trace;  // PDN_GRU_TRACE=1: globaltimer stamps of one phase A and one phase B CTA at step 100
+};
+
+__device__ __forceinline__ void gp_stamp(const GruPersistArgs& g, int t, bool phaseA, int c, int bt, int slot) {
+  if (g.trace && t == 100 && bt == 0 && c == (phaseA ? g.ct1 / 2 : 0)) {
+    unsigned long long v;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(v));
+    g.trace[(phaseA ? 0 : 16) + slot] = v;
+  }
+}
+
+// The reference's piecewise forms (tensor.py:1000-1015: x > 0 ? 1/(1+e^-x) : 1 - 1/(1+e^x), and the same shape for tanh) written
+// BRANCH-FREE on |x|: both pieces evaluate the same p = 1/(1 + e^-|x|), so one exponential, one reciprocal and a select per element.
+// The epilogue runs one warp per scheduler with nothing to hide latency behind: the first version (two divergent pieces per element,
+// full-range expf and IEEE division) spent 340 cycles per element, 11 us of a 22 us phase.
+__device__ __forceinline__ float gp_sigmoid(float x) {
+  const float p = __fdividef(1.f, 1.f + __expf(-fabsf(x)));
+  return x > 0.f ? p : 1.f - p;
+}
+__device__ __forceinline__ float gp_tanh(float x) {
+  const float q = __fdividef(2.f, 1.f + __expf(-2.f * fabsf(x))) - 1.f;
+  return x > 0.f ? q : -q;
+}
+
+__device__ __forceinline__ unsigned int ld_acquire_u32(const unsigned int* p) {
+  unsigned int v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+// spin until *p >= target; a producer that never arrives must surface as an error, never as a hung GPU (~2 s)
+__device__ __forceinline__ void wait_count(const unsigned int* p, unsigned int target) {
+  long long t0 = 0;
+  int       spins = 0;
+  while (ld_acquire_u32(p) < target) {
+    if (++spins == 2048) {
+      spins = 0;
+      if (t0 == 0) t0 = clock64();
+      else if (clock64() - t0 > 4000000000LL) __trap();
+    }
+  }
+}
+__device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+
+// 4 consecutive values -> bf16 hi / lo planes (8 bytes each; 16 lanes of a row write 128 contiguous bytes per plane)
+__device__ __forceinline__ void put_planes4(__nv_bfloat16* hi, int64_t plane_stride, const float4& a) {
+  const __nv_bfloat16 h0 = __float2bfloat16_rn(a.x), h1 = __float2bfloat16_rn(a.y), h2 = __float2bfloat16_rn(a.z), h3 = __float2bfloat16_rn(a.w);
+  const __nv_bfloat16 l0 = __float2bfloat16_rn(a.x - __bfloat162float(h0)), l1 = __float2bfloat16_rn(a.y - __bfloat162float(h1));
+  const __nv_bfloat16 l2 = __float2bfloat16_rn(a.z - __bfloat162float(h2)), l3 = __float2bfloat16_rn(a.w - __bfloat162float(h3));
+  uint2 H, L;
+  H.x = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16), H.y = (uint32_t)__bfloat16_as_ushort(h2) | ((uint32_t)__bfloat16_as_ushort(h3) << 16);
+  L.x = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16), L.y = (uint32_t)__bfloat16_as_ushort(l2) | ((uint32_t)__bfloat16_as_ushort(l3) << 16);
+  *reinterpret_cast<uint2*>(hi) = H;
+  *reinterpret_cast<uint2*>(hi + plane_stride) = L;
+}
+
+//   warp 0     TMA producer (activation planes of every step; waits for the batch tile's counters)
+//   warp 1     MMA issuer
+//   warp 2     TMEM allocator
+//   warps 4-11 epilogue: the four warps that may read TMEM lanes 0-63 (warp % 4 < 2) move the accumulator to shared memory, then all
+//              eight apply the gate math ROW-MAJOR (16 lanes x float4 per row): every load and store is a whole 256-byte row segment
+__global__ void __launch_bounds__(384, 1)
+k_gru_persist_fwd(const __grid_constant__ CUtensorMap mapH0, const __grid_constant__ CUtensorMap mapH1, const __grid_constant__ CUtensorMap mapRH,
+                  const __grid_constant__ CUtensorMap mapW1, const __grid_constant__ CUtensorMap mapW2, GruPersistArgs g) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t*  smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  const int KB = g.H / GP_BK;
+  uint8_t*  wsm = smem;                                  // [KB][2 planes][64 cols][64 k] resident weights
+  uint8_t*  asm_ = smem + (size_t)KB * 2 * GP_WBLOCK;    // [STAGES][hi 16 KB | lo 16 KB]
+  uint64_t* full_bar = (uint64_t*)(asm_ + GP_STAGES * GP_ASTAGE);
+  uint64_t* empty_bar = full_bar + GP_STAGES;
+  uint64_t* wfull_bar = empty_bar + GP_STAGES;
+  uint64_t* tfull_bar = wfull_bar + 1;
+  uint64_t* tempty_bar = tfull_bar + 1;
+  uint32_t* tmem_slot = (uint32_t*)(tempty_bar + 1);
+
+  const int  warp = warp_id_uniform(), lane = threadIdx.x & 31;
+  const int  nA = g.ct1 * g.nbt;
+  const bool phaseA = (int)blockIdx.x < nA;
+  const int  idx = phaseA ? (int)blockIdx.x : (int)blockIdx.x - nA;
+  const int  ct = phaseA ? g.ct1 : g.ct2;
+  const int  c = idx % ct, bt = idx / ct;  // column tile, batch tile
+  const bool rcols = phaseA && c >= g.ct1 / 2;
+  unsigned int* cnt = g.cnt + bt * 4;
+  const unsigned int per_r = (unsigned int)(g.ct1 / 2), per_h = (unsigned int)g.ct2;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(phaseA ? &mapW1 : &mapW2);
+    tma_prefetch_desc(&mapH0);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < GP_STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(wfull_bar, 1);
+    mbar_init(tfull_bar, 1);
+    mbar_init(tempty_bar, 4);
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc(tmem_slot, 64);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===== TMA producer =====
+    const bool leader = elect_one();
+    if (leader) {  // the CTA's weight columns, once
+      mbar_expect_tx(wfull_bar, (uint32_t)(KB * 2 * GP_WBLOCK));
+      for (int kb = 0; kb < KB; ++kb)
+        for (int pl = 0; pl < 2; ++pl)
+          tma_load_4d(phaseA ? &mapW1 : &mapW2, wfull_bar, wsm + (size_t)(kb * 2 + pl) * GP_WBLOCK, kb * GP_BK, c * GP_BN, pl, 0);
+    }
+    int      stage = 0;
+    uint32_t phase = 0;
+    for (int t = 0; t < g.T; ++t) {
+      // inputs of this step: phase A reads h_{t-1} (planes written by the phase B CTAs of step t-1), phase B reads r o h of step t
+      if (phaseA) {
+        if (t > 0) wait_count(cnt + 2, per_h * (unsigned int)t);
+      } else {
+        wait_count(cnt + 0, per_r * (unsigned int)(t + 1));
+      }
+      if (lane == 0) gp_stamp(g, t, phaseA, c, bt, 0);
+      asm volatile("fence.proxy.async.global;" ::: "memory");  // other SMs' generic-proxy stores -> this SM's async-proxy (TMA) reads
+      if (lane == 0) gp_stamp(g, t, phaseA, c, bt, 1);
+      const CUtensorMap* mA = phaseA ? ((t & 1) ? &mapH1 : &mapH0) : &mapRH;
+      for (int kb = 0; kb < KB; ++kb) {
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        if (leader) {
+          uint8_t* st = asm_ + stage * GP_ASTAGE;
+          mbar_expect_tx(&full_bar[stage], GP_ALOAD);
+          tma_load_4d(mA, &full_bar[stage], st, kb * GP_BK, bt * GP_BMV, 0, 0);
+          tma_load_4d(mA, &full_bar[stage], st + GP_BM * GP_BK * 2, kb * GP_BK, bt * GP_BMV, 1, 0);
+        }
+        if (++stage == GP_STAGES) { stage = 0; phase ^= 1; }
+      }
+      if (lane == 0) gp_stamp(g, t, phaseA, c, bt, 2);
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer =====
+    const bool     leader = elect_one();
+    const uint32_t idesc = make_idesc_bf16(GP_BM, GP_BN);
+    int            stage = 0;
+    uint32_t       phase = 0;
+    mbar_wait(wfull_bar, 0);
+    tc_fence_after();
+    for (int t = 0; t < g.T; ++t) {
+      mbar_wait(tempty_bar, (uint32_t)(t & 1) ^ 1);  // the epilogue of the previous step has drained the accumulator
+      tc_fence_after();
+      for (int kb = 0; kb < KB; ++kb) {
+        mbar_wait(&full_bar[stage], phase);
+        tc_fence_after();
+        if (kb == 0 && lane == 0) gp_stamp(g, t, phaseA, c, bt, 3);
+        if (leader) {
+          const uint32_t sa = smem_u32(asm_ + stage * GP_ASTAGE), sb = smem_u32(wsm + (size_t)kb * 2 * GP_WBLOCK);
+          const uint64_t d_ahi = make_smem_desc_sw128(sa), d_alo = make_smem_desc_sw128(sa + GP_BM * GP_BK * 2);
+          const uint64_t d_bhi = make_smem_desc_sw128(sb), d_blo = make_smem_desc_sw128(sb + GP_WBLOCK);
+#pragma unroll
+          for (int k = 0; k < GP_BK / 16; ++k) {
+            const uint64_t o = 2 * k;  // 32 bytes inside the swizzle span, in 16-byte units
+            umma_bf16(tmem_base, d_alo + o, d_bhi + o, idesc, (kb | k) ? 1u : 0u);
+            umma_bf16(tmem_base, d_ahi + o, d_blo + o, idesc, 1u);
+            umma_bf16(tmem_base, d_ahi + o, d_bhi + o, idesc, 1u);
+          }
+          umma_commit(&empty_bar[stage]);
+        }
+        if (++stage == GP_STAGES) { stage = 0; phase ^= 1; }
+      }
+      if (leader) umma_commit(tfull_bar);
+      if (lane == 0) gp_stamp(g, t, phaseA, c, bt, 4);
+    }
+  } else if (warp >= 4) {
+    // ===== epilogue =====
+    // The accumulator sits in TMEM with one batch row per lane; read that way, every global access of a warp would touch 32 different
+    // lines with 16 bytes each (measured: ~1 us of partial-sector transactions per stored tile, four tiles per step). So the readers
+    // drop the 64 x 64 fp32 tile into shared memory (the idle activation ring) and the math runs row-major.
+    const bool     reader = (warp & 3) < 2;                   // may access TMEM lanes 32 * (warp % 4) ...
+    const int      rq = warp & 1, rc0 = ((warp - 4) >> 2) * 32;  // reader: lane quarter, first of its 32 columns
+    const uint32_t taddr = tmem_base + ((uint32_t)(rq * 32) << 16) + (uint32_t)rc0;
+    float4*        acc4 = reinterpret_cast<float4*>(asm_);    // [64 rows][16 float4], chunk index XOR-swizzled by (row & 7)
+    const int      ew = warp - 4, cch = lane & 15;            // math: rows ew * 8 + 2 i + (lane >> 4), columns 4 * cch .. + 3
+    const int64_t  H = g.H, BH = (int64_t)g.B * H;
+    const int      j0 = c * GP_BN + 4 * cch;  // this thread's first column (phase A: in [0, 2H); phase B: in [0, H))
+    for (int t = 0; t < g.T; ++t) {
+      const float* hprev = t == 0 ? g.h0 : g.hs + (int64_t)(t - 1) * BH;
+      // The operands of the gate math do not depend on the accumulator: they are requested before it is waited for (and before
+      // anything is stored); the input projection even before the step's dependencies have arrived.
+      float4 xr[4], zv[4], hv[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int64_t b = (int64_t)bt * GP_BMV + ew * 8 + 2 * i + (lane >> 4);
+        if (b < g.B) xr[i] = __ldg(reinterpret_cast<const float4*>(phaseA ? g.xp1 + ((int64_t)t * g.B + b) * 2 * H + j0 : g.xp2 + ((int64_t)t * g.B + b) * H + j0));
+      }
+      if (!phaseA) {  // z of this step comes from the z-column CTAs of phase A; h_{t-1} from the previous step's phase B
+        if (lane == 0) wait_count(cnt + 1, per_r * (unsigned int)(t + 1));
+        __syncwarp();
+      } else if (rcols && t > 0) {
+        if (lane == 0) wait_count(cnt + 2, per_h * (unsigned int)t);
+        __syncwarp();
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int64_t b = (int64_t)bt * GP_BMV + ew * 8 + 2 * i + (lane >> 4);
+        if (b < g.B) {
+          if (rcols) hv[i] = __ldcg(reinterpret_cast<const float4*>(hprev + b * H + (j0 - (int)H)));
+          else if (!phaseA) {
+            zv[i] = __ldcg(reinterpret_cast<const float4*>(g.zr + ((int64_t)t * g.B + b) * 2 * H + j0));
+            hv[i] = __ldcg(reinterpret_cast<const float4*>(hprev + b * H + j0));
+          }
+        }
+      }
+      if (threadIdx.x == 128) gp_stamp(g, t, phaseA, c, bt, 5);
+      if (reader) {
+        mbar_wait(tfull_bar, (uint32_t)(t & 1));
+        tc_fence_after();
+        if (threadIdx.x == 128) gp_stamp(g, t, phaseA, c, bt, 6);
+        float v[32];
+        tmem_ld_32x32(taddr, v);
+        tmem_ld_wait();
+        tc_fence_before();  // accumulator is in registers: hand it back
+        __syncwarp();
+        if (lane == 0) mbar_arrive(tempty_bar);
+        const int row = rq * 32 + lane;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) acc4[row * 16 + ((rc0 / 4 + k) ^ (row & 7))] = make_float4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
+      }
+      epi_bar();
+      if (threadIdx.x == 128) gp_stamp(g, t, phaseA, c, bt, 10);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int     row = ew * 8 + 2 * i + (lane >> 4);
+        const int64_t b = (int64_t)bt * GP_BMV + row;
+        if (b >= g.B) continue;
+        float4 a = acc4[row * 16 + (cch ^ (row & 7))];
+        if (phaseA) {
+          a.x = gp_sigmoid(a.x + xr[i].x), a.y = gp_sigmoid(a.y + xr[i].y), a.z = gp_sigmoid(a.z + xr[i].z), a.w = gp_sigmoid(a.w + xr[i].w);
+          *reinterpret_cast<float4*>(g.zr + ((int64_t)t * g.B + b) * 2 * H + j0) = a;
+          if (rcols) {  // r o h_{t-1} -> operand planes of phase B
+            a.x *= hv[i].x, a.y *= hv[i].y, a.z *= hv[i].z, a.w *= hv[i].w;
+            put_planes4(g.rhP + b * g.Kp + (j0 - (int)H), (int64_t)g.B * g.Kp, a);
+          }
+        } else {
+          const int64_t off = ((int64_t)t * g.B + b) * H + j0;
+          a.x = gp_tanh(a.x + xr[i].x), a.y = gp_tanh(a.y + xr[i].y), a.z = gp_tanh(a.z + xr[i].z), a.w = gp_tanh(a.w + xr[i].w);
+          *reinterpret_cast<float4*>(g.nn + off) = a;
+          a.x = (1.f - zv[i].x) * hv[i].x + zv[i].x * a.x, a.y = (1.f - zv[i].y) * hv[i].y + zv[i].y * a.y;
+          a.z = (1.f - zv[i].z) * hv[i].z + zv[i].z * a.z, a.w = (1.f - zv[i].w) * hv[i].w + zv[i].w * a.w;
+          *reinterpret_cast<float4*>(g.hs + off) = a;
+          put_planes4((((t + 1) & 1) ? g.hP1 : g.hP0) + b * g.Kp + j0, (int64_t)g.B * g.Kp, a);
+        }
+      }
+      // this CTA's part of the step is in global memory: publish it to the batch tile's consumers
+      if (threadIdx.x == 128) gp_stamp(g, t, phaseA, c, bt, 7);
+      fence_proxy_async_smem();  // the scratch lives in the activation ring: generic-proxy accesses before the next TMA writes
+      epi_bar();
+      if (threadIdx.x == 128) {
+        gp_stamp(g, t, phaseA, c, bt, 8);
+        __threadfence();
+        atomicAdd(cnt + (phaseA ? (rcols ? 0 : 1) : 2), 1u);
+        gp_stamp(g, t, phaseA, c, bt, 9);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc(tmem_base, 64);
+}
+
+static bool g_persist_off = getenv("PDN_GRU_PERSIST") && getenv("PDN_GRU_PERSIST")[0] == '0';
+
+bool gru_persist_ok(int64_t T, int64_t B, int64_t H) {
+  if (g_persist_off || H % GP_BK != 0 || H / GP_BK > GP_MAXKB || T < 4) return false;
+  const int64_t nbt = (B + GP_BMV - 1) / GP_BMV, ctas = (3 * H / GP_BN) * nbt;
+  return ctas <= sm_count();
+}
+
+// planes: hP0 holds h0 on entry ([2][B][Kp]); W1p / W2p are K-major weight planes [2][2H or H rows][Kp]
+int gru_persist_forward(const float* xp1, const float* xp2, const float* h0, const PackedOperand& W1p, const PackedOperand& W2p, const PackedOperand& hP0,
+                        const PackedOperand& hP1, const PackedOperand& rhP, float* hs, float* zr, float* nn, int64_t T, int64_t B, int64_t H) {
+  const int nbt = (int)((B + GP_BMV - 1) / GP_BMV), ct1 = (int)(2 * H / GP_BN), ct2 = (int)(H / GP_BN);
+  CUtensorMap mH0, mH1, mRH, mW1, mW2;
+  PDN_TRY(tc_make_map(&mH0, hP0.planes, B, H, hP0.Kp, 1, GP_BMV));
+  PDN_TRY(tc_make_map(&mH1, hP1.planes, B, H, hP1.Kp, 1, GP_BMV));
+  PDN_TRY(tc_make_map(&mRH, rhP.planes, B, H, rhP.Kp, 1, GP_BMV));
+  PDN_TRY(tc_make_map(&mW1, W1p.planes, 2 * H, H, W1p.Kp, 1, GP_BN));
+  PDN_TRY(tc_make_map(&mW2, W2p.planes, H, H, W2p.Kp, 1, GP_BN));
+  Scratch* cnt = new Scratch();  // freed stream-ordered below
+  PDN_TRY(cnt->alloc((size_t)nbt * 4 * sizeof(unsigned int)));
+  PDN_CUDA(cudaMemsetAsync(cnt->p, 0, (size_t)nbt * 4 * sizeof(unsigned int), stream()));
+  GruPersistArgs g;
+  g.xp1 = xp1, g.xp2 = xp2, g.h0 = h0, g.hs = hs, g.zr = zr, g.nn = nn;
+  g.hP0 = (__nv_bfloat16*)hP0.planes, g.hP1 = (__nv_bfloat16*)hP1.planes, g.rhP = (__nv_bfloat16*)rhP.planes;
+  g.T = (int)T, g.B = (int)B, g.H = (int)H, g.Kp = (int)hP0.Kp, g.nbt = nbt, g.ct1 = ct1, g.ct2 = ct2;
+  g.cnt = (unsigned int*)cnt->p;
+  g.trace = nullptr;
+  static unsigned long long* trace_buf = nullptr;
+  if (getenv("PDN_GRU_TRACE")) {
+    if (!trace_buf) cudaMalloc(&trace_buf, 32 * 8);
+    cudaMemsetAsync(trace_buf, 0, 32 * 8, stream());
+    g.trace = trace_buf;
+  }
+  const size_t smem = (size_t)(H / GP_BK) * 2 * GP_WBLOCK + (size_t)GP_STAGES * GP_ASTAGE + 1024 + 256;
+  PDN_CUDA(cudaFuncSetAttribute(k_gru_persist_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  void* params[] = {&mH0, &mH1, &mRH, &mW1, &mW2, &g};
+  PDN_CUDA(cudaLaunchCooperativeKernel((const void*)k_gru_persist_fwd, dim3((ct1 + ct2) * nbt), dim3(384), params, smem, stream()));
+  PDN_LAUNCHED("gru_persist_fwd");
+  if (g.trace && T > 100) {
+    unsigned long long h[32];
+    cudaStreamSynchronize(stream());
+    cudaMemcpy(h, g.trace, sizeof(h), cudaMemcpyDeviceToHost);
+    const char* names[16] = {"dep ready", "proxy fence", "TMA issued", "first tile landed", "MMAs committed", "epilogue waiting", "accumulator ready",
+                             "stores issued", "epilogue warps joined", "published", "c0 tmem", "c0 math", "c0 stored", "c1 tmem", "c1 math", "c1 stored"};
+    const unsigned long long t0 = h[0];
+    for (int ph = 0; ph < 2; ++ph) {
+      fprintf(stderr, "[gru trace] step 100, phase %c CTA (ns after phase A's inputs were ready):", ph ? 'B' : 'A');
+      for (int i = 0; i < (ph ? 10 : 16); ++i) fprintf(stderr, " %s=%lld", names[i], (long long)(h[ph * 16 + i] - t0));
+      fprintf(stderr, "\n");
+    }
+  }
+  delete cnt;  // Scratch returns its block to the stream-ordered allocator: reuse is ordered after this kernel
+  return 0;
+}
+
+}  // namespace pdn

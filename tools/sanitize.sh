@@ -13,7 +13,7 @@ mkdir -p gpurun_out
 run() {
   local t=$1
   local extra=""
-  [ "$t" = "memcheck" ] && extra="--leak-check full"
+  # (no --leak-check: the stream-ordered caching allocator keeps its blocks until process exit by design; pdn_empty_cache releases them)
   [ "$t" != "memcheck" ] && expr="$expr and not llama and not plan and not reference_llama"
   echo "== compute-sanitizer --tool $t (pytest -m gpu -k \"$expr\")"
   PDN_SANITIZE=1 timeout 3000 compute-sanitizer --tool "$t" $extra --error-exitcode 9 --print-limit 20 \
