@@ -55,5 +55,8 @@ int gemm_tc_packed(const PackedOperand& A, const PackedOperand& B, TcArgs t, int
 bool gru_persist_ok(int64_t T, int64_t B, int64_t H);
 int  gru_persist_forward(const float* xp1, const float* xp2, const float* h0, const PackedOperand& W1p, const PackedOperand& W2p, const PackedOperand& hP0,
                          const PackedOperand& hP1, const PackedOperand& rhP, float* hs, float* zr, float* nn, int64_t T, int64_t B, int64_t H);
+int  gru_persist_backward(const float* g_hs, const float* h0, const float* hs, const float* zr, const float* nn, const PackedOperand& W2t,
+                          const PackedOperand& W1t, const PackedOperand& dl2P, const PackedOperand& dl1zP, const PackedOperand& dl1rP, float* u1, float* uz,
+                          float* dxp1, float* dxp2, float* dh0, int64_t T, int64_t B, int64_t H);
 
 }  // namespace pdn

@@ -211,6 +211,15 @@ int pdn_gru_seq_bwd(const float* g_hs, const float* h0, const float* hs, const f
   PDN_TRY(pack_operand_ex(Wh2, H, H, H, 1, 0, 0, kOne, kZero, &sW2, &W2t));
   PDN_TRY(pack_operand_ex(Wh1, H, 2 * H, 2 * H, 1, 0, 0, kOne, kZero, &sW1, &W1t));
   PDN_TRY(alloc_planes(&sD2, &D2p, B, H));
+  if (gru_persist_ok(T, B, H)) {  // BPTT of the whole sequence as ONE persistent cooperative launch (rnn_persist.cu)
+    Scratch       sZ, sR, sU1, sUz;
+    PackedOperand D1z, D1r;
+    PDN_TRY(alloc_planes(&sZ, &D1z, B, H));
+    PDN_TRY(alloc_planes(&sR, &D1r, B, H));
+    PDN_TRY(sU1.alloc((size_t)BH * sizeof(float)));
+    PDN_TRY(sUz.alloc((size_t)BH * sizeof(float)));
+    PDN_TRY(gru_persist_backward(g_hs, h0, hs, zr, nn, W2t, W1t, D2p, D1z, D1r, (float*)sU1.p, (float*)sUz.p, dxp1, dxp2, dh0, T, B, H));
+  } else {
   PDN_TRY(alloc_planes(&sD1, &D1p, B, 2 * H));
   PDN_TRY(sDrh.alloc((size_t)BH * sizeof(float)));
   float* dh = dh0;  // running gradient wrt the hidden state lives in the dh0 output buffer
@@ -229,6 +238,7 @@ int pdn_gru_seq_bwd(const float* g_hs, const float* h0, const float* hs, const f
     PDN_LAUNCHED("gru_bwd2");
     tc_init(t, dh, B, H, 2 * H, 1);
     PDN_TRY(gemm_tc_packed(D1p, W1t, t, 1));
+  }
   }
   // weight gradients: single GEMMs over all T*B rows.  dWh1 = Hprevᵀ · dxp1 with Hprev = [h0 ; hs[0..T-2]]
   if (dWh1) {

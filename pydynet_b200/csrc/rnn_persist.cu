@@ -313,6 +313,244 @@ k_gru_persist_fwd(const __grid_constant__ CUtensorMap mapH0, const __grid_consta
   if (warp == 2) tmem_dealloc(tmem_base, 64);
 }
 
+// ------------------------------------------------------------------------------------------------------------------ BPTT
+// Per step s (T-1 ... 0), element (b, k), with hp = h_{s-1}, the saved z, r, n and the running gradient dh (rnn.py:529-544 reversed):
+//   d = dh + g_hs[s];  dl2 = d z (1 - n^2) -> dxp2[s];  dl1z = d (n - hp) z (1 - z) -> dxp1[s][:, k]
+//   drh = dl2 Wh2^T;   dl1r = drh hp r (1 - r) -> dxp1[s][:, H + k]
+//   dh' = d (1 - z) + drh r + dl1z Wh1[:, :H]^T + dl1r Wh1[:, H:]^T
+// Three CTA sets per 64-row batch tile, each CTA with 64 rows k of a weight matrix resident in shared memory (K-major over j):
+//   X1  drh = dl2 . Wh2^T          epilogue: dl1r -> dxp1 + operand planes, u1 = drh r
+//   X2  uz  = dl1z . Wh1[:, :H]^T  (independent of X1: runs beside it)
+//   Y   ur  = dl1r . Wh1[:, H:]^T  epilogue: dh' = d (1 - z) + u1 + uz + ur, then the elementwise part of step s - 1 (dl2, dl1z -> dxp2,
+//       dxp1 and the operand planes of X1 / X2); dh, d and z of a thread's elements stay in REGISTERS across the whole sequence
+// Hand-over counters per batch tile: cY (planes of the next step ready), cX1, cX2. The weight gradients are single large GEMMs over all
+// T*B rows after the loop (rnn.cu), as before.
+struct GruBwdArgs {
+  const float *g_hs, *h0, *hs, *zr, *nn;
+  float *      dxp1, *dxp2, *dh0, *u1, *uz;  // u1, uz: [B][H] fp32 hand-over buffers
+  __nv_bfloat16 *dl2P, *dl1zP, *dl1rP;       // operand planes [2][B][Kp]
+  int           T, B, H, Kp, nbt, ctk;
+  unsigned int* cnt;  // [nbt][4]: 0 cY, 1 cX1, 2 cX2
+};
+
+__global__ void __launch_bounds__(384, 1)
+k_gru_persist_bwd(const __grid_constant__ CUtensorMap mapDl2, const __grid_constant__ CUtensorMap mapDl1z, const __grid_constant__ CUtensorMap mapDl1r,
+                  const __grid_constant__ CUtensorMap mapW2t, const __grid_constant__ CUtensorMap mapW1t, GruBwdArgs g) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t*  smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  const int KB = g.H / GP_BK;
+  uint8_t*  wsm = smem;
+  uint8_t*  asm_ = smem + (size_t)KB * 2 * GP_WBLOCK;
+  uint64_t* full_bar = (uint64_t*)(asm_ + GP_STAGES * GP_ASTAGE);
+  uint64_t* empty_bar = full_bar + GP_STAGES;
+  uint64_t* wfull_bar = empty_bar + GP_STAGES;
+  uint64_t* tfull_bar = wfull_bar + 1;
+  uint64_t* tempty_bar = tfull_bar + 1;
+  uint32_t* tmem_slot = (uint32_t*)(tempty_bar + 1);
+
+  const int  warp = warp_id_uniform(), lane = threadIdx.x & 31;
+  const int  per_set = g.ctk * g.nbt;
+  const int  role = (int)blockIdx.x / per_set;  // 0: X1, 1: X2, 2: Y
+  const int  idx = (int)blockIdx.x - role * per_set;
+  const int  c = idx % g.ctk, bt = idx / g.ctk;
+  unsigned int*      cnt = g.cnt + bt * 4;
+  const unsigned int per = (unsigned int)g.ctk;
+  const CUtensorMap* mW = role == 0 ? &mapW2t : &mapW1t;
+  const CUtensorMap* mA = role == 0 ? &mapDl2 : (role == 1 ? &mapDl1z : &mapDl1r);
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(mW);
+    tma_prefetch_desc(mA);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < GP_STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(wfull_bar, 1);
+    mbar_init(tfull_bar, 1);
+    mbar_init(tempty_bar, 4);
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc(tmem_slot, 64);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===== TMA producer =====
+    const bool leader = elect_one();
+    if (leader) {  // rows k of this CTA; Y contracts over the r half of Wh1's columns
+      mbar_expect_tx(wfull_bar, (uint32_t)(KB * 2 * GP_WBLOCK));
+      for (int kb = 0; kb < KB; ++kb)
+        for (int pl = 0; pl < 2; ++pl)
+          tma_load_4d(mW, wfull_bar, wsm + (size_t)(kb * 2 + pl) * GP_WBLOCK, (role == 2 ? g.H : 0) + kb * GP_BK, c * GP_BN, pl, 0);
+    }
+    int      stage = 0;
+    uint32_t phase = 0;
+    for (int i = 0; i < g.T; ++i) {
+      wait_count(cnt + (role == 2 ? 1 : 0), per * (unsigned int)(i + 1));
+      asm volatile("fence.proxy.async.global;" ::: "memory");
+      for (int kb = 0; kb < KB; ++kb) {
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        if (leader) {
+          uint8_t* st = asm_ + stage * GP_ASTAGE;
+          mbar_expect_tx(&full_bar[stage], GP_ALOAD);
+          tma_load_4d(mA, &full_bar[stage], st, kb * GP_BK, bt * GP_BMV, 0, 0);
+          tma_load_4d(mA, &full_bar[stage], st + GP_BM * GP_BK * 2, kb * GP_BK, bt * GP_BMV, 1, 0);
+        }
+        if (++stage == GP_STAGES) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer =====
+    const bool     leader = elect_one();
+    const uint32_t idesc = make_idesc_bf16(GP_BM, GP_BN);
+    int            stage = 0;
+    uint32_t       phase = 0;
+    mbar_wait(wfull_bar, 0);
+    tc_fence_after();
+    for (int i = 0; i < g.T; ++i) {
+      mbar_wait(tempty_bar, (uint32_t)(i & 1) ^ 1);
+      tc_fence_after();
+      for (int kb = 0; kb < KB; ++kb) {
+        mbar_wait(&full_bar[stage], phase);
+        tc_fence_after();
+        if (leader) {
+          const uint32_t sa = smem_u32(asm_ + stage * GP_ASTAGE), sb = smem_u32(wsm + (size_t)kb * 2 * GP_WBLOCK);
+          const uint64_t d_ahi = make_smem_desc_sw128(sa), d_alo = make_smem_desc_sw128(sa + GP_BM * GP_BK * 2);
+          const uint64_t d_bhi = make_smem_desc_sw128(sb), d_blo = make_smem_desc_sw128(sb + GP_WBLOCK);
+#pragma unroll
+          for (int k = 0; k < GP_BK / 16; ++k) {
+            const uint64_t o = 2 * k;
+            umma_bf16(tmem_base, d_alo + o, d_bhi + o, idesc, (kb | k) ? 1u : 0u);
+            umma_bf16(tmem_base, d_ahi + o, d_blo + o, idesc, 1u);
+            umma_bf16(tmem_base, d_ahi + o, d_bhi + o, idesc, 1u);
+          }
+          umma_commit(&empty_bar[stage]);
+        }
+        if (++stage == GP_STAGES) { stage = 0; phase ^= 1; }
+      }
+      if (leader) umma_commit(tfull_bar);
+    }
+  } else if (warp >= 4) {
+    // ===== epilogue (accumulator -> shared memory by the four TMEM readers, row-major math by all eight warps) =====
+    const bool     reader = (warp & 3) < 2;
+    const int      rq = warp & 1, rc0 = ((warp - 4) >> 2) * 32;
+    const uint32_t taddr = tmem_base + ((uint32_t)(rq * 32) << 16) + (uint32_t)rc0;
+    float4*        acc4 = reinterpret_cast<float4*>(asm_);
+    const int      ew = warp - 4, cch = lane & 15;
+    const int64_t  H = g.H, BH = (int64_t)g.B * H, PS = (int64_t)g.B * g.Kp;
+    const int      k0 = c * GP_BN + 4 * cch;  // this thread's first hidden index k
+    int64_t        brow[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) brow[e] = (int64_t)bt * GP_BMV + ew * 8 + 2 * e + (lane >> 4);
+    float4 dh[4], dd[4], zz[4];  // Y: running dh, d and z of the step being processed
+    // elementwise part of step s for this thread's elements (Y): d = dh + g_hs[s]; dl2, dl1z -> dxp2 / dxp1 / operand planes
+    auto elementwise = [&](int s) {
+      const float* hprev = s == 0 ? g.h0 : g.hs + (int64_t)(s - 1) * BH;
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int64_t b = brow[e];
+        if (b >= g.B) continue;
+        const int64_t o1 = ((int64_t)s * g.B + b) * H + k0, o2 = ((int64_t)s * g.B + b) * 2 * H + k0;
+        const float4  gg = g.g_hs ? __ldg(reinterpret_cast<const float4*>(g.g_hs + o1)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        const float4  z = __ldg(reinterpret_cast<const float4*>(g.zr + o2)), n = __ldg(reinterpret_cast<const float4*>(g.nn + o1));
+        const float4  hp = __ldg(reinterpret_cast<const float4*>(hprev + b * H + k0));
+        float4        d = make_float4(dh[e].x + gg.x, dh[e].y + gg.y, dh[e].z + gg.z, dh[e].w + gg.w);
+        const float4  dl2 = make_float4(d.x * z.x * (1.f - n.x * n.x), d.y * z.y * (1.f - n.y * n.y), d.z * z.z * (1.f - n.z * n.z), d.w * z.w * (1.f - n.w * n.w));
+        const float4  dl1 = make_float4(d.x * (n.x - hp.x) * z.x * (1.f - z.x), d.y * (n.y - hp.y) * z.y * (1.f - z.y), d.z * (n.z - hp.z) * z.z * (1.f - z.z),
+                                        d.w * (n.w - hp.w) * z.w * (1.f - z.w));
+        *reinterpret_cast<float4*>(g.dxp2 + o1) = dl2;
+        *reinterpret_cast<float4*>(g.dxp1 + o2) = dl1;
+        put_planes4(g.dl2P + b * g.Kp + k0, PS, dl2);
+        put_planes4(g.dl1zP + b * g.Kp + k0, PS, dl1);
+        dd[e] = d, zz[e] = z;
+      }
+    };
+    auto publish = [&](int which) {
+      fence_proxy_async_smem();
+      epi_bar();
+      if (threadIdx.x == 128) {
+        __threadfence();
+        atomicAdd(cnt + which, 1u);
+      }
+    };
+    if (role == 2) {  // prologue: the last time step starts from dh = 0
+#pragma unroll
+      for (int e = 0; e < 4; ++e) dh[e] = make_float4(0.f, 0.f, 0.f, 0.f);
+      elementwise(g.T - 1);
+      publish(0);
+    }
+    for (int i = 0; i < g.T; ++i) {
+      const int    s = g.T - 1 - i;
+      const float* hprev = s == 0 ? g.h0 : g.hs + (int64_t)(s - 1) * BH;
+      float4       rr[4], hp[4], u1[4], uz[4];
+      if (role == 0) {  // r and h_{s-1} do not depend on the accumulator
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+          if (brow[e] < g.B) {
+            rr[e] = __ldg(reinterpret_cast<const float4*>(g.zr + ((int64_t)s * g.B + brow[e]) * 2 * H + H + k0));
+            hp[e] = __ldg(reinterpret_cast<const float4*>(hprev + brow[e] * H + k0));
+          }
+      } else if (role == 2) {  // u1 / uz of this step come from the X1 / X2 CTAs
+        if (lane == 0) {
+          wait_count(cnt + 1, per * (unsigned int)(i + 1));
+          wait_count(cnt + 2, per * (unsigned int)(i + 1));
+        }
+        __syncwarp();
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+          if (brow[e] < g.B) {
+            u1[e] = __ldcg(reinterpret_cast<const float4*>(g.u1 + brow[e] * H + k0));
+            uz[e] = __ldcg(reinterpret_cast<const float4*>(g.uz + brow[e] * H + k0));
+          }
+      }
+      if (reader) {
+        mbar_wait(tfull_bar, (uint32_t)(i & 1));
+        tc_fence_after();
+        float v[32];
+        tmem_ld_32x32(taddr, v);
+        tmem_ld_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(tempty_bar);
+        const int row = rq * 32 + lane;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) acc4[row * 16 + ((rc0 / 4 + k) ^ (row & 7))] = make_float4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
+      }
+      epi_bar();
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int     row = ew * 8 + 2 * e + (lane >> 4);
+        const int64_t b = brow[e];
+        if (b >= g.B) continue;
+        const float4 a = acc4[row * 16 + (cch ^ (row & 7))];
+        if (role == 0) {
+          const float4 r = rr[e], h = hp[e];
+          const float4 dl1r = make_float4(a.x * h.x * r.x * (1.f - r.x), a.y * h.y * r.y * (1.f - r.y), a.z * h.z * r.z * (1.f - r.z), a.w * h.w * r.w * (1.f - r.w));
+          *reinterpret_cast<float4*>(g.dxp1 + ((int64_t)s * g.B + b) * 2 * H + H + k0) = dl1r;
+          put_planes4(g.dl1rP + b * g.Kp + k0, PS, dl1r);
+          *reinterpret_cast<float4*>(g.u1 + b * H + k0) = make_float4(a.x * r.x, a.y * r.y, a.z * r.z, a.w * r.w);
+        } else if (role == 1) {
+          *reinterpret_cast<float4*>(g.uz + b * H + k0) = a;
+        } else {
+          const float4 d = dd[e], z = zz[e];
+          dh[e] = make_float4(d.x * (1.f - z.x) + u1[e].x + uz[e].x + a.x, d.y * (1.f - z.y) + u1[e].y + uz[e].y + a.y, d.z * (1.f - z.z) + u1[e].z + uz[e].z + a.z,
+                              d.w * (1.f - z.w) + u1[e].w + uz[e].w + a.w);
+          if (s == 0) *reinterpret_cast<float4*>(g.dh0 + b * H + k0) = dh[e];
+        }
+      }
+      if (role == 2 && s > 0) elementwise(s - 1);
+      publish(role == 0 ? 1 : (role == 1 ? 2 : 0));
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc(tmem_base, 64);
+}
+
 static bool g_persist_off = getenv("PDN_GRU_PERSIST") && getenv("PDN_GRU_PERSIST")[0] == '0';
 
 bool gru_persist_ok(int64_t T, int64_t B, int64_t H) {
@@ -365,6 +603,33 @@ int gru_persist_forward(const float* xp1, const float* xp2, const float* h0, con
     }
   }
   delete cnt;  // Scratch returns its block to the stream-ordered allocator: reuse is ordered after this kernel
+  return 0;
+}
+
+// W2t: K-major planes of Wh2 as [H rows k][Kp over j]; W1t: Wh1 as [H rows k][Kp over 2H columns j]; dl2P / dl1zP / dl1rP / u1 / uz: scratch
+int gru_persist_backward(const float* g_hs, const float* h0, const float* hs, const float* zr, const float* nn, const PackedOperand& W2t,
+                         const PackedOperand& W1t, const PackedOperand& dl2P, const PackedOperand& dl1zP, const PackedOperand& dl1rP, float* u1, float* uz,
+                         float* dxp1, float* dxp2, float* dh0, int64_t T, int64_t B, int64_t H) {
+  const int nbt = (int)((B + GP_BMV - 1) / GP_BMV), ctk = (int)(H / GP_BN);
+  CUtensorMap m2, m1z, m1r, mW2, mW1;
+  PDN_TRY(tc_make_map(&m2, dl2P.planes, B, H, dl2P.Kp, 1, GP_BMV));
+  PDN_TRY(tc_make_map(&m1z, dl1zP.planes, B, H, dl1zP.Kp, 1, GP_BMV));
+  PDN_TRY(tc_make_map(&m1r, dl1rP.planes, B, H, dl1rP.Kp, 1, GP_BMV));
+  PDN_TRY(tc_make_map(&mW2, W2t.planes, H, H, W2t.Kp, 1, GP_BN));
+  PDN_TRY(tc_make_map(&mW1, W1t.planes, H, 2 * H, W1t.Kp, 1, GP_BN));
+  Scratch cnt;
+  PDN_TRY(cnt.alloc((size_t)nbt * 4 * sizeof(unsigned int)));
+  PDN_CUDA(cudaMemsetAsync(cnt.p, 0, (size_t)nbt * 4 * sizeof(unsigned int), stream()));
+  GruBwdArgs g;
+  g.g_hs = g_hs, g.h0 = h0, g.hs = hs, g.zr = zr, g.nn = nn, g.dxp1 = dxp1, g.dxp2 = dxp2, g.dh0 = dh0, g.u1 = u1, g.uz = uz;
+  g.dl2P = (__nv_bfloat16*)dl2P.planes, g.dl1zP = (__nv_bfloat16*)dl1zP.planes, g.dl1rP = (__nv_bfloat16*)dl1rP.planes;
+  g.T = (int)T, g.B = (int)B, g.H = (int)H, g.Kp = (int)dl2P.Kp, g.nbt = nbt, g.ctk = ctk;
+  g.cnt = (unsigned int*)cnt.p;
+  const size_t smem = (size_t)(H / GP_BK) * 2 * GP_WBLOCK + (size_t)GP_STAGES * GP_ASTAGE + 1024 + 256;
+  PDN_CUDA(cudaFuncSetAttribute(k_gru_persist_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  void* params[] = {&m2, &m1z, &m1r, &mW2, &mW1, &g};
+  PDN_CUDA(cudaLaunchCooperativeKernel((const void*)k_gru_persist_bwd, dim3(3 * ctk * nbt), dim3(384), params, smem, stream()));
+  PDN_LAUNCHED("gru_persist_bwd");
   return 0;
 }
 
