@@ -112,45 +112,61 @@ struct PoolGeom {
 };
 
 __global__ void __launch_bounds__(256) k_pool_fwd(const float* __restrict__ x, float* __restrict__ y, PoolGeom g) {
-  const int64_t total = g.N * g.C * g.oh * g.ow;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t ox = i % g.ow, oy = (i / g.ow) % g.oh, nc = i / (g.ow * g.oh);
-    const float* xp = x + nc * g.H * g.W;
-    float acc = g.mode == 0 ? -INFINITY : 0.f;
-    for (int ky = 0; ky < g.k; ++ky)
-      for (int kx = 0; kx < g.k; ++kx) {
-        const int64_t iy = oy * g.stride + ky - g.pad, ix = ox * g.stride + kx - g.pad;
+  const unsigned total = (unsigned)(g.N * g.C * g.oh * g.ow);  // 32-bit index arithmetic (checked on the host)
+  const unsigned ow = (unsigned)g.ow, oh = (unsigned)g.oh;
+  const int      H = (int)g.H, W = (int)g.W, k = g.k;
+  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const unsigned r = i / ow, ox = i - r * ow, nc = r / oh, oy = r - nc * oh;
+    const float*   xp = x + (size_t)nc * H * W;
+    float          acc = g.mode == 0 ? -INFINITY : 0.f;
+    for (int ky = 0; ky < k; ++ky)
+      for (int kx = 0; kx < k; ++kx) {
+        const int iy = (int)oy * g.stride + ky - g.pad, ix = (int)ox * g.stride + kx - g.pad;
         // zero padding takes part in the max / mean exactly like the reference's xp.pad (functional.py:235-251)
-        const float v = (iy < 0 || iy >= g.H || ix < 0 || ix >= g.W) ? 0.f : xp[iy * g.W + ix];
+        const float v = (iy < 0 || iy >= H || ix < 0 || ix >= W) ? 0.f : __ldg(xp + iy * W + ix);
         acc = g.mode == 0 ? fmaxf(acc, v) : acc + v;
       }
-    y[i] = g.mode == 0 ? acc : acc / (float)(g.k * g.k);
+    y[i] = g.mode == 0 ? acc : acc / (float)(k * k);
   }
 }
 
 // one thread per INPUT element gathers from every window that contains it (no atomics): max mode gives the window's full
-// gradient to every element equal to the window max (tensor.py:741-747)
+// gradient to every element equal to the window max (tensor.py:741-747). Index arithmetic is 32-bit (the host checks the tensor has
+// fewer than 2^31 elements): the first version did its div / mod in 64 bits inside the window loops and took 76 us for the 4 M-element
+// tensor of LeNet's first pooling layer - 19 % of the recorded training step.
 __global__ void __launch_bounds__(256) k_pool_bwd(const float* __restrict__ x, const float* __restrict__ y, const float* __restrict__ gy,
                                                   float* __restrict__ dx, PoolGeom g) {
-  const int64_t total = g.N * g.C * g.H * g.W;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t ix = i % g.W, iy = (i / g.W) % g.H, nc = i / (g.W * g.H);
-    const float xv = x[i];
-    const float *yp = y + nc * g.oh * g.ow, *gp = gy + nc * g.oh * g.ow;
-    float acc = 0.f;
-    for (int ky = 0; ky < g.k; ++ky) {
-      const int64_t ty = iy + g.pad - ky;
-      if (ty < 0 || ty % g.stride) continue;
-      const int64_t oy = ty / g.stride;
-      if (oy >= g.oh) continue;
-      for (int kx = 0; kx < g.k; ++kx) {
-        const int64_t tx = ix + g.pad - kx;
-        if (tx < 0 || tx % g.stride) continue;
-        const int64_t ox = tx / g.stride;
-        if (ox >= g.ow) continue;
-        const float gg = gp[oy * g.ow + ox];
-        if (g.mode == 0) acc += (yp[oy * g.ow + ox] == xv) ? gg : 0.f;
-        else acc += gg / (float)(g.k * g.k);
+  const unsigned total = (unsigned)(g.N * g.C * g.H * g.W);
+  const unsigned W = (unsigned)g.W, H = (unsigned)g.H, ow = (unsigned)g.ow, oh = (unsigned)g.oh;
+  const int      k = g.k, stride = g.stride, pad = g.pad;
+  const float    kk = (float)(k * k);
+  const bool     tiled = (stride == k) && pad == 0;  // non-overlapping windows: an element belongs to at most one
+  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const unsigned r = i / W, ix = i - r * W, nc = r / H, iy = r - nc * H;
+    const float    xv = x[i];
+    const float *  yp = y + (size_t)nc * oh * ow, *gp = gy + (size_t)nc * oh * ow;
+    float          acc = 0.f;
+    if (tiled) {
+      const unsigned oy = iy / (unsigned)k, ox = ix / (unsigned)k;
+      if (oy < oh && ox < ow) {
+        const float gg = __ldg(gp + oy * ow + ox);
+        acc = g.mode == 0 ? ((__ldg(yp + oy * ow + ox) == xv) ? gg : 0.f) : gg / kk;
+      }
+    } else {
+      for (int ky = 0; ky < k; ++ky) {
+        const int ty = (int)iy + pad - ky;
+        if (ty < 0 || ty % stride) continue;
+        const int oy = ty / stride;
+        if (oy >= (int)oh) continue;
+        for (int kx = 0; kx < k; ++kx) {
+          const int tx = (int)ix + pad - kx;
+          if (tx < 0 || tx % stride) continue;
+          const int ox = tx / stride;
+          if (ox >= (int)ow) continue;
+          const float gg = __ldg(gp + oy * ow + ox);
+          if (g.mode == 0) acc += (__ldg(yp + oy * ow + ox) == xv) ? gg : 0.f;
+          else acc += gg / kk;
+        }
       }
     }
     dx[i] = acc;
@@ -257,6 +273,7 @@ int pdn_pool2d_fwd(const float* x, float* y, int64_t N, int64_t C, int64_t H, in
   PoolGeom g{N, C, H, W, (H + 2 * pad - k) / stride + 1, (W + 2 * pad - k) / stride + 1, k, stride, pad, mode};
   const int64_t total = N * C * g.oh * g.ow;
   if (total == 0) return 0;
+  PDN_CHECK(N * C * H * W < (int64_t)1 << 31, "pool2d_fwd: tensors of 2^31 elements or more are not supported");
   k_pool_fwd<<<grid_for(total, 256), 256, 0, stream()>>>(x, y, g);
   PDN_LAUNCHED("pool_fwd");
   return 0;
@@ -269,6 +286,7 @@ int pdn_pool2d_bwd(const float* x, const float* y, const float* gy, float* dx, i
   PoolGeom g{N, C, H, W, (H + 2 * pad - k) / stride + 1, (W + 2 * pad - k) / stride + 1, k, stride, pad, mode};
   const int64_t total = N * C * H * W;
   if (total == 0) return 0;
+  PDN_CHECK(total < (int64_t)1 << 31, "pool2d_bwd: tensors of 2^31 elements or more are not supported");
   k_pool_bwd<<<grid_for(total, 256), 256, 0, stream()>>>(x, y, gy, dx, g);
   PDN_LAUNCHED("pool_bwd");
   return 0;

@@ -874,7 +874,12 @@ int pdn_decoder_step(void* handle, const int64_t* ids, int64_t ids_stride, int64
   a.nsplit = ns;
   a.epoch = (unsigned int)((h->launches % 0xfffffffeull) + 1);
   void* params[] = {&a};
-  PDN_CUDA(cudaLaunchCooperativeKernel(h->fn, dim3(h->grid), dim3(MEGA_THREADS), params, h->dyn_smem, stream()));
+  // Cooperative launch: the runtime guarantees that all CTAs are co-resident, which is what makes the polling between them safe.
+  // (PDN_MEGA_COOP=0 launches the same grid as an ordinary kernel - one CTA per SM by its shared-memory footprint, so co-resident
+  // on an otherwise idle device - to measure what the cooperative launch path itself costs per token.)
+  static const bool coop = !(getenv("PDN_MEGA_COOP") && getenv("PDN_MEGA_COOP")[0] == '0');
+  if (coop) PDN_CUDA(cudaLaunchCooperativeKernel(h->fn, dim3(h->grid), dim3(MEGA_THREADS), params, h->dyn_smem, stream()));
+  else PDN_CUDA(cudaLaunchKernel(h->fn, dim3(h->grid), dim3(MEGA_THREADS), params, h->dyn_smem, stream()));
   PDN_LAUNCHED("decode_mega");
   h->launches++;  // only a launch that was accepted advances the epoch
   if (a.trace && logits && (h->launches % 64) == 40) {  // debug timeline of one step (CTA 0 and the last CTA), in ns from kernel entry
