@@ -33,6 +33,9 @@ METRIC = "llama3_6L_greedy_generation_tokens_per_s"
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE k_attention_rows launch from `ncu --set full`, keyed by (batch, keys):
 # profiles/r1g_ncu_extract.txt (605.26 MB read + 17.01 MB written at batch 1024, 256 keys; algorithmic 606.3 MB)
 ATT_NCU_TRAFFIC = {(1024, 256): 622.27e6}
+# the same for ONE k_decode_mega launch at batch 1, context 48 (profiles/r2_ncu_extract.txt: 61.32 MB read + 0.35 MB written; the fp32
+# weights are 60.9 MB)
+MEGA_NCU_TRAFFIC = 61.67e6
 PROMPT_LEN, TOTAL_LEN = 4, int(os.environ.get("PDN_BENCH_TOTAL_LEN", 256))  # the env override exists for short ncu captures only
 
 
@@ -247,7 +250,7 @@ def bench_b1(Llama, how, device, steps, warmup):
             "gpu_launches": int(launches), "us_per_token_device": us_tok,
             "roofline": {"kernel": "k_decode_mega (whole decode step, one cooperative launch per token)", "bound": "hbm",
                          "achieved": (w_bytes + kv_bytes_mean) / (us_tok * 1e-6) / 1e9, "peak": hbm, "unit": "GB/s",
-                         "frac": (w_bytes + kv_bytes_mean) / (us_tok * 1e-6) / 1e9 / hbm, "traffic": None, "peak_source": which,
+                         "frac": (w_bytes + kv_bytes_mean) / (us_tok * 1e-6) / 1e9 / hbm, "traffic": MEGA_NCU_TRAFFIC, "peak_source": which,
                          "note": "algorithmic bytes per token = every fp32 weight once (60.9 MB) + K and V rows of the mean context; at one "
                                  "row the step is a chain of dependent grid-wide phases (latency-bound), not bandwidth-bound"}}, ids, prompt_host
 

@@ -25,6 +25,8 @@ _DT = {
 }
 _FLOATS = (np.dtype(np.float16), np.dtype(np.float32), np.dtype(np.float64))
 _I64A = C.c_int64 * 8
+_F32 = np.dtype(np.float32)
+_ONE3, _ZERO3 = (C.c_int64 * 3)(1, 1, 1), (C.c_int64 * 3)(0, 0, 0)
 # bumped by every USER-LEVEL in-place write to a device buffer (setitem, fill, += ...): inference plans (nn/_plans.py) compare it
 # against the value they saw last and re-check their weight signatures only when it moved
 WRITE_EPOCH = [0]
@@ -691,6 +693,20 @@ def gemm_into(out: ndarray | None, a: ndarray, b: ndarray, bias: ndarray | None 
     K2, N = b.shape[-2:]
     if K != K2:
         raise ValueError(f"matmul: Input operand 1 has a mismatch in its core dimension 0 (size {K2} is different from {K})")
+    if a.ndim == 2 and b.ndim == 2 and a.dtype == _F32 and b.dtype == _F32 and (bias is None or bias.dtype == _F32):
+        # the common case (every Linear layer, every 2-D matmul and its two gradient products): no batch logic, no promotion
+        if out is None:
+            out = ndarray.empty((M, N), _F32)
+        else:
+            assert out.shape == (M, N) and out.dtype == _F32 and out.estrides[-1] == 1
+        if out.size == 0:
+            return out
+        if bias is not None:
+            assert bias.shape == (N, ) and bias.is_contiguous
+        out.buf.version += 1
+        L.call("pdn_gemm_cached", 0, a.ptr, b.ptr, out.ptr, M, N, K, a.estrides[0], a.estrides[1], b.estrides[0], b.estrides[1], out.estrides[0],
+               _ONE3, _ZERO3, _ZERO3, _ZERO3, bias.ptr if bias is not None else None, 1 if accumulate else 0, prec, a.buf.version, b.buf.version)
+        return out
     batch = np.broadcast_shapes(a.shape[:-2], b.shape[:-2])
     dt = np.result_type(a.dtype, b.dtype)
     if dt not in _FLOATS:
