@@ -93,6 +93,16 @@ constexpr int MEGA_LMROWS = 1024;   // lm_head rows per CTA (vocabulary <= 1024 
 constexpr int MEGA_PV = 12;         // partial rows a P3 thread polls in its first batch (heads x splits at one sequence, typical)
 constexpr int MEGA_NJ = 6;          // float4 chunks of one weight row a lane keeps prefetched (row widths up to 768 floats)
 
+// PDN_MEGA_TRACE: stamps INSIDE the phases of layer 2 for CTA 0 (a row CTA with a task in every phase, slots 256..) and for the first
+// attention-unit CTA (slots 288..)
+__device__ __forceinline__ void mega_fine(const MegaArgs& a, int layer, bool unit, int id) {
+  if (a.trace && layer == 2 && threadIdx.x == 0) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    a.trace[(unit ? 288 : 256) + id] = t;
+  }
+}
+
 __device__ __forceinline__ void ll_store(unsigned long long* p, float v, unsigned ep) {
   const unsigned long long w = ((unsigned long long)ep << 32) | (unsigned long long)__float_as_uint(v);
   asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(w) : "memory");
@@ -321,7 +331,10 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) k_decode_mega(MegaArgs a) {
     const MegaLayer&    Lw = a.layers[l];
     unsigned long long* X = a.ll + (size_t)l * ll_layer;  // this layer's exchange words
     // ================= P1: RMSNorm -> Q/K/V columns (pairs) -> RoPE -> q / new K, V row (exchange) + KV cache ==========================
+    const bool f0 = cta == 0, fu = unitcta && u_id == 0;
+    if (f0) mega_fine(a, l, false, 0);
     if (rowcta) load_norm_rows<NB>(l == 0 ? rows : nullptr, l == 0 ? nullptr : (X - ll_layer) + o_hout, ep, B, nw, Lw.eps1, dim, xs, hn, red);
+    if (f0) mega_fine(a, l, false, 1);
     pf_norm(Lw.n2, dim, nw);  // for P3
     if (gw < npairs) {
       float y0[NB], y1[NB];
@@ -390,6 +403,7 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) k_decode_mega(MegaArgs a) {
         else if (knew_i >= 0 && tid < 3 * HD) vnew[tid - 2 * HD] = ll_load(X + o_vn + hoff + tid - 2 * HD, ep);
       }
       __syncthreads();
+      if (fu) mega_fine(a, l, true, 1);  // q (and the new K / V row) arrived
       float         m_loc = -INFINITY;
       for (int kb = 0; kb < nk; kb += MEGA_THREADS / 4) {
         const int kk = kb + (tid >> 2);
@@ -418,6 +432,7 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) k_decode_mega(MegaArgs a) {
 #pragma unroll
       for (int i = 0; i < MEGA_WARPS; ++i) M = fmaxf(M, red[i]);
       __syncthreads();
+      if (fu) mega_fine(a, l, true, 2);  // scores + block max
       float l_loc = 0.f;
       for (int kk = tid; kk < nk; kk += MEGA_THREADS) {
         const float p = __expf(sc[kk] - M);
@@ -430,6 +445,7 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) k_decode_mega(MegaArgs a) {
       float lsum = 0.f;
 #pragma unroll
       for (int i = 0; i < MEGA_WARPS; ++i) lsum += red[i];
+      if (fu) mega_fine(a, l, true, 3);  // softmax numerators + sum
       // P.V: thread (key group, float4 column) walks its keys
       if (kg < NKG) {
         float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -442,10 +458,22 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) k_decode_mega(MegaArgs a) {
             acc.x = fmaf(p, v.x, acc.x), acc.y = fmaf(p, v.y, acc.y), acc.z = fmaf(p, v.z, acc.z), acc.w = fmaf(p, v.w, acc.w);
           }
         }
-        for (int kk = kg + 4 * NKG; kk < nk; kk += NKG) {
-          const float4 v = kk == knew_i ? reinterpret_cast<const float4*>(vnew)[d4] : __ldg(vc + (size_t)kk * kstr4 + d4);
-          const float  p = sc[kk];
-          acc.x = fmaf(p, v.x, acc.x), acc.y = fmaf(p, v.y, acc.y), acc.z = fmaf(p, v.z, acc.z), acc.w = fmaf(p, v.w, acc.w);
+        for (int k4 = kg + 4 * NKG; k4 < nk; k4 += 4 * NKG) {  // further keys: four rows in flight at a time
+          float4 vv[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int kk = k4 + i * NKG;
+            vv[i] = (kk < nk && kk != knew_i) ? __ldg(vc + (size_t)kk * kstr4 + d4) : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int kk = k4 + i * NKG;
+            if (kk < nk) {
+              const float  p = sc[kk];
+              const float4 v = kk == knew_i ? reinterpret_cast<const float4*>(vnew)[d4] : vv[i];
+              acc.x = fmaf(p, v.x, acc.x), acc.y = fmaf(p, v.y, acc.y), acc.z = fmaf(p, v.z, acc.z), acc.w = fmaf(p, v.w, acc.w);
+            }
+          }
         }
         reinterpret_cast<float4*>(pvs)[kg * HD4 + d4] = acc;
       }
@@ -460,7 +488,11 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) k_decode_mega(MegaArgs a) {
         if (j == 0) accs[d] = s;
       }
       __syncthreads();
+      if (fu) mega_fine(a, l, true, 4);  // P.V reduced
       unsigned long long* dst = X + o_part + (size_t)u_id * (dim + 2);
+      // a single split per head needs no merge: its partial is normalised here and P3 just adds the heads (no (max, sum) exchange,
+      // no softmax-weight stage on P3's critical path: 1.35 us per layer in the timeline of the multi-split version)
+      const float onorm = ns == 1 ? 1.f / lsum : 1.f;
       if (tid < dim) {
         float o = 0.f;
 #pragma unroll
@@ -468,7 +500,7 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) k_decode_mega(MegaArgs a) {
           const float4 x = reinterpret_cast<const float4*>(accs)[i];
           o = fmaf(wreg[i].x, x.x, fmaf(wreg[i].y, x.y, fmaf(wreg[i].z, x.z, fmaf(wreg[i].w, x.w, o))));
         }
-        ll_store(dst + tid, o, ep);
+        ll_store(dst + tid, o * onorm, ep);
       }
       for (int n = tid + MEGA_THREADS; n < dim; n += MEGA_THREADS) {  // models wider than the CTA: rows loaded here
         const float4* p = reinterpret_cast<const float4*>(Lw.wo_h + ((size_t)u_hh * dim + n) * HD);
@@ -478,12 +510,13 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) k_decode_mega(MegaArgs a) {
           const float4 wv = __ldg(p + i), x = reinterpret_cast<const float4*>(accs)[i];
           o = fmaf(wv.x, x.x, fmaf(wv.y, x.y, fmaf(wv.z, x.z, fmaf(wv.w, x.w, o))));
         }
-        ll_store(dst + n, o, ep);
+        ll_store(dst + n, o * onorm, ep);
       }
       if (tid == 0) {
         ll_store(dst + dim, M, ep);  // -inf for an empty split
         ll_store(dst + dim + 1, lsum, ep);
       }
+      if (fu) mega_fine(a, l, true, 5);  // partial O projection stored
     }
     // next: gate / up rows of hidden unit gw
     if (gw < FF) {
@@ -496,17 +529,21 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) k_decode_mega(MegaArgs a) {
       const unsigned long long* P = X + o_part;
       const int                 hs = H * ns;
       // the partial rows this thread combines are requested first (they do not depend on the softmax weights) ...
+      if (f0) mega_fine(a, l, false, 3);
       float pv[MEGA_PV];  // (first sequence; further sequences are polled in the combine loop)
       if (tid < dim) ll_load_n<MEGA_PV>(P + tid, (size_t)(dim + 2), min(MEGA_PV, hs), ep, pv);
-      // ... while the (max, sum) pairs of the units are fetched and turned into e^{m-M} / den
-      if (tid < units) {
+      if (f0) mega_fine(a, l, false, 4);  // first batch of partial rows arrived
+      // ... while the (max, sum) pairs of the units are fetched and turned into e^{m-M} / den (several splits per head only)
+      if (ns == 1) {
+        if (tid < units) fac[tid] = 1.f;
+      } else if (tid < units) {
         float ml[2];
         ll_load_n<2>(P + (size_t)tid * (dim + 2) + dim, 1, 2, ep, ml);
         ml_m[tid] = ml[0];
         ml_l[tid] = ml[1];
       }
-      __syncthreads();
-      if (tid < units) {
+      if (ns > 1) __syncthreads();
+      if (ns > 1 && tid < units) {
         const int bh = tid / ns;
         float     M = -INFINITY;
         for (int s = 0; s < ns; ++s) M = fmaxf(M, ml_m[bh * ns + s]);
@@ -519,6 +556,7 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) k_decode_mega(MegaArgs a) {
         fac[tid] = (mt == -INFINITY) ? 0.f : __expf(mt - M) / den;
       }
       __syncthreads();
+      if (f0) mega_fine(a, l, false, 5);  // softmax weights of the units ready
       float ss[NB];
 #pragma unroll
       for (int b = 0; b < NB; ++b) {
@@ -546,6 +584,7 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) k_decode_mega(MegaArgs a) {
           }
         }
       }
+      if (f0) mega_fine(a, l, false, 6);  // partials combined
       float rstd[NB];
       block_rstd<NB>(ss, dim, Lw.eps2, red, rstd);
 #pragma unroll
@@ -557,6 +596,7 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) k_decode_mega(MegaArgs a) {
         }
       }
       __syncthreads();
+      if (f0) mega_fine(a, l, false, 7);  // normalised
     }
     pf_norm(l + 1 < a.n_layers ? a.layers[l + 1].n1 : a.norm_w, dim, nw);  // for the next P1 / the final normalisation
     if (gw < FF) {
@@ -569,6 +609,7 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) k_decode_mega(MegaArgs a) {
           if (b < B) ll_store(X + o_hid + (size_t)b * FF + gw, g[b] / (1.f + __expf(-g[b])) * u[b], ep);  // x / (1 + exp(-x)), functional.py:39-40
       }
     }
+    if (f0) mega_fine(a, l, false, 8);  // gate / up / SwiGLU stored
     if (gw < dim) pf_row(Lw.wd_t + (size_t)gw * FF, FF4, wreg);
     mega_stamp(a, tslot);
     // ================= P4: down projection + residual -> next layer's input ==============================================================
@@ -584,6 +625,7 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) k_decode_mega(MegaArgs a) {
         if (cnt > 1) xs[b * MEGA_MAXK + tid + MEGA_THREADS] = hv[1];
       }
       __syncthreads();
+      if (f0) mega_fine(a, l, false, 9);  // hidden row arrived
       if (gw < dim) {
         float y[NB];
         dot_row<NB>(Lw.wd_t + (size_t)gw * FF, FF4, wreg, xs, y);
@@ -869,6 +911,7 @@ int pdn_decoder_step(void* handle, const int64_t* ids, int64_t ids_stride, int64
   const double keys = (double)pos + 1.0, bh = (double)a.B * a.H;
   int          ns = (int)std::lround(std::sqrt(keys * 2.0 * a.hd / (bh * (a.dim + 2))));
   const int    cap = h->grid / (a.B * a.H) < MEGA_MAXUNITS / (a.B * a.H) ? h->grid / (a.B * a.H) : MEGA_MAXUNITS / (a.B * a.H);
+  if (keys <= 320.0) ns = 1;  // short contexts: one unit per head reads all keys (<= 120 KB of cache) and P3 needs no merge stage
   ns = ns < 1 ? 1 : (ns > cap ? cap : ns);
   while (((int)keys + ns - 1) / ns > MEGA_SC) ++ns;  // unreachable for S <= MEGA_SC, kept as a guard
   a.nsplit = ns;
@@ -892,6 +935,14 @@ int pdn_decoder_step(void* handle, const int64_t* ids, int64_t ids_stride, int64
     fprintf(stderr, "\n ctaL:");
     for (int i = 1; i < n; ++i) fprintf(stderr, "%s%llu", (i % 4) == 1 ? " | " : " ", t[512 + i] - t[512 + i - 1]);
     fprintf(stderr, "\n total cta0 %llu ns\n", t[n - 1] - t[0]);
+    const char* rn[10] = {"P1 start", "h polled + normalised", "QKV stored", "P3 start", "partials arrived", "weights ready", "combined", "normalised",
+                          "hidden stored", "P4 hidden arrived"};
+    fprintf(stderr, " layer 2, CTA 0 (ns after its P1 start):");
+    for (int i = 0; i < 10; ++i) fprintf(stderr, " %s=%lld", rn[i], (long long)(t[256 + i] - t[256]));
+    const char* un[6] = {"P2 start", "q arrived", "scores+max", "softmax", "P.V", "O-partial stored"};
+    fprintf(stderr, "\n layer 2, first attention unit (ns after CTA 0's P1 start):");
+    for (int i = 0; i < 6; ++i) fprintf(stderr, " %s=%lld", un[i], (long long)(t[288 + i] - t[256]));
+    fprintf(stderr, "\n");
   }
   return 0;
 }
