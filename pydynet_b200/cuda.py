@@ -118,17 +118,24 @@ class Device:
         return backend
 
     def __enter__(self):
+        # Device objects are shared between tensors, and `with dev:` blocks nest (an optimizer step that touches a lazily created
+        # gradient re-enters the same object): every entry pushes what it has to restore, every exit pops its own entry
+        prev = None
         if self.device == "cuda":
             cur = current_device()
             if cur != self.device_id:
-                self._prev = cur
+                prev = cur
                 set_device(self.device_id)
+        if self._prev is None:
+            self._prev = [prev]
+        else:
+            self._prev.append(prev)
         return self
 
     def __exit__(self, *exc):
-        if self._prev is not None:
-            set_device(self._prev)
-            self._prev = None
+        prev = self._prev.pop() if self._prev else None
+        if prev is not None:
+            set_device(prev)
 
 
 _inited = set()

@@ -124,11 +124,15 @@ def _im2col(x: Tensor, k: int, stride: int, nsp: int) -> Tensor:
 
 
 def conv1d(x: Tensor, kernel: Tensor, padding: int = 0, stride: int = 1):
-    """1-D convolution. The reference's own expression (functional.py:113-140) multiplies (k, n_out) by (k, O) windows
-    and raises for every input with n_out != k, so there is no reference result to match; this is the intended
-    contraction over (C, k): out[n, o, l] = sum_{c,j} x_pad[n, c, l*stride + j] * kernel[o, c, j]."""
+    """1-D convolution (reference functional.py:113-140). The reference's expression ``(col @ kernel.transpose(1, 2, 0)).sum(1)``
+    multiplies (k, n_out) windows by (k, O) kernels, so it is only defined when the number of output positions equals the kernel size
+    (it raises otherwise) and then contracts the window POSITIONS with the kernel taps: out[n, o, j] = sum_{c,l} x_pad[n, c, j + l*stride]
+    * kernel[o, c, l]. Exactly that is computed for those inputs (pinned by tests/golden/family_1d.npz); where the reference raises,
+    this is the ordinary strided correlation out[n, o, l] = sum_{c,j} x_pad[n, c, l*stride + j] * kernel[o, c, j]."""
     col = _im2col(_pad_nd(x, padding, 1), kernel.shape[-1], stride, 1)  # (N, C, k, L)
     N, C, k, L = col.shape
+    if L == k:
+        return (col @ kernel.transpose(1, 2, 0)).sum(1).swapaxes(1, 2)
     out = col.transpose(0, 3, 1, 2).reshape(N * L, C * k) @ kernel.reshape(kernel.shape[0], -1).T
     return out.reshape(N, L, -1).swapaxes(1, 2)
 
