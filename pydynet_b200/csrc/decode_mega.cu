@@ -169,8 +169,9 @@ __device__ __forceinline__ void pf_row(const float* __restrict__ row, int K4, fl
 template <int NB>
 __device__ __forceinline__ void dot_row(const float* __restrict__ row, int K4, const float4* w, const float* xs, float* acc) {
   const int lane = threadIdx.x & 31;
+  float odd[NB];  // chunks alternate between two accumulators: two independent FMA chains instead of one
 #pragma unroll
-  for (int b = 0; b < NB; ++b) acc[b] = 0.f;
+  for (int b = 0; b < NB; ++b) acc[b] = odd[b] = 0.f;
 #pragma unroll
   for (int j = 0; j < MEGA_NJ; ++j) {
     const int k = lane + 32 * j;
@@ -178,10 +179,13 @@ __device__ __forceinline__ void dot_row(const float* __restrict__ row, int K4, c
 #pragma unroll
       for (int b = 0; b < NB; ++b) {
         const float4 x = *reinterpret_cast<const float4*>(xs + b * MEGA_MAXK + 4 * k);
-        acc[b] = fmaf(w[j].x, x.x, fmaf(w[j].y, x.y, fmaf(w[j].z, x.z, fmaf(w[j].w, x.w, acc[b]))));
+        float&       t = (j & 1) ? odd[b] : acc[b];
+        t = fmaf(w[j].x, x.x, fmaf(w[j].y, x.y, fmaf(w[j].z, x.z, fmaf(w[j].w, x.w, t))));
       }
     }
   }
+#pragma unroll
+  for (int b = 0; b < NB; ++b) acc[b] += odd[b];
   const float4* p = reinterpret_cast<const float4*>(row);
   for (int k = lane + 32 * MEGA_NJ; k < K4; k += 32) {
     const float4 wv = __ldg(p + k);
@@ -193,6 +197,46 @@ __device__ __forceinline__ void dot_row(const float* __restrict__ row, int K4, c
   }
 #pragma unroll
   for (int b = 0; b < NB; ++b) acc[b] = warp_sum(acc[b]);
+}
+
+// two rows at once (Q/K/V rotation pairs, gate | up): the two dependency chains (LDS -> 4 FMA per chunk, then the 5-step shuffle tree)
+// are interleaved, so the warp - alone on its scheduler in these phases - hides one chain's latency behind the other
+template <int NB>
+__device__ __forceinline__ void dot_row2(const float* __restrict__ row0, const float* __restrict__ row1, int K4, const float4* w0, const float4* w1,
+                                         const float* xs, float* acc0, float* acc1) {
+  const int lane = threadIdx.x & 31;
+#pragma unroll
+  for (int b = 0; b < NB; ++b) acc0[b] = acc1[b] = 0.f;
+#pragma unroll
+  for (int j = 0; j < MEGA_NJ; ++j) {
+    const int k = lane + 32 * j;
+    if (k < K4) {
+#pragma unroll
+      for (int b = 0; b < NB; ++b) {
+        const float4 x = *reinterpret_cast<const float4*>(xs + b * MEGA_MAXK + 4 * k);
+        acc0[b] = fmaf(w0[j].x, x.x, fmaf(w0[j].y, x.y, fmaf(w0[j].z, x.z, fmaf(w0[j].w, x.w, acc0[b]))));
+        acc1[b] = fmaf(w1[j].x, x.x, fmaf(w1[j].y, x.y, fmaf(w1[j].z, x.z, fmaf(w1[j].w, x.w, acc1[b]))));
+      }
+    }
+  }
+  const float4 *p0 = reinterpret_cast<const float4*>(row0), *p1 = reinterpret_cast<const float4*>(row1);
+  for (int k = lane + 32 * MEGA_NJ; k < K4; k += 32) {
+    const float4 a0 = __ldg(p0 + k), a1 = __ldg(p1 + k);
+#pragma unroll
+    for (int b = 0; b < NB; ++b) {
+      const float4 x = *reinterpret_cast<const float4*>(xs + b * MEGA_MAXK + 4 * k);
+      acc0[b] = fmaf(a0.x, x.x, fmaf(a0.y, x.y, fmaf(a0.z, x.z, fmaf(a0.w, x.w, acc0[b]))));
+      acc1[b] = fmaf(a1.x, x.x, fmaf(a1.y, x.y, fmaf(a1.z, x.z, fmaf(a1.w, x.w, acc1[b]))));
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+    for (int b = 0; b < NB; ++b) {
+      acc0[b] += __shfl_xor_sync(0xffffffffu, acc0[b], o);
+      acc1[b] += __shfl_xor_sync(0xffffffffu, acc1[b], o);
+    }
+  }
 }
 
 // rstd[b] = 1 / sqrt(mean_k x[b]^2 + eps) from per-thread partial sums of squares (reference norm.py:245-248)
@@ -338,8 +382,7 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) k_decode_mega(MegaArgs a) {
     pf_norm(Lw.n2, dim, nw);  // for P3
     if (gw < npairs) {
       float y0[NB], y1[NB];
-      dot_row<NB>(Lw.wqkv_t + (size_t)(2 * gw) * dim, dim4, wreg, xs, y0);
-      dot_row<NB>(Lw.wqkv_t + (size_t)(2 * gw + 1) * dim, dim4, wreg + MEGA_NJ, xs, y1);
+      dot_row2<NB>(Lw.wqkv_t + (size_t)(2 * gw) * dim, Lw.wqkv_t + (size_t)(2 * gw + 1) * dim, dim4, wreg, wreg + MEGA_NJ, xs, y0, y1);
       if (lane == 0) {
         const int   col = 2 * gw, which = col / dim, c = col - which * dim;  // 0: q, 1: k, 2: v
         const int   hh = c / HD, d = c - hh * HD;
@@ -601,8 +644,7 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) k_decode_mega(MegaArgs a) {
     pf_norm(l + 1 < a.n_layers ? a.layers[l + 1].n1 : a.norm_w, dim, nw);  // for the next P1 / the final normalisation
     if (gw < FF) {
       float g[NB], u[NB];
-      dot_row<NB>(Lw.wgu_t + (size_t)(2 * gw) * dim, dim4, wreg, xs, g);
-      dot_row<NB>(Lw.wgu_t + (size_t)(2 * gw + 1) * dim, dim4, wreg + MEGA_NJ, xs, u);
+      dot_row2<NB>(Lw.wgu_t + (size_t)(2 * gw) * dim, Lw.wgu_t + (size_t)(2 * gw + 1) * dim, dim4, wreg, wreg + MEGA_NJ, xs, g, u);
       if (lane == 0) {
 #pragma unroll
         for (int b = 0; b < NB; ++b)
