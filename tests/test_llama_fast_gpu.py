@@ -145,3 +145,26 @@ def test_plan_survives_weight_update_and_held_logits():
         O.check_greedy_tokens(toks, ref_toks, margins)
     finally:
         pdn.autograd.set_grad_enabled(True)
+
+
+@pytest.mark.parametrize("B", [1, 3])
+def test_persistent_decode_kernel_long_context(B):
+    """Contexts beyond 320 keys make the persistent decode kernel split every head's keys over several attention units (partials merged
+    with softmax weights in P3); below that each head is one unit. Both regimes, and the switch between them, against the oracle."""
+    import pydynet_b200 as pdn
+    from oracle import pdn_oracle as O
+    from workloads.llama import Llama
+    cfg = (V, D, H, FF, S, L) = (384, 96, 2, 128, 512, 2)
+    total = 430
+    params = O.synthetic_llama_params(V, D, H, FF, L, seed=21, std=0.08)
+    prompt = np.random.default_rng(8).integers(1, V, (B, 4))
+    ref_toks, margins = O.LlamaOracle(params, H, S, B, L).generate_with_margins(prompt, total)
+    try:
+        net = _build(Llama, B, cfg, params)
+        toks = _generate(net, prompt, total)
+        plan = net.__dict__.get("_pdn_plan")
+        assert plan and not plan.dead and ("decode", "mega") in plan.verified
+    finally:
+        pdn.autograd.set_grad_enabled(True)
+    exact, near = O.check_greedy_tokens(toks, ref_toks, margins)
+    assert exact + near == B
