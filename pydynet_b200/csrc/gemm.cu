@@ -155,6 +155,43 @@ __global__ void __launch_bounds__(256) k_gemm_skinny_f32(GemmArgs g) {
   }
 }
 
+// ---- small products the tensor-core path does not take (N or K below 32: a classifier head with 10 classes and its two gradient
+// products, LeNet fc2): the 64x64-tile kernel runs them on 4-8 CTAs with an un-pipelined K loop (38 us each). Here one WARP owns an
+// output element when K >= 32 (lanes stride over k, xor-shuffle tree) and one THREAD when K is short; any strides, fp32, fixed
+// summation order.
+template <bool WARP>
+__global__ void __launch_bounds__(256) k_gemm_small_f32(GemmArgs g) {
+  int64_t oa, ob, oc;
+  batch_offsets(g, blockIdx.z, oa, ob, oc);
+  const float* Ap = (const float*)g.A + oa;
+  const float* Bp = (const float*)g.B + ob;
+  float*       Cp = (float*)g.C + oc;
+  const int    M = (int)g.M, N = (int)g.N, K = (int)g.K;
+  const int    lane = threadIdx.x & 31;
+  const int    per_block = WARP ? 8 : 256;
+  for (int o = blockIdx.x * per_block + (WARP ? (int)(threadIdx.x >> 5) : (int)threadIdx.x); o < M * N; o += gridDim.x * per_block) {
+    const int    m = o / N, n = o - m * N;
+    const float *ap = Ap + (int64_t)m * g.a_rs, *bp = Bp + (int64_t)n * g.b_cs;
+    float        acc0 = 0.f, acc1 = 0.f;
+    if (WARP) {
+      int k = lane;
+      for (; k + 32 < K; k += 64) {
+        acc0 = fmaf(__ldg(ap + (int64_t)k * g.a_cs), __ldg(bp + (int64_t)k * g.b_rs), acc0);
+        acc1 = fmaf(__ldg(ap + (int64_t)(k + 32) * g.a_cs), __ldg(bp + (int64_t)(k + 32) * g.b_rs), acc1);
+      }
+      if (k < K) acc0 = fmaf(__ldg(ap + (int64_t)k * g.a_cs), __ldg(bp + (int64_t)k * g.b_rs), acc0);
+      acc0 = warp_sum(acc0 + acc1);
+      if (lane != 0) continue;
+    } else {
+      for (int k = 0; k < K; ++k) acc0 = fmaf(__ldg(ap + (int64_t)k * g.a_cs), __ldg(bp + (int64_t)k * g.b_rs), acc0);
+    }
+    if (g.bias) acc0 += ((const float*)g.bias)[n];
+    float* cp = Cp + (int64_t)m * g.ldc + n;
+    if (g.accumulate) acc0 += *cp;
+    *cp = acc0;
+  }
+}
+
 }  // namespace pdn
 
 using namespace pdn;
@@ -219,6 +256,16 @@ int pdn_gemm_cached(int dtype, const void* A, const void* B, void* C, int64_t M,
     return 0;
   }
   PDN_CHECK(nbatch <= 65535, "too many GEMM batches for the tiled kernel (%lld)", (long long)nbatch);
+  if (dtype == PDN_F32 && (N < 32 || K < 32) && M * N <= (1 << 22) && (double)M * N * K <= (double)(1 << 26)) {
+    const bool    warp = K >= 32;
+    const int64_t blocks = warp ? (M * N + 7) / 8 : (M * N + 255) / 256;
+    dim3          grd((unsigned)(blocks < 8192 ? blocks : 8192), 1, (unsigned)nbatch);
+    if (warp) k_gemm_small_f32<true><<<grd, 256, 0, stream()>>>(g);
+    else k_gemm_small_f32<false><<<grd, 256, 0, stream()>>>(g);
+    PDN_LAUNCHED("gemm_small_f32");
+    g_last_path = 3;
+    return 0;
+  }
   dim3 grd((unsigned)((N + 63) / 64), (unsigned)((M + 63) / 64), (unsigned)nbatch);
   PDN_CHECK((M + 63) / 64 <= 65535, "M too large for the tiled kernel grid");
   switch (dtype) {
