@@ -88,21 +88,36 @@ class ndarray:
     def __init__(self, buf, ptr, shape, estrides, dtype):
         self.buf = buf
         self.ptr = ptr
-        self.shape = tuple(int(s) for s in shape)
-        self.estrides = tuple(int(s) for s in estrides)
-        self.dtype = np.dtype(dtype)
-        self.size = _prod(self.shape)
+        self.shape = tuple(map(int, shape))
+        self.estrides = tuple(map(int, estrides))
+        self.dtype = dtype if isinstance(dtype, np.dtype) else np.dtype(dtype)
+        n = 1
+        for d in self.shape:
+            n *= d
+        self.size = n
 
     # ------------------------------------------------------------------ construction ------------
     @staticmethod
     def empty(shape, dtype=np.float32) -> "ndarray":
         if isinstance(shape, numbers.Integral):
             shape = (int(shape), )
-        shape = tuple(int(s) for s in shape)
-        dtype = np.dtype(dtype)
-        _code(dtype)
-        buf = _Buffer(_prod(shape) * dtype.itemsize)
-        return ndarray(buf, buf.ptr, shape, _contig_strides(shape), dtype)
+        shape = tuple(map(int, shape))
+        if not isinstance(dtype, np.dtype):
+            dtype = np.dtype(dtype)
+        if dtype not in _DT:
+            _code(dtype)  # raises the TypeError
+        # (one pass: contiguous strides and the element count together; the object is filled without re-validating what was just built)
+        st, n = [], 1
+        for d in reversed(shape):
+            st.append(n)
+            n *= d if d != 0 else 1
+        size = 1
+        for d in shape:
+            size *= d
+        buf = _Buffer(size * dtype.itemsize)
+        out = ndarray.__new__(ndarray)
+        out.buf, out.ptr, out.shape, out.estrides, out.dtype, out.size = buf, buf.ptr, shape, tuple(reversed(st)), dtype, size
+        return out
 
     @staticmethod
     def from_host(a, dtype=None) -> "ndarray":
@@ -268,7 +283,9 @@ class ndarray:
         return self.transpose(ax)
 
     def broadcast_to(self, shape) -> "ndarray":
-        shape = tuple(int(s) for s in shape)
+        shape = tuple(map(int, shape))
+        if shape == self.shape:
+            return self
         nd = len(shape)
         if nd < self.ndim:
             raise ValueError("cannot broadcast to fewer dimensions")
