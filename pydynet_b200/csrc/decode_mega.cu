@@ -159,6 +159,7 @@ __device__ __forceinline__ void pf_row(const float* __restrict__ row, int K4, fl
   const int     lane = threadIdx.x & 31;
 #pragma unroll
   for (int j = 0; j < MEGA_NJ; ++j) {
+    if (32 * j >= K4) break;  // warp-uniform; chunks beyond the row are never read by dot_row
     const int k = lane + 32 * j;
     w[j] = k < K4 ? __ldg(p + k) : make_float4(0.f, 0.f, 0.f, 0.f);
   }
@@ -174,6 +175,8 @@ __device__ __forceinline__ void dot_row(const float* __restrict__ row, int K4, c
   for (int b = 0; b < NB; ++b) acc[b] = odd[b] = 0.f;
 #pragma unroll
   for (int j = 0; j < MEGA_NJ; ++j) {
+    if (32 * j >= K4) break;  // warp-uniform: rows narrower than 32 * MEGA_NJ float4 skip the rest (the phases are issue-bound:
+                              // 16 warps x ~120 instructions per task on 4 schedulers, tools/probe/dot_probe.cu)
     const int k = lane + 32 * j;
     if (k < K4) {
 #pragma unroll
@@ -209,6 +212,7 @@ __device__ __forceinline__ void dot_row2(const float* __restrict__ row0, const f
   for (int b = 0; b < NB; ++b) acc0[b] = acc1[b] = 0.f;
 #pragma unroll
   for (int j = 0; j < MEGA_NJ; ++j) {
+    if (32 * j >= K4) break;  // warp-uniform
     const int k = lane + 32 * j;
     if (k < K4) {
 #pragma unroll
@@ -645,10 +649,11 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) k_decode_mega(MegaArgs a) {
     if (gw < FF) {
       float g[NB], u[NB];
       dot_row2<NB>(Lw.wgu_t + (size_t)(2 * gw) * dim, Lw.wgu_t + (size_t)(2 * gw + 1) * dim, dim4, wreg, wreg + MEGA_NJ, xs, g, u);
+      if (f0) mega_fine(a, l, false, 10);  // gate / up dot products done
       if (lane == 0) {
 #pragma unroll
         for (int b = 0; b < NB; ++b)
-          if (b < B) ll_store(X + o_hid + (size_t)b * FF + gw, g[b] / (1.f + __expf(-g[b])) * u[b], ep);  // x / (1 + exp(-x)), functional.py:39-40
+          if (b < B) ll_store(X + o_hid + (size_t)b * FF + gw, __fdividef(g[b], 1.f + __expf(-g[b])) * u[b], ep);  // x / (1 + exp(-x)), functional.py:39-40
       }
     }
     if (f0) mega_fine(a, l, false, 8);  // gate / up / SwiGLU stored
@@ -977,10 +982,10 @@ int pdn_decoder_step(void* handle, const int64_t* ids, int64_t ids_stride, int64
     fprintf(stderr, "\n ctaL:");
     for (int i = 1; i < n; ++i) fprintf(stderr, "%s%llu", (i % 4) == 1 ? " | " : " ", t[512 + i] - t[512 + i - 1]);
     fprintf(stderr, "\n total cta0 %llu ns\n", t[n - 1] - t[0]);
-    const char* rn[10] = {"P1 start", "h polled + normalised", "QKV stored", "P3 start", "partials arrived", "weights ready", "combined", "normalised",
-                          "hidden stored", "P4 hidden arrived"};
+    const char* rn[11] = {"P1 start", "h polled + normalised", "QKV stored", "P3 start", "partials arrived", "weights ready", "combined", "normalised",
+                          "hidden stored", "P4 hidden arrived", "gate/up dots done"};
     fprintf(stderr, " layer 2, CTA 0 (ns after its P1 start):");
-    for (int i = 0; i < 10; ++i) fprintf(stderr, " %s=%lld", rn[i], (long long)(t[256 + i] - t[256]));
+    for (int i = 0; i < 11; ++i) fprintf(stderr, " %s=%lld", rn[i], (long long)(t[256 + i] - t[256]));
     const char* un[6] = {"P2 start", "q arrived", "scores+max", "softmax", "P.V", "O-partial stored"};
     fprintf(stderr, "\n layer 2, first attention unit (ns after CTA 0's P1 start):");
     for (int i = 0; i < 6; ++i) fprintf(stderr, " %s=%lld", un[i], (long long)(t[288 + i] - t[256]));
