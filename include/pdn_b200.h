@@ -97,6 +97,9 @@ int pdn_nvtx_pop(void);
 /* launch accounting (bench.py "gpu_launches") and device-side timing on the library stream */
 uint64_t pdn_kernel_launch_count(void);
 void pdn_reset_launch_count(void);
+/* test aid: count the launches whose entry-point name equals `name` from now on (nullptr = stop watching); the count so far */
+void pdn_watch_launches(const char* name);
+uint64_t pdn_watched_launch_count(void);
 int pdn_event_create(void** ev);
 int pdn_event_destroy(void* ev);
 int pdn_event_record(void* ev); /* while a graph is being recorded: an event-record NODE (cudaEventRecordExternal), re-stamped by every replay */

@@ -172,6 +172,10 @@ def load():
     lib.pdn_kernel_launch_count.argtypes = []
     lib.pdn_reset_launch_count.restype = None
     lib.pdn_reset_launch_count.argtypes = []
+    lib.pdn_watch_launches.restype = None
+    lib.pdn_watch_launches.argtypes = [C.c_char_p]
+    lib.pdn_watched_launch_count.restype = u64
+    lib.pdn_watched_launch_count.argtypes = []
     for name, args in _PROTOS.items():
         try:
             fn = getattr(lib, name)
@@ -185,7 +189,7 @@ def load():
 
 
 def declared_symbols():
-    return sorted(list(_PROTOS) + ["pdn_last_error", "pdn_kernel_launch_count", "pdn_reset_launch_count"])
+    return sorted(list(_PROTOS) + ["pdn_last_error", "pdn_kernel_launch_count", "pdn_reset_launch_count", "pdn_watch_launches", "pdn_watched_launch_count"])
 
 
 def check(status: int):
@@ -226,3 +230,12 @@ def launch_count() -> int:
 
 def reset_launch_count():
     load().pdn_reset_launch_count()
+
+
+def watch_launches(name):
+    """Test aid: count launches of the kernel entry point `name` from now on (None stops)."""
+    load().pdn_watch_launches(name.encode() if name else None)
+
+
+def watched_launch_count() -> int:
+    return int(load().pdn_watched_launch_count())

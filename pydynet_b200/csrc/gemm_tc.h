@@ -55,6 +55,12 @@ int gemm_tc_packed(const PackedOperand& A, const PackedOperand& B, TcArgs t, int
 bool gru_persist_ok(int64_t T, int64_t B, int64_t H);
 int  gru_persist_forward(const float* xp1, const float* xp2, const float* h0, const PackedOperand& W1p, const PackedOperand& W2p, const PackedOperand& hP0,
                          const PackedOperand& hP1, const PackedOperand& rhP, float* hs, float* zr, float* nn, int64_t T, int64_t B, int64_t H);
+bool lstm_persist_ok(int64_t T, int64_t B, int64_t H);
+int  lstm_persist_forward(const float* xp, const float* h0, const float* c0, const PackedOperand& Wp, const PackedOperand& hP0, const PackedOperand& hP1,
+                          float* hs, float* cs, float* gates, int64_t T, int64_t B, int64_t H);
+bool lstm_persist_bwd_ok(int64_t T, int64_t B, int64_t H);
+int  lstm_persist_backward(const float* g_hs, const float* g_cT, const float* c0, const float* cs, const float* gates, const PackedOperand& Wt,
+                           const PackedOperand& dlP, float* part, float* dxp, float* dh0, float* dc0, int64_t T, int64_t B, int64_t H);
 int  gru_persist_backward(const float* g_hs, const float* h0, const float* hs, const float* zr, const float* nn, const PackedOperand& W2t,
                           const PackedOperand& W1t, const PackedOperand& dl2P, const PackedOperand& dl1zP, const PackedOperand& dl1rP, float* u1, float* uz,
                           float* dxp1, float* dxp2, float* dh0, int64_t T, int64_t B, int64_t H);

@@ -261,7 +261,6 @@ int pdn_lstm_seq_fwd(const float* xp, const float* h0, const float* c0, const fl
   PDN_TRY(ensure_init());
   if (T == 0 || B == 0 || H == 0) return 0;
   const int64_t BH = B * H;
-  PDN_CUDA(cudaMemcpyAsync(gates, xp, (size_t)T * BH * 4 * sizeof(float), cudaMemcpyDeviceToDevice, stream()));
   Scratch       sW, sH;
   PackedOperand W, Hp;
   PDN_TRY(pack_operand_ex(Wh, 4 * H, H, 1, 4 * H, 0, 0, kOne, kZero, &sW, &W));
@@ -269,6 +268,13 @@ int pdn_lstm_seq_fwd(const float* xp, const float* h0, const float* c0, const fl
   const int grd = grid_for(BH, 256);
   k_rows_to_planes<<<grd, 256, 0, stream()>>>(h0, H, (__nv_bfloat16*)Hp.planes, B, H, Hp.Kp);
   PDN_LAUNCHED("rows_to_planes");
+  if (lstm_persist_ok(T, B, H)) {  // the whole recurrence as ONE persistent cooperative launch (rnn_persist.cu)
+    Scratch       sH1;
+    PackedOperand Hp1;
+    PDN_TRY(alloc_planes(&sH1, &Hp1, B, H));
+    return lstm_persist_forward(xp, h0, c0, W, Hp, Hp1, hs, cs, gates, T, B, H);
+  }
+  PDN_CUDA(cudaMemcpyAsync(gates, xp, (size_t)T * BH * 4 * sizeof(float), cudaMemcpyDeviceToDevice, stream()));
   TcArgs t;
   for (int64_t s = 0; s < T; ++s) {
     tc_init(t, gates + s * BH * 4, B, 4 * H, H, 1);
@@ -290,6 +296,11 @@ int pdn_lstm_seq_bwd(const float* g_hs, const float* g_cT, const float* h0, cons
   // dlin · Whᵀ : rows = j (hidden), k over 4H: Wh[j, k]
   PDN_TRY(pack_operand_ex(Wh, H, 4 * H, 4 * H, 1, 0, 0, kOne, kZero, &sW, &Wt));
   PDN_TRY(alloc_planes(&sD, &Dp, B, 4 * H));
+  if (lstm_persist_bwd_ok(T, B, H)) {  // BPTT of the whole sequence as ONE persistent cooperative launch (rnn_persist.cu)
+    Scratch sP;
+    PDN_TRY(sP.alloc((size_t)3 * BH * sizeof(float)));
+    PDN_TRY(lstm_persist_backward(g_hs, g_cT, c0, cs, gates, Wt, Dp, (float*)sP.p, dxp, dh0, dc0, T, B, H));
+  } else {
   float *dh = dh0, *dc = dc0;
   PDN_CUDA(cudaMemsetAsync(dh, 0, (size_t)BH * sizeof(float), stream()));
   if (g_cT) PDN_CUDA(cudaMemcpyAsync(dc, g_cT, (size_t)BH * sizeof(float), cudaMemcpyDeviceToDevice, stream()));
@@ -302,6 +313,7 @@ int pdn_lstm_seq_bwd(const float* g_hs, const float* g_cT, const float* h0, cons
     PDN_LAUNCHED("lstm_bwd");
     tc_init(t, dh, B, H, 4 * H, 0);
     PDN_TRY(gemm_tc_packed(Dp, Wt, t, 1));
+  }
   }
   if (dWh) {
     PDN_TRY(pdn_gemm(PDN_F32, h0, dxp, dWh, H, 4 * H, B, 1, H, 4 * H, 1, 4 * H, nullptr, nullptr, nullptr, nullptr, nullptr, 0, 0));

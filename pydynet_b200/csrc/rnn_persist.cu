@@ -313,6 +313,180 @@ k_gru_persist_fwd(const __grid_constant__ CUtensorMap mapH0, const __grid_consta
   if (warp == 2) tmem_dealloc(tmem_base, 64);
 }
 
+// ------------------------------------------------------------------------------------------------------------------ LSTM forward
+// lin = x Wx + h Wh + b -> f, i, o = sigmoid (that order), g = tanh; c' = f c + i g; h' = o tanh(c') (rnn.py:280-288): ONE product
+// per step, so one phase per step. A CTA owns 16 hidden units x 4 gates = 64 weight columns (the rows f_j, i_j, o_j, g_j of Wh^T are
+// gathered by four 16-row TMA boxes per k-block), so all four gates of a unit meet in its epilogue; the cell state of a thread's
+// four units lives in registers for the whole sequence.
+struct LstmPersistArgs {
+  const float *xp, *h0, *c0;
+  float *      hs, *cs, *gates;
+  __nv_bfloat16 *hP0, *hP1;
+  int           T, B, H, Kp, nbt, ctj;  // ctj = H / 16 column tiles
+  unsigned int* cnt;                    // [nbt]: h planes of a step complete (monotonic)
+};
+
+__global__ void __launch_bounds__(384, 1)
+k_lstm_persist_fwd(const __grid_constant__ CUtensorMap mapH0, const __grid_constant__ CUtensorMap mapH1, const __grid_constant__ CUtensorMap mapW,
+                   LstmPersistArgs g) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t*  smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  const int KB = g.H / GP_BK;
+  uint8_t*  wsm = smem;
+  uint8_t*  asm_ = smem + (size_t)KB * 2 * GP_WBLOCK;
+  uint64_t* full_bar = (uint64_t*)(asm_ + GP_STAGES * GP_ASTAGE);
+  uint64_t* empty_bar = full_bar + GP_STAGES;
+  uint64_t* wfull_bar = empty_bar + GP_STAGES;
+  uint64_t* tfull_bar = wfull_bar + 1;
+  uint64_t* tempty_bar = tfull_bar + 1;
+  uint32_t* tmem_slot = (uint32_t*)(tempty_bar + 1);
+
+  const int warp = warp_id_uniform(), lane = threadIdx.x & 31;
+  const int c = (int)blockIdx.x % g.ctj, bt = (int)blockIdx.x / g.ctj;
+  unsigned int*      cnt = g.cnt + bt;
+  const unsigned int per = (unsigned int)g.ctj;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&mapW);
+    tma_prefetch_desc(&mapH0);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < GP_STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(wfull_bar, 1);
+    mbar_init(tfull_bar, 1);
+    mbar_init(tempty_bar, 4);
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc(tmem_slot, 64);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    const bool leader = elect_one();
+    if (leader) {  // 16 rows of each gate: tile row q * 16 + jj <-> weight column q * H + 16 c + jj
+      mbar_expect_tx(wfull_bar, (uint32_t)(KB * 2 * GP_WBLOCK));
+      for (int kb = 0; kb < KB; ++kb)
+        for (int pl = 0; pl < 2; ++pl)
+          for (int q = 0; q < 4; ++q)
+            tma_load_4d(&mapW, wfull_bar, wsm + (size_t)(kb * 2 + pl) * GP_WBLOCK + q * 2048, kb * GP_BK, q * g.H + 16 * c, pl, 0);
+    }
+    int      stage = 0;
+    uint32_t phase = 0;
+    for (int t = 0; t < g.T; ++t) {
+      if (t > 0) wait_count(cnt, per * (unsigned int)t);
+      asm volatile("fence.proxy.async.global;" ::: "memory");
+      const CUtensorMap* mA = (t & 1) ? &mapH1 : &mapH0;
+      for (int kb = 0; kb < KB; ++kb) {
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        if (leader) {
+          uint8_t* st = asm_ + stage * GP_ASTAGE;
+          mbar_expect_tx(&full_bar[stage], GP_ALOAD);
+          tma_load_4d(mA, &full_bar[stage], st, kb * GP_BK, bt * GP_BMV, 0, 0);
+          tma_load_4d(mA, &full_bar[stage], st + GP_BM * GP_BK * 2, kb * GP_BK, bt * GP_BMV, 1, 0);
+        }
+        if (++stage == GP_STAGES) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    const bool     leader = elect_one();
+    const uint32_t idesc = make_idesc_bf16(GP_BM, GP_BN);
+    int            stage = 0;
+    uint32_t       phase = 0;
+    mbar_wait(wfull_bar, 0);
+    tc_fence_after();
+    for (int t = 0; t < g.T; ++t) {
+      mbar_wait(tempty_bar, (uint32_t)(t & 1) ^ 1);
+      tc_fence_after();
+      for (int kb = 0; kb < KB; ++kb) {
+        mbar_wait(&full_bar[stage], phase);
+        tc_fence_after();
+        if (leader) {
+          const uint32_t sa = smem_u32(asm_ + stage * GP_ASTAGE), sb = smem_u32(wsm + (size_t)kb * 2 * GP_WBLOCK);
+          const uint64_t d_ahi = make_smem_desc_sw128(sa), d_alo = make_smem_desc_sw128(sa + GP_BM * GP_BK * 2);
+          const uint64_t d_bhi = make_smem_desc_sw128(sb), d_blo = make_smem_desc_sw128(sb + GP_WBLOCK);
+#pragma unroll
+          for (int k = 0; k < GP_BK / 16; ++k) {
+            const uint64_t o = 2 * k;
+            umma_bf16(tmem_base, d_alo + o, d_bhi + o, idesc, (kb | k) ? 1u : 0u);
+            umma_bf16(tmem_base, d_ahi + o, d_blo + o, idesc, 1u);
+            umma_bf16(tmem_base, d_ahi + o, d_bhi + o, idesc, 1u);
+          }
+          umma_commit(&empty_bar[stage]);
+        }
+        if (++stage == GP_STAGES) { stage = 0; phase ^= 1; }
+      }
+      if (leader) umma_commit(tfull_bar);
+    }
+  } else if (warp >= 4) {
+    // epilogue: the four TMEM readers drop the 64 x 64 accumulator into shared memory; thread (row, jq) then owns hidden units
+    // 16 c + 4 jq .. + 3 of batch row `row`: their four gates sit in chunks q * 4 + jq of the tile row
+    const bool     reader = (warp & 3) < 2;
+    const int      rq = warp & 1, rc0 = ((warp - 4) >> 2) * 32;
+    const uint32_t taddr = tmem_base + ((uint32_t)(rq * 32) << 16) + (uint32_t)rc0;
+    float4*        acc4 = reinterpret_cast<float4*>(asm_);
+    const int      item = (int)threadIdx.x - 128, row = item >> 2, jq = item & 3;
+    const int64_t  H = g.H, BH = (int64_t)g.B * H, b = (int64_t)bt * GP_BMV + row;
+    const bool     live = b < g.B;
+    const int      j = 16 * c + 4 * jq;
+    float4         cst = live ? __ldg(reinterpret_cast<const float4*>(g.c0 + b * H + j)) : make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int t = 0; t < g.T; ++t) {
+      float4 x[4];
+      if (live) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) x[q] = __ldg(reinterpret_cast<const float4*>(g.xp + ((int64_t)t * g.B + b) * 4 * H + q * H + j));
+      }
+      if (reader) {
+        mbar_wait(tfull_bar, (uint32_t)(t & 1));
+        tc_fence_after();
+        float v[32];
+        tmem_ld_32x32(taddr, v);
+        tmem_ld_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(tempty_bar);
+        const int r = rq * 32 + lane;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) acc4[r * 16 + ((rc0 / 4 + k) ^ (r & 7))] = make_float4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
+      }
+      epi_bar();
+      if (live) {
+        float4 a[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) a[q] = acc4[row * 16 + ((q * 4 + jq) ^ (row & 7))];
+        const float4 f = make_float4(gp_sigmoid(a[0].x + x[0].x), gp_sigmoid(a[0].y + x[0].y), gp_sigmoid(a[0].z + x[0].z), gp_sigmoid(a[0].w + x[0].w));
+        const float4 i = make_float4(gp_sigmoid(a[1].x + x[1].x), gp_sigmoid(a[1].y + x[1].y), gp_sigmoid(a[1].z + x[1].z), gp_sigmoid(a[1].w + x[1].w));
+        const float4 o = make_float4(gp_sigmoid(a[2].x + x[2].x), gp_sigmoid(a[2].y + x[2].y), gp_sigmoid(a[2].z + x[2].z), gp_sigmoid(a[2].w + x[2].w));
+        const float4 gg = make_float4(gp_tanh(a[3].x + x[3].x), gp_tanh(a[3].y + x[3].y), gp_tanh(a[3].z + x[3].z), gp_tanh(a[3].w + x[3].w));
+        cst = make_float4(f.x * cst.x + i.x * gg.x, f.y * cst.y + i.y * gg.y, f.z * cst.z + i.z * gg.z, f.w * cst.w + i.w * gg.w);
+        const float4 h = make_float4(o.x * gp_tanh(cst.x), o.y * gp_tanh(cst.y), o.z * gp_tanh(cst.z), o.w * gp_tanh(cst.w));
+        float*       gout = g.gates + ((int64_t)t * g.B + b) * 4 * H + j;
+        *reinterpret_cast<float4*>(gout) = f;
+        *reinterpret_cast<float4*>(gout + H) = i;
+        *reinterpret_cast<float4*>(gout + 2 * H) = o;
+        *reinterpret_cast<float4*>(gout + 3 * H) = gg;
+        const int64_t off = ((int64_t)t * g.B + b) * H + j;
+        *reinterpret_cast<float4*>(g.cs + off) = cst;
+        *reinterpret_cast<float4*>(g.hs + off) = h;
+        put_planes4((((t + 1) & 1) ? g.hP1 : g.hP0) + b * g.Kp + j, (int64_t)g.B * g.Kp, h);
+      }
+      fence_proxy_async_smem();
+      epi_bar();
+      if (threadIdx.x == 128) {
+        __threadfence();
+        atomicAdd(cnt, 1u);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc(tmem_base, 64);
+}
+
 // ------------------------------------------------------------------------------------------------------------------ BPTT
 // Per step s (T-1 ... 0), element (b, k), with hp = h_{s-1}, the saved z, r, n and the running gradient dh (rnn.py:529-544 reversed):
 //   d = dh + g_hs[s];  dl2 = d z (1 - n^2) -> dxp2[s];  dl1z = d (n - hp) z (1 - z) -> dxp1[s][:, k]
@@ -551,6 +725,231 @@ k_gru_persist_bwd(const __grid_constant__ CUtensorMap mapDl2, const __grid_const
   if (warp == 2) tmem_dealloc(tmem_base, 64);
 }
 
+// ------------------------------------------------------------------------------------------------------------------ LSTM BPTT
+// Per step s (T-1 ... 0), element (b, k), saved gates f, i, o, g, cell states c_s, c_{s-1}, running dh, dc (rnn.py:280-288 reversed):
+//   d = dh + g_hs[s];  tc = tanh(c_s);  dct = dc + d o (1 - tc^2)
+//   dl = [dct c_{s-1} f (1 - f), dct g i (1 - i), d tc o (1 - o), dct i (1 - g^2)] -> dxp[s];  dc' = dct f;  dh' = dl . Wh^T (K = 4H)
+// The contraction over 4H is cut by gate: role q (0..3) holds rows k of Wh[:, qH:(q+1)H] in shared memory and produces the partial
+// product of gate q; roles 1..3 hand theirs over in fp32 (part), role 0 adds them to its own accumulator in a fixed order
+// (deterministic), then runs the elementwise part of step s - 1 with dh and dc of its elements in registers.
+// Counters per batch tile: [0] operand planes of the next step ready (role 0), [1] accumulators drained = planes of this step consumed
+// and partials published (all four roles): role 0 overwrites the planes only past it.
+struct LstmBwdArgs {
+  const float *g_hs, *g_cT, *c0, *cs, *gates;
+  float *      dxp, *dh0, *dc0, *part;  // part: [3][B][H]
+  __nv_bfloat16* dlP;                   // operand planes [2][B][Kp4]
+  int           T, B, H, Kp4, nbt, ctk;
+  unsigned int* cnt;  // [nbt][16]
+};
+
+__global__ void __launch_bounds__(384, 1)
+k_lstm_persist_bwd(const __grid_constant__ CUtensorMap mapDl, const __grid_constant__ CUtensorMap mapWt, LstmBwdArgs g) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t*  smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  const int KB = g.H / GP_BK;
+  uint8_t*  wsm = smem;
+  uint8_t*  asm_ = smem + (size_t)KB * 2 * GP_WBLOCK;
+  uint64_t* full_bar = (uint64_t*)(asm_ + GP_STAGES * GP_ASTAGE);
+  uint64_t* empty_bar = full_bar + GP_STAGES;
+  uint64_t* wfull_bar = empty_bar + GP_STAGES;
+  uint64_t* tfull_bar = wfull_bar + 1;
+  uint64_t* tempty_bar = tfull_bar + 1;
+  uint32_t* tmem_slot = (uint32_t*)(tempty_bar + 1);
+
+  const int          warp = warp_id_uniform(), lane = threadIdx.x & 31;
+  const int          per_set = g.ctk * g.nbt;
+  const int          role = (int)blockIdx.x / per_set;  // gate q
+  const int          idx = (int)blockIdx.x - role * per_set;
+  const int          c = idx % g.ctk, bt = idx / g.ctk;
+  unsigned int*      cnt = g.cnt + bt * 16;
+  const unsigned int per = (unsigned int)g.ctk;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&mapWt);
+    tma_prefetch_desc(&mapDl);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < GP_STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(wfull_bar, 1);
+    mbar_init(tfull_bar, 1);
+    mbar_init(tempty_bar, 4);
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc(tmem_slot, 64);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    const bool leader = elect_one();
+    if (leader) {
+      mbar_expect_tx(wfull_bar, (uint32_t)(KB * 2 * GP_WBLOCK));
+      for (int kb = 0; kb < KB; ++kb)
+        for (int pl = 0; pl < 2; ++pl)
+          tma_load_4d(&mapWt, wfull_bar, wsm + (size_t)(kb * 2 + pl) * GP_WBLOCK, role * g.H + kb * GP_BK, c * GP_BN, pl, 0);
+    }
+    int      stage = 0;
+    uint32_t phase = 0;
+    for (int i = 0; i < g.T; ++i) {
+      wait_count(cnt, per * (unsigned int)(i + 1));
+      asm volatile("fence.proxy.async.global;" ::: "memory");
+      for (int kb = 0; kb < KB; ++kb) {
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        if (leader) {
+          uint8_t* st = asm_ + stage * GP_ASTAGE;
+          mbar_expect_tx(&full_bar[stage], GP_ALOAD);
+          tma_load_4d(&mapDl, &full_bar[stage], st, role * g.H + kb * GP_BK, bt * GP_BMV, 0, 0);
+          tma_load_4d(&mapDl, &full_bar[stage], st + GP_BM * GP_BK * 2, role * g.H + kb * GP_BK, bt * GP_BMV, 1, 0);
+        }
+        if (++stage == GP_STAGES) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    const bool     leader = elect_one();
+    const uint32_t idesc = make_idesc_bf16(GP_BM, GP_BN);
+    int            stage = 0;
+    uint32_t       phase = 0;
+    mbar_wait(wfull_bar, 0);
+    tc_fence_after();
+    for (int i = 0; i < g.T; ++i) {
+      mbar_wait(tempty_bar, (uint32_t)(i & 1) ^ 1);
+      tc_fence_after();
+      for (int kb = 0; kb < KB; ++kb) {
+        mbar_wait(&full_bar[stage], phase);
+        tc_fence_after();
+        if (leader) {
+          const uint32_t sa = smem_u32(asm_ + stage * GP_ASTAGE), sb = smem_u32(wsm + (size_t)kb * 2 * GP_WBLOCK);
+          const uint64_t d_ahi = make_smem_desc_sw128(sa), d_alo = make_smem_desc_sw128(sa + GP_BM * GP_BK * 2);
+          const uint64_t d_bhi = make_smem_desc_sw128(sb), d_blo = make_smem_desc_sw128(sb + GP_WBLOCK);
+#pragma unroll
+          for (int k = 0; k < GP_BK / 16; ++k) {
+            const uint64_t o = 2 * k;
+            umma_bf16(tmem_base, d_alo + o, d_bhi + o, idesc, (kb | k) ? 1u : 0u);
+            umma_bf16(tmem_base, d_ahi + o, d_blo + o, idesc, 1u);
+            umma_bf16(tmem_base, d_ahi + o, d_bhi + o, idesc, 1u);
+          }
+          umma_commit(&empty_bar[stage]);
+        }
+        if (++stage == GP_STAGES) { stage = 0; phase ^= 1; }
+      }
+      if (leader) umma_commit(tfull_bar);
+    }
+  } else if (warp >= 4) {
+    const bool     reader = (warp & 3) < 2;
+    const int      rq = warp & 1, rc0 = ((warp - 4) >> 2) * 32;
+    const uint32_t taddr = tmem_base + ((uint32_t)(rq * 32) << 16) + (uint32_t)rc0;
+    float4*        acc4 = reinterpret_cast<float4*>(asm_);
+    const int      ew = warp - 4, cch = lane & 15;
+    const int64_t  H = g.H, BH = (int64_t)g.B * H, PS = (int64_t)g.B * g.Kp4;
+    const int      k0 = c * GP_BN + 4 * cch;
+    int64_t        brow[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) brow[e] = (int64_t)bt * GP_BMV + ew * 8 + 2 * e + (lane >> 4);
+    float4 dh[4], dc[4];
+    auto   elementwise = [&](int s) {
+      const float* cprev = s == 0 ? g.c0 : g.cs + (int64_t)(s - 1) * BH;
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int64_t b = brow[e];
+        if (b >= g.B) continue;
+        const int64_t o1 = ((int64_t)s * g.B + b) * H + k0, o4 = ((int64_t)s * g.B + b) * 4 * H + k0;
+        const float4  gg = g.g_hs ? __ldg(reinterpret_cast<const float4*>(g.g_hs + o1)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        const float4  f = __ldg(reinterpret_cast<const float4*>(g.gates + o4)), ii = __ldg(reinterpret_cast<const float4*>(g.gates + o4 + H));
+        const float4  o = __ldg(reinterpret_cast<const float4*>(g.gates + o4 + 2 * H)), gt = __ldg(reinterpret_cast<const float4*>(g.gates + o4 + 3 * H));
+        const float4  ct = __ldg(reinterpret_cast<const float4*>(g.cs + o1)), cp = __ldg(reinterpret_cast<const float4*>(cprev + b * H + k0));
+        float4        v[4];
+#define LSTM_BWD_LANE(m)                                                                                  \
+  {                                                                                                       \
+    const float d = dh[e].m + gg.m, tc = gp_tanh(ct.m), dct = dc[e].m + d * o.m * (1.f - tc * tc);        \
+    v[0].m = dct * cp.m * f.m * (1.f - f.m), v[1].m = dct * gt.m * ii.m * (1.f - ii.m);                   \
+    v[2].m = d * tc * o.m * (1.f - o.m), v[3].m = dct * ii.m * (1.f - gt.m * gt.m);                       \
+    dc[e].m = dct * f.m;                                                                                  \
+  }
+        LSTM_BWD_LANE(x) LSTM_BWD_LANE(y) LSTM_BWD_LANE(z) LSTM_BWD_LANE(w)
+#undef LSTM_BWD_LANE
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          *reinterpret_cast<float4*>(g.dxp + o4 + q * H) = v[q];
+          put_planes4(g.dlP + b * g.Kp4 + q * H + k0, PS, v[q]);
+        }
+      }
+    };
+    auto publish = [&](int which) {
+      fence_proxy_async_smem();
+      epi_bar();
+      if (threadIdx.x == 128) {
+        __threadfence();
+        atomicAdd(cnt + which, 1u);
+      }
+    };
+    if (role == 0) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        dh[e] = make_float4(0.f, 0.f, 0.f, 0.f);
+        dc[e] = (g.g_cT && brow[e] < g.B) ? __ldg(reinterpret_cast<const float4*>(g.g_cT + brow[e] * H + k0)) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+      elementwise(g.T - 1);
+      publish(0);
+    }
+    for (int i = 0; i < g.T; ++i) {
+      const int s = g.T - 1 - i;
+      if (reader) {
+        mbar_wait(tfull_bar, (uint32_t)(i & 1));
+        tc_fence_after();
+        float v[32];
+        tmem_ld_32x32(taddr, v);
+        tmem_ld_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(tempty_bar);
+        const int row = rq * 32 + lane;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) acc4[row * 16 + ((rc0 / 4 + k) ^ (row & 7))] = make_float4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
+      }
+      epi_bar();
+      if (role == 0) {  // every CTA of this batch tile has consumed the operand planes of step s (and roles 1..3 have published)
+        if (threadIdx.x == 128) atomicAdd(cnt + 1, 1u);
+        if (lane == 0) wait_count(cnt + 1, 4u * per * (unsigned int)(i + 1));
+        __syncwarp();
+      }
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int     row = ew * 8 + 2 * e + (lane >> 4);
+        const int64_t b = brow[e];
+        if (b >= g.B) continue;
+        const float4 a = acc4[row * 16 + (cch ^ (row & 7))];
+        if (role != 0) {
+          *reinterpret_cast<float4*>(g.part + (int64_t)(role - 1) * BH + b * H + k0) = a;
+        } else {
+          const float4 p1 = __ldcg(reinterpret_cast<const float4*>(g.part + b * H + k0));
+          const float4 p2 = __ldcg(reinterpret_cast<const float4*>(g.part + BH + b * H + k0));
+          const float4 p3 = __ldcg(reinterpret_cast<const float4*>(g.part + 2 * BH + b * H + k0));
+          dh[e] = make_float4(((a.x + p1.x) + p2.x) + p3.x, ((a.y + p1.y) + p2.y) + p3.y, ((a.z + p1.z) + p2.z) + p3.z, ((a.w + p1.w) + p2.w) + p3.w);
+          if (s == 0) *reinterpret_cast<float4*>(g.dh0 + b * H + k0) = dh[e];
+        }
+      }
+      if (role == 0) {
+        if (s > 0) elementwise(s - 1);
+        else {
+#pragma unroll
+          for (int e = 0; e < 4; ++e)
+            if (brow[e] < g.B) *reinterpret_cast<float4*>(g.dc0 + brow[e] * H + k0) = dc[e];
+        }
+        publish(0);
+      } else {
+        publish(1);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc(tmem_base, 64);
+}
+
 static bool g_persist_off = getenv("PDN_GRU_PERSIST") && getenv("PDN_GRU_PERSIST")[0] == '0';
 
 bool gru_persist_ok(int64_t T, int64_t B, int64_t H) {
@@ -603,6 +1002,65 @@ int gru_persist_forward(const float* xp1, const float* xp2, const float* h0, con
     }
   }
   delete cnt;  // Scratch returns its block to the stream-ordered allocator: reuse is ordered after this kernel
+  return 0;
+}
+
+bool lstm_persist_ok(int64_t T, int64_t B, int64_t H) {
+  if (g_persist_off || H % GP_BK != 0 || H / GP_BK > GP_MAXKB || T < 4) return false;
+  const int64_t nbt = (B + GP_BMV - 1) / GP_BMV;
+  return (H / 16) * nbt <= sm_count();
+}
+
+// Wp: K-major planes of Wh as [2][4H rows (output columns)][Kp]; hP0 holds h0 on entry
+int lstm_persist_forward(const float* xp, const float* h0, const float* c0, const PackedOperand& Wp, const PackedOperand& hP0, const PackedOperand& hP1,
+                         float* hs, float* cs, float* gates, int64_t T, int64_t B, int64_t H) {
+  const int nbt = (int)((B + GP_BMV - 1) / GP_BMV), ctj = (int)(H / 16);
+  CUtensorMap mH0, mH1, mW;
+  PDN_TRY(tc_make_map(&mH0, hP0.planes, B, H, hP0.Kp, 1, GP_BMV));
+  PDN_TRY(tc_make_map(&mH1, hP1.planes, B, H, hP1.Kp, 1, GP_BMV));
+  PDN_TRY(tc_make_map(&mW, Wp.planes, 4 * H, H, Wp.Kp, 1, 16));
+  Scratch cnt;
+  PDN_TRY(cnt.alloc((size_t)nbt * sizeof(unsigned int)));
+  PDN_CUDA(cudaMemsetAsync(cnt.p, 0, (size_t)nbt * sizeof(unsigned int), stream()));
+  LstmPersistArgs g;
+  g.xp = xp, g.h0 = h0, g.c0 = c0, g.hs = hs, g.cs = cs, g.gates = gates;
+  g.hP0 = (__nv_bfloat16*)hP0.planes, g.hP1 = (__nv_bfloat16*)hP1.planes;
+  g.T = (int)T, g.B = (int)B, g.H = (int)H, g.Kp = (int)hP0.Kp, g.nbt = nbt, g.ctj = ctj;
+  g.cnt = (unsigned int*)cnt.p;
+  const size_t smem = (size_t)(H / GP_BK) * 2 * GP_WBLOCK + (size_t)GP_STAGES * GP_ASTAGE + 1024 + 256;
+  PDN_CUDA(cudaFuncSetAttribute(k_lstm_persist_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  void* params[] = {&mH0, &mH1, &mW, &g};
+  PDN_CUDA(cudaLaunchCooperativeKernel((const void*)k_lstm_persist_fwd, dim3(ctj * nbt), dim3(384), params, smem, stream()));
+  PDN_LAUNCHED("lstm_persist_fwd");
+  return 0;
+}
+
+bool lstm_persist_bwd_ok(int64_t T, int64_t B, int64_t H) {
+  if (!lstm_persist_ok(T, B, H)) return false;
+  const int64_t nbt = (B + GP_BMV - 1) / GP_BMV;
+  return 4 * (H / GP_BN) * nbt <= sm_count();
+}
+
+// Wt: K-major planes of Wh as [H rows j][Kp4 over the 4H gate columns]; dlP: operand planes [2][B][Kp4]; part: [3][B][H]
+int lstm_persist_backward(const float* g_hs, const float* g_cT, const float* c0, const float* cs, const float* gates, const PackedOperand& Wt,
+                          const PackedOperand& dlP, float* part, float* dxp, float* dh0, float* dc0, int64_t T, int64_t B, int64_t H) {
+  const int nbt = (int)((B + GP_BMV - 1) / GP_BMV), ctk = (int)(H / GP_BN);
+  CUtensorMap mDl, mW;
+  PDN_TRY(tc_make_map(&mDl, dlP.planes, B, 4 * H, dlP.Kp, 1, GP_BMV));
+  PDN_TRY(tc_make_map(&mW, Wt.planes, H, 4 * H, Wt.Kp, 1, GP_BN));
+  Scratch cnt;
+  PDN_TRY(cnt.alloc((size_t)nbt * 16 * sizeof(unsigned int)));
+  PDN_CUDA(cudaMemsetAsync(cnt.p, 0, (size_t)nbt * 16 * sizeof(unsigned int), stream()));
+  LstmBwdArgs g;
+  g.g_hs = g_hs, g.g_cT = g_cT, g.c0 = c0, g.cs = cs, g.gates = gates;
+  g.dxp = dxp, g.dh0 = dh0, g.dc0 = dc0, g.part = part, g.dlP = (__nv_bfloat16*)dlP.planes;
+  g.T = (int)T, g.B = (int)B, g.H = (int)H, g.Kp4 = (int)dlP.Kp, g.nbt = nbt, g.ctk = ctk;
+  g.cnt = (unsigned int*)cnt.p;
+  const size_t smem = (size_t)(H / GP_BK) * 2 * GP_WBLOCK + (size_t)GP_STAGES * GP_ASTAGE + 1024 + 256;
+  PDN_CUDA(cudaFuncSetAttribute(k_lstm_persist_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  void* params[] = {&mDl, &mW, &g};
+  PDN_CUDA(cudaLaunchCooperativeKernel((const void*)k_lstm_persist_bwd, dim3(4 * ctk * nbt), dim3(384), params, smem, stream()));
+  PDN_LAUNCHED("lstm_persist_bwd");
   return 0;
 }
 

@@ -1,6 +1,7 @@
 // runtime.cu — device/stream/allocator/event/graph plumbing of libpdn_b200.so.
 // Replaces what the reference gets from CuPy's runtime + memory pool (reference pydynet/cuda.py:16-32,
 // tensor.py:80,90): nothing here is ported, the reference has no native runtime.
+#include <cstring>
 #include "common.cuh"
 #include <nvtx3/nvToolsExt.h>  // header-only: resolves the profiler's injection library at run time, no link dependency
 
@@ -29,8 +30,12 @@ int cuda_fail(cudaError_t e, const char* what, const char* file, int line) {
 
 static bool g_nvtx = getenv("PDN_NVTX") != nullptr;  // PDN_NVTX=1: every kernel launch is marked by its entry-point name
 
+static char     g_watch[64] = "";
+static uint64_t g_watched = 0;
+
 int after_launch(const char* name) {
   ++g_launches;
+  if (g_watch[0] && strcmp(g_watch, name) == 0) ++g_watched;
   if (g_nvtx) nvtxMarkA(name);
   cudaError_t e = cudaPeekAtLastError();
   if (e != cudaSuccess) {
@@ -370,6 +375,11 @@ int pdn_sync(void) {
 
 uint64_t pdn_kernel_launch_count(void) { return g_launches; }
 void     pdn_reset_launch_count(void) { g_launches = 0; }
+void     pdn_watch_launches(const char* name) {
+  g_watched = 0;
+  snprintf(g_watch, sizeof g_watch, "%s", name ? name : "");
+}
+uint64_t pdn_watched_launch_count(void) { return g_watched; }
 
 int pdn_event_create(void** ev) {
   PDN_TRY(ensure_init());
