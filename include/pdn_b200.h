@@ -94,6 +94,16 @@ int pdn_sync(void);
 int pdn_nvtx_push(const char* name);
 int pdn_nvtx_pop(void);
 
+/* Recorded fork regions: inside pdn_graph_begin .. pdn_graph_end, fork the compute stream into n <= 4 branches, direct the
+ * following launches and allocations of the calling thread to branch i, add an ordering edge between two branches (mark / wait), join. The
+ * branches of a replayed graph run concurrently (independent batch slices of the decode step: the launch-latency-bound chain of one
+ * slice fills the gaps of the others). No-ops outside a recording. Nothing in the reference corresponds to this (one NumPy thread). */
+int pdn_branch_begin(int n);
+int pdn_branch_select(int i);
+int pdn_branch_mark(int* token);  /* edge source: the current tail of the selected branch */
+int pdn_branch_wait(int token);   /* the selected branch's next work waits for that point */
+int pdn_branch_end(void);
+
 /* launch accounting (bench.py "gpu_launches") and device-side timing on the library stream */
 uint64_t pdn_kernel_launch_count(void);
 void pdn_reset_launch_count(void);

@@ -60,6 +60,7 @@ _PROTOS = {
     "pdn_event_record": [vp],
     "pdn_event_elapsed_ms": [vp, vp, C.POINTER(f32)],
     "pdn_graph_begin": [],
+    "pdn_branch_begin": [i32], "pdn_branch_select": [i32], "pdn_branch_mark": [C.POINTER(i32)], "pdn_branch_wait": [i32], "pdn_branch_end": [],
     "pdn_graph_end": [C.POINTER(vp)],
     "pdn_graph_launch": [vp],
     "pdn_graph_destroy": [vp],

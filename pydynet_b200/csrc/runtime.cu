@@ -59,10 +59,20 @@ struct DevState {
     size_t size;
     int    graph;      // 0 = ordinary; else id of the CUDA graph whose kernels reference this block
     bool   user_live;  // still owned by a caller (false: only the graph keeps it reserved)
+    int    fork = 0;   // fork region (pdn_branch_begin) and branch the block was allocated in while recording; 0 = none
+    int    branch = 0;
   };
   std::multimap<size_t, void*>     free_blocks;
   std::unordered_map<void*, Block> live;
   std::multimap<size_t, void*>     capture_free;  // blocks freed DURING the active capture: reusable inside it only
+  // recorded fork region (pdn_branch_begin .. pdn_branch_end): the branches run concurrently when the graph replays, so a block
+  // freed in a branch may only be handed out again in THAT branch, and only if it was allocated there (nobody else can hold it);
+  // everything else waits for the join
+  std::multimap<size_t, void*> branch_free[4];
+  std::vector<std::pair<size_t, void*>> parked;
+  cudaStream_t                 branch[4] = {nullptr, nullptr, nullptr, nullptr};
+  std::vector<cudaEvent_t>     edge_events;  // fork / join / ordering edges of recorded branches
+  size_t                       edge_next = 0;
   uint64_t in_use = 0, cached = 0, n_malloc = 0;
 };
 static DevState   g_dev[16];
@@ -73,6 +83,7 @@ static int        g_next_graph_id = 1;
 static std::unordered_map<void*, int> g_exec_graph;  // cudaGraphExec_t -> graph id
 static std::unordered_map<void*, uint64_t> g_exec_kernels;  // kernels recorded in the graph (for the launch counter)
 static uint64_t g_capture_launch0 = 0;
+static int      g_nbranch = 1, g_branch = 0, g_fork = 0, g_next_fork = 1;  // recorded fork region: see pdn_branch_begin
 
 static DevState* cur() {
   int d = 0;
@@ -102,7 +113,8 @@ int ensure_init() {
 
 cudaStream_t stream() {
   DevState* s = cur();
-  return s && s->inited ? s->compute : nullptr;
+  if (!s || !s->inited) return nullptr;
+  return g_branch > 0 ? s->branch[g_branch] : s->compute;
 }
 cudaStream_t comm_stream() {
   DevState* s = cur();
@@ -132,11 +144,14 @@ int dev_alloc(void** p, size_t bytes) {
   std::lock_guard<std::mutex> lk(g_mu);
   const int gid = g_capturing ? g_capture_id : 0;
   if (g_capturing) {  // memory released earlier in this capture is ordered before us inside the graph: reuse it first
-    auto it = s->capture_free.lower_bound(want);
-    if (it != s->capture_free.end() && it->first <= want + want / 4) {
+    auto& pool = g_fork ? s->branch_free[g_branch] : s->capture_free;
+    auto  it = pool.lower_bound(want);
+    if (it != pool.end() && it->first <= want + want / 4) {
       *p = it->second;
-      s->capture_free.erase(it);
-      s->live[*p].user_live = true;
+      pool.erase(it);
+      auto& blk = s->live[*p];
+      blk.user_live = true;
+      blk.fork = g_fork, blk.branch = g_branch;
       return 0;
     }
   }
@@ -147,7 +162,7 @@ int dev_alloc(void** p, size_t bytes) {
     size_t got = it->first;
     s->free_blocks.erase(it);
     s->cached -= got;
-    s->live[*p] = DevState::Block{got, gid, true};
+    s->live[*p] = DevState::Block{got, gid, true, g_fork, g_branch};
     s->in_use += got;
     return 0;
   }
@@ -164,7 +179,7 @@ int dev_alloc(void** p, size_t bytes) {
     return cuda_fail(e, "cudaMalloc", __FILE__, __LINE__);
   }
   s->n_malloc++;
-  s->live[*p] = DevState::Block{want, gid, true};
+  s->live[*p] = DevState::Block{want, gid, true, g_fork, g_branch};
   s->in_use += want;
   return 0;
 }
@@ -174,7 +189,11 @@ static void free_in(DevState& d, std::unordered_map<void*, DevState::Block>::ite
   if (it->second.graph != 0) {
     // referenced by a CUDA graph: never hand it to unrelated work while the graph exists
     it->second.user_live = false;
-    if (g_capturing && it->second.graph == g_capture_id) d.capture_free.emplace(it->second.size, p);
+    if (g_capturing && it->second.graph == g_capture_id) {
+      if (!g_fork) d.capture_free.emplace(it->second.size, p);
+      else if (it->second.fork == g_fork && it->second.branch == g_branch) d.branch_free[g_branch].emplace(it->second.size, p);
+      else d.parked.emplace_back(it->second.size, p);  // may still be read by another branch: reusable after the join
+    }
     return;
   }
   // single compute stream => a freed block can be handed out again immediately (stream order)
@@ -405,6 +424,82 @@ int pdn_event_elapsed_ms(void* start, void* stop, float* ms) {
   return 0;
 }
 
+// ---- recorded fork regions ---------------------------------------------------------------------------------------------------
+// Inside a graph recording, pdn_branch_begin(n) forks the compute stream into n branches (branch 0 is the compute stream itself),
+// pdn_branch_select(i) makes branch i the stream every following launch / allocation of this thread goes to, pdn_branch_mark /
+// pdn_branch_wait add an edge from a marked point of one branch to what another does next, pdn_branch_end joins. When the graph replays
+// the branches run concurrently: a latency-bound launch chain of one batch slice fills the gaps of another's. Outside a recording
+// the calls are no-ops (everything stays on the one compute stream, which is what the caching allocator's reuse rule assumes).
+static int next_edge_event(DevState* s, cudaEvent_t* ev) {
+  if (s->edge_next == s->edge_events.size()) {
+    cudaEvent_t e;
+    PDN_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    s->edge_events.push_back(e);
+  }
+  *ev = s->edge_events[s->edge_next++];
+  return 0;
+}
+int pdn_branch_begin(int n) {
+  PDN_TRY(ensure_init());
+  PDN_CHECK(n >= 1 && n <= 4, "pdn_branch_begin: 1..4 branches");
+  if (!g_capturing || n == 1) return 0;
+  PDN_CHECK(g_fork == 0, "pdn_branch_begin: fork regions do not nest");
+  DevState*   s = cur();
+  cudaEvent_t ev;
+  PDN_TRY(next_edge_event(s, &ev));
+  PDN_CUDA(cudaEventRecord(ev, s->compute));
+  for (int i = 1; i < n; ++i) {
+    if (!s->branch[i]) PDN_CUDA(cudaStreamCreateWithFlags(&s->branch[i], cudaStreamNonBlocking));
+    PDN_CUDA(cudaStreamWaitEvent(s->branch[i], ev, 0));
+  }
+  std::lock_guard<std::mutex> lk(g_mu);
+  g_nbranch = n, g_branch = 0, g_fork = g_next_fork++;
+  return 0;
+}
+int pdn_branch_select(int i) {
+  if (!g_fork) return 0;
+  PDN_CHECK(i >= 0 && i < g_nbranch, "pdn_branch_select: branch %d of %d", i, g_nbranch);
+  std::lock_guard<std::mutex> lk(g_mu);
+  g_branch = i;
+  return 0;
+}
+int pdn_branch_mark(int* token) {  // an edge source at the current tail of the selected branch
+  *token = -1;
+  if (!g_fork) return 0;
+  DevState*   s = cur();
+  cudaEvent_t ev;
+  PDN_TRY(next_edge_event(s, &ev));
+  PDN_CUDA(cudaEventRecord(ev, stream()));
+  *token = (int)s->edge_next - 1;
+  return 0;
+}
+int pdn_branch_wait(int token) {  // what the selected branch does next waits for the marked point
+  if (!g_fork || token < 0) return 0;
+  DevState* s = cur();
+  PDN_CHECK((size_t)token < s->edge_next, "pdn_branch_wait: unknown token %d", token);
+  PDN_CUDA(cudaStreamWaitEvent(stream(), s->edge_events[token], 0));
+  return 0;
+}
+int pdn_branch_end(void) {
+  if (!g_fork) return 0;
+  DevState* s = cur();
+  for (int i = 1; i < g_nbranch; ++i) {
+    cudaEvent_t ev;
+    PDN_TRY(next_edge_event(s, &ev));
+    PDN_CUDA(cudaEventRecord(ev, s->branch[i]));
+    PDN_CUDA(cudaStreamWaitEvent(s->compute, ev, 0));
+  }
+  std::lock_guard<std::mutex> lk(g_mu);
+  for (int i = 0; i < 4; ++i) {  // after the join everything the branches released is ordered before what follows
+    for (auto& kv : s->branch_free[i]) s->capture_free.emplace(kv.first, kv.second);
+    s->branch_free[i].clear();
+  }
+  for (auto& kv : s->parked) s->capture_free.emplace(kv.first, kv.second);
+  s->parked.clear();
+  g_nbranch = 1, g_branch = 0, g_fork = 0;
+  return 0;
+}
+
 int pdn_graph_begin(void) {
   PDN_TRY(ensure_init());
   PDN_CHECK(!g_capturing, "graph capture already active");
@@ -413,6 +508,7 @@ int pdn_graph_begin(void) {
   g_capturing = true;
   g_capture_id = g_next_graph_id++;
   g_capture_launch0 = g_launches;
+  if (DevState* s = cur()) s->edge_next = 0;  // edge events are only graph edges: reusable by every recording
   return 0;
 }
 /* debugging aid: 0 = no capture, 1 = capture active, 2 = capture invalidated by an operation that cannot be recorded */
@@ -433,6 +529,7 @@ int pdn_graph_end(void** graph_exec) {
     g_capture_id = 0;
     for (auto& d : g_dev) d.capture_free.clear();  // stay reserved for the graph (user_live == false)
   }
+  PDN_CHECK(g_fork == 0, "graph capture ended inside a fork region (pdn_branch_end missing)");
   cudaGraph_t g;
   cudaError_t e = cudaStreamEndCapture(stream(), &g);
   if (e != cudaSuccess) {

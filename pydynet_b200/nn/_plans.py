@@ -27,6 +27,7 @@ drops recorded graphs and packed weights that no longer match.
 ``logits[:, -1, :].argmax(-1, True)`` (reference model.py:268) on a plan's logits returns the argmax the lm_head GEMM
 epilogue / the decode kernel already produced (``Tensor._pdn_hint``): same values, no second pass over [B, 32000].
 """
+import ctypes
 import math
 import os
 import sys
@@ -47,6 +48,18 @@ STRUCT_EPOCH = [0]
 F32 = np.dtype(np.float32)
 I64 = np.dtype(np.int64)
 MEGA_MAX_ROWS = 8  # batch rows one decode_mega launch serves (register accumulators per warp)
+
+
+def decode_branches(B):
+    """Concurrent batch slices of the recorded decode step: 1 (one launch chain) unless PDN_DECODE_BRANCHES=2|4 asks for a fork.
+    Measured at batch 1024 on B200: 1.455 M tokens/s unforked, 1.354 M with 2 slices, 1.235 M with 4 — the
+    KV-cache attention and the lm_head GEMM lose more at half / quarter batch (partial last wave; the 37 MB of lm_head weight
+    planes re-read per slice) than the overlapped launch chains win, so the fork stays an opt-in experiment."""
+    nb = int(os.environ.get("PDN_DECODE_BRANCHES", "1"))
+    nb = max(1, min(4, nb))
+    while nb > 1 and (B % nb or B // nb < 32):
+        nb //= 2
+    return nb
 
 
 def note_structure_change():
@@ -95,10 +108,14 @@ class _LogitsCore:
             m = plan.model
             V = m.lm_head.weight.shape[1]
             bias = m.lm_head.bias
+            parts = pl if isinstance(pl, list) else [pl]  # a forked step leaves one set of planes per batch slice
             with plan.device:
-                out = _empty((pl.M, V))
-                _call("pdn_gemm_prepacked_planes", pl.ptr, pl.M, pl.Kp, _fused._packed(m.lm_head.weight).handle, out.ptr, V,
-                      _c(bias.data).ptr if bias is not None else None, 0)
+                out = _empty((sum(q.M for q in parts), V))
+                row = 0
+                for q in parts:
+                    _call("pdn_gemm_prepacked_planes", q.ptr, q.M, q.Kp, _fused._packed(m.lm_head.weight).handle, out.ptr + row * V * 4, V,
+                          _c(bias.data).ptr if bias is not None else None, 0)
+                    row += q.M
             self.buf, self.planes = out, None
         return self.buf
 
@@ -396,8 +413,10 @@ class DecoderPlan:
         _call("pdn_gemm_prepacked_planes", pl.ptr, pl.M, pl.Kp, pw.handle, out.ptr, N, None, 0)
         return out
 
-    def _block(self, i, x, start_pos, mask, B, L):
-        """One transformer block in place on the residual stream ``x`` [B, L, dim] (reference model.py:142-150, 95-121)."""
+    def _block(self, i, x, start_pos, mask, B, L, b0=0, chain=None):
+        """One transformer block in place on the residual stream ``x`` [B, L, dim] (reference model.py:142-150, 95-121);
+        ``b0``: first sequence of the KV cache this batch slice belongs to; ``chain``: [token] of the previous attention launch
+        of a forked step (the attention launches of all branches run one after the other)."""
         blk, att, ffn, n1, n2 = self.blocks[i]
         m = self.model
         H, D = att.n_heads, att.head_dim
@@ -406,6 +425,8 @@ class DecoderPlan:
         q3 = qkv.reshape(B, L, 3, H, D)
         q, k, v = q3[:, :, 0], q3[:, :, 1], q3[:, :, 2]
         ck, cv = att.cache_k.data, att.cache_v.data
+        if B != ck.shape[0]:
+            ck, cv = ck[b0:b0 + B], cv[b0:b0 + B]  # views: same buffer (and version counter)
         S = ck.shape[1]
         cos, sin = m.freqs_cos.data, m.freqs_sin.data
         pl = Planes((B, L), dim, self.device)
@@ -415,7 +436,13 @@ class DecoderPlan:
         if isinstance(start_pos, DevicePos):
             pp = start_pos.tensor.data.ptr
             _call("pdn_rope_kv_append_dev", q.ptr, k.ptr, v.ptr, cos.ptr, sin.ptr, ck.ptr, cv.ptr, B, L, H, D, S, pp, ld)
+            if chain is not None:
+                _call("pdn_branch_wait", chain[0])
             _call("pdn_attention_fwd_dev", q.ptr, ck.ptr, cv.ptr, None, B, H, L, D, _bhl_strides(q), cstr, cstr, scale, pp, L, pl.ptr, pl.Kp)
+            if chain is not None:
+                tok = ctypes.c_int32(-1)
+                _call("pdn_branch_mark", ctypes.byref(tok))
+                chain[0] = tok.value
         else:
             _call("pdn_rope_kv_append", q.ptr, k.ptr, v.ptr, cos.ptr, sin.ptr, ck.ptr, cv.ptr, B, L, H, D, S, start_pos, ld)
             Lk = start_pos + L
@@ -473,6 +500,9 @@ class DecoderPlan:
         (GEMM epilogue); ``pos`` is a host int (eager launches) or the state's DevicePos (graph recording; the recorded step
         also advances it). Returns the planes."""
         m, B = self.model, st.B
+        nb = decode_branches(B) if isinstance(pos, DevicePos) else 1
+        if nb > 1:
+            return self._decode_step_forked(st, slot_in, slot_out, pos, nb)
         ids_t = _result(st.ids[slot_in], self.device, (), None, "ids")
         h = self._hidden_tc(ids_t, pos, B, 1)
         pl = self._head_planes(h, B, 1)
@@ -482,6 +512,42 @@ class DecoderPlan:
         if isinstance(pos, DevicePos):
             pos.tensor += 1
         return pl
+
+    def _decode_step_forked(self, st, slot_in, slot_out, pos, nb):
+        """The recorded decode step as ``nb`` concurrent branches over batch slices (``pdn_branch_*``): sequences are independent,
+        and at batch 1024 half of the step is a chain of ~50 launch-latency-bound kernels (GEMMs of 40-120 CTAs, row kernels)
+        between the HBM-bound KV-cache attention launches — the chain of one slice runs in the shadow of another slice's
+        attention. Layers are issued round-robin over the branches; the attention launches are ordered one after the other across
+        branches (each keeps the whole HBM bandwidth, and its CUDA-event timing stays that of one kernel)."""
+        from . import functional as F
+        m, B = self.model, st.B
+        Bs = B // nb
+        bias = m.lm_head.bias
+        bptr = _c(bias.data).ptr if bias is not None else None
+        _call("pdn_branch_begin", nb)
+        try:
+            hs = []
+            for r in range(nb):
+                _call("pdn_branch_select", r)
+                ids_t = _result(st.ids[slot_in][r * Bs:(r + 1) * Bs], self.device, (), None, "ids")
+                hs.append(F.embedding(ids_t, m.tok_embedding.weight, None))
+            chain = [-1] if os.environ.get("PDN_DECODE_ORDER", "1") != "0" else None
+            for i in range(len(self.blocks)):
+                for r in range(nb):
+                    _call("pdn_branch_select", r)
+                    hs[r] = self._block(i, hs[r], pos, None, Bs, 1, r * Bs, chain)
+            planes = []
+            for r in range(nb):
+                _call("pdn_branch_select", r)
+                pl = self._head_planes(hs[r], Bs, 1)
+                _call("pdn_gemm_prepacked_planes_argmax", pl.ptr, pl.M, pl.Kp, _fused._packed(m.lm_head.weight).handle, bptr,
+                      st.ids[slot_out].ptr + r * Bs * 8)
+                planes.append(pl)
+            del hs
+        finally:
+            _call("pdn_branch_end")
+        pos.tensor += 1
+        return planes
 
     def _decode_tc(self, ids, start_pos, B):
         import weakref

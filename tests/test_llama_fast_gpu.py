@@ -168,3 +168,39 @@ def test_persistent_decode_kernel_long_context(B):
         pdn.autograd.set_grad_enabled(True)
     exact, near = O.check_greedy_tokens(toks, ref_toks, margins)
     assert exact + near == B
+
+
+def test_forked_decode_step_matches_single_chain():
+    """PDN_DECODE_BRANCHES=2: the recorded decode step as two concurrent branches over batch slices (pdn_branch_*; allocator reuse
+    confined to a branch) must produce the ids of the single launch chain bit for bit — sequences are independent and every kernel
+    computes a row from that row's data only — and serve logits that are read after the step (one lm_head GEMM per slice)."""
+    import pydynet_b200 as pdn
+    from oracle import pdn_oracle as O
+    from workloads.llama import Llama
+    cfg = (V, D, H, FF, S, L) = (512, 96, 4, 256, 64, 3)
+    B, total = 64, 40
+    params = O.synthetic_llama_params(V, D, H, FF, L, seed=3, std=0.08)
+    prompt = np.random.default_rng(5).integers(1, V, (B, 4))
+    ref_toks, margins = O.LlamaOracle(params, H, S, B, L).generate_with_margins(prompt, total)
+    try:
+        net = _build(Llama, B, cfg, params)
+        single = _generate(net, prompt, total)
+        os.environ["PDN_DECODE_BRANCHES"] = "2"
+        net.__dict__["_pdn_plan"]._drop_recorded()
+        forked = _generate(net, prompt, total)
+        # logits held across a later step are materialised from the per-slice planes
+        with pdn.no_grad():
+            ids = pdn.Tensor(prompt, device="cuda:0")
+            net(ids, 0)
+            t = pdn.Tensor(prompt[:, :1], device="cuda:0")
+            a = net(t, 4)
+            b = net(t, 5)
+            held = a.numpy()
+        assert held.shape == (B, 1, V) and np.isfinite(held).all()
+        np.testing.assert_array_equal(held[:, 0].argmax(-1), a[:, -1, :].argmax(-1, True).numpy()[:, 0])
+        del b
+    finally:
+        os.environ.pop("PDN_DECODE_BRANCHES", None)
+        pdn.autograd.set_grad_enabled(True)
+    np.testing.assert_array_equal(forked, single)
+    O.check_greedy_tokens(forked, ref_toks, margins)
