@@ -43,6 +43,7 @@ constexpr int AT_C = 64;   // column tile
 constexpr int AT_KA = 2 * AT_R * 64 * 2;  // resident row operand, hi + lo: 32 KB
 constexpr int AT_KB = 2 * AT_C * 64 * 2;  // one column-tile operand, hi + lo: 16 KB
 constexpr int AT_KP = 2 * AT_R * AT_C * 2;  // P / dS tile, hi + lo: 32 KB
+constexpr int AT_STAT = 2048;               // query columns whose statistics fit the shared-memory staging of the key-row passes
 
 struct AtArgs {
   int64_t rows, cols;  // (Lq, Lk) in the query-row passes, (Lk, Lq) in the key-row passes
@@ -68,11 +69,25 @@ struct AtCfg {
   static constexpr int  kStage = AT_KB * (1 + (TWO ? 1 : 0) + (ACC ? 1 : 0));
   static constexpr int  kOffStages = AT_KA * (TWO ? 2 : 1);
   static constexpr int  kOffBars = kOffStages + kNst * kStage;
-  static constexpr int  kSmem = kOffBars + 512 + 1024;
+  // key-row passes: lse (and delta) of ALL query columns of this (batch, head) staged once in shared memory
+  static constexpr int  kOffStat = kOffBars + 512;
+  static constexpr int  kStat = TRANS ? (TWO ? 2 : 1) * AT_STAT * 4 : 0;
+  static constexpr int  kSmem = kOffStat + kStat + 1024;
 };
 
 // 16-byte chunk c (8 bf16) of row r in a K-major [rows x 64] bf16 tile with 128-byte swizzle (what TMA writes / UMMA reads)
 __device__ __forceinline__ uint32_t sw128_off(int r, int c) { return (uint32_t)((r >> 3) * 1024 + (r & 7) * 128 + ((c ^ (r & 7)) << 4)); }
+
+// two fp32 -> packed bf16x2 (lo in the low half), round-to-nearest-even: one F2FP instruction
+__device__ __forceinline__ uint32_t cvt_bf16x2(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+#ifndef PDN_AT_PACKED_CVT
+#define PDN_AT_PACKED_CVT 1
+#endif
+constexpr bool kPackedCvt = PDN_AT_PACKED_CVT != 0;
 
 __device__ __forceinline__ float ex2f(float x) {
   float y;
@@ -308,6 +323,19 @@ k_attn_tc(const __grid_constant__ CUtensorMap mA1, const __grid_constant__ CUten
       __syncwarp();
       if (lane == 0) mbar_arrive(a_tmem);
     }
+    // Key-row passes read lse / delta per COLUMN: staged once per CTA (zero-filled to the tile boundary) instead of 8-16 global
+    // 128-bit loads per thread and tile in the middle of the softmax chain (DV / DK spent 1500-2400 cycles per tile in this phase
+    // against 700-800 in the query-row passes, PDN_TC_TRACE).
+    float*     stat = reinterpret_cast<float*>(smem + Cfg::kOffStat);
+    const bool stat_smem = TRANS && (int64_t)n * AT_C <= AT_STAT;
+    if (stat_smem) {
+      const int tid = (int)threadIdx.x - 128, ncols = (int)a.cols;
+      for (int i = tid; i < n * AT_C; i += 256) {
+        stat[i] = i < ncols ? __ldg(a.lse + (int64_t)bh * Lq + i) : 0.f;
+        if (TWO) stat[AT_STAT + i] = i < ncols ? __ldg(a.delta + (int64_t)bh * Lq + i) : 0.f;
+      }
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+    }
     float m_run = -INFINITY, l_run = 0.f;
     for (int j = 0; j < n; ++j) {
       const int sb = j & 1;
@@ -369,7 +397,17 @@ k_attn_tc(const __grid_constant__ CUtensorMap mA1, const __grid_constant__ CUten
           const float* lp = a.lse + (int64_t)bh * Lq + col0;
           const float* dpn = TWO ? a.delta + (int64_t)bh * Lq + col0 : nullptr;
           float cl[32], cd[TWO ? 32 : 1];
-          if (col0 + 32 <= ncols && (Lq & 3) == 0) {
+          if (stat_smem) {
+#pragma unroll
+            for (int e4 = 0; e4 < 8; ++e4) {
+              const float4 t = reinterpret_cast<const float4*>(stat + col0)[e4];
+              cl[e4 * 4] = t.x; cl[e4 * 4 + 1] = t.y; cl[e4 * 4 + 2] = t.z; cl[e4 * 4 + 3] = t.w;
+              if (TWO) {
+                const float4 u = reinterpret_cast<const float4*>(stat + AT_STAT + col0)[e4];
+                cd[e4 * 4] = u.x; cd[e4 * 4 + 1] = u.y; cd[e4 * 4 + 2] = u.z; cd[e4 * 4 + 3] = u.w;
+              }
+            }
+          } else if (col0 + 32 <= ncols && (Lq & 3) == 0) {
 #pragma unroll
             for (int e4 = 0; e4 < 8; ++e4) {
               const float4 t = __ldg(reinterpret_cast<const float4*>(lp) + e4);
@@ -412,10 +450,16 @@ k_attn_tc(const __grid_constant__ CUtensorMap mA1, const __grid_constant__ CUten
 #pragma unroll
         for (int t = 0; t < 16; ++t) {
           const float v0 = s[2 * t], v1 = s[2 * t + 1];
-          const uint32_t b0 = (__float_as_uint(v0) + 0x8000u) & 0xffff0000u, b1 = (__float_as_uint(v1) + 0x8000u) & 0xffff0000u;
-          hw[t] = __byte_perm(b0, b1, 0x7632);
-          const uint32_t r0 = __float_as_uint(v0 - __uint_as_float(b0)) + 0x8000u, r1 = __float_as_uint(v1 - __uint_as_float(b1)) + 0x8000u;
-          lw[t] = __byte_perm(r0, r1, 0x7632);
+          if (kPackedCvt) {  // 6 instructions per pair: packed convert, two unpacks, two subtractions, packed convert
+            const uint32_t hp = cvt_bf16x2(v0, v1);
+            hw[t] = hp;
+            lw[t] = cvt_bf16x2(v0 - __uint_as_float(hp << 16), v1 - __uint_as_float(hp & 0xffff0000u));
+          } else {
+            const uint32_t b0 = (__float_as_uint(v0) + 0x8000u) & 0xffff0000u, b1 = (__float_as_uint(v1) + 0x8000u) & 0xffff0000u;
+            hw[t] = __byte_perm(b0, b1, 0x7632);
+            const uint32_t r0 = __float_as_uint(v0 - __uint_as_float(b0)) + 0x8000u, r1 = __float_as_uint(v1 - __uint_as_float(b1)) + 0x8000u;
+            lw[t] = __byte_perm(r0, r1, 0x7632);
+          }
         }
         const uint32_t pdst = tmP(pb) + ((uint32_t)(q * 32) << 16) + (uint32_t)(half * 16);
         tmem_st_32x16(pdst, hw);
