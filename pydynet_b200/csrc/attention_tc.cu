@@ -57,6 +57,7 @@ struct AtArgs {
   float* lse_out;      // [BH][Lq] (LSE)
   float* out;          // [B, rows, H, D] fp32 (FWD: O, DQ: dQ, DV: dV, DK: dK)
   int ncol_tiles;
+  int prefetch_ahead;  // linear CTA distance of the L2 prefetch of the row operand (0 = off)
   long long* trace;  // debug (PDN_TC_TRACE): clock64 stamps of CTA (0,0)
 };
 
@@ -207,6 +208,21 @@ k_attn_tc(const __grid_constant__ CUtensorMap mA1, const __grid_constant__ CUten
       if (TWO) {
         tma_load_4d(&mA2, a_full, smem + AT_KA, 0, (int)row0, 0, bh);
         tma_load_4d(&mA2, a_full, smem + AT_KA + AT_KA / 2, 0, (int)row0, 1, bh);
+      }
+    }
+    // The row operand of a CTA is read by nobody else, so its TMA load misses L2 and the CTA (one per SM, nothing to overlap
+    // with) waits 1.5-2.5 us of its ~10 for it. CTAs start in linear order as SMs free up: the CTA one wave ahead prefetches this
+    // tile into L2 at ITS start.
+    if (leader && a.prefetch_ahead > 0) {
+      const long long lin = (long long)blockIdx.y * gridDim.x + blockIdx.x + a.prefetch_ahead;
+      if (lin < (long long)gridDim.x * gridDim.y) {
+        const int pbh = (int)(lin / gridDim.x), prow = (int)(lin % gridDim.x) * AT_R;
+        tma_prefetch_l2_4d(&mA1, 0, prow, 0, pbh);
+        tma_prefetch_l2_4d(&mA1, 0, prow, 1, pbh);
+        if (TWO) {
+          tma_prefetch_l2_4d(&mA2, 0, prow, 0, pbh);
+          tma_prefetch_l2_4d(&mA2, 0, prow, 1, pbh);
+        }
       }
     }
     constexpr int kScoreBytes = AT_KB * (TWO ? 2 : 1);
@@ -594,6 +610,8 @@ static int at_launch(const CUtensorMap& A1, const CUtensorMap& A2, const CUtenso
   static const bool trace_on = getenv("PDN_TC_TRACE") != nullptr;
   AtArgs aa = a;
   aa.trace = nullptr;
+  static const int ahead_env = getenv("PDN_AT_PREFETCH") ? atoi(getenv("PDN_AT_PREFETCH")) : -1;
+  aa.prefetch_ahead = ahead_env >= 0 ? ahead_env : sm_count();
   if (trace_on) {
     if (!trace_buf) PDN_CUDA(cudaMalloc(&trace_buf, 32 * sizeof(long long)));
     PDN_CUDA(cudaMemsetAsync(trace_buf, 0, 32 * sizeof(long long), stream()));

@@ -105,6 +105,124 @@ __global__ void __launch_bounds__(256) k_channel_sum(const float* __restrict__ g
   if (threadIdx.x == 0) atomicAdd(out + o, s);
 }
 
+// ---------------------------------------------------------------- thin first layers -------------------------------
+// A stride-1 convolution over 1-3 input channels (the 1-channel first layer of BASELINE config 2: C k k = 9) is 1/7 of one 64-wide
+// k-block of the tensor-core path, which then spends its time on padding (48 us for 36 MFLOP). Direct fp32, window shape known at
+// compile time (KS x KS taps, up to CM channels; no runtime index arithmetic in the inner loops):
+//   forward          one thread per output pixel keeps its window in registers and walks the output channels (weights + bias in
+//                    shared memory, stores coalesced along the pixels of a channel plane)
+//   backward-weight  one CTA per image stages gy[n] and the zero-haloed x[n] in shared memory; thread (o, row group) keeps the
+//                    whole window's partial sums (and the bias sum) in registers over its pixels and over the CTA's images, then
+//                    shared-memory atomics per CTA, one global atomicAdd per CTA and weight
+constexpr int kThinMaxO = 64;
+
+template <int KS, int CM>
+__global__ void __launch_bounds__(256) k_conv_thin_fwd(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
+                                                       float* __restrict__ y, ConvGeom g) {
+  constexpr int WIN = CM * KS * KS;
+  __shared__ float ws[kThinMaxO * WIN + kThinMaxO];
+  const int C = (int)g.C, O = (int)g.O, win = C * KS * KS;
+  for (int i = threadIdx.x; i < O * WIN; i += blockDim.x) {
+    const int o = i / WIN, r = i - o * WIN;
+    ws[i] = r < win ? w[o * win + r] : 0.f;
+  }
+  for (int i = threadIdx.x; i < O; i += blockDim.x) ws[kThinMaxO * WIN + i] = bias ? bias[i] : 0.f;
+  __syncthreads();
+  const int64_t hw = g.oh * g.ow, total = g.N * hw;
+  for (int64_t m = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; m < total; m += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t n = m / hw;
+    const int     pix = (int)(m - n * hw), oy = pix / (int)g.ow, ox = pix - oy * (int)g.ow;
+    const int     y0 = oy - g.pad, x0 = ox - g.pad;
+    float         v[WIN];
+#pragma unroll
+    for (int c = 0; c < CM; ++c)
+#pragma unroll
+      for (int ky = 0; ky < KS; ++ky)
+#pragma unroll
+        for (int kx = 0; kx < KS; ++kx) {
+          const int yy = y0 + ky, xx = x0 + kx;
+          v[(c * KS + ky) * KS + kx] =
+              (c < C && yy >= 0 && yy < g.H && xx >= 0 && xx < g.W) ? __ldg(x + ((n * C + c) * g.H + yy) * g.W + xx) : 0.f;
+        }
+    float* yo = y + n * O * hw + pix;
+    for (int o = 0; o < O; ++o) {
+      const float* wo = ws + o * WIN;
+      float        acc = ws[kThinMaxO * WIN + o];
+#pragma unroll
+      for (int i = 0; i < WIN; ++i) acc = fmaf(v[i], wo[i], acc);
+      yo[(int64_t)o * hw] = acc;
+    }
+  }
+}
+
+// dynamic shared memory: gy[n] as [O][oh*ow + 1] | x[n] with a zero halo as [C][H + 2 pad][W + 2 pad] | dw partials [O][WIN + 1]
+template <int KS, int CM>
+__global__ void __launch_bounds__(256) k_conv_thin_bwd_weight(const float* __restrict__ x, const float* __restrict__ gy, float* __restrict__ dw,
+                                                              float* __restrict__ dbias, ConvGeom g) {
+  constexpr int WIN = CM * KS * KS;
+  extern __shared__ float sm[];
+  const int C = (int)g.C, O = (int)g.O, ow = (int)g.ow, oh = (int)g.oh, hw = oh * ow, gst = hw + 1;
+  const int Hp = (int)g.H + 2 * g.pad, Wp = (int)g.W + 2 * g.pad, win = C * KS * KS;
+  float *gs = sm, *xs = gs + O * gst, *part = xs + C * Hp * Wp;
+  const int G = 256 / O;  // row groups per output channel
+  const int o = threadIdx.x % O, grp = threadIdx.x / O;
+  const bool worker = grp < G;
+  float acc[WIN], accb = 0.f;
+#pragma unroll
+  for (int i = 0; i < WIN; ++i) acc[i] = 0.f;
+  for (int i = threadIdx.x; i < C * Hp * Wp; i += blockDim.x) xs[i] = 0.f;  // the halo stays zero for every image
+  for (int i = threadIdx.x; i < O * (WIN + 1); i += blockDim.x) part[i] = 0.f;
+  for (int64_t n = blockIdx.x; n < g.N; n += gridDim.x) {
+    __syncthreads();
+    for (int i = threadIdx.x; i < O * hw; i += blockDim.x) gs[(i / hw) * gst + i % hw] = gy[n * O * hw + i];
+    for (int i = threadIdx.x; i < C * (int)(g.H * g.W); i += blockDim.x) {
+      const int c = i / (int)(g.H * g.W), r = i - c * (int)(g.H * g.W), yy = r / (int)g.W, xx = r - yy * (int)g.W;
+      xs[(c * Hp + yy + g.pad) * Wp + xx + g.pad] = x[n * C * g.H * g.W + i];
+    }
+    __syncthreads();
+    if (worker) {
+      for (int oy = grp; oy < oh; oy += G) {
+        const float* grow = gs + o * gst + oy * ow;
+        for (int ox = 0; ox < ow; ++ox) {
+          const float gv = grow[ox];
+          accb += gv;
+#pragma unroll
+          for (int c = 0; c < CM; ++c)
+            if (c < C) {
+#pragma unroll
+              for (int ky = 0; ky < KS; ++ky)
+#pragma unroll
+                for (int kx = 0; kx < KS; ++kx) acc[(c * KS + ky) * KS + kx] = fmaf(gv, xs[(c * Hp + oy + ky) * Wp + ox + kx], acc[(c * KS + ky) * KS + kx]);
+            }
+        }
+      }
+    }
+  }
+  if (worker) {
+#pragma unroll
+    for (int i = 0; i < WIN; ++i)
+      if (i < win) atomicAdd(part + o * (WIN + 1) + i, acc[i]);
+    atomicAdd(part + o * (WIN + 1) + WIN, accb);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < O * win; i += blockDim.x) atomicAdd(dw + i, part[(i / win) * (WIN + 1) + i % win]);
+  if (dbias)
+    for (int i = threadIdx.x; i < O; i += blockDim.x) atomicAdd(dbias + i, part[i * (WIN + 1) + WIN]);
+}
+
+// window shapes the direct kernels are instantiated for: 3x3 over <= 3 channels, 5x5 over 1 channel
+static int conv_thin_kind(const ConvGeom& g) {
+  static const bool off = getenv("PDN_CONV_THIN") && getenv("PDN_CONV_THIN")[0] == '0';
+  if (off || g.stride != 1 || g.O > kThinMaxO || g.O < 1) return 0;
+  if (g.k == 3 && g.C == 1) return 31;
+  if (g.k == 3 && g.C <= 3) return 33;
+  if (g.k == 5 && g.C == 1) return 51;
+  return 0;
+}
+static size_t conv_thin_bw_smem(const ConvGeom& g, int WIN) {
+  return (size_t)(g.O * (g.oh * g.ow + 1) + g.C * (g.H + 2 * g.pad) * (g.W + 2 * g.pad) + g.O * (WIN + 1)) * sizeof(float);
+}
+
 // ---------------------------------------------------------------- pooling ----------------------------------------
 struct PoolGeom {
   int64_t N, C, H, W, oh, ow;
@@ -189,6 +307,13 @@ int pdn_conv2d_fwd(const float* x, const float* w, const float* bias, float* y, 
   Scratch       bufA, bufB;
   PackedOperand A, B;
   const int64_t one[3] = {1, 1, 1}, zero[3] = {0, 0, 0};
+  if (const int kind = conv_thin_kind(g)) {
+    if (kind == 31) k_conv_thin_fwd<3, 1><<<grid_for(M, 256), 256, 0, stream()>>>(x, w, bias, y, g);
+    else if (kind == 33) k_conv_thin_fwd<3, 3><<<grid_for(M, 256), 256, 0, stream()>>>(x, w, bias, y, g);
+    else k_conv_thin_fwd<5, 1><<<grid_for(M, 256), 256, 0, stream()>>>(x, w, bias, y, g);
+    PDN_LAUNCHED("conv_thin_fwd");
+    return 0;
+  }
   if (conv_tma_ok(C, stride, N, C, H, W)) {
     // weights per tap as K-major planes [tap][O][C]: w[o, c, ky, kx] -> rows o (stride C k k), contraction c (stride k k), batch tap
     const int64_t kk = (int64_t)k * k, tnb[3] = {1, 1, kk}, tbs[3] = {0, 0, 1};
@@ -240,6 +365,24 @@ int pdn_conv2d_bwd_weight(const float* x, const float* gy, float* dw, float* dbi
   ConvGeom g;
   PDN_TRY(make_geom(g, N, C, H, W, O, k, stride, pad));
   const int64_t hw = g.oh * g.ow, M = N * hw, K = C * k * k;
+  if (const int kind = (dw && M > 0) ? conv_thin_kind(g) : 0) {
+    const int    WIN = kind == 31 ? 9 : (kind == 33 ? 27 : 25), slot = kind == 31 ? 0 : (kind == 33 ? 1 : 2);
+    const size_t smem = conv_thin_bw_smem(g, WIN);
+    if (smem <= 200 * 1024) {
+      auto fn = kind == 31 ? k_conv_thin_bwd_weight<3, 1> : (kind == 33 ? k_conv_thin_bwd_weight<3, 3> : k_conv_thin_bwd_weight<5, 1>);
+      static size_t smem_set[3] = {0, 0, 0};
+      if (smem > smem_set[slot]) {
+        PDN_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        smem_set[slot] = smem;
+      }
+      PDN_CUDA(cudaMemsetAsync(dw, 0, (size_t)O * K * sizeof(float), stream()));
+      if (dbias) PDN_CUDA(cudaMemsetAsync(dbias, 0, (size_t)O * sizeof(float), stream()));
+      const int64_t ctas = N < 2 * sm_count() ? N : 2 * sm_count();
+      fn<<<(unsigned)ctas, 256, smem, stream()>>>(x, gy, dw, dbias, g);
+      PDN_LAUNCHED("conv_thin_bwd_weight");
+      return 0;
+    }
+  }
   if (dbias && O > 0) {
     PDN_CUDA(cudaMemsetAsync(dbias, 0, (size_t)O * sizeof(float), stream()));
     int64_t chunks = (sm_count() * 8 + O - 1) / O;

@@ -42,3 +42,49 @@ def test_conv2d_fwd_bwd(case):
         assert np.isfinite(a).all(), name
         e = _err(a, r)
         assert e < 1e-4, f"conv {case} {name}: normwise rel err {e:.3e}"
+
+
+@pytest.mark.parametrize("shape", [(5, 1, 28, 28, 20, 3, 1), (3, 3, 17, 13, 7, 3, 0), (4, 1, 12, 9, 6, 5, 2), (2, 2, 8, 8, 64, 3, 2),
+                                   (300, 1, 28, 28, 20, 3, 1)])
+def test_thin_first_layer_kernels(shape):
+    """Direct fp32 kernels for stride-1 convolutions over 1-3 input channels (k_conv_thin_fwd / k_conv_thin_bwd_weight: the first
+    layer of BASELINE config 2 is 1 -> 20 channels, 3x3): output, weight gradient and bias gradient against an fp64 evaluation of
+    functional.py:254-281, 5e-6 normwise (plain fp32 FMA chains, no BF16 split); the launch counter proves the direct kernels ran."""
+    import pydynet_b200 as pdn
+    import pydynet_b200.nn as nn
+    from pydynet_b200.backend import lib
+    N, C, H, W, Oc, k, pad = shape
+    rng = np.random.default_rng(0)
+    x = rng.standard_normal((N, C, H, W)).astype(np.float32)
+    w = (rng.standard_normal((Oc, C, k, k)) * .3).astype(np.float32)
+    b = rng.standard_normal(Oc).astype(np.float32)
+    conv = nn.Conv2d(C, Oc, k, 1, pad, dtype=np.float32).to("cuda:0")
+    with conv.weight.device:
+        conv.weight.data[...] = w
+        conv.bias.data[...] = b.reshape(1, -1, 1, 1)
+    tx = pdn.Tensor(x, dtype=np.float32, device="cuda:0")
+    lib.watch_launches("conv_thin_fwd")
+    y = conv(tx)
+    assert lib.watched_launch_count() == 1
+    gyv = rng.standard_normal(y.shape).astype(np.float32)
+    lib.watch_launches("conv_thin_bwd_weight")
+    (y * pdn.Tensor(gyv, dtype=np.float32, device="cuda:0")).sum().backward()
+    assert lib.watched_launch_count() == 1
+    lib.watch_launches(None)
+    xp = np.pad(x.astype(np.float64), ((0, 0), (0, 0), (pad, pad), (pad, pad)))
+    oh, ow = H + 2 * pad - k + 1, W + 2 * pad - k + 1
+    yr, dwr = np.zeros((N, Oc, oh, ow)), np.zeros((Oc, C, k, k))
+    for ky in range(k):
+        for kx in range(k):
+            patch = xp[:, :, ky:ky + oh, kx:kx + ow]
+            yr += np.einsum("nchw,oc->nohw", patch, w[:, :, ky, kx].astype(np.float64))
+            dwr[:, :, ky, kx] = np.einsum("nohw,nchw->oc", gyv.astype(np.float64), patch)
+    yr += b[None, :, None, None]
+
+    def err(a, r):
+        a = np.asarray(a.get() if hasattr(a, "get") else a, np.float64).reshape(r.shape)
+        return np.linalg.norm(a - r) / np.linalg.norm(r)
+
+    assert err(y.numpy(), yr) < 5e-6
+    assert err(conv.weight.grad, dwr) < 5e-6
+    assert err(conv.bias.grad, gyv.sum((0, 2, 3))) < 5e-6
