@@ -303,16 +303,17 @@ def c5(args):
          **with_ref({}, sec, base))
 
 
-def lstm(args):
-    """The LSTM of the recurrent family at the C5 shape (nn.LSTM in512 / h512, batch-first input, loss on the last hidden state)."""
+def lstm(args, cls="LSTM"):
+    """The LSTM / plain RNN of the recurrent family at the C5 shape (in512 / h512, batch-first input, loss on the last hidden state)."""
     np.random.seed(0)
     B, Tn = (64, 128) if args.small else (256, 1024)
-    rnn, head = nn.LSTM(512, 512, 1, batch_first=True, dtype=f32).to(DEV), nn.Linear(512, 1, dtype=f32).to(DEV)
+    rnn, head = getattr(nn, cls)(512, 512, 1, batch_first=True, dtype=f32).to(DEV), nn.Linear(512, 1, dtype=f32).to(DEV)
     opt = Adam(list(rnn.parameters()) + list(head.parameters()), lr=0.01)
     X, Y = T(np.random.randn(B, Tn, 512).astype(f32)), T(np.random.randn(B, 1).astype(f32))
 
     def step():
-        _, (h, c) = rnn(X, None)
+        _, h = rnn(X, None)
+        h = h[0] if cls == "LSTM" else h
         loss = F.mse_loss(head(h[:, 0, :]), Y)
         opt.zero_grad(); loss.backward(); opt.step()
 
@@ -321,21 +322,27 @@ def lstm(args):
 
     def build(ns):
         np.random.seed(0)
-        rg = ns["nn"].LSTM(512, 512, 1, batch_first=True, dtype=f32)
+        rg = getattr(ns["nn"], cls)(512, 512, 1, batch_first=True, dtype=f32)
         rh = ns["nn"].Linear(512, 1, dtype=f32)
         ropt = ns["refload"]._REF_PKG["mods"]["pydynet.optim"].Adam(list(rg.parameters()) + list(rh.parameters()), lr=0.01)
         rX, rY = ns["pdn"].Tensor(X.numpy()[:, :Tc], dtype=f32), ns["pdn"].Tensor(Y.numpy(), dtype=f32)
 
         def rstep():
-            _, (h, c) = rg(rX, None)
+            _, h = rg(rX, None)
+            h = h[0] if cls == "LSTM" else h
             loss = ns["F"].mse_loss(rh(h[:, 0, :]), rY)
             ropt.zero_grad(); loss.backward(); ropt.step()
         return rstep
-    base = cpu_ref(build, 1, f"reference nn.LSTM at T = {Tc} of {Tn} time steps, batch {B}; time scaled LINEARLY in T, which favours the CPU",
+    base = cpu_ref(build, 1, f"reference nn.{cls} at T = {Tc} of {Tn} time steps, batch {B}; time scaled LINEARLY in T, which favours the CPU",
                    scale=Tn / Tc, warm=0)
-    # per time step: x Wx and h Wh, 4H columns each, forward + two backward products apiece
-    emit(f"LSTM in512 h512 T{Tn} B{B} train step (persistent whole-sequence kernels)", sec, flops=3 * 2.0 * 2 * 512 * 2048 * Tn * B, launches=nl,
+    # per time step: x Wx and h Wh, G*H columns each (G = 4 gates, 1 for the plain RNN), forward + two backward products apiece
+    cols = 2048 if cls == "LSTM" else 512
+    emit(f"{cls} in512 h512 T{Tn} B{B} train step (persistent whole-sequence kernels)", sec, flops=3 * 2.0 * 2 * 512 * cols * Tn * B, launches=nl,
          us_per_time_step=sec / Tn * 1e6, **with_ref({}, sec, base))
+
+
+def rnn(args):
+    lstm(args, "RNN")
 
 
 def decode(args):
@@ -439,7 +446,7 @@ def micro(args, conv=True):
 
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
-    ap.add_argument("--only", default="c1,c2,c4,c5,lstm,micro")
+    ap.add_argument("--only", default="c1,c2,c4,c5,lstm,rnn,micro")
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--small", action="store_true")
     ap.add_argument("--no-cpu", dest="cpu", action="store_false", help="skip the reference-on-host-cores run beside every config")
@@ -447,7 +454,7 @@ if __name__ == "__main__":
     ARGS = args
     for name in args.only.split(","):
         try:
-            {"c1": c1, "c2": c2, "c4": c4, "c5": c5, "lstm": lstm, "micro": micro, "micro_att": micro_att, "gemm": gemm, "rows": rows, "decode": decode}[name](args)
+            {"c1": c1, "c2": c2, "c4": c4, "c5": c5, "lstm": lstm, "rnn": rnn, "micro": micro, "micro_att": micro_att, "gemm": gemm, "rows": rows, "decode": decode}[name](args)
         except Exception as e:  # keep going: one config must not hide the others
             import traceback
             traceback.print_exc()

@@ -309,6 +309,12 @@ int pdn_gru_seq_fwd(const float* xp1, const float* xp2, const float* h0, const f
 int pdn_gru_seq_bwd(const float* g_hs, const float* h0, const float* hs, const float* zr, const float* nn,
                     const float* Wh1, const float* Wh2, float* dxp1, float* dxp2, float* dh0, float* dWh1,
                     float* dWh2, int64_t T, int64_t B, int64_t H);
+/* Plain RNN sequence (rnn.py:38-49 cell, :196-214 loop): xp [T,B,H] = x@Wx+b hoisted; hs[t] = act(xp[t] + hs[t-1]@Wh),
+ * act = tanh (relu = 0) or relu (relu = 1). Backward: g_hs [T,B,H] (nullable = zeros) -> dxp [T,B,H], dh0 [B,H], dWh [H,H]
+ * (nullable). H a multiple of 64 (<= 512): one persistent cooperative launch per direction (rnn_persist.cu). */
+int pdn_rnn_seq_fwd(const float* xp, const float* h0, const float* Wh, float* hs, int64_t T, int64_t B, int64_t H, int relu);
+int pdn_rnn_seq_bwd(const float* g_hs, const float* h0, const float* hs, const float* Wh, float* dxp, float* dh0, float* dWh,
+                    int64_t T, int64_t B, int64_t H, int relu);
 /* LSTM sequence (rnn.py:268-288): xp [T,B,4H] = x@Wx+b hoisted, gate order f,i,o,g. */
 int pdn_lstm_seq_fwd(const float* xp, const float* h0, const float* c0, const float* Wh, float* hs, float* cs,
                      float* gates, int64_t T, int64_t B, int64_t H);

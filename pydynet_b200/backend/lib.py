@@ -98,6 +98,8 @@ _PROTOS = {
     "pdn_attention_bwd": [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i64, i64, i64, i64, i64, pi64, pi64, pi64, pi64, f32],
     "pdn_gru_seq_fwd": [vp, vp, vp, vp, vp, vp, vp, vp, i64, i64, i64],
     "pdn_gru_seq_bwd": [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i64, i64, i64],
+    "pdn_rnn_seq_fwd": [vp, vp, vp, vp, i64, i64, i64, i32],
+    "pdn_rnn_seq_bwd": [vp, vp, vp, vp, vp, vp, vp, i64, i64, i64, i32],
     "pdn_lstm_seq_fwd": [vp, vp, vp, vp, vp, vp, vp, i64, i64, i64],
     "pdn_lstm_seq_bwd": [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i64, i64, i64],
     "pdn_ce_loss_fwd": [vp, vp, vp, vp, i64, i64, i32],

@@ -55,6 +55,9 @@ int gemm_tc_packed(const PackedOperand& A, const PackedOperand& B, TcArgs t, int
 bool gru_persist_ok(int64_t T, int64_t B, int64_t H);
 int  gru_persist_forward(const float* xp1, const float* xp2, const float* h0, const PackedOperand& W1p, const PackedOperand& W2p, const PackedOperand& hP0,
                          const PackedOperand& hP1, const PackedOperand& rhP, float* hs, float* zr, float* nn, int64_t T, int64_t B, int64_t H);
+bool rnn_persist_ok(int64_t T, int64_t B, int64_t H);
+int  rnn_persist_run(int dir, const float* xp, const float* hs_in, const float* g_hs, const PackedOperand& Wp, const PackedOperand& P0,
+                     const PackedOperand& P1, float* hs, float* dxp, float* dh0, int64_t T, int64_t B, int64_t H, int relu);
 bool lstm_persist_ok(int64_t T, int64_t B, int64_t H);
 int  lstm_persist_forward(const float* xp, const float* h0, const float* c0, const PackedOperand& Wp, const PackedOperand& hP0, const PackedOperand& hP1,
                           float* hs, float* cs, float* gates, int64_t T, int64_t B, int64_t H);

@@ -102,6 +102,30 @@ __global__ void __launch_bounds__(256) k_gru_rh_all(const float* __restrict__ zr
   }
 }
 
+// ---- plain RNN -------------------------------------------------------------------------------------------------
+// h = act(lin) in place (lin = x Wx + b + h_prev Wh, accumulated by the GEMM), + the next step's operand planes
+__global__ void __launch_bounds__(256) k_rnn_act(float* __restrict__ h, __nv_bfloat16* __restrict__ planes, int64_t B, int64_t H, int64_t Kp,
+                                                 int relu) {
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < B * H; idx += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t b = idx / H, j = idx - b * H;
+    const float   v = relu ? fmaxf(h[idx], 0.f) : tanh_ref(h[idx]);
+    h[idx] = v;
+    put_planes(planes, B, Kp, b, j, v);
+  }
+}
+// dl = (dh + g_t) act'(h_t) -> dxp[t] and operand planes
+__global__ void __launch_bounds__(256) k_rnn_bwd(const float* __restrict__ dh, const float* __restrict__ g_t, const float* __restrict__ h_t,
+                                                 float* __restrict__ dxp, __nv_bfloat16* __restrict__ planes, int64_t B, int64_t H, int64_t Kp,
+                                                 int relu) {
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < B * H; idx += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t b = idx / H, j = idx - b * H;
+    const float   d = dh[idx] + (g_t ? g_t[idx] : 0.f), h = h_t[idx];
+    const float   v = relu ? (h > 0.f ? d : 0.f) : d * (1.f - h * h);
+    dxp[idx] = v;
+    put_planes(planes, B, Kp, b, j, v);
+  }
+}
+
 // ---- LSTM ------------------------------------------------------------------------------------------------------
 // gates[b, 0:4H]: pre-activations in, activations (f, i, o, g) out; c = f c_prev + i g ; h = o tanh(c)
 __global__ void __launch_bounds__(256) k_lstm_gate(float* __restrict__ gates, const float* __restrict__ cprev, float* __restrict__ cout,
@@ -252,6 +276,70 @@ int pdn_gru_seq_bwd(const float* g_hs, const float* h0, const float* hs, const f
     k_gru_rh_all<<<grid_for(T * BH, 256), 256, 0, stream()>>>(zr, h0, hs, (float*)sRh.p, T, B, H);
     PDN_LAUNCHED("gru_rh_all");
     PDN_TRY(pdn_gemm(PDN_F32, sRh.p, dxp2, dWh2, H, H, T * B, 1, H, H, 1, H, nullptr, nullptr, nullptr, nullptr, nullptr, 0, 0));
+  }
+  return 0;
+}
+
+// hs[t] = act(xp[t] + hs[t-1] Wh), hs[-1] = h0 (reference rnn.py:46-49 applied over a sequence, rnn.py:196-214)
+int pdn_rnn_seq_fwd(const float* xp, const float* h0, const float* Wh, float* hs, int64_t T, int64_t B, int64_t H, int relu) {
+  PDN_TRY(ensure_init());
+  if (T == 0 || B == 0 || H == 0) return 0;
+  const int64_t BH = B * H;
+  Scratch       sW, sH;
+  PackedOperand W, Hp;
+  PDN_TRY(pack_operand_ex(Wh, H, H, 1, H, 0, 0, kOne, kZero, &sW, &W));  // rows = output column j, contraction over k: Wh[k, j]
+  PDN_TRY(alloc_planes(&sH, &Hp, B, H));
+  const int grd = grid_for(BH, 256);
+  k_rows_to_planes<<<grd, 256, 0, stream()>>>(h0, H, (__nv_bfloat16*)Hp.planes, B, H, Hp.Kp);
+  PDN_LAUNCHED("rows_to_planes");
+  if (rnn_persist_ok(T, B, H)) {
+    Scratch       sH1;
+    PackedOperand Hp1;
+    PDN_TRY(alloc_planes(&sH1, &Hp1, B, H));
+    return rnn_persist_run(0, xp, nullptr, nullptr, W, Hp, Hp1, hs, nullptr, nullptr, T, B, H, relu);
+  }
+  PDN_CUDA(cudaMemcpyAsync(hs, xp, (size_t)T * BH * sizeof(float), cudaMemcpyDeviceToDevice, stream()));
+  TcArgs t;
+  for (int64_t s = 0; s < T; ++s) {
+    tc_init(t, hs + s * BH, B, H, H, 1);
+    PDN_TRY(gemm_tc_packed(Hp, W, t, 1));
+    k_rnn_act<<<grd, 256, 0, stream()>>>(hs + s * BH, (__nv_bfloat16*)Hp.planes, B, H, Hp.Kp, relu);
+    PDN_LAUNCHED("rnn_act");
+  }
+  return 0;
+}
+
+int pdn_rnn_seq_bwd(const float* g_hs, const float* h0, const float* hs, const float* Wh, float* dxp, float* dh0, float* dWh, int64_t T,
+                    int64_t B, int64_t H, int relu) {
+  PDN_TRY(ensure_init());
+  if (T == 0 || B == 0 || H == 0) return 0;
+  const int64_t BH = B * H;
+  Scratch       sW, sD;
+  PackedOperand Wt, Dp;
+  PDN_TRY(pack_operand_ex(Wh, H, H, H, 1, 0, 0, kOne, kZero, &sW, &Wt));  // dl . Wh^T: rows = k, contraction over j: Wh[k, j]
+  PDN_TRY(alloc_planes(&sD, &Dp, B, H));
+  if (rnn_persist_ok(T, B, H)) {
+    Scratch       sD1;
+    PackedOperand Dp1;
+    PDN_TRY(alloc_planes(&sD1, &Dp1, B, H));
+    PDN_TRY(rnn_persist_run(1, nullptr, hs, g_hs, Wt, Dp, Dp1, nullptr, dxp, dh0, T, B, H, relu));
+  } else {
+    float* dh = dh0;
+    PDN_CUDA(cudaMemsetAsync(dh, 0, (size_t)BH * sizeof(float), stream()));
+    const int grd = grid_for(BH, 256);
+    TcArgs    t;
+    for (int64_t s = T - 1; s >= 0; --s) {
+      k_rnn_bwd<<<grd, 256, 0, stream()>>>(dh, g_hs ? g_hs + s * BH : nullptr, hs + s * BH, dxp + s * BH, (__nv_bfloat16*)Dp.planes, B, H, Dp.Kp,
+                                           relu);
+      PDN_LAUNCHED("rnn_bwd");
+      tc_init(t, dh, B, H, H, 0);
+      PDN_TRY(gemm_tc_packed(Dp, Wt, t, 1));
+    }
+  }
+  if (dWh) {  // dWh = Hprev^T . dxp with Hprev = [h0 ; hs[0..T-2]]
+    PDN_TRY(pdn_gemm(PDN_F32, h0, dxp, dWh, H, H, B, 1, H, H, 1, H, nullptr, nullptr, nullptr, nullptr, nullptr, 0, 0));
+    if (T > 1)
+      PDN_TRY(pdn_gemm(PDN_F32, hs, dxp + BH, dWh, H, H, (T - 1) * B, 1, H, H, 1, H, nullptr, nullptr, nullptr, nullptr, nullptr, 1, 0));
   }
   return 0;
 }

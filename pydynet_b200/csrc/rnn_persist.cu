@@ -950,6 +950,207 @@ k_lstm_persist_bwd(const __grid_constant__ CUtensorMap mapDl, const __grid_const
   if (warp == 2) tmem_dealloc(tmem_base, 64);
 }
 
+// ------------------------------------------------------------------------------------------------------------------ plain RNN
+// h_t = act(x_t Wx + b + h_{t-1} Wh), act = tanh | relu (rnn.py:46-49): one product per step and direction, one CTA set.
+//   forward   CTA = (64 columns j of Wh, 64-row batch tile); epilogue: h_t -> hs + the next step's operand planes
+//   BPTT      CTA = (64 rows k of Wh as K-major planes over j, batch tile): dh' = dl . Wh^T; epilogue = the element-wise part of
+//             step s - 1: d = dh' + g_hs[s-1], dl = d act'(h_{s-1}) -> dxp + operand planes. The first dl (step T-1) is the prologue.
+// DIR = 0 forward, 1 backward. Counters: [bt] = operand planes of the next step complete.
+struct RnnPersistArgs {
+  const float *xp, *hs_in, *g_hs;  // fwd: xp [T][B][H]; bwd: hs (saved), g_hs
+  float *      hs, *dxp, *dh0;
+  __nv_bfloat16 *P0, *P1;          // ping-pong operand planes [2][B][Kp]
+  int           T, B, H, Kp, nbt, ctn, relu;
+  unsigned int* cnt;
+};
+
+template <int DIR>
+__global__ void __launch_bounds__(384, 1)
+k_rnn_persist(const __grid_constant__ CUtensorMap mapP0, const __grid_constant__ CUtensorMap mapP1, const __grid_constant__ CUtensorMap mapW,
+              RnnPersistArgs g) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t*  smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  const int KB = g.H / GP_BK;
+  uint8_t*  wsm = smem;
+  uint8_t*  asm_ = smem + (size_t)KB * 2 * GP_WBLOCK;
+  uint64_t* full_bar = (uint64_t*)(asm_ + GP_STAGES * GP_ASTAGE);
+  uint64_t* empty_bar = full_bar + GP_STAGES;
+  uint64_t* wfull_bar = empty_bar + GP_STAGES;
+  uint64_t* tfull_bar = wfull_bar + 1;
+  uint64_t* tempty_bar = tfull_bar + 1;
+  uint32_t* tmem_slot = (uint32_t*)(tempty_bar + 1);
+
+  const int          warp = warp_id_uniform(), lane = threadIdx.x & 31;
+  const int          c = (int)blockIdx.x % g.ctn, bt = (int)blockIdx.x / g.ctn;
+  unsigned int*      cnt = g.cnt + bt;
+  const unsigned int per = (unsigned int)g.ctn;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&mapW);
+    tma_prefetch_desc(&mapP0);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < GP_STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(wfull_bar, 1);
+    mbar_init(tfull_bar, 1);
+    mbar_init(tempty_bar, 4);
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc(tmem_slot, 64);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  // step i (0-based in processing order) reads planes P[i & 1] and its epilogue writes P[(i + 1) & 1]; forward: P0 holds h0 on
+  // entry (count target per * i); backward: the prologue writes P0 (count target per * (i + 1))
+  if (warp == 0) {
+    const bool leader = elect_one();
+    if (leader) {
+      mbar_expect_tx(wfull_bar, (uint32_t)(KB * 2 * GP_WBLOCK));
+      for (int kb = 0; kb < KB; ++kb)
+        for (int pl = 0; pl < 2; ++pl) tma_load_4d(&mapW, wfull_bar, wsm + (size_t)(kb * 2 + pl) * GP_WBLOCK, kb * GP_BK, c * GP_BN, pl, 0);
+    }
+    int      stage = 0;
+    uint32_t phase = 0;
+    for (int i = 0; i < g.T; ++i) {
+      const unsigned int target = per * (unsigned int)(DIR == 0 ? i : i + 1);
+      if (target) wait_count(cnt, target);
+      asm volatile("fence.proxy.async.global;" ::: "memory");
+      const CUtensorMap* mA = (i & 1) ? &mapP1 : &mapP0;
+      for (int kb = 0; kb < KB; ++kb) {
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        if (leader) {
+          uint8_t* st = asm_ + stage * GP_ASTAGE;
+          mbar_expect_tx(&full_bar[stage], GP_ALOAD);
+          tma_load_4d(mA, &full_bar[stage], st, kb * GP_BK, bt * GP_BMV, 0, 0);
+          tma_load_4d(mA, &full_bar[stage], st + GP_BM * GP_BK * 2, kb * GP_BK, bt * GP_BMV, 1, 0);
+        }
+        if (++stage == GP_STAGES) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    const bool     leader = elect_one();
+    const uint32_t idesc = make_idesc_bf16(GP_BM, GP_BN);
+    int            stage = 0;
+    uint32_t       phase = 0;
+    mbar_wait(wfull_bar, 0);
+    tc_fence_after();
+    for (int i = 0; i < g.T; ++i) {
+      mbar_wait(tempty_bar, (uint32_t)(i & 1) ^ 1);
+      tc_fence_after();
+      for (int kb = 0; kb < KB; ++kb) {
+        mbar_wait(&full_bar[stage], phase);
+        tc_fence_after();
+        if (leader) {
+          const uint32_t sa = smem_u32(asm_ + stage * GP_ASTAGE), sb = smem_u32(wsm + (size_t)kb * 2 * GP_WBLOCK);
+          const uint64_t d_ahi = make_smem_desc_sw128(sa), d_alo = make_smem_desc_sw128(sa + GP_BM * GP_BK * 2);
+          const uint64_t d_bhi = make_smem_desc_sw128(sb), d_blo = make_smem_desc_sw128(sb + GP_WBLOCK);
+#pragma unroll
+          for (int k = 0; k < GP_BK / 16; ++k) {
+            const uint64_t o = 2 * k;
+            umma_bf16(tmem_base, d_alo + o, d_bhi + o, idesc, (kb | k) ? 1u : 0u);
+            umma_bf16(tmem_base, d_ahi + o, d_blo + o, idesc, 1u);
+            umma_bf16(tmem_base, d_ahi + o, d_bhi + o, idesc, 1u);
+          }
+          umma_commit(&empty_bar[stage]);
+        }
+        if (++stage == GP_STAGES) { stage = 0; phase ^= 1; }
+      }
+      if (leader) umma_commit(tfull_bar);
+    }
+  } else if (warp >= 4) {
+    const bool     reader = (warp & 3) < 2;
+    const int      rq = warp & 1, rc0 = ((warp - 4) >> 2) * 32;
+    const uint32_t taddr = tmem_base + ((uint32_t)(rq * 32) << 16) + (uint32_t)rc0;
+    float4*        acc4 = reinterpret_cast<float4*>(asm_);
+    const int      ew = warp - 4, cch = lane & 15;
+    const int64_t  H = g.H, BH = (int64_t)g.B * H, PS = (int64_t)g.B * g.Kp;
+    const int      j0 = c * GP_BN + 4 * cch;
+    int64_t        brow[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) brow[e] = (int64_t)bt * GP_BMV + ew * 8 + 2 * e + (lane >> 4);
+    auto publish = [&]() {
+      fence_proxy_async_smem();
+      epi_bar();
+      if (threadIdx.x == 128) {
+        __threadfence();
+        atomicAdd(cnt, 1u);
+      }
+    };
+    // BPTT element-wise part of time step s from the running gradient dh: dl = (dh + g_hs[s]) act'(h_s) -> dxp[s], planes `dst`
+    auto bwd_elementwise = [&](int s, const float4* dh, __nv_bfloat16* dst) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int64_t b = brow[e];
+        if (b >= g.B) continue;
+        const int64_t off = ((int64_t)s * g.B + b) * H + j0;
+        const float4  gg = g.g_hs ? __ldg(reinterpret_cast<const float4*>(g.g_hs + off)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        const float4  h = __ldg(reinterpret_cast<const float4*>(g.hs_in + off));
+        float4        dl = make_float4(dh[e].x + gg.x, dh[e].y + gg.y, dh[e].z + gg.z, dh[e].w + gg.w);
+        if (g.relu) dl.x = h.x > 0.f ? dl.x : 0.f, dl.y = h.y > 0.f ? dl.y : 0.f, dl.z = h.z > 0.f ? dl.z : 0.f, dl.w = h.w > 0.f ? dl.w : 0.f;
+        else dl.x *= 1.f - h.x * h.x, dl.y *= 1.f - h.y * h.y, dl.z *= 1.f - h.z * h.z, dl.w *= 1.f - h.w * h.w;
+        *reinterpret_cast<float4*>(g.dxp + off) = dl;
+        put_planes4(dst + b * g.Kp + j0, PS, dl);
+      }
+    };
+    float4 dh[4];
+    if (DIR == 1) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) dh[e] = make_float4(0.f, 0.f, 0.f, 0.f);
+      bwd_elementwise(g.T - 1, dh, g.P0);
+      publish();
+    }
+    for (int i = 0; i < g.T; ++i) {
+      float4 xr[4];
+      if (DIR == 0) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+          if (brow[e] < g.B) xr[e] = __ldg(reinterpret_cast<const float4*>(g.xp + ((int64_t)i * g.B + brow[e]) * H + j0));
+      }
+      if (reader) {
+        mbar_wait(tfull_bar, (uint32_t)(i & 1));
+        tc_fence_after();
+        float v[32];
+        tmem_ld_32x32(taddr, v);
+        tmem_ld_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(tempty_bar);
+        const int row = rq * 32 + lane;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) acc4[row * 16 + ((rc0 / 4 + k) ^ (row & 7))] = make_float4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
+      }
+      epi_bar();
+      __nv_bfloat16* dst = ((i + 1) & 1) ? g.P1 : g.P0;
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int     row = ew * 8 + 2 * e + (lane >> 4);
+        const int64_t b = brow[e];
+        if (b >= g.B) continue;
+        float4 a = acc4[row * 16 + (cch ^ (row & 7))];
+        if (DIR == 0) {
+          a.x += xr[e].x, a.y += xr[e].y, a.z += xr[e].z, a.w += xr[e].w;
+          if (g.relu) a.x = fmaxf(a.x, 0.f), a.y = fmaxf(a.y, 0.f), a.z = fmaxf(a.z, 0.f), a.w = fmaxf(a.w, 0.f);
+          else a.x = gp_tanh(a.x), a.y = gp_tanh(a.y), a.z = gp_tanh(a.z), a.w = gp_tanh(a.w);
+          *reinterpret_cast<float4*>(g.hs + ((int64_t)i * g.B + b) * H + j0) = a;
+          put_planes4(dst + b * g.Kp + j0, PS, a);
+        } else {
+          dh[e] = a;
+          if (i == g.T - 1) *reinterpret_cast<float4*>(g.dh0 + b * H + j0) = a;
+        }
+      }
+      if (DIR == 1 && i + 1 < g.T) bwd_elementwise(g.T - 2 - i, dh, dst);
+      publish();
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc(tmem_base, 64);
+}
+
 static bool g_persist_off = getenv("PDN_GRU_PERSIST") && getenv("PDN_GRU_PERSIST")[0] == '0';
 
 bool gru_persist_ok(int64_t T, int64_t B, int64_t H) {
@@ -1002,6 +1203,38 @@ int gru_persist_forward(const float* xp1, const float* xp2, const float* h0, con
     }
   }
   delete cnt;  // Scratch returns its block to the stream-ordered allocator: reuse is ordered after this kernel
+  return 0;
+}
+
+bool rnn_persist_ok(int64_t T, int64_t B, int64_t H) {
+  if (g_persist_off || H % GP_BK != 0 || H / GP_BK > GP_MAXKB || T < 4) return false;
+  const int64_t nbt = (B + GP_BMV - 1) / GP_BMV;
+  return (H / GP_BN) * nbt <= sm_count();
+}
+
+// dir 0: forward (Wp = K-major planes of Wh^T: rows = output columns j, contraction over the previous hidden index; P0 holds h0);
+// dir 1: BPTT (Wp = K-major planes of Wh: rows = k, contraction over j; hs = the saved hidden states)
+int rnn_persist_run(int dir, const float* xp, const float* hs_in, const float* g_hs, const PackedOperand& Wp, const PackedOperand& P0,
+                    const PackedOperand& P1, float* hs, float* dxp, float* dh0, int64_t T, int64_t B, int64_t H, int relu) {
+  const int nbt = (int)((B + GP_BMV - 1) / GP_BMV), ctn = (int)(H / GP_BN);
+  CUtensorMap m0, m1, mW;
+  PDN_TRY(tc_make_map(&m0, P0.planes, B, H, P0.Kp, 1, GP_BMV));
+  PDN_TRY(tc_make_map(&m1, P1.planes, B, H, P1.Kp, 1, GP_BMV));
+  PDN_TRY(tc_make_map(&mW, Wp.planes, H, H, Wp.Kp, 1, GP_BN));
+  Scratch cnt;
+  PDN_TRY(cnt.alloc((size_t)nbt * sizeof(unsigned int)));
+  PDN_CUDA(cudaMemsetAsync(cnt.p, 0, (size_t)nbt * sizeof(unsigned int), stream()));
+  RnnPersistArgs g;
+  g.xp = xp, g.hs_in = hs_in, g.g_hs = g_hs, g.hs = hs, g.dxp = dxp, g.dh0 = dh0;
+  g.P0 = (__nv_bfloat16*)P0.planes, g.P1 = (__nv_bfloat16*)P1.planes;
+  g.T = (int)T, g.B = (int)B, g.H = (int)H, g.Kp = (int)P0.Kp, g.nbt = nbt, g.ctn = ctn, g.relu = relu;
+  g.cnt = (unsigned int*)cnt.p;
+  const size_t smem = (size_t)(H / GP_BK) * 2 * GP_WBLOCK + (size_t)GP_STAGES * GP_ASTAGE + 1024 + 256;
+  const void*  fn = dir == 0 ? (const void*)k_rnn_persist<0> : (const void*)k_rnn_persist<1>;
+  PDN_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  void* params[] = {&m0, &m1, &mW, &g};
+  PDN_CUDA(cudaLaunchCooperativeKernel(fn, dim3(ctn * nbt), dim3(384), params, smem, stream()));
+  PDN_LAUNCHED(dir == 0 ? "rnn_persist_fwd" : "rnn_persist_bwd");
   return 0;
 }
 

@@ -481,13 +481,48 @@ def _seq_inputs(x):
 def sequence(cell, x, state):
     """Whole-sequence forward of one recurrent layer/direction as ONE tape entry (csrc/rnn.cu). Returns
     ([state sequences], [last states]) like the per-step loop in nn/modules/rnn.py, or None when not applicable."""
-    from .modules.rnn import GRUCell, LSTMCell
-    if not _ENABLED or type(cell) not in (GRUCell, LSTMCell) or x.ndim not in (2, 3):
+    from .modules.rnn import GRUCell, LSTMCell, RNNCell
+    if not _ENABLED or type(cell) not in (GRUCell, LSTMCell, RNNCell) or x.ndim not in (2, 3):
         return None
     tensors = [x] + list(state) + list(cell._parameters.values())
     if not all(t.device.is_cuda and t.data.dtype == F32 for t in tensors):
         return None
+    if type(cell) is RNNCell:
+        return _rnn_sequence(cell, x, state[0]) if cell.nonlinearity in ("tanh", "relu") else None
     return _gru_sequence(cell, x, state[0]) if type(cell) is GRUCell else _lstm_sequence(cell, x, state[0], state[1])
+
+
+def _rnn_sequence(cell, x, h0):
+    """h_t = act(x_t Wx + b + h_{t-1} Wh) over a whole sequence (reference rnn.py:38-49 per step): hoisted input GEMM, the
+    recurrence and its BPTT as one C call each (pdn_rnn_seq_fwd / _bwd)."""
+    bk = _bk()
+    H = cell.hidden_size
+    Wx, Wh = cell.Wx, cell.Wh
+    b = cell.bias if cell.has_bias else None
+    relu = 1 if cell.nonlinearity == "relu" else 0
+    unb = x.ndim == 2
+    with x.device:
+        x2, T, B, I = _seq_inputs(x)
+        h0d = _c(h0.data).reshape(B, H)
+        xp = bk.gemm_into(None, x2, Wx.data, bias=_c(b.data) if b is not None else None)
+        hs = _empty((T, B, H))
+        wh = _c(Wh.data)
+        _call("pdn_rnn_seq_fwd", xp.ptr, h0d.ptr, wh.ptr, hs.ptr, T, B, H, relu)
+        del xp
+
+    def backward(g):
+        g = _c(g.reshape(T, B, H))
+        dxp, dh0, dWh = _empty((T * B, H)), _empty((B, H)), _empty((H, H))
+        _call("pdn_rnn_seq_bwd", g.ptr, h0d.ptr, hs.ptr, wh.ptr, dxp.ptr, dh0.ptr, dWh.ptr, T, B, H, relu)
+        dx = bk.gemm_into(None, dxp, Wx.data.swapaxes(0, 1)).reshape(x.shape) if x.requires_grad else None
+        outs = [dx, dh0.reshape(h0.shape), bk.gemm_into(None, x2.swapaxes(0, 1), dxp), dWh]
+        if b is not None:
+            outs.append(dxp.sum(axis=0))
+        return tuple(outs)
+
+    ins = (x, h0, Wx, Wh) + ((b, ) if b is not None else ())
+    seq = _result(hs.reshape(T, H) if unb else hs, x.device, ins, backward, "rnn_sequence")
+    return [seq], [seq[T - 1:T]]
 
 
 def _gru_sequence(cell, x, h0):

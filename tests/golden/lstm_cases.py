@@ -1,8 +1,12 @@
-"""Shapes, seeded inputs and fixture thinning shared by make_golden_lstm.py (the reference side) and tests/test_lstm_sizes.py."""
+"""Shapes, seeded inputs and fixture thinning shared by make_golden_lstm.py (the reference side) and tests/test_lstm_sizes.py
+(LSTM and plain-RNN cases at sizes the persistent whole-sequence kernels take)."""
 import numpy as np
 
 f32 = np.float32
-CASES = {"a": dict(I=192, H=256, T=48, B=40, kw=dict(num_layers=1)), "b": dict(I=64, H=128, T=20, B=72, kw=dict(num_layers=2, bidirectional=True))}
+CASES = {"a": dict(cls="LSTM", I=192, H=256, T=48, B=40, kw=dict(num_layers=1)),
+         "b": dict(cls="LSTM", I=64, H=128, T=20, B=72, kw=dict(num_layers=2, bidirectional=True)),
+         "r": dict(cls="RNN", I=96, H=128, T=24, B=40, kw=dict(num_layers=1, nonlinearity="tanh")),
+         "s": dict(cls="RNN", I=32, H=64, T=16, B=72, kw=dict(num_layers=2, bidirectional=True, nonlinearity="relu"))}
 
 
 def inputs(c, seed):

@@ -1,4 +1,5 @@
-"""Golden vectors for the LSTM at a size the persistent whole-sequence kernels take (H % 64 == 0): one forward + backward of the
+"""Golden vectors for the LSTM (and the plain RNN: cases r, s — tanh 1 layer H128 / T24 / B40, relu 2 layers bidirectional H64 / T16 /
+B72) at a size the persistent whole-sequence kernels take (H % 64 == 0): one forward + backward of the
 UNMODIFIED reference (NumPy CPU path) for LSTM in192 / h256 / T48 / B40 (B not a multiple of the 64-row batch tile) with given
 (h0, c0), a loss that feeds gradients into the whole output sequence, h_n and c_n, and the same for a 2-layer bidirectional LSTM
 h128 / T20 / B72 (two batch tiles).  Inputs / initial parameters are rebuilt from seeds on both sides; fingerprints of the initial
@@ -30,18 +31,24 @@ if __name__ == "__main__":
     d = {}
     for nm, c in CASES.items():
         np.random.seed(11)
-        mod = nn.LSTM(c["I"], c["H"], dtype=f32, **c["kw"])
+        mod = getattr(nn, c["cls"])(c["I"], c["H"], dtype=f32, **c["kw"])
         x, h0, c0, w = inputs(c, 5)
         params = list(mod.parameters())
         for i, p in enumerate(params):
             a = np.asarray(p.data, np.float64).ravel()
             d[f"{nm}.fp.{i}"] = np.concatenate([[a.sum(), np.abs(a).sum()], a[:6]])
         tx, th, tc = T(x, True), T(h0, True), T(c0, True)
-        out, (hn, cn) = mod(tx, (th, tc))
-        loss = (out * T(w)).sum() + (hn * hn).sum() + (cn * cn).sum() * 0.5
+        if c["cls"] == "LSTM":
+            out, (hn, cn) = mod(tx, (th, tc))
+            loss = (out * T(w)).sum() + (hn * hn).sum() + (cn * cn).sum() * 0.5
+        else:
+            out, hn = mod(tx, th)
+            loss = (out * T(w)).sum() + (hn * hn).sum()
         loss.backward()
-        d[f"{nm}.out"], d[f"{nm}.hn"], d[f"{nm}.cn"], d[f"{nm}.loss"] = out.data.copy(), hn.data.copy(), cn.data.copy(), loss.data.copy()
-        d[f"{nm}.dx"], d[f"{nm}.dh0"], d[f"{nm}.dc0"] = tx.grad.copy(), th.grad.copy(), tc.grad.copy()
+        d[f"{nm}.out"], d[f"{nm}.hn"], d[f"{nm}.loss"] = out.data.copy(), hn.data.copy(), loss.data.copy()
+        d[f"{nm}.dx"], d[f"{nm}.dh0"] = tx.grad.copy(), th.grad.copy()
+        if c["cls"] == "LSTM":
+            d[f"{nm}.cn"], d[f"{nm}.dc0"] = cn.data.copy(), tc.grad.copy()
         for i, p in enumerate(params):
             d[f"{nm}.g.{i}"] = np.array(p.grad, copy=True)
         print(nm, "done", float(loss.data), flush=True)

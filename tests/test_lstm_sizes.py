@@ -1,8 +1,9 @@
-"""LSTM at sizes the persistent whole-sequence kernels take (k_lstm_persist_fwd / k_lstm_persist_bwd, H % 64 == 0) against what the
+"""LSTM and plain RNN at sizes the persistent whole-sequence kernels take (k_lstm_persist_fwd / _bwd, k_rnn_persist<0|1>, H % 64 == 0)
+against what the
 unmodified reference produced (tests/golden/lstm_sizes.npz, tests/golden/make_golden_lstm.py): forward outputs, h_n, c_n and the
 gradients wrt x, h0, c0 and every parameter, with given initial states and gradients flowing into the whole output sequence, h_n and
 c_n.  Case a: 1 layer in192 / h256 / T48 / B40 (ragged batch tile); case b: 2 layers bidirectional h128 / T20 / B72 (two batch
-tiles).  Tolerance 1e-4 normwise (BF16x3 recurrent products, fp32 gates)."""
+tiles); case r: RNN tanh 1 layer h128 / T24 / B40; case s: RNN relu 2 layers bidirectional h64 / T16 / B72.  Tolerance 1e-4 normwise (BF16x3 recurrent products, fp32 gates)."""
 import os
 import sys
 
@@ -20,6 +21,7 @@ from lstm_cases import CASES, inputs, thin  # noqa: E402  (shared with the fixtu
 G = np.load(os.path.join(ROOT, "tests", "golden", "lstm_sizes.npz"))
 DEVICES = ["cpu", pytest.param("cuda:0", marks=pytest.mark.gpu)]
 f32 = np.float32
+LOOP = os.environ.get("PDN_GRU_PERSIST") == "0"  # the per-step host loop was asked for: same results, no persistent launches
 
 
 def close(got, ref, what, rtol=1e-4):
@@ -39,7 +41,9 @@ def T(a, dev, rg=False):
 def test_lstm_sequence_against_reference(dev, nm):
     c = CASES[nm]
     np.random.seed(11)
-    mod = nn.LSTM(c["I"], c["H"], dtype=f32, **c["kw"])
+    mod = getattr(nn, c["cls"])(c["I"], c["H"], dtype=f32, **c["kw"])
+    lstm = c["cls"] == "LSTM"
+    kern = "lstm_persist" if lstm else "rnn_persist"
     mod.to(dev)
     params = list(mod.parameters())
     for i, p in enumerate(params):
@@ -50,23 +54,28 @@ def test_lstm_sequence_against_reference(dev, nm):
     tx, th, tc = T(x, dev, True), T(h0, dev, True), T(c0, dev, True)
     if dev != "cpu":
         from pydynet_b200.backend import lib
-        lib.watch_launches("lstm_persist_fwd")
-    out, (hn, cn) = mod(tx, (th, tc))
-    loss = (out * T(w, dev)).sum() + (hn * hn).sum() + (cn * cn).sum() * 0.5
+        lib.watch_launches(kern + "_fwd")
+    if lstm:
+        out, (hn, cn) = mod(tx, (th, tc))
+        loss = (out * T(w, dev)).sum() + (hn * hn).sum() + (cn * cn).sum() * 0.5
+    else:
+        out, hn = mod(tx, th)
+        loss = (out * T(w, dev)).sum() + (hn * hn).sum()
     if dev != "cpu":
         nd = c["kw"].get("num_layers", 1) * (2 if c["kw"].get("bidirectional") else 1)
-        assert lib.watched_launch_count() == nd, "the persistent LSTM forward kernel did not run"
-        lib.watch_launches("lstm_persist_bwd")
+        assert lib.watched_launch_count() == (0 if LOOP else nd), "the persistent forward kernel did not run"
+        lib.watch_launches(kern + "_bwd")
     loss.backward()
     if dev != "cpu":
-        assert lib.watched_launch_count() == nd, "the persistent LSTM backward kernel did not run"
+        assert lib.watched_launch_count() == (0 if LOOP else nd), "the persistent backward kernel did not run"
         lib.watch_launches(None)
     close(out, G[f"{nm}.out"], "out")
     close(hn, G[f"{nm}.hn"], "hn")
-    close(cn, G[f"{nm}.cn"], "cn")
     np.testing.assert_allclose(float(loss.item()), float(G[f"{nm}.loss"]), rtol=1e-4)
     close(tx.grad, G[f"{nm}.dx"], "dx")
     close(th.grad, G[f"{nm}.dh0"], "dh0")
-    close(tc.grad, G[f"{nm}.dc0"], "dc0")
+    if lstm:
+        close(cn, G[f"{nm}.cn"], "cn")
+        close(tc.grad, G[f"{nm}.dc0"], "dc0")
     for i, p in enumerate(params):
         close(p.grad, G[f"{nm}.g.{i}"], f"grad of parameter {i}")
