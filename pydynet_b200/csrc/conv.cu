@@ -174,7 +174,19 @@ __global__ void __launch_bounds__(256) k_conv_thin_bwd_weight(const float* __res
   for (int i = threadIdx.x; i < O * (WIN + 1); i += blockDim.x) part[i] = 0.f;
   for (int64_t n = blockIdx.x; n < g.N; n += gridDim.x) {
     __syncthreads();
-    for (int i = threadIdx.x; i < O * hw; i += blockDim.x) gs[(i / hw) * gst + i % hw] = gy[n * O * hw + i];
+    if ((hw & 3) == 0 && ((uintptr_t)gy & 15) == 0) {  // 128-bit loads, several in flight per thread (the copy is latency-bound)
+      const float4* src = reinterpret_cast<const float4*>(gy + n * O * hw);
+      const int     n4 = O * hw / 4, hw4 = hw / 4;
+#pragma unroll 4
+      for (int i = threadIdx.x; i < n4; i += blockDim.x) {
+        const float4 v = __ldg(src + i);
+        const int    o2 = i / hw4;
+        float*       d = gs + o2 * gst + (i - o2 * hw4) * 4;
+        d[0] = v.x, d[1] = v.y, d[2] = v.z, d[3] = v.w;
+      }
+    } else {
+      for (int i = threadIdx.x; i < O * hw; i += blockDim.x) gs[(i / hw) * gst + i % hw] = gy[n * O * hw + i];
+    }
     for (int i = threadIdx.x; i < C * (int)(g.H * g.W); i += blockDim.x) {
       const int c = i / (int)(g.H * g.W), r = i - c * (int)(g.H * g.W), yy = r / (int)g.W, xx = r - yy * (int)g.W;
       xs[(c * Hp + yy + g.pad) * Wp + xx + g.pad] = x[n * C * g.H * g.W + i];
