@@ -345,6 +345,54 @@ def rnn(args):
     lstm(args, "RNN")
 
 
+def c3(args):
+    """BASELINE config 3 side views: prefill of a 256-token prompt (tokens/s, batch 1) and greedy generation to total
+    length 256 at batch 1 / 32 / 128 — the reference's own llm/llama/model.py where it is staged, through the unchanged Module surface
+    (the inference plan serves it); the unmodified reference on the host cores beside each line (batch 32 / 128: a bounded sample —
+    the 4-token prefill + one decode step at contexts 5 / 130 / 255, as in bench.py's cpu_baseline)."""
+    import bench
+    Llama, how = bench.model_class()
+    rng = np.random.default_rng(0)
+    pdn.autograd.set_grad_enabled(False)
+    try:
+        # ---- prefill(256)
+        net, _ = bench.build_model(Llama, 1, DEV)
+        ids = rng.integers(1, bench.CFG["V"], (1, 256))
+        tid = T(ids)
+        sec, nl = timed(lambda: net(tid, 0), max(3, args.steps // 2), warmup=2)
+        base = None
+        if args.cpu:
+            ref, kind = bench._reference_llama(1)
+            t0 = time.perf_counter()
+            ref(ids, 0)
+            dt = time.perf_counter() - t0
+            base = {"ms_per_step": dt * 1e3, "kind": kind, "cores": bench._host_threads(), "sample": "one forward over the same 256-token prompt"}
+        emit(f"C3 Llama prefill, 256-token prompt, batch 1 ({how})", sec, flops=3.529e9, launches=nl, tokens_per_s=256 / sec, **with_ref({}, sec, base))
+        del net
+        # ---- greedy generation to total length 256
+        for B in ((1, 8) if args.small else (1, 32, 128)):
+            net, _ = bench.build_model(Llama, B, DEV)
+            prompt = T(np.tile(np.array([[1, 100, 200, 300]]), (B, 1)))
+            sec, nl = timed(lambda: bench.generate_resident(net, prompt), 3, warmup=2)
+            base = None
+            if args.cpu:
+                cb = bench.cpu_baseline(B, steps=1, warmup=0, b1_steps=1) if B > 1 else None
+                if B == 1:
+                    ref, kind = bench._reference_llama(1)
+                    t0 = time.perf_counter()
+                    for _ in ref.generate(np.array([[1, 100, 200, 300]]), 256):
+                        pass
+                    dt = time.perf_counter() - t0
+                    base = {"ms_per_step": dt * 1e3, "kind": kind, "cores": bench._host_threads(), "sample": "the full workload: batch 1, total length 256"}
+                elif cb and cb.get("value"):
+                    base = {"ms_per_step": B * 256 / cb["value"] * 1e3, "kind": cb.get("kind"), "cores": cb.get("cores"), "sample": cb.get("sample")}
+            emit(f"C3 Llama greedy generation to total length 256, batch {B} ({how})", sec, launches=nl, tokens_per_s=B * 256 / sec,
+                 us_per_token_step=sec / 252 * 1e6, **with_ref({}, sec, base))
+            del net
+    finally:
+        pdn.autograd.set_grad_enabled(True)
+
+
 def decode(args):
     """Decode-step micro-benchmarks at BASELINE config-3 shapes (batch 1024 sequences): the KV-cache attention of one layer at
     a context of 130 keys (HBM-bound: K and V rows once) and the four per-layer GEMMs + lm_head on cached weight planes."""
@@ -446,7 +494,7 @@ def micro(args, conv=True):
 
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
-    ap.add_argument("--only", default="c1,c2,c4,c5,lstm,rnn,micro")
+    ap.add_argument("--only", default="c1,c2,c3,c4,c5,lstm,rnn,micro")
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--small", action="store_true")
     ap.add_argument("--no-cpu", dest="cpu", action="store_false", help="skip the reference-on-host-cores run beside every config")
@@ -454,7 +502,7 @@ if __name__ == "__main__":
     ARGS = args
     for name in args.only.split(","):
         try:
-            {"c1": c1, "c2": c2, "c4": c4, "c5": c5, "lstm": lstm, "rnn": rnn, "micro": micro, "micro_att": micro_att, "gemm": gemm, "rows": rows, "decode": decode}[name](args)
+            {"c1": c1, "c2": c2, "c3": c3, "c4": c4, "c5": c5, "lstm": lstm, "rnn": rnn, "micro": micro, "micro_att": micro_att, "gemm": gemm, "rows": rows, "decode": decode}[name](args)
         except Exception as e:  # keep going: one config must not hide the others
             import traceback
             traceback.print_exc()
