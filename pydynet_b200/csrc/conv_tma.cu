@@ -61,6 +61,11 @@ __device__ __forceinline__ void tma_load_5d(const CUtensorMap* map, uint64_t* ba
       : "memory");
 }
 
+#ifndef PDN_CONV_W3_WIDE
+#define PDN_CONV_W3_WIDE 1
+#endif
+constexpr bool kWideW3 = PDN_CONV_W3_WIDE != 0;
+
 template <int BN, int MODE>
 __global__ void __launch_bounds__(256, 1)
 k_conv_tma(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, CtArgs g) {
@@ -185,6 +190,20 @@ k_conv_tma(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUt
             nks = left >= 64 ? 4 : (left + 15) >> 4;
           }
           const uint64_t step = kW ? 128 : 2;  // one UMMA_K = 16: 16 pixel rows of 128 B (MN-major) or 32 B of channels
+          if (MODE == CT_W3 && BN == 64 && kWideW3) {
+            // The three taps' x tiles sit kBBytes apart in the stage: read as ONE MN-major B operand of N = 192 (three 64-column
+            // blocks, leading-dimension offset kBBytes) into the three adjacent accumulators. A 128x64x16 MMA with both operands
+            // in shared memory is bound by the 6 KB it re-reads (~65 cycles against a 32-cycle tensor floor); 128x192x16 reads
+            // 10 KB for a 96-cycle floor: a third of the instructions and about half the time per k-step.
+            const uint64_t d_bhi = make_smem_desc_sw128_mn(sb, Cfg::kBBytes), d_blo = make_smem_desc_sw128_mn(sb + BN * 128, Cfg::kBBytes);
+            constexpr uint32_t idesc3 = make_idesc_bf16(128, 3 * 64) | IDESC_A_MN_MAJOR | IDESC_B_MN_MAJOR;
+            for (int k = 0; k < nks; ++k) {
+              const uint64_t o = step * (uint64_t)k;
+              umma_bf16(tmem_d, d_alo + o, d_bhi + o, idesc3, (kb | k) ? 1u : 0u);
+              umma_bf16(tmem_d, d_ahi + o, d_blo + o, idesc3, 1u);
+              umma_bf16(tmem_d, d_ahi + o, d_bhi + o, idesc3, 1u);
+            }
+          } else
 #pragma unroll
           for (int tp = 0; tp < T; ++tp) {
             const uint32_t sbt = sb + tp * Cfg::kBBytes;
