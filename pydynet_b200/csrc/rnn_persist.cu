@@ -30,6 +30,14 @@ constexpr int GP_BMV = 64;    // batch rows per tile that are real: only they ar
                               // also multiplies whatever lies in the other half of the shared-memory tile into accumulator rows
                               // nobody reads. Half the activation stream per CTA and twice the CTAs per sequence (measured: the
                               // 256 KB stream of a full tile was 3 us of an 11 us phase)
+#ifndef PDN_GP_M64
+#define PDN_GP_M64 1
+#endif
+// tcgen05 M = 64 instead of a half-filled M = 128: with both operands in shared memory a 128x64x16 MMA is bound by the 6 KB it
+// re-reads per k-step (~65 cycles), and 2 KB of that are the tile's unused rows; M = 64 reads 4 KB (measured on the plain RNN:
+// 12.9 -> 11.0 us per time step). Its accumulator puts rows 16 q .. 16 q + 15 into lanes 32 q .. 32 q + 15 of TMEM lane quarter q,
+// so all eight epilogue warps read (16 useful lanes each) instead of four.
+constexpr bool GP_M64 = PDN_GP_M64 != 0;
 constexpr int GP_BN = 64;     // weight columns per CTA (MMA N)
 constexpr int GP_BK = 64;     // k-block: 64 bf16 = one 128-byte swizzle span
 constexpr int GP_STAGES = 3;  // activation ring
@@ -140,7 +148,7 @@ k_gru_persist_fwd(const __grid_constant__ CUtensorMap mapH0, const __grid_consta
     }
     mbar_init(wfull_bar, 1);
     mbar_init(tfull_bar, 1);
-    mbar_init(tempty_bar, 4);
+    mbar_init(tempty_bar, GP_M64 ? 8 : 4);
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc(tmem_slot, 64);
@@ -186,7 +194,7 @@ k_gru_persist_fwd(const __grid_constant__ CUtensorMap mapH0, const __grid_consta
   } else if (warp == 1) {
     // ===== MMA issuer =====
     const bool     leader = elect_one();
-    const uint32_t idesc = make_idesc_bf16(GP_BM, GP_BN);
+    const uint32_t idesc = make_idesc_bf16(GP_M64 ? 64 : GP_BM, GP_BN);
     int            stage = 0;
     uint32_t       phase = 0;
     mbar_wait(wfull_bar, 0);
@@ -221,8 +229,8 @@ k_gru_persist_fwd(const __grid_constant__ CUtensorMap mapH0, const __grid_consta
     // The accumulator sits in TMEM with one batch row per lane; read that way, every global access of a warp would touch 32 different
     // lines with 16 bytes each (measured: ~1 us of partial-sector transactions per stored tile, four tiles per step). So the readers
     // drop the 64 x 64 fp32 tile into shared memory (the idle activation ring) and the math runs row-major.
-    const bool     reader = (warp & 3) < 2;                   // may access TMEM lanes 32 * (warp % 4) ...
-    const int      rq = warp & 1, rc0 = ((warp - 4) >> 2) * 32;  // reader: lane quarter, first of its 32 columns
+    const bool     reader = GP_M64 ? true : (warp & 3) < 2;   // may access TMEM lanes 32 * (warp % 4) ...
+    const int      rq = GP_M64 ? (warp & 3) : (warp & 1), rc0 = ((warp - 4) >> 2) * 32;  // reader: lane quarter, first of its 32 columns
     const uint32_t taddr = tmem_base + ((uint32_t)(rq * 32) << 16) + (uint32_t)rc0;
     float4*        acc4 = reinterpret_cast<float4*>(asm_);    // [64 rows][16 float4], chunk index XOR-swizzled by (row & 7)
     const int      ew = warp - 4, cch = lane & 15;            // math: rows ew * 8 + 2 i + (lane >> 4), columns 4 * cch .. + 3
@@ -267,9 +275,11 @@ k_gru_persist_fwd(const __grid_constant__ CUtensorMap mapH0, const __grid_consta
         tc_fence_before();  // accumulator is in registers: hand it back
         __syncwarp();
         if (lane == 0) mbar_arrive(tempty_bar);
-        const int row = rq * 32 + lane;
+        const int row = GP_M64 ? rq * 16 + lane : rq * 32 + lane;
+        if (!GP_M64 || lane < 16) {
 #pragma unroll
-        for (int k = 0; k < 8; ++k) acc4[row * 16 + ((rc0 / 4 + k) ^ (row & 7))] = make_float4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
+          for (int k = 0; k < 8; ++k) acc4[row * 16 + ((rc0 / 4 + k) ^ (row & 7))] = make_float4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
+        }
       }
       epi_bar();
       if (threadIdx.x == 128) gp_stamp(g, t, phaseA, c, bt, 10);
@@ -357,7 +367,7 @@ k_lstm_persist_fwd(const __grid_constant__ CUtensorMap mapH0, const __grid_const
     }
     mbar_init(wfull_bar, 1);
     mbar_init(tfull_bar, 1);
-    mbar_init(tempty_bar, 4);
+    mbar_init(tempty_bar, GP_M64 ? 8 : 4);
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc(tmem_slot, 64);
@@ -394,7 +404,7 @@ k_lstm_persist_fwd(const __grid_constant__ CUtensorMap mapH0, const __grid_const
     }
   } else if (warp == 1) {
     const bool     leader = elect_one();
-    const uint32_t idesc = make_idesc_bf16(GP_BM, GP_BN);
+    const uint32_t idesc = make_idesc_bf16(GP_M64 ? 64 : GP_BM, GP_BN);
     int            stage = 0;
     uint32_t       phase = 0;
     mbar_wait(wfull_bar, 0);
@@ -425,8 +435,8 @@ k_lstm_persist_fwd(const __grid_constant__ CUtensorMap mapH0, const __grid_const
   } else if (warp >= 4) {
     // epilogue: the four TMEM readers drop the 64 x 64 accumulator into shared memory; thread (row, jq) then owns hidden units
     // 16 c + 4 jq .. + 3 of batch row `row`: their four gates sit in chunks q * 4 + jq of the tile row
-    const bool     reader = (warp & 3) < 2;
-    const int      rq = warp & 1, rc0 = ((warp - 4) >> 2) * 32;
+    const bool     reader = GP_M64 ? true : (warp & 3) < 2;
+    const int      rq = GP_M64 ? (warp & 3) : (warp & 1), rc0 = ((warp - 4) >> 2) * 32;
     const uint32_t taddr = tmem_base + ((uint32_t)(rq * 32) << 16) + (uint32_t)rc0;
     float4*        acc4 = reinterpret_cast<float4*>(asm_);
     const int      item = (int)threadIdx.x - 128, row = item >> 2, jq = item & 3;
@@ -449,9 +459,11 @@ k_lstm_persist_fwd(const __grid_constant__ CUtensorMap mapH0, const __grid_const
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(tempty_bar);
-        const int r = rq * 32 + lane;
+        const int r = GP_M64 ? rq * 16 + lane : rq * 32 + lane;
+        if (!GP_M64 || lane < 16) {
 #pragma unroll
-        for (int k = 0; k < 8; ++k) acc4[r * 16 + ((rc0 / 4 + k) ^ (r & 7))] = make_float4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
+          for (int k = 0; k < 8; ++k) acc4[r * 16 + ((rc0 / 4 + k) ^ (r & 7))] = make_float4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
+        }
       }
       epi_bar();
       if (live) {
@@ -543,7 +555,7 @@ k_gru_persist_bwd(const __grid_constant__ CUtensorMap mapDl2, const __grid_const
     }
     mbar_init(wfull_bar, 1);
     mbar_init(tfull_bar, 1);
-    mbar_init(tempty_bar, 4);
+    mbar_init(tempty_bar, GP_M64 ? 8 : 4);
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc(tmem_slot, 64);
@@ -580,7 +592,7 @@ k_gru_persist_bwd(const __grid_constant__ CUtensorMap mapDl2, const __grid_const
   } else if (warp == 1) {
     // ===== MMA issuer =====
     const bool     leader = elect_one();
-    const uint32_t idesc = make_idesc_bf16(GP_BM, GP_BN);
+    const uint32_t idesc = make_idesc_bf16(GP_M64 ? 64 : GP_BM, GP_BN);
     int            stage = 0;
     uint32_t       phase = 0;
     mbar_wait(wfull_bar, 0);
@@ -610,8 +622,8 @@ k_gru_persist_bwd(const __grid_constant__ CUtensorMap mapDl2, const __grid_const
     }
   } else if (warp >= 4) {
     // ===== epilogue (accumulator -> shared memory by the four TMEM readers, row-major math by all eight warps) =====
-    const bool     reader = (warp & 3) < 2;
-    const int      rq = warp & 1, rc0 = ((warp - 4) >> 2) * 32;
+    const bool     reader = GP_M64 ? true : (warp & 3) < 2;
+    const int      rq = GP_M64 ? (warp & 3) : (warp & 1), rc0 = ((warp - 4) >> 2) * 32;
     const uint32_t taddr = tmem_base + ((uint32_t)(rq * 32) << 16) + (uint32_t)rc0;
     float4*        acc4 = reinterpret_cast<float4*>(asm_);
     const int      ew = warp - 4, cch = lane & 15;
@@ -690,9 +702,11 @@ k_gru_persist_bwd(const __grid_constant__ CUtensorMap mapDl2, const __grid_const
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(tempty_bar);
-        const int row = rq * 32 + lane;
+        const int row = GP_M64 ? rq * 16 + lane : rq * 32 + lane;
+        if (!GP_M64 || lane < 16) {
 #pragma unroll
-        for (int k = 0; k < 8; ++k) acc4[row * 16 + ((rc0 / 4 + k) ^ (row & 7))] = make_float4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
+          for (int k = 0; k < 8; ++k) acc4[row * 16 + ((rc0 / 4 + k) ^ (row & 7))] = make_float4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
+        }
       }
       epi_bar();
 #pragma unroll
@@ -775,7 +789,7 @@ k_lstm_persist_bwd(const __grid_constant__ CUtensorMap mapDl, const __grid_const
     }
     mbar_init(wfull_bar, 1);
     mbar_init(tfull_bar, 1);
-    mbar_init(tempty_bar, 4);
+    mbar_init(tempty_bar, GP_M64 ? 8 : 4);
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc(tmem_slot, 64);
@@ -810,7 +824,7 @@ k_lstm_persist_bwd(const __grid_constant__ CUtensorMap mapDl, const __grid_const
     }
   } else if (warp == 1) {
     const bool     leader = elect_one();
-    const uint32_t idesc = make_idesc_bf16(GP_BM, GP_BN);
+    const uint32_t idesc = make_idesc_bf16(GP_M64 ? 64 : GP_BM, GP_BN);
     int            stage = 0;
     uint32_t       phase = 0;
     mbar_wait(wfull_bar, 0);
@@ -839,8 +853,8 @@ k_lstm_persist_bwd(const __grid_constant__ CUtensorMap mapDl, const __grid_const
       if (leader) umma_commit(tfull_bar);
     }
   } else if (warp >= 4) {
-    const bool     reader = (warp & 3) < 2;
-    const int      rq = warp & 1, rc0 = ((warp - 4) >> 2) * 32;
+    const bool     reader = GP_M64 ? true : (warp & 3) < 2;
+    const int      rq = GP_M64 ? (warp & 3) : (warp & 1), rc0 = ((warp - 4) >> 2) * 32;
     const uint32_t taddr = tmem_base + ((uint32_t)(rq * 32) << 16) + (uint32_t)rc0;
     float4*        acc4 = reinterpret_cast<float4*>(asm_);
     const int      ew = warp - 4, cch = lane & 15;
@@ -906,9 +920,11 @@ k_lstm_persist_bwd(const __grid_constant__ CUtensorMap mapDl, const __grid_const
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(tempty_bar);
-        const int row = rq * 32 + lane;
+        const int row = GP_M64 ? rq * 16 + lane : rq * 32 + lane;
+        if (!GP_M64 || lane < 16) {
 #pragma unroll
-        for (int k = 0; k < 8; ++k) acc4[row * 16 + ((rc0 / 4 + k) ^ (row & 7))] = make_float4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
+          for (int k = 0; k < 8; ++k) acc4[row * 16 + ((rc0 / 4 + k) ^ (row & 7))] = make_float4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
+        }
       }
       epi_bar();
       if (role == 0) {  // every CTA of this batch tile has consumed the operand planes of step s (and roles 1..3 have published)
@@ -996,7 +1012,7 @@ k_rnn_persist(const __grid_constant__ CUtensorMap mapP0, const __grid_constant__
     }
     mbar_init(wfull_bar, 1);
     mbar_init(tfull_bar, 1);
-    mbar_init(tempty_bar, 4);
+    mbar_init(tempty_bar, GP_M64 ? 8 : 4);
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc(tmem_slot, 64);
@@ -1033,7 +1049,7 @@ k_rnn_persist(const __grid_constant__ CUtensorMap mapP0, const __grid_constant__
     }
   } else if (warp == 1) {
     const bool     leader = elect_one();
-    const uint32_t idesc = make_idesc_bf16(GP_BM, GP_BN);
+    const uint32_t idesc = make_idesc_bf16(GP_M64 ? 64 : GP_BM, GP_BN);
     int            stage = 0;
     uint32_t       phase = 0;
     mbar_wait(wfull_bar, 0);
@@ -1062,8 +1078,9 @@ k_rnn_persist(const __grid_constant__ CUtensorMap mapP0, const __grid_constant__
       if (leader) umma_commit(tfull_bar);
     }
   } else if (warp >= 4) {
-    const bool     reader = (warp & 3) < 2;
-    const int      rq = warp & 1, rc0 = ((warp - 4) >> 2) * 32;
+    // M = 64 accumulator: 16 rows per TMEM lane quarter (rows 16 q .. 16 q + 15 in lanes 32 q .. 32 q + 15), so all eight warps read
+    const bool     reader = GP_M64 ? true : (warp & 3) < 2;
+    const int      rq = GP_M64 ? (warp & 3) : (warp & 1), rc0 = ((warp - 4) >> 2) * 32;
     const uint32_t taddr = tmem_base + ((uint32_t)(rq * 32) << 16) + (uint32_t)rc0;
     float4*        acc4 = reinterpret_cast<float4*>(asm_);
     const int      ew = warp - 4, cch = lane & 15;
@@ -1119,9 +1136,11 @@ k_rnn_persist(const __grid_constant__ CUtensorMap mapP0, const __grid_constant__
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(tempty_bar);
-        const int row = rq * 32 + lane;
+        const int row = GP_M64 ? rq * 16 + lane : rq * 32 + lane;
+        if (!GP_M64 || lane < 16) {
 #pragma unroll
-        for (int k = 0; k < 8; ++k) acc4[row * 16 + ((rc0 / 4 + k) ^ (row & 7))] = make_float4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
+          for (int k = 0; k < 8; ++k) acc4[row * 16 + ((rc0 / 4 + k) ^ (row & 7))] = make_float4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
+        }
       }
       epi_bar();
       __nv_bfloat16* dst = ((i + 1) & 1) ? g.P1 : g.P0;
