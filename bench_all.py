@@ -199,6 +199,13 @@ def rows(args):
 
     sec, nl = timed(lnstep, args.steps)
     emit(f"micro batch-statistic LayerNorm fwd+bwd [{R},{Cn}] fp32", sec, nbytes=4.0 * R * Cn * (4 + 5), launches=nl)
+    try:  # the same step recorded once and replayed as a CUDA graph: the ~16 eager launches cost more host time than GPU time
+        gstep = pdn.cuda.graphed_step(lnstep)
+        sec, nl = timed(gstep, args.steps)
+        emit(f"micro batch-statistic LayerNorm fwd+bwd [{R},{Cn}] fp32, step recorded with pdn.cuda.graphed_step (CUDA-graph replay)", sec,
+             nbytes=4.0 * R * Cn * (4 + 5), launches=nl)
+    except Exception as e:  # noqa: BLE001
+        print(json.dumps({"config": "LayerNorm graphed", "error": repr(e)[:200]}), flush=True)
     n = 1 << 20 if args.small else 1 << 26
     p = T(rng.standard_normal(n).astype(f32), True)
     opt = Adam([p], lr=1e-3)

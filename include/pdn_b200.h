@@ -226,6 +226,8 @@ int pdn_rmsnorm_bwd(const float* x, const float* w, const float* rstd, const flo
  * 132-147,203-218): x viewed as [outer, C, inner], statistics per channel c over outer*inner elements
  * (biased variance), y = (x-mean)/sqrt(var+eps)*scale+shift. mean/var out are [C]. */
 int pdn_bnorm_stats(const float* x, float* mean, float* var, int64_t outer, int64_t C, int64_t inner);
+/* running statistics in place: r <- (1 - momentum) r + momentum stat (norm.py:66-69, 140-143, 211-214), both vectors in one launch */
+int pdn_bnorm_running(float* running_mean, float* running_var, const float* mean, const float* var, float momentum, int64_t C);
 int pdn_bnorm_apply(const float* x, const float* mean, const float* var, const float* scale, const float* shift,
                     float* y, int64_t outer, int64_t C, int64_t inner, float eps);
 /* backward of the composite: given g, x, mean, var → dx, dscale[C], dshift[C] */

@@ -85,6 +85,7 @@ _PROTOS = {
     "pdn_rmsnorm_fwd": [vp, vp, vp, vp, i64, i64, f32],
     "pdn_rmsnorm_bwd": [vp, vp, vp, vp, vp, vp, i64, i64],
     "pdn_bnorm_stats": [vp, vp, vp, i64, i64, i64],
+    "pdn_bnorm_running": [vp, vp, vp, vp, f32, i64],
     "pdn_bnorm_apply": [vp, vp, vp, vp, vp, vp, i64, i64, i64, f32],
     "pdn_bnorm_bwd": [vp, vp, vp, vp, vp, vp, vp, vp, i64, i64, i64, f32],
     "pdn_conv2d_fwd": [vp, vp, vp, vp, i64, i64, i64, i64, i64, i32, i32, i32, i64],

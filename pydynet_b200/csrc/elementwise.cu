@@ -356,6 +356,13 @@ static int copy_from(const void* src, void* dst, int ddtype, const StridedDesc& 
 
 extern "C" {
 
+// dst[i] = *src : a broadcast scalar materialised (the upstream gradient of `.sum()`: ones expanded to the operand's shape)
+__global__ void __launch_bounds__(256) k_bcast_scalar_f32(const float* __restrict__ s, float4* __restrict__ d, int64_t n4) {
+  const float  v = __ldg(s);
+  const float4 v4 = make_float4(v, v, v, v);
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) d[i] = v4;
+}
+
 int pdn_copy(const void* src, int sdtype, void* dst, int ddtype, int ndim, const int64_t* shape, const int64_t* ss,
              const int64_t* ds) {
   PDN_TRY(ensure_init());
@@ -371,6 +378,11 @@ int pdn_copy(const void* src, int sdtype, void* dst, int ddtype, int ndim, const
     } else {
       PDN_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, stream()));
     }
+    return 0;
+  }
+  if (sdtype == PDN_F32 && ddtype == PDN_F32 && d.ndim == 1 && d.s[0][0] == 0 && desc_dense(d, 1) && aligned16(dst) && d.n % 4 == 0) {
+    k_bcast_scalar_f32<<<grid_for(d.n / 4, 256, 4), 256, 0, stream()>>>((const float*)src, (float4*)dst, d.n / 4);
+    PDN_LAUNCHED("bcast_scalar");
     return 0;
   }
   DISPATCH_ALL(sdtype, return copy_from<T>(src, dst, ddtype, d));

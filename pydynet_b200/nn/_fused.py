@@ -6,6 +6,7 @@ import ctypes as C
 import os
 
 import numpy as np
+from ..backend.array import WRITE_EPOCH
 
 from ..autograd import is_grad_enable
 from ..core.tensor import Tensor, _result, _sum_to
@@ -443,10 +444,16 @@ def feature_norm(mod, x, axes, keep):
         sc, sh = _c(scale.data).reshape(-1), _c(shift.data).reshape(-1)
         _call("pdn_bnorm_apply", xd.ptr, mean.ptr, var.ptr, sc.ptr, sh.ptr, y.ptr, outer, Cn, inner, mod.eps)
         rm, rv = mod.running_mean.data, mod.running_var.data
-        rm *= (1 - mod.momentum)
-        rm += (mean * mod.momentum).reshape(rm.shape)
-        rv *= (1 - mod.momentum)
-        rv += (var * mod.momentum).reshape(rv.shape)
+        if rm.dtype == F32 and rv.dtype == F32 and rm.size == Cn and rv.size == Cn and rm.is_contiguous and rv.is_contiguous:
+            _call("pdn_bnorm_running", rm.ptr, rv.ptr, mean.ptr, var.ptr, float(mod.momentum), Cn)  # one launch instead of six
+            rm.buf.version += 1
+            rv.buf.version += 1
+            WRITE_EPOCH[0] += 1
+        else:
+            rm *= (1 - mod.momentum)
+            rm += (mean * mod.momentum).reshape(rm.shape)
+            rv *= (1 - mod.momentum)
+            rv += (var * mod.momentum).reshape(rv.shape)
 
     def backward(g):
         g = _c(g)
