@@ -889,7 +889,11 @@ int gemm_tc_packed(const PackedOperand& A, const PackedOperand& B, TcArgs t, int
   if (splits <= 0) {
     splits = 1;
     if (tiles < sms / 2 && num_kb >= 8) {
-      int64_t want = (sms + tiles - 1) / tiles;
+      // tiles x splits work items run as ONE wave of persistent CTAs: rounding the split count UP put 8 tiles x 19 splits = 152
+      // items on 148 SMs, i.e. a second wave for 4 items (dW = x^T g of the encoder, K = 65536: 0.53 of the ceiling); rounding down
+      // keeps every item in the first wave (144 CTAs)
+      int64_t want = sms / tiles;
+      if (want < 1) want = 1;
       int64_t cap = num_kb / 4;
       splits = (int)(want < cap ? want : cap);
       if (splits < 1) splits = 1;
