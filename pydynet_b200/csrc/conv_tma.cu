@@ -419,7 +419,9 @@ int conv_tma_bwd_weight(const float* x, const float* gy, float* dw, int64_t N, i
   const int64_t patches = N * g.TY * g.TX;
   PDN_CHECK(patches < 0x7fffffff, "conv_tma: too many patches");
   const int64_t base_tiles = (int64_t)(w3 ? k : taps) * g.m_tiles * g.n_tiles_n;
-  int64_t splits = (sm_count() + base_tiles - 1) / base_tiles;
+  // rounded DOWN: base_tiles x splits work items must fit ONE wave of persistent CTAs (3 x 50 = 150 items on 148 SMs made two CTAs
+  // run a second item and doubled the kernel's time)
+  int64_t splits = sm_count() / base_tiles;
   if (splits > patches) splits = patches;
   if (splits < 1) splits = 1;
   const int64_t per = (patches + splits - 1) / splits;
