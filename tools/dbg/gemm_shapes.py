@@ -5,7 +5,9 @@ import pydynet_b200 as pdn
 from pydynet_b200.backend import lib
 rng = np.random.default_rng(0)
 PEAK = 1416e12
-for (M, N, K) in [(65536, 512, 512), (65536, 1536, 512), (65536, 512, 1536), (512, 512, 65536), (512, 1536, 65536), (8192, 8192, 8192)]:
+SHAPES = {'encoder': [(65536, 512, 512), (65536, 1536, 512), (65536, 512, 1536), (512, 512, 65536), (512, 1536, 65536), (8192, 8192, 8192)],
+          'other': [(256, 500, 2450), (2450, 500, 256), (256, 2450, 500), (262144, 1536, 512), (512, 1536, 262144), (512, 2048, 262144), (1024, 1024, 1024), (2048, 2048, 2048), (4096, 512, 4096), (512, 4096, 4096)]}
+for (M, N, K) in SHAPES[os.environ.get('SHAPES', 'encoder')]:
     with pdn.Device("cuda:0"):
         a = pdn.backend.array(rng.standard_normal((M, K)).astype(np.float32)); b = pdn.backend.array(rng.standard_normal((K, N)).astype(np.float32))
         out = pdn.backend.empty((M, N), np.float32)
